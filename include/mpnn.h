@@ -1,0 +1,210 @@
+/* libmpnn_sm100 -- C ABI of the B200 (sm_100a) hot path of multipath-nn.
+ *
+ * The reference (MasonMcGill/multipath-nn) has no FFI boundary: its hot path
+ * is a TensorFlow graph built by scripts/lib/layer_types.py and
+ * scripts/lib/net_types.py and executed by `net.train.run(...)`
+ * (scripts/train-nets:141-143) and `session.run(state_tensors)`
+ * (scripts/lib/desc.py:17-18).  Each entry point below replaces the TF op
+ * call sites named in its comment (paths relative to /root/reference/scripts).
+ *
+ * Conventions
+ *   - every function returns 0 or a negative error code; mpnn_last_error()
+ *     gives the text.  Nothing is allocated or freed on behalf of the caller.
+ *   - all pointers are DEVICE pointers unless stated; `stream` is a
+ *     cudaStream_t passed as void*.
+ *   - activations use the "padded planes" layout
+ *         T x[C/8][P][8],  row p = G + n*(H+1)*(W+1) + (h+1)*(W+1) + (w+1)
+ *     (zero pad row/column 0 of every image block, G zero guard rows in
+ *     front, >=192 behind).  dtype: 0 = fp32, 1 = bf16.  C is padded to a
+ *     multiple of 8 (16 in bf16 mode).
+ *   - feature matrices (inputs of fully-connected heads) use the same
+ *     layout with one row per example: T x[F/8][Balloc][8].
+ */
+#ifndef MPNN_H
+#define MPNN_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+const char* mpnn_last_error(void);
+int mpnn_version(void);
+/* 1 if the tcgen05 (bf16) kernels were compiled in */
+int mpnn_has_umma(void);
+
+/* ---- input / weight packing ------------------------------------------- */
+/* ToPyramid (lib/layer_types.py:118-125): scale i of the pyramid is
+ * x0[:, ::step, ::step, :] (legacy bilinear resize at integer factors).
+ * x0 is NHWC fp32 (B,H0,W0,C0); writes the valid pixels of `planes`
+ * (H = H0/step, W = W0/step, Cpad channels, extra channels zero). */
+int mpnn_pack_input(const float* x0, int B, int H0, int W0, int C0, int step,
+                    void* planes, int Cpad, int G, int P, int dtype, void* stream);
+
+/* HWIO fp32 conv weights (lib/layer_types.py:158-173) or (n_in,n_chan) FC
+ * weights -> packed operand  Wp[tap][Ktot/8][Ntot][8].
+ *   mode 0 (forward):  k = k_off + i, n = n_off + o, tap = t
+ *   mode 1 (dgrad):    k = k_off + o, n = n_off + i, tap = ntaps-1-t
+ * Elements not written (channel padding) must have been zeroed by the caller. */
+int mpnn_pack_weights(const float* w, int ntaps, int I, int O, int mode,
+                      int k_off, int Ktot, int n_off, int Ntot,
+                      void* packed, int dtype, void* stream);
+
+/* ---- stencil GEMM: tf.nn.conv2d SAME (lib/layer_types.py:106-107,181-185) */
+/* out[p][n] = bias[n] + sum_tap sum_k A[p+off(tap)][k] * Wp[tap][k][n]
+ * A = concat(A0 (K0 ch), A1 (K1 ch)); columns [0,N0) go to out0, [N0,N0+N1)
+ * to out1.  ntaps = 9 (3x3) or 1.  impl: 0 = fp32 SIMT, 1 = tcgen05 (bf16).
+ * stats (optional): per-CTA partial sums over VALID pixels of out:
+ *   stats[cta][0][n] = sum, stats[cta][1][n] = sum of squares; returns the
+ *   number of partial rows written through *n_parts (host pointer).
+ * Pad rows of the outputs are unspecified. acc0/acc1: add into out. */
+int mpnn_stencil_gemm(const void* A0, int K0, const void* A1, int K1,
+                      const void* Wp, int ntaps, const float* bias,
+                      void* out0, int N0, int acc0, void* out1, int N1, int acc1,
+                      int B, int H, int W, int G, int P,
+                      float* stats, int stats_cap, int* n_parts,
+                      int dtype, int out_dtype, int impl, void* stream);
+
+/* weight gradient of the above:
+ *   dW0[tap][k][n] += sum_p A0[p+off][k] * Gd[p][n]   (k < K0real, n < Nreal)
+ *   dW1 likewise for A1;  dbias[n] += sum_p Gd[p][n]
+ * dW0/dW1/dbias are fp32 HWIO gradient tensors ([tap][Kreal][Nreal]). */
+int mpnn_stencil_wgrad(const void* A0, int K0, int K0real, float* dW0,
+                       const void* A1, int K1, int K1real, float* dW1,
+                       const void* Gd, int N, int Nreal, float* dbias, int ntaps,
+                       int B, int H, int W, int G, int P,
+                       int dtype, int impl, void* stream);
+
+/* ---- BatchNorm + ReLU + max-pool (lib/layer_types.py:109-110,219-249,196-199) */
+/* partial sums -> scale/shift.  train: batch mean / biased var over `count`
+ * elements, EMA update of m_avg/v_avg with decay d; else uses the EMAs.
+ * ss[0][c] = gamma*rstd, ss[1][c] = beta - mean*gamma*rstd,
+ * mr[0][c] = mean, mr[1][c] = rstd. */
+int mpnn_bn_finalize(const float* partials, int n_parts, int C, double count,
+                     const float* gamma, const float* beta, float* m_avg, float* v_avg,
+                     float d, float eps, int train, float* ss, float* mr, void* stream);
+/* act = relu(ss0*lin+ss1) on valid pixels (skipped if act==NULL);
+ * pooled = 2x2/2 max of lin, written in the (H/2,W/2) geometry (if !NULL);
+ * feat[(h*W+w)*(C/8)+kg][n][8] = act (if !NULL; the LinTrans flatten order). */
+int mpnn_bn_relu_pool_fwd(const void* lin, int C, int B, int H, int W, int G, int P,
+                          const float* ss, void* act, void* pooled, int Pp,
+                          void* feat, int Balloc, int dtype, void* stream);
+/* backward, pass 1: partial sums of dy' and dy'*xhat (dy' = relu-masked sum
+ * of dAct and dFeat); *n_parts rows written. */
+int mpnn_bn_bwd_reduce(const void* lin, const void* dAct, const void* dFeat, int Balloc,
+                       const float* ss, const float* mr, int C,
+                       int B, int H, int W, int G, int P,
+                       float* partials, int cap, int* n_parts, int dtype, void* stream);
+/* sums[0][c] = sum dy', sums[1][c] = sum dy'*xhat; dgamma += sums1, dbeta += sums0 */
+int mpnn_bn_bwd_finalize(const float* partials, int n_parts, int C,
+                         float* sums, float* dgamma, float* dbeta, void* stream);
+/* backward, pass 2: dLin = ss0*(dy' - mean(dy') - xhat*mean(dy'*xhat))
+ *                        + unpool(dPooled)   [argmax recomputed from lin]
+ * ss==NULL: BN branch absent (dead scale) -> only the unpool term. */
+int mpnn_bn_relu_pool_bwd(const void* lin, const void* dAct, const void* dFeat, int Balloc,
+                          const void* dPooled, int Pp,
+                          const float* ss, const float* mr, const float* sums, double count,
+                          int C, int B, int H, int W, int G, int P,
+                          void* dLin, int dtype, void* stream);
+
+/* ---- heads: LinTrans / Softmax / CrossEntropyError (lib/layer_types.py:39-53,81-84,262-272) */
+/* Z[b][j] = sum_f X[f][b] W[f][j] (+ extra[b]*W[F][j]) + bias[j] */
+int mpnn_fc_fwd(const void* X, int F, int Balloc, int B, const float* W, const float* bias,
+                const float* extra, int n, float* Z, int dtype, void* stream);
+/* dX[f][b] = sum_j dZ0[b][j] W0[f][j] (+ dZ1 W1) */
+int mpnn_fc_bwd_data(const float* dZ0, const float* W0, int n0,
+                     const float* dZ1, const float* W1, int n1,
+                     int F, int Balloc, int B, void* dX, int dtype, void* stream);
+/* dW[f][j] += sum_b X[f][b] dZ[b][j]; dW[F][j] += sum_b extra[b] dZ[b][j]; db[j] += sum_b dZ[b][j] */
+int mpnn_fc_bwd_weight(const void* X, int F, int Balloc, int B, const float* extra,
+                       const float* dZ, int n, float* dW, float* db, int dtype, void* stream);
+/* prob = softmax(Z); c_err = -sum y log(eps/n + (1-eps) prob); d_cor = [argmax prob == argmax y]
+ * (first maximal index). */
+int mpnn_softmax_ce_fwd(const float* Z, const float* y, int B, int n, float eps,
+                        float* prob, float* c_err, float* d_cor, void* stream);
+/* dZ[b][j] = coef[b]*coef_scale * d c_err[b] / d Z[b][j]   (coef==NULL -> 1) */
+int mpnn_softmax_ce_bwd(const float* prob, const float* y, int B, int n, float eps,
+                        const float* coef, float coef_scale, float* dZ, void* stream);
+
+/* Router tail (arch_and_hypers.py:45-49): BN -> ReLU -> FC(16) -> BN -> ReLU -> FC(ns)
+ * applied to Z1 = output of the first router FC.  One CTA.
+ * bn{1,2}: gamma,beta,m_avg,v_avg (C=16 each). save: >= 4*C floats (mean1,rstd1,mean2,rstd2). */
+int mpnn_router_tail_fwd(const float* Z1, int B, int C,
+                         const float* g1, const float* b1, float* m1, float* v1,
+                         const float* W2, const float* bias2,
+                         const float* g2, const float* b2, float* m2, float* v2,
+                         const float* W3, const float* bias3, int ns,
+                         float d, float eps, int train,
+                         float* Z2, float* R, float* save, void* stream);
+/* gradients are ACCUMULATED into dW*, db*, dg*, dbt*; dZ1 is written. */
+int mpnn_router_tail_bwd(const float* Z1, const float* Z2, const float* dR, int B, int C, int ns,
+                         const float* g1, const float* b1, const float* W2,
+                         const float* g2, const float* b2, const float* W3,
+                         const float* save,
+                         float* dg1, float* dbt1, float* dW2, float* dbias2,
+                         float* dg2, float* dbt2, float* dW3, float* dbias3,
+                         float* dZ1, float* scratch /* >= 2*B*C */, void* stream);
+
+/* ---- routing (lib/net_types.py:108-131,193-243) ------------------------ */
+/* Tree tables (device int/float arrays, nodes in preorder, node 0 = root):
+ *   parent[i], sink_idx[i] (position among parent's sinks), n_sinks[i],
+ *   floor[i] = eps*n_leaves(i)/n_leaves(root), sw[i] = switch slot or -1,
+ *   ops[i] = n_ops + router.n_ops, err[i] = leaf slot or -1.
+ * logits: R[slot] -> float* table (device array of pointers), each [B][n_sinks].
+ * Outputs p_tr, p_ev: [n_nodes][B]; dec: [n_switch][B] int32 (argmax, first max). */
+int mpnn_route_fwd(const int* parent, const int* sink_idx, const int* n_sinks,
+                   const float* floor_, const int* sw, int n_nodes,
+                   const float* const* R, float tau, int B,
+                   float* p_tr, float* p_ev, int* dec, void* stream);
+/* Actor (critic=0): gradient of c_tot wrt router logits and per-leaf CE
+ * coefficients (net_types.py:167-177):
+ *   coef[slot][b] = p_tr[leaf][b]
+ *   dR[slot][b][i] = d/dR of mean_b( sum_l p_tr(c_err + k_cpt ops) + sg(p_tr) k_dec |R|^2 )
+ * Critic (critic=1; net_types.py:201-243,275-280): also computes c_ev/c_opt
+ * bottom-up and dR = p_tr/B * 2 k_cre (R_i + target_i).
+ *   c_err: table of per-leaf [B] arrays; d_cor likewise (use_cls_err).
+ *   k_cpt: [B] if k_cpt_vec else scalar k_cpt_s.  scratch: >= 3*n_nodes*B floats. */
+int mpnn_route_bwd(const int* parent, const int* sink_idx, const int* n_sinks,
+                   const int* child /* [n_nodes][8] child node per sink */,
+                   const float* floor_, const int* sw, const float* ops, const int* err,
+                   int n_nodes, const float* const* R, float tau, int B,
+                   const float* p_tr, const float* p_ev,
+                   const float* const* c_err, const float* const* d_cor,
+                   const float* k_cpt, float k_cpt_s,
+                   int critic, float k_dec, float k_cre, int optimistic, int use_cls_err,
+                   float* const* dR, float* scratch, float* c_data /* [B] per-example cost or NULL */,
+                   void* stream);
+/* per-node batch moments of p_tr: stats[i][0] = mean p_tr^2, stats[i][1] = mean p_tr */
+int mpnn_node_moments(const float* p_tr, int n_nodes, int B, float* stats, void* stream);
+
+/* Path compaction: for every node, the ascending list of examples with
+ * p_ev == 1 (ballot + prefix scan); idx[node][B], count[node]. */
+int mpnn_compact_paths(const float* p_ev, int n_nodes, int B, int* idx, int* count, void* stream);
+/* gather / scatter-add whole image blocks between padded-planes tensors:
+ * dst image j <- src image idx[j] (gather); dst image idx[j] += src image j (scatter). */
+int mpnn_gather_images(const void* src, int Bs, int Ps, const int* idx, const int* count,
+                       void* dst, int Bd, int Pd, int C, int H, int W, int G, int dtype, void* stream);
+int mpnn_scatter_add_images(const void* src, int Bs, int Ps, const int* idx, const int* count,
+                            void* dst, int Bd, int Pd, int C, int H, int W, int G, int dtype, void* stream);
+
+/* ---- optimiser: minimize_expectation + MomentumOptimizer (lib/net_types.py:24-37) */
+/* For segment s covering theta[seg_start[s] : seg_start[s+1]):
+ *   g = grad*grad_scale + 2*seg_l2[s]*coef*theta,  coef = node mean p_tr (1 if node_stats==NULL)
+ *   g *= seg_mult[s] / sqrt(node mean p_tr^2)       (TALR; skipped if !talr or node_stats==NULL)
+ *   a = mu*a + g ; theta -= lr*a
+ * seg_node[s] = preorder node index. */
+int mpnn_talr_momentum_step(float* theta, const float* grad, float* accum, int n,
+                            const int* seg_start, const int* seg_node, const float* seg_mult,
+                            const float* seg_l2, int n_seg, const float* node_stats, int talr,
+                            float lr, float mu, float grad_scale, void* stream);
+
+/* ---- tcgen05 bring-up probe (tests only) -------------------------------- */
+/* D[128][N] = A[128][K] * B[N][K]^T through one CTA of tcgen05.mma; all
+ * operands in the interleaved (no-swizzle) core-matrix layout. */
+int mpnn_umma_selftest(const void* A, const void* Bm, float* D, int N, int K,
+                       int a_mn_major, int b_mn_major,
+                       int lbo_a, int sbo_a, int lbo_b, int sbo_b, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

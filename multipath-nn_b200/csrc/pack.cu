@@ -1,0 +1,107 @@
+// Error plumbing, input pyramid packing and weight packing.
+#include "common.cuh"
+#include "../../include/mpnn.h"
+#include <cstdarg>
+#include <cstdio>
+
+static thread_local char g_err[512] = "";
+
+void mpnn_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int mpnn_check_launch(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        mpnn_set_error("%s: %s", what, cudaGetErrorString(e));
+        return MPNN_ERR_CUDA;
+    }
+    return MPNN_OK;
+}
+
+extern "C" const char* mpnn_last_error(void) { return g_err; }
+extern "C" int mpnn_version(void) { return 100; }
+
+// --------------------------------------------------------------------------- //
+// ToPyramid: strided subsample of NHWC fp32 into padded planes.
+// One thread per (plane kg, valid pixel); 8 channels each.
+// --------------------------------------------------------------------------- //
+template <typename T>
+__global__ void pack_input_kernel(const float* __restrict__ x0, int H0, int W0, int C0, int step,
+                                  T* __restrict__ planes, int Cpad, Geom g) {
+    const int KG = Cpad / 8;
+    const long long total = (long long)KG * g.B * g.H * g.W;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        int w = i % g.W;
+        long long r = i / g.W;
+        int h = r % g.H; r /= g.H;
+        int n = r % g.B;
+        int kg = r / g.B;
+        const float* src = x0 + (((size_t)n * H0 + (size_t)h * step) * W0 + (size_t)w * step) * C0;
+        float v[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            int ch = kg * 8 + c;
+            v[c] = ch < C0 ? __ldg(src + ch) : 0.f;
+        }
+        Row8<T>::store(plane_row(planes, kg, g.P, row_of(g, n, h, w)), v);
+    }
+}
+
+extern "C" int mpnn_pack_input(const float* x0, int B, int H0, int W0, int C0, int step,
+                               void* planes, int Cpad, int G, int P, int dtype, void* stream) {
+    MPNN_REQUIRE(step >= 1 && H0 % step == 0 && W0 % step == 0, "pack_input: bad step %d", step);
+    MPNN_REQUIRE(Cpad % 8 == 0 && Cpad >= C0, "pack_input: Cpad=%d C0=%d", Cpad, C0);
+    Geom g = make_geom(B, H0 / step, W0 / step, G, P);
+    MPNN_REQUIRE(G + g.rows <= P, "pack_input: P too small");
+    long long total = (long long)(Cpad / 8) * B * g.H * g.W;
+    int grid = (int)((total + 255) / 256);
+    if (grid > 148 * 16) grid = 148 * 16;
+    if (grid < 1) grid = 1;
+    MPNN_DISPATCH_DTYPE(dtype, (pack_input_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(
+        x0, H0, W0, C0, step, (T*)planes, Cpad, g)));
+    return mpnn_check_launch("pack_input");
+}
+
+// --------------------------------------------------------------------------- //
+// Weight packing:  w[t][i][o] (HWIO / (n_in,n_chan)) -> Wp[tap][Ktot/8][Ntot][8]
+// --------------------------------------------------------------------------- //
+template <typename T> __device__ __forceinline__ T cvt_from_float(float v);
+template <> __device__ __forceinline__ float cvt_from_float<float>(float v) { return v; }
+template <> __device__ __forceinline__ __nv_bfloat16 cvt_from_float<__nv_bfloat16>(float v) {
+    return __float2bfloat16_rn(v);
+}
+
+template <typename T>
+__global__ void pack_weights_kernel(const float* __restrict__ w, int ntaps, int I, int O, int mode,
+                                    int k_off, int Ktot, int n_off, int Ntot, T* __restrict__ packed) {
+    const int total = ntaps * I * O;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+        int o = e % O;
+        int i = (e / O) % I;
+        int t = e / (O * I);
+        int k, n, tap;
+        if (mode == 0) { k = k_off + i; n = n_off + o; tap = t; }
+        else           { k = k_off + o; n = n_off + i; tap = ntaps - 1 - t; }
+        size_t dst = (((size_t)tap * (Ktot / 8) + (k >> 3)) * Ntot + n) * 8 + (k & 7);
+        packed[dst] = cvt_from_float<T>(w[e]);
+    }
+}
+
+extern "C" int mpnn_pack_weights(const float* w, int ntaps, int I, int O, int mode,
+                                 int k_off, int Ktot, int n_off, int Ntot,
+                                 void* packed, int dtype, void* stream) {
+    MPNN_REQUIRE(Ktot % 8 == 0, "pack_weights: Ktot %% 8");
+    if (mode == 0) MPNN_REQUIRE(k_off + I <= Ktot && n_off + O <= Ntot, "pack_weights: range");
+    else           MPNN_REQUIRE(k_off + O <= Ktot && n_off + I <= Ntot, "pack_weights: range (dgrad)");
+    int total = ntaps * I * O;
+    int grid = (total + 255) / 256;
+    if (grid > 148 * 8) grid = 148 * 8;
+    MPNN_DISPATCH_DTYPE(dtype, (pack_weights_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(
+        w, ntaps, I, O, mode, k_off, Ktot, n_off, Ntot, (T*)packed)));
+    return mpnn_check_launch("pack_weights");
+}

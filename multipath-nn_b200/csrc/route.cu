@@ -1,0 +1,287 @@
+// Routing: per-example walk of the sink tree (policy softmax, epsilon floor,
+// first-max argmax, child probabilities), its backward (actor expectation
+// gradient / critic cost regression), per-node batch moments for TALR, and
+// path compaction + image gather / scatter-add.
+// Reference: lib/net_types.py:108-131 (actor), :193-243 (critic), :24-27 (TALR).
+#include "common.cuh"
+#include "../../include/mpnn.h"
+
+#define RT_MAXS 8   // max sinks per switch
+
+__device__ __forceinline__ int route_softmax(const float* __restrict__ r, int ns, float tau, float* sm) {
+    float x[RT_MAXS];
+    float mx = -INFINITY, mr = -INFINITY;
+    int dec = 0;
+    for (int j = 0; j < ns; ++j) {
+        float v = r[j];
+        if (v > mr) { mr = v; dec = j; }          // first maximal index (tf.argmax)
+        x[j] = v / tau;
+        mx = fmaxf(mx, x[j]);
+    }
+    float s = 0.f;
+    for (int j = 0; j < ns; ++j) { x[j] = expf(x[j] - mx); s += x[j]; }
+    float inv = 1.f / s;
+    for (int j = 0; j < ns; ++j) sm[j] = x[j] * inv;
+    return dec;
+}
+
+__global__ void route_fwd_kernel(const int* __restrict__ parent, const int* __restrict__ sink_idx,
+                                 const int* __restrict__ n_sinks, const float* __restrict__ floor_,
+                                 const int* __restrict__ sw, int n_nodes,
+                                 const float* const* __restrict__ R, float tau, int B,
+                                 float* __restrict__ p_tr, float* __restrict__ p_ev, int* __restrict__ dec) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    p_tr[b] = 1.f; p_ev[b] = 1.f;
+    for (int i = 1; i < n_nodes; ++i) {
+        int par = parent[i];
+        int ns = n_sinks[par];
+        float pt = p_tr[(size_t)par * B + b], pe = p_ev[(size_t)par * B + b];
+        if (ns >= 2) {
+            float sm[RT_MAXS];
+            int slot = sw[par];
+            int d = route_softmax(R[slot] + (size_t)b * ns, ns, tau, sm);
+            int si = sink_idx[i];
+            if (si == 0 && dec) dec[(size_t)slot * B + b] = d;
+            pt = (pt - floor_[par]) * sm[si] + floor_[i];
+            pe = pe * (d == si ? 1.f : 0.f);
+        }
+        p_tr[(size_t)i * B + b] = pt;
+        p_ev[(size_t)i * B + b] = pe;
+    }
+}
+
+extern "C" int mpnn_route_fwd(const int* parent, const int* sink_idx, const int* n_sinks,
+                              const float* floor_, const int* sw, int n_nodes,
+                              const float* const* R, float tau, int B,
+                              float* p_tr, float* p_ev, int* dec, void* stream) {
+    MPNN_REQUIRE(n_nodes >= 1 && B >= 1 && tau > 0.f, "route_fwd: args");
+    route_fwd_kernel<<<ceil_div(B, 128), 128, 0, (cudaStream_t)stream>>>(
+        parent, sink_idx, n_sinks, floor_, sw, n_nodes, R, tau, B, p_tr, p_ev, dec);
+    return mpnn_check_launch("route_fwd");
+}
+
+__global__ void route_bwd_kernel(const int* __restrict__ parent, const int* __restrict__ sink_idx,
+                                 const int* __restrict__ n_sinks, const int* __restrict__ child,
+                                 const float* __restrict__ floor_, const int* __restrict__ sw,
+                                 const float* __restrict__ ops, const int* __restrict__ err, int n_nodes,
+                                 const float* const* __restrict__ R, float tau, int B,
+                                 const float* __restrict__ p_tr, const float* __restrict__ p_ev,
+                                 const float* const* __restrict__ c_err, const float* const* __restrict__ d_cor,
+                                 const float* __restrict__ k_cpt, float k_cpt_s,
+                                 int critic, float k_dec, float k_cre, int optimistic, int use_cls_err,
+                                 float* const* __restrict__ dR, float* __restrict__ scratch,
+                                 float* __restrict__ c_data) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const float invB = 1.f / (float)B;
+    const float kc = k_cpt ? k_cpt[b] : k_cpt_s;
+    float* gp = scratch;                              // [n_nodes][B]
+    float* cev = scratch + (size_t)n_nodes * B;       // critic
+    float* cop = scratch + (size_t)2 * n_nodes * B;   // critic
+    float total = 0.f;
+    if (!critic) {
+        for (int i = 0; i < n_nodes; ++i) {
+            float ce = err[i] >= 0 ? c_err[err[i]][b] : 0.f;
+            float local = ce + kc * ops[i];
+            gp[(size_t)i * B + b] = local * invB;
+            total += p_tr[(size_t)i * B + b] * local;
+        }
+        for (int i = n_nodes - 1; i >= 1; --i) {
+            int par = parent[i];
+            int ns = n_sinks[par];
+            float g = gp[(size_t)i * B + b];
+            if (ns >= 2) {
+                float sm[RT_MAXS];
+                route_softmax(R[sw[par]] + (size_t)b * ns, ns, tau, sm);
+                g *= sm[sink_idx[i]];
+            }
+            gp[(size_t)par * B + b] += g;
+        }
+        for (int i = 0; i < n_nodes; ++i) {
+            int ns = n_sinks[i];
+            if (ns < 2) continue;
+            const float* r = R[sw[i]] + (size_t)b * ns;
+            float sm[RT_MAXS], gs[RT_MAXS];
+            route_softmax(r, ns, tau, sm);
+            float pt = p_tr[(size_t)i * B + b];
+            float dot = 0.f, r2 = 0.f;
+            for (int j = 0; j < ns; ++j) {
+                gs[j] = gp[(size_t)child[i * RT_MAXS + j] * B + b] * (pt - floor_[i]);
+                dot = fmaf(sm[j], gs[j], dot);
+                r2 = fmaf(r[j], r[j], r2);
+            }
+            float* out = dR[sw[i]] + (size_t)b * ns;
+            for (int j = 0; j < ns; ++j)
+                out[j] = sm[j] * (gs[j] - dot) / tau + pt * k_dec * 2.f * r[j] * invB;
+            total += pt * k_dec * r2;
+        }
+    } else {
+        for (int i = n_nodes - 1; i >= 0; --i) {
+            int ns = n_sinks[i];
+            float ce;
+            if (use_cls_err) ce = err[i] >= 0 ? 1.f - d_cor[err[i]][b] : 0.f;
+            else ce = err[i] >= 0 ? c_err[err[i]][b] : 0.f;
+            float base = ce + kc * ops[i];
+            float pt = p_tr[(size_t)i * B + b];
+            float cre = 0.f;
+            if (ns < 2) {
+                float e = base, o = base;
+                for (int j = 0; j < ns; ++j) {
+                    int ch = child[i * RT_MAXS + j];
+                    e += cev[(size_t)ch * B + b]; o += cop[(size_t)ch * B + b];
+                }
+                cev[(size_t)i * B + b] = e; cop[(size_t)i * B + b] = o;
+            } else {
+                const float* r = R[sw[i]] + (size_t)b * ns;
+                float sm[RT_MAXS];
+                int d = route_softmax(r, ns, tau, sm);
+                float mn = INFINITY;
+                float* out = dR[sw[i]] + (size_t)b * ns;
+                for (int j = 0; j < ns; ++j) {
+                    int ch = child[i * RT_MAXS + j];
+                    float ev = cev[(size_t)ch * B + b], op = cop[(size_t)ch * B + b];
+                    mn = fminf(mn, op);
+                    float tgt = optimistic ? op : ev;
+                    float dlt = r[j] + tgt;
+                    cre = fmaf(dlt, dlt, cre);
+                    out[j] = pt * invB * k_cre * 2.f * dlt;
+                }
+                cre *= k_cre;
+                cev[(size_t)i * B + b] = base + cev[(size_t)child[i * RT_MAXS + d] * B + b];
+                cop[(size_t)i * B + b] = base + mn;
+            }
+            float ce_true = err[i] >= 0 ? c_err[err[i]][b] : 0.f;
+            total += pt * (ce_true + cre);
+        }
+    }
+    if (c_data) c_data[b] = total;
+}
+
+extern "C" int mpnn_route_bwd(const int* parent, const int* sink_idx, const int* n_sinks, const int* child,
+                              const float* floor_, const int* sw, const float* ops, const int* err,
+                              int n_nodes, const float* const* R, float tau, int B,
+                              const float* p_tr, const float* p_ev,
+                              const float* const* c_err, const float* const* d_cor,
+                              const float* k_cpt, float k_cpt_s,
+                              int critic, float k_dec, float k_cre, int optimistic, int use_cls_err,
+                              float* const* dR, float* scratch, float* c_data, void* stream) {
+    MPNN_REQUIRE(n_nodes >= 1 && B >= 1 && tau > 0.f, "route_bwd: args");
+    route_bwd_kernel<<<ceil_div(B, 128), 128, 0, (cudaStream_t)stream>>>(
+        parent, sink_idx, n_sinks, child, floor_, sw, ops, err, n_nodes, R, tau, B, p_tr, p_ev, c_err, d_cor,
+        k_cpt, k_cpt_s, critic, k_dec, k_cre, optimistic, use_cls_err, dR, scratch, c_data);
+    return mpnn_check_launch("route_bwd");
+}
+
+// ------------------------------------------------------------- node moments
+__global__ void node_moments_kernel(const float* __restrict__ p_tr, int B, float* __restrict__ stats) {
+    const int i = blockIdx.x;
+    float s2 = 0.f, s1 = 0.f;
+    for (int b = threadIdx.x; b < B; b += blockDim.x) {
+        float v = p_tr[(size_t)i * B + b];
+        s2 = fmaf(v, v, s2); s1 += v;
+    }
+    __shared__ float red[2][8];
+    s2 = warp_sum(s2); s1 = warp_sum(s1);
+    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = s2; red[1][threadIdx.x >> 5] = s1; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float a = 0.f, c = 0.f;
+        for (int w = 0; w < 8; ++w) { a += red[0][w]; c += red[1][w]; }
+        stats[i * 2] = a / B;
+        stats[i * 2 + 1] = c / B;
+    }
+}
+
+extern "C" int mpnn_node_moments(const float* p_tr, int n_nodes, int B, float* stats, void* stream) {
+    node_moments_kernel<<<n_nodes, 256, 0, (cudaStream_t)stream>>>(p_tr, B, stats);
+    return mpnn_check_launch("node_moments");
+}
+
+// ---------------------------------------------------------- path compaction
+// One CTA per node; ballot + warp/CTA prefix scan; order preserving.
+__global__ void __launch_bounds__(1024)
+compact_paths_kernel(const float* __restrict__ p_ev, int B, int* __restrict__ idx, int* __restrict__ count) {
+    const int node = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __shared__ int wcount[32];
+    __shared__ int base_s;
+    if (threadIdx.x == 0) base_s = 0;
+    __syncthreads();
+    for (int b0 = 0; b0 < B; b0 += 1024) {
+        int b = b0 + threadIdx.x;
+        bool take = b < B && p_ev[(size_t)node * B + b] > 0.5f;
+        unsigned m = __ballot_sync(0xffffffffu, take);
+        if (lane == 0) wcount[warp] = __popc(m);
+        __syncthreads();
+        int wbase = 0, tot = 0;
+        for (int w = 0; w < 32; ++w) { int c = wcount[w]; if (w < warp) wbase += c; tot += c; }
+        int base = base_s;
+        if (take) idx[(size_t)node * B + base + wbase + __popc(m & ((1u << lane) - 1u))] = b;
+        __syncthreads();
+        if (threadIdx.x == 0) base_s = base + tot;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) count[node] = base_s;
+}
+
+extern "C" int mpnn_compact_paths(const float* p_ev, int n_nodes, int B, int* idx, int* count, void* stream) {
+    compact_paths_kernel<<<n_nodes, 1024, 0, (cudaStream_t)stream>>>(p_ev, B, idx, count);
+    return mpnn_check_launch("compact_paths");
+}
+
+// --------------------------------------------------- gather / scatter-add
+// Image blocks are S contiguous rows per plane, so both are row-vector copies.
+template <typename T, bool SCATTER>
+__global__ void move_images_kernel(const T* __restrict__ src, int Ps, const int* __restrict__ idx,
+                                   const int* __restrict__ count, T* __restrict__ dst, int Pd,
+                                   int KG, int S, int G) {
+    const int n = *count;
+    const long long total = (long long)KG * n * S;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        int r = i % S;
+        long long t = i / S;
+        int j = t % n;
+        int kg = t / n;
+        int img = idx[j];
+        if (!SCATTER) {
+            const uint4* s = reinterpret_cast<const uint4*>(plane_row(src, kg, Ps, G + img * S + r));
+            uint4* d = reinterpret_cast<uint4*>(plane_row(dst, kg, Pd, G + j * S + r));
+            d[0] = s[0];
+            if (sizeof(T) == 4) d[1] = s[1];
+        } else {
+            float a[8], c[8];
+            Row8<T>::load(plane_row(src, kg, Ps, G + j * S + r), a);
+            T* d = plane_row(dst, kg, Pd, G + img * S + r);
+            Row8<T>::load(d, c);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) c[q] += a[q];
+            Row8<T>::store(d, c);
+        }
+    }
+}
+
+template <bool SCATTER>
+static int move_images(const void* src, int Bs, int Ps, const int* idx, const int* count,
+                       void* dst, int Bd, int Pd, int C, int H, int W, int G, int dtype, void* stream) {
+    MPNN_REQUIRE(C % 8 == 0, "gather/scatter: C=%d", C);
+    int S = (H + 1) * (W + 1);
+    int cap = SCATTER ? Bs : Bd;
+    long long total = (long long)(C / 8) * cap * S;
+    int grid = (int)((total + 255) / 256);
+    if (grid > 148 * 16) grid = 148 * 16;
+    if (grid < 1) grid = 1;
+    MPNN_DISPATCH_DTYPE(dtype, (move_images_kernel<T, SCATTER><<<grid, 256, 0, (cudaStream_t)stream>>>(
+        (const T*)src, Ps, idx, count, (T*)dst, Pd, C / 8, S, G)));
+    return mpnn_check_launch(SCATTER ? "scatter_add_images" : "gather_images");
+}
+
+extern "C" int mpnn_gather_images(const void* src, int Bs, int Ps, const int* idx, const int* count,
+                                  void* dst, int Bd, int Pd, int C, int H, int W, int G, int dtype, void* stream) {
+    return move_images<false>(src, Bs, Ps, idx, count, dst, Bd, Pd, C, H, W, G, dtype, stream);
+}
+extern "C" int mpnn_scatter_add_images(const void* src, int Bs, int Ps, const int* idx, const int* count,
+                                       void* dst, int Bd, int Pd, int C, int H, int W, int G, int dtype, void* stream) {
+    return move_images<true>(src, Bs, Ps, idx, count, dst, Bd, Pd, C, H, W, G, dtype, stream);
+}

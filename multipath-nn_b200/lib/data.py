@@ -1,0 +1,86 @@
+"""Datasets in the reference's `.npz` schema (x0_tr, x0_ts, y_tr, y_ts, m_sym;
+/root/reference/scripts/lib/data.py:54-85, scripts/prep-data) plus a synthetic
+generator of the same schema (datasets cannot be downloaded offline).
+
+CPU data preparation is outside the GPU hot path; the
+augmentation here is a vectorised NumPy restatement of data.py:10-34 (random
+flip for symmetric classes, +-r_shift pixel shift with per-image-mean fill,
+sampling with replacement, float64 output).
+"""
+import numpy as np
+
+__all__ = ['Dataset', 'synthetic_archive']
+
+
+def synthetic_archive(n_tr=512, n_ts=256, shape=(32, 32, 3), n_cls=10, seed=0):
+    """Random data with prep-data's output schema: images uniform in [0,1)
+    (CIFAR is gamma-decoded into [0,1], prep-data:94-96), one-hot labels."""
+    rng = np.random.default_rng(seed)
+
+    def labels(n):
+        y = np.zeros((n, n_cls))
+        y[np.arange(n), rng.integers(0, n_cls, n)] = 1
+        return y
+    return dict(x0_tr=rng.random((n_tr, *shape)), x0_ts=rng.random((n_ts, *shape)),
+                y_tr=labels(n_tr), y_ts=labels(n_ts), m_sym=np.ones(n_cls, bool))
+
+
+class Dataset:
+    def __init__(self, path=None, archive=None, seed=None):
+        if archive is None:
+            archive = np.load(path, allow_pickle=True)['arr_0'][()]
+        self.x0_tr = archive['x0_tr']
+        self.x0_ts = archive['x0_ts']
+        self.y_tr = archive['y_tr']
+        self.y_ts = archive['y_ts']
+        self.m_sym = archive['m_sym']
+        self.x0_vl = self.x0_tr[:0]
+        self.y_vl = self.y_tr[:0]
+        self.rng = np.random.default_rng(seed)
+
+    @property
+    def x0_shape(self):
+        return self.x0_tr.shape[1:]
+
+    @property
+    def y_shape(self):
+        return self.y_tr.shape[1:]
+
+    def augmented_training_batch(self, n=128, r_shift=4):
+        rng = self.rng
+        j = rng.integers(0, len(self.x0_tr), n)
+        x = np.asarray(self.x0_tr[j], dtype=np.float64)
+        y = np.asarray(self.y_tr[j], dtype=np.float64)
+        flip = np.asarray(self.m_sym)[np.argmax(y, 1)] & (rng.random(n) >= 0.5)
+        x[flip] = x[flip][:, :, ::-1]
+        h, w = x.shape[1:3]
+        out = np.empty_like(x)
+        out[:] = x.mean((1, 2), keepdims=True)
+        du = rng.integers(-r_shift, r_shift + 1, n)
+        dv = rng.integers(-r_shift, r_shift + 1, n)
+        for i in range(n):
+            a, b = du[i], dv[i]
+            out[i, max(-a, 0):min(h - a, h), max(-b, 0):min(w - b, w)] = \
+                x[i, max(a, 0):min(h + a, h), max(b, 0):min(w + b, w)]
+        return out, y
+
+    def _batch(self, x0, y, n):
+        i = self.rng.integers(0, len(x0), n)
+        return np.take(x0, i, axis=0), np.take(y, i, axis=0)
+
+    def training_batch(self, n=128):
+        return self._batch(self.x0_tr, self.y_tr, n)
+
+    def test_batch(self, n=128):
+        return self._batch(self.x0_ts, self.y_ts, n)
+
+    @staticmethod
+    def _full_set(x0, y, n):
+        for i in range(0, len(x0), n):
+            yield x0[i:i + n], y[i:i + n]
+
+    def training_set(self, n=128):
+        yield from self._full_set(self.x0_tr, self.y_tr, n)
+
+    def test_set(self, n=128):
+        yield from self._full_set(self.x0_ts, self.y_ts, n)
