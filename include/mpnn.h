@@ -27,6 +27,11 @@
 extern "C" {
 #endif
 
+/* Per-step scalars live in a small DEVICE float array `hyp` so that a captured
+ * CUDA graph can be replayed with new values (net_types.py:139-145 feeds). */
+enum { MPNN_HYP_LR = 0, MPNN_HYP_MU = 1, MPNN_HYP_TAU = 2, MPNN_HYP_EPS = 3,
+       MPNN_HYP_KCPT = 4, MPNN_HYP_GSCALE = 5, MPNN_HYP_COUNT = 8 };
+
 const char* mpnn_last_error(void);
 int mpnn_version(void);
 /* 1 if the tcgen05 (bf16) kernels were compiled in */
@@ -147,13 +152,14 @@ int mpnn_router_tail_bwd(const float* Z1, const float* Z2, const float* dR, int 
 /* ---- routing (lib/net_types.py:108-131,193-243) ------------------------ */
 /* Tree tables (device int/float arrays, nodes in preorder, node 0 = root):
  *   parent[i], sink_idx[i] (position among parent's sinks), n_sinks[i],
- *   floor[i] = eps*n_leaves(i)/n_leaves(root), sw[i] = switch slot or -1,
+ *   floor[i] = n_leaves(i)/n_leaves(root) (multiplied by hyp[EPS] on device),
+ *   sw[i] = switch slot or -1,
  *   ops[i] = n_ops + router.n_ops, err[i] = leaf slot or -1.
  * logits: R[slot] -> float* table (device array of pointers), each [B][n_sinks].
  * Outputs p_tr, p_ev: [n_nodes][B]; dec: [n_switch][B] int32 (argmax, first max). */
 int mpnn_route_fwd(const int* parent, const int* sink_idx, const int* n_sinks,
                    const float* floor_, const int* sw, int n_nodes,
-                   const float* const* R, float tau, int B,
+                   const float* const* R, const float* hyp, int B,
                    float* p_tr, float* p_ev, int* dec, void* stream);
 /* Actor (critic=0): gradient of c_tot wrt router logits and per-leaf CE
  * coefficients (net_types.py:167-177):
@@ -162,14 +168,14 @@ int mpnn_route_fwd(const int* parent, const int* sink_idx, const int* n_sinks,
  * Critic (critic=1; net_types.py:201-243,275-280): also computes c_ev/c_opt
  * bottom-up and dR = p_tr/B * 2 k_cre (R_i + target_i).
  *   c_err: table of per-leaf [B] arrays; d_cor likewise (use_cls_err).
- *   k_cpt: [B] if k_cpt_vec else scalar k_cpt_s.  scratch: >= 3*n_nodes*B floats. */
+ *   scratch: >= 3*n_nodes*B floats. */
 int mpnn_route_bwd(const int* parent, const int* sink_idx, const int* n_sinks,
                    const int* child /* [n_nodes][8] child node per sink */,
                    const float* floor_, const int* sw, const float* ops, const int* err,
-                   int n_nodes, const float* const* R, float tau, int B,
+                   int n_nodes, const float* const* R, const float* hyp, int B,
                    const float* p_tr, const float* p_ev,
                    const float* const* c_err, const float* const* d_cor,
-                   const float* k_cpt, float k_cpt_s,
+                   const float* k_cpt /* [B] or NULL -> hyp[KCPT] */,
                    int critic, float k_dec, float k_cre, int optimistic, int use_cls_err,
                    float* const* dR, float* scratch, float* c_data /* [B] per-example cost or NULL */,
                    void* stream);
@@ -188,20 +194,20 @@ int mpnn_scatter_add_images(const void* src, int Bs, int Ps, const int* idx, con
 
 /* ---- optimiser: minimize_expectation + MomentumOptimizer (lib/net_types.py:24-37) */
 /* For segment s covering theta[seg_start[s] : seg_start[s+1]):
- *   g = grad*grad_scale + 2*seg_l2[s]*coef*theta,  coef = node mean p_tr (1 if node_stats==NULL)
+ *   g = grad*hyp[GSCALE] + 2*seg_l2[s]*coef*theta,  coef = node mean p_tr (1 if node_stats==NULL)
  *   g *= seg_mult[s] / sqrt(node mean p_tr^2)       (TALR; skipped if !talr or node_stats==NULL)
  *   a = mu*a + g ; theta -= lr*a
  * seg_node[s] = preorder node index. */
 int mpnn_talr_momentum_step(float* theta, const float* grad, float* accum, int n,
                             const int* seg_start, const int* seg_node, const float* seg_mult,
                             const float* seg_l2, int n_seg, const float* node_stats, int talr,
-                            float lr, float mu, float grad_scale, void* stream);
+                            const float* hyp /* LR, MU, GSCALE */, void* stream);
 
 /* ---- tcgen05 bring-up probe (tests only) -------------------------------- */
 /* D[128][N] = A[128][K] * B[N][K]^T through one CTA of tcgen05.mma; all
  * operands in the interleaved (no-swizzle) core-matrix layout. */
-int mpnn_umma_selftest(const void* A, const void* Bm, float* D, int N, int K,
-                       int a_mn_major, int b_mn_major,
+int mpnn_umma_selftest(const void* A, int a_bytes, int a_off, const void* Bm, int b_bytes,
+                       float* D, int N, int K, int a_mn_major, int b_mn_major,
                        int lbo_a, int sbo_a, int lbo_b, int sbo_b, void* stream);
 
 #ifdef __cplusplus

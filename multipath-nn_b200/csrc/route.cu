@@ -28,10 +28,11 @@ __device__ __forceinline__ int route_softmax(const float* __restrict__ r, int ns
 __global__ void route_fwd_kernel(const int* __restrict__ parent, const int* __restrict__ sink_idx,
                                  const int* __restrict__ n_sinks, const float* __restrict__ floor_,
                                  const int* __restrict__ sw, int n_nodes,
-                                 const float* const* __restrict__ R, float tau, int B,
+                                 const float* const* __restrict__ R, const float* __restrict__ hyp, int B,
                                  float* __restrict__ p_tr, float* __restrict__ p_ev, int* __restrict__ dec) {
     int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
+    const float tau = hyp[MPNN_HYP_TAU], eps = hyp[MPNN_HYP_EPS];
     p_tr[b] = 1.f; p_ev[b] = 1.f;
     for (int i = 1; i < n_nodes; ++i) {
         int par = parent[i];
@@ -43,7 +44,7 @@ __global__ void route_fwd_kernel(const int* __restrict__ parent, const int* __re
             int d = route_softmax(R[slot] + (size_t)b * ns, ns, tau, sm);
             int si = sink_idx[i];
             if (si == 0 && dec) dec[(size_t)slot * B + b] = d;
-            pt = (pt - floor_[par]) * sm[si] + floor_[i];
+            pt = (pt - eps * floor_[par]) * sm[si] + eps * floor_[i];
             pe = pe * (d == si ? 1.f : 0.f);
         }
         p_tr[(size_t)i * B + b] = pt;
@@ -53,11 +54,11 @@ __global__ void route_fwd_kernel(const int* __restrict__ parent, const int* __re
 
 extern "C" int mpnn_route_fwd(const int* parent, const int* sink_idx, const int* n_sinks,
                               const float* floor_, const int* sw, int n_nodes,
-                              const float* const* R, float tau, int B,
+                              const float* const* R, const float* hyp, int B,
                               float* p_tr, float* p_ev, int* dec, void* stream) {
-    MPNN_REQUIRE(n_nodes >= 1 && B >= 1 && tau > 0.f, "route_fwd: args");
+    MPNN_REQUIRE(n_nodes >= 1 && B >= 1 && hyp, "route_fwd: args");
     route_fwd_kernel<<<ceil_div(B, 128), 128, 0, (cudaStream_t)stream>>>(
-        parent, sink_idx, n_sinks, floor_, sw, n_nodes, R, tau, B, p_tr, p_ev, dec);
+        parent, sink_idx, n_sinks, floor_, sw, n_nodes, R, hyp, B, p_tr, p_ev, dec);
     return mpnn_check_launch("route_fwd");
 }
 
@@ -65,17 +66,18 @@ __global__ void route_bwd_kernel(const int* __restrict__ parent, const int* __re
                                  const int* __restrict__ n_sinks, const int* __restrict__ child,
                                  const float* __restrict__ floor_, const int* __restrict__ sw,
                                  const float* __restrict__ ops, const int* __restrict__ err, int n_nodes,
-                                 const float* const* __restrict__ R, float tau, int B,
+                                 const float* const* __restrict__ R, const float* __restrict__ hyp, int B,
                                  const float* __restrict__ p_tr, const float* __restrict__ p_ev,
                                  const float* const* __restrict__ c_err, const float* const* __restrict__ d_cor,
-                                 const float* __restrict__ k_cpt, float k_cpt_s,
+                                 const float* __restrict__ k_cpt,
                                  int critic, float k_dec, float k_cre, int optimistic, int use_cls_err,
                                  float* const* __restrict__ dR, float* __restrict__ scratch,
                                  float* __restrict__ c_data) {
     int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
     const float invB = 1.f / (float)B;
-    const float kc = k_cpt ? k_cpt[b] : k_cpt_s;
+    const float tau = hyp[MPNN_HYP_TAU], eps = hyp[MPNN_HYP_EPS];
+    const float kc = k_cpt ? k_cpt[b] : hyp[MPNN_HYP_KCPT];
     float* gp = scratch;                              // [n_nodes][B]
     float* cev = scratch + (size_t)n_nodes * B;       // critic
     float* cop = scratch + (size_t)2 * n_nodes * B;   // critic
@@ -107,7 +109,7 @@ __global__ void route_bwd_kernel(const int* __restrict__ parent, const int* __re
             float pt = p_tr[(size_t)i * B + b];
             float dot = 0.f, r2 = 0.f;
             for (int j = 0; j < ns; ++j) {
-                gs[j] = gp[(size_t)child[i * RT_MAXS + j] * B + b] * (pt - floor_[i]);
+                gs[j] = gp[(size_t)child[i * RT_MAXS + j] * B + b] * (pt - eps * floor_[i]);
                 dot = fmaf(sm[j], gs[j], dot);
                 r2 = fmaf(r[j], r[j], r2);
             }
@@ -160,16 +162,16 @@ __global__ void route_bwd_kernel(const int* __restrict__ parent, const int* __re
 
 extern "C" int mpnn_route_bwd(const int* parent, const int* sink_idx, const int* n_sinks, const int* child,
                               const float* floor_, const int* sw, const float* ops, const int* err,
-                              int n_nodes, const float* const* R, float tau, int B,
+                              int n_nodes, const float* const* R, const float* hyp, int B,
                               const float* p_tr, const float* p_ev,
                               const float* const* c_err, const float* const* d_cor,
-                              const float* k_cpt, float k_cpt_s,
+                              const float* k_cpt,
                               int critic, float k_dec, float k_cre, int optimistic, int use_cls_err,
                               float* const* dR, float* scratch, float* c_data, void* stream) {
-    MPNN_REQUIRE(n_nodes >= 1 && B >= 1 && tau > 0.f, "route_bwd: args");
+    MPNN_REQUIRE(n_nodes >= 1 && B >= 1 && hyp, "route_bwd: args");
     route_bwd_kernel<<<ceil_div(B, 128), 128, 0, (cudaStream_t)stream>>>(
-        parent, sink_idx, n_sinks, child, floor_, sw, ops, err, n_nodes, R, tau, B, p_tr, p_ev, c_err, d_cor,
-        k_cpt, k_cpt_s, critic, k_dec, k_cre, optimistic, use_cls_err, dR, scratch, c_data);
+        parent, sink_idx, n_sinks, child, floor_, sw, ops, err, n_nodes, R, hyp, B, p_tr, p_ev, c_err, d_cor,
+        k_cpt, critic, k_dec, k_cre, optimistic, use_cls_err, dR, scratch, c_data);
     return mpnn_check_launch("route_bwd");
 }
 

@@ -1,15 +1,428 @@
-// placeholder until the tcgen05 kernels land
+// tcgen05 / TMEM implementation of the stencil GEMM (conv forward and data
+// gradient) for sm_100a, bf16 operands, fp32 accumulation in tensor memory.
+//
+// Why this shape of kernel: in the padded-planes layout (common.cuh) a 3x3 SAME
+// convolution over a tile of 128 consecutive rows needs the rows
+// [p0-halo, p0+128+halo) of every 8-channel plane, each a CONTIGUOUS run of
+// 16-byte rows in HBM.  One cp.async.bulk per plane lands it in shared memory
+// exactly in the UMMA "interleaved / no-swizzle" K-major core-matrix layout
+// (8 rows x 16 B contiguous; SBO = 128 B between 8-row groups; LBO = plane
+// stride between the two 8-channel halves of a K=16 step).  The nine taps are
+// then nine descriptor START ADDRESSES into the same staged tile (row shift
+// dh*(W+1)+dw), so the input is read from L2/HBM once, not nine times.
+//
+// Roles (192 threads): warp 0 bulk-copy producer, warp 1 TMEM owner + MMA
+// issuer (one elected lane), warps 2-5 epilogue (tcgen05.ld -> bias -> BN
+// partial moments -> coalesced 16 B row stores).  Persistent over tiles, A
+// stages ring-buffered with mbarriers, two TMEM accumulators so the epilogue
+// of tile i overlaps the MMAs of tile i+1.  Weights for the CTA's N-slice stay
+// resident in shared memory for the kernel's lifetime.
 #include "common.cuh"
 #include "../../include/mpnn.h"
-extern "C" int mpnn_has_umma(void) { return 0; }
-int mpnn_stencil_gemm_umma(const void*, int, const void*, int, const void*, int, const float*, void*, int, int,
-                           void*, int, int, Geom, float*, int, int*, int, cudaStream_t) {
-    mpnn_set_error("tcgen05 path not built"); return MPNN_ERR_UNSUPPORTED;
+
+extern "C" int mpnn_has_umma(void) { return 1; }
+
+namespace {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
 }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, float v[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+// shared-memory matrix descriptor, SWIZZLE_NONE ("interleaved") layout, sm_100 version bit
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) |
+           ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46);
+}
+// kind::f16 instruction descriptor: D=f32, A=B=bf16, M=128
+__device__ __forceinline__ uint32_t make_idesc(int N, int a_mn, int b_mn) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
+           ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
+}
+__device__ __forceinline__ uint32_t tmem_cols_pow2(int c) {
+    uint32_t n = 32;
+    while ((int)n < c) n <<= 1;
+    return n;
+}
+
+// sum over the 32 lanes of v[0..16): afterwards every lane holds the total of column (lane & 15)
+__device__ __forceinline__ float warp_colsum16(float v[16], int lane) {
+#pragma unroll
+    for (int s = 8; s >= 1; s >>= 1) {
+        const bool up = (lane & s) != 0;
+#pragma unroll
+        for (int i = 0; i < s; ++i) {
+            float send = up ? v[i] : v[i + s];
+            float keep = up ? v[i + s] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+        }
+    }
+    return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 16);
+}
+
+struct GemmArgs {
+    const __nv_bfloat16* A0; const __nv_bfloat16* A1; const __nv_bfloat16* Wp;
+    const float* bias;
+    void* out0; void* out1;
+    float* stats;
+    Geom g;
+    int K0, K1, N, N0, NB, ntaps, acc0, acc1, out_f32, n_tiles, nstage, rowsA, halo;
+};
+
+constexpr int kThreads = 192;
+
+__global__ void __launch_bounds__(kThreads, 1)
+stencil_gemm_umma_kernel(const GemmArgs a) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int KG = (a.K0 + a.K1) >> 3, KG0 = a.K0 >> 3;
+    const int NB = a.NB, n0 = blockIdx.y * NB;
+    const uint32_t w_bytes = (uint32_t)a.ntaps * KG * NB * 16;
+    const uint32_t PS = (uint32_t)a.rowsA * 16;          // plane stride inside a stage
+    const uint32_t stage_bytes = PS * KG;
+    uint8_t* sW = smem;
+    uint8_t* sA = smem + ((w_bytes + 127) & ~127u);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sA + (size_t)a.nstage * stage_bytes);
+    // bars: full[nstage], empty[nstage], tfull[2], tempty[2], wbar
+    const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * a.nstage;
+    const uint32_t tfull0 = empty0 + 8 * a.nstage, tempty0 = tfull0 + 16, wbar = tempty0 + 16;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * a.nstage + 5);
+    float* sstat = reinterpret_cast<float*>(tmem_slot + 4);      // [4 warps][2][NB]
+    const uint32_t ncols = tmem_cols_pow2(2 * NB);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < a.nstage; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(tfull0 + 8 * s, 1); mbar_init(tempty0 + 8 * s, 4); }
+        mbar_init(wbar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     ::"r"(smem_u32(tmem_slot)), "r"(ncols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (a.stats && threadIdx.x >= 64)
+        for (int i = threadIdx.x - 64; i < 4 * 2 * NB; i += 128) sstat[i] = 0.f;
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ------------------------------------------------ producer
+        if (lane == 0) {
+            mbar_expect_tx(wbar, w_bytes);
+            for (int t = 0; t < a.ntaps * KG; ++t)
+                bulk_g2s(smem_u32(sW) + (uint32_t)t * NB * 16,
+                         a.Wp + ((size_t)t * a.N + n0) * 8, (uint32_t)NB * 16, wbar);
+            int it = 0;
+            for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
+                const int s = it % a.nstage;
+                const uint32_t ph = (uint32_t)(it / a.nstage) & 1u;
+                mbar_wait(empty0 + 8 * s, ph ^ 1u);
+                mbar_expect_tx(full0 + 8 * s, stage_bytes);
+                const size_t row0 = (size_t)(a.g.G + tile * 128 - a.halo);
+                const uint32_t dst = smem_u32(sA) + (uint32_t)s * stage_bytes;
+                for (int kg = 0; kg < KG; ++kg) {
+                    const __nv_bfloat16* src = kg < KG0 ? a.A0 + ((size_t)kg * a.g.P + row0) * 8
+                                                        : a.A1 + ((size_t)(kg - KG0) * a.g.P + row0) * 8;
+                    bulk_g2s(dst + (uint32_t)kg * PS, src, PS, full0 + 8 * s);
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc(NB, 0, 0);
+            mbar_wait(wbar, 0);
+            int it = 0;
+            for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
+                const int s = it % a.nstage;
+                const uint32_t ph = (uint32_t)(it / a.nstage) & 1u;
+                const int acc = it & 1;
+                const uint32_t aph = (uint32_t)(it >> 1) & 1u;
+                mbar_wait(tempty0 + 8 * acc, aph ^ 1u);
+                mbar_wait(full0 + 8 * s, ph);
+                tc_fence_after();
+                const uint32_t abase = smem_u32(sA) + (uint32_t)s * stage_bytes;
+                const uint32_t wbase = smem_u32(sW);
+                const uint32_t dcol = tmem_base + (uint32_t)acc * NB;
+                uint32_t first = 0;
+                for (int tap = 0; tap < a.ntaps; ++tap) {
+                    const int off = a.ntaps == 9 ? (tap / 3 - 1) * a.g.Wp + (tap % 3 - 1) : 0;
+                    const uint32_t arow = abase + (uint32_t)(a.halo + off) * 16;
+                    for (int kk = 0; kk < KG; kk += 2) {
+                        const uint64_t ad = make_desc(arow + (uint32_t)kk * PS, PS, 128);
+                        const uint64_t bd = make_desc(wbase + (uint32_t)(tap * KG + kk) * NB * 16, (uint32_t)NB * 16, 128);
+                        tc_mma(dcol, ad, bd, idesc, first);
+                        first = 1;
+                    }
+                }
+                tc_commit(empty0 + 8 * s);          // smem stage reusable once the MMAs retire
+                tc_commit(tfull0 + 8 * acc);        // accumulator ready for the epilogue
+            }
+        }
+        __syncwarp();
+    } else {
+        // ------------------------------------------------ epilogue (warps 2..5)
+        const int quad = warp & 3;                       // TMEM lane quadrant this warp may read
+        const int m = quad * 32 + lane;
+        float* wstat = sstat + (size_t)(warp - 2) * 2 * NB;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
+            const int acc = it & 1;
+            const uint32_t aph = (uint32_t)(it >> 1) & 1u;
+            mbar_wait(tfull0 + 8 * acc, aph);
+            tc_fence_after();
+            const int q = tile * 128 + m;
+            const int p = a.g.G + q;
+            int n_, h_, w_;
+            const bool valid = row_valid(a.g, q, n_, h_, w_);
+            const bool inrange = q < a.g.rows;
+            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)acc * NB;
+            for (int c = 0; c < NB; c += 16) {
+                float v[16];
+                tc_ld16(taddr + c, v);
+                const int col = n0 + c;
+                if (a.bias) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] += __ldg(a.bias + col + i);
+                }
+                if (inrange) {
+#pragma unroll
+                    for (int hh = 0; hh < 2; ++hh) {
+                        const int cc = col + hh * 8;
+                        void* base; int accf, kgp;
+                        if (cc < a.N0) { base = a.out0; accf = a.acc0; kgp = cc >> 3; }
+                        else { base = a.out1; accf = a.acc1; kgp = (cc - a.N0) >> 3; }
+                        float o[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) o[i] = v[hh * 8 + i];
+                        if (a.out_f32) {
+                            float* d = plane_row((float*)base, kgp, a.g.P, p);
+                            if (accf) { float t[8]; Row8<float>::load(d, t);
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) o[i] += t[i]; }
+                            Row8<float>::store(d, o);
+                        } else {
+                            __nv_bfloat16* d = plane_row((__nv_bfloat16*)base, kgp, a.g.P, p);
+                            if (accf) { float t[8]; Row8<__nv_bfloat16>::load(d, t);
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) o[i] += t[i]; }
+                            Row8<__nv_bfloat16>::store(d, o);
+                        }
+                    }
+                }
+                if (a.stats) {
+                    float s1[16], s2[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) { s1[i] = valid ? v[i] : 0.f; s2[i] = s1[i] * s1[i]; }
+                    float t1 = warp_colsum16(s1, lane);
+                    float t2 = warp_colsum16(s2, lane);
+                    if (lane < 16) { wstat[c + lane] += t1; wstat[NB + c + lane] += t2; }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (a.stats) {
+        for (int i = threadIdx.x; i < 2 * NB; i += kThreads) {
+            const int which = i / NB, j = i % NB;
+            float t = 0.f;
+            for (int w = 0; w < 4; ++w) t += sstat[(size_t)w * 2 * NB + which * NB + j];
+            a.stats[((size_t)blockIdx.x * 2 + which) * a.N + n0 + j] = t;
+        }
+    }
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ncols) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------
+// bring-up probe: one CTA, operands copied verbatim into shared memory
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(128, 1)
+umma_selftest_kernel(const uint8_t* __restrict__ A, int a_bytes, int a_off, const uint8_t* __restrict__ Bm,
+                     int b_bytes, float* __restrict__ D, int N, int K, int a_mn, int b_mn,
+                     int lbo_a, int sbo_a, int lbo_b, int sbo_b) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + ((a_bytes + 127) & ~127);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(sB + ((b_bytes + 127) & ~127));
+    uint32_t* slot = reinterpret_cast<uint32_t*>(bar + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < a_bytes / 16; i += blockDim.x)
+        reinterpret_cast<uint4*>(sA)[i] = reinterpret_cast<const uint4*>(A)[i];
+    for (int i = threadIdx.x; i < b_bytes / 16; i += blockDim.x)
+        reinterpret_cast<uint4*>(sB)[i] = reinterpret_cast<const uint4*>(Bm)[i];
+    const uint32_t ncols = tmem_cols_pow2(N);
+    if (threadIdx.x == 0) {
+        mbar_init(smem_u32(bar), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     ::"r"(smem_u32(slot)), "r"(ncols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy smem writes -> async proxy
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *slot;
+    if (threadIdx.x == 0) {
+        const uint32_t idesc = make_idesc(N, a_mn, b_mn);
+        for (int k = 0; k < K / 16; ++k) {
+            const uint64_t ad = make_desc(smem_u32(sA) + a_off + (uint32_t)k * 2 * lbo_a, lbo_a, sbo_a);
+            const uint64_t bd = make_desc(smem_u32(sB) + (uint32_t)k * 2 * lbo_b, lbo_b, sbo_b);
+            tc_mma(tmem_base, ad, bd, idesc, k > 0);
+        }
+        tc_commit(smem_u32(bar));
+    }
+    mbar_wait(smem_u32(bar), 0);
+    tc_fence_after();
+    const int m = warp * 32 + lane;
+    for (int c = 0; c < N; c += 16) {
+        float v[16];
+        tc_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + c, v);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) D[(size_t)m * N + c + i] = v[i];
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ncols) : "memory");
+    }
+}
+
+}  // namespace
+
+int mpnn_stencil_gemm_umma(const void* A0, int K0, const void* A1, int K1, const void* Wp, int ntaps,
+                           const float* bias, void* out0, int N0, int acc0, void* out1, int N1, int acc1,
+                           Geom g, float* stats, int stats_cap, int* n_parts, int out_dtype, cudaStream_t st) {
+    const int N = N0 + N1;
+    MPNN_REQUIRE(K0 % 16 == 0 && K1 % 16 == 0, "stencil_gemm(tcgen05): K0=%d K1=%d must be multiples of 16", K0, K1);
+    MPNN_REQUIRE(N % 16 == 0 && N0 % 16 == 0, "stencil_gemm(tcgen05): N0=%d N1=%d must be multiples of 16", N0, N1);
+    const int KG = (K0 + K1) / 8;
+    const int halo = ntaps == 9 ? g.Wp + 1 : 0;
+    const int rowsA = 128 + 2 * halo;
+    const size_t stage = (size_t)rowsA * 16 * KG;
+    const size_t kMax = 227 * 1024 - 1024;
+    int split = 0, nstage = 0, NB = 0;
+    for (int s = 1; s <= 8; s *= 2) {
+        if (N % (16 * s)) break;
+        NB = N / s;
+        if (NB > 256) continue;
+        size_t w = ((size_t)ntaps * KG * NB * 16 + 127) & ~(size_t)127;
+        size_t fixed = w + 256 + (size_t)4 * 2 * NB * 4;
+        if (fixed + 2 * stage <= kMax) {
+            split = s;
+            nstage = (int)((kMax - fixed) / stage);
+            if (nstage > 4) nstage = 4;
+            break;
+        }
+    }
+    MPNN_REQUIRE(split > 0, "stencil_gemm(tcgen05): K=%d N=%d does not fit shared memory", K0 + K1, N);
+    size_t w = ((size_t)ntaps * KG * NB * 16 + 127) & ~(size_t)127;
+    size_t smem = w + (size_t)nstage * stage + 256 + (size_t)4 * 2 * NB * 4;
+    // CTAs per SM by shared memory and by TMEM columns (alloc blocks when exhausted)
+    int ncols = 32;
+    while (ncols < 2 * NB) ncols <<= 1;
+    int per_sm = (int)((227 * 1024) / (smem + 1024));
+    if (per_sm > 512 / ncols) per_sm = 512 / ncols;
+    if (per_sm > 4) per_sm = 4;
+    if (per_sm < 1) per_sm = 1;
+    GemmArgs a;
+    a.A0 = (const __nv_bfloat16*)A0; a.A1 = (const __nv_bfloat16*)A1; a.Wp = (const __nv_bfloat16*)Wp;
+    a.bias = bias; a.out0 = out0; a.out1 = out1; a.stats = stats; a.g = g;
+    a.K0 = K0; a.K1 = K1; a.N = N; a.N0 = N0; a.NB = NB; a.ntaps = ntaps; a.acc0 = acc0; a.acc1 = acc1;
+    a.out_f32 = out_dtype == MPNN_F32; a.n_tiles = ceil_div(g.rows, 128); a.nstage = nstage;
+    a.rowsA = rowsA; a.halo = halo;
+    int gx = 148 * per_sm / split;
+    if (gx > a.n_tiles) gx = a.n_tiles;
+    if (stats && gx > stats_cap) gx = stats_cap;
+    if (gx < 1) gx = 1;
+    if (n_parts) *n_parts = stats ? gx : 0;
+    static size_t attr_set = 0;
+    if (smem > attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(stencil_gemm_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMax + 1024);
+        if (e != cudaSuccess) { mpnn_set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return MPNN_ERR_CUDA; }
+        attr_set = kMax + 1024;
+    }
+    stencil_gemm_umma_kernel<<<dim3(gx, split), kThreads, smem, st>>>(a);
+    return mpnn_check_launch("stencil_gemm_umma");
+}
+
 int mpnn_stencil_wgrad_umma(const void*, int, int, float*, const void*, int, int, float*, const void*, int,
                             int, float*, int, Geom, cudaStream_t) {
-    mpnn_set_error("tcgen05 path not built"); return MPNN_ERR_UNSUPPORTED;
+    mpnn_set_error("stencil_wgrad: tcgen05 path not implemented yet (use impl=0)");
+    return MPNN_ERR_UNSUPPORTED;
 }
-extern "C" int mpnn_umma_selftest(const void*, const void*, float*, int, int, int, int, int, int, int, int, void*) {
-    mpnn_set_error("tcgen05 path not built"); return MPNN_ERR_UNSUPPORTED;
+
+extern "C" int mpnn_umma_selftest(const void* A, int a_bytes, int a_off, const void* Bm, int b_bytes,
+                                  float* D, int N, int K, int a_mn_major, int b_mn_major,
+                                  int lbo_a, int sbo_a, int lbo_b, int sbo_b, void* stream) {
+    MPNN_REQUIRE(N % 16 == 0 && N >= 16 && N <= 256 && K % 16 == 0, "umma_selftest: N=%d K=%d", N, K);
+    MPNN_REQUIRE(a_bytes % 16 == 0 && b_bytes % 16 == 0 && a_off % 16 == 0, "umma_selftest: alignment");
+    size_t smem = ((a_bytes + 127) & ~127) + ((b_bytes + 127) & ~127) + 64;
+    MPNN_REQUIRE(smem <= 200 * 1024, "umma_selftest: operands too large");
+    cudaError_t e = cudaFuncSetAttribute(umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) { mpnn_set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return MPNN_ERR_CUDA; }
+    umma_selftest_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(
+        (const uint8_t*)A, a_bytes, a_off, (const uint8_t*)Bm, b_bytes, D, N, K, a_mn_major, b_mn_major,
+        lbo_a, sbo_a, lbo_b, sbo_b);
+    return mpnn_check_launch("umma_selftest");
 }

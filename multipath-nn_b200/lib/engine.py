@@ -1,0 +1,818 @@
+"""Execution engine: compiles a linked net (lib.net_types) into a static plan
+of libmpnn_sm100 kernel launches over preallocated "padded planes" buffers and
+runs forward / backward / TALR+momentum on one B200.  PyTorch supplies device
+memory, streams, CUDA graphs and torch.distributed -- no arithmetic.
+
+What the reference expresses as a TF graph + autodiff
+(/root/reference/scripts/lib/net_types.py:137-181, 245-284) is laid out here
+explicitly:  forward in preorder over the sink tree, routing walk, backward in
+reverse preorder, one fused optimiser kernel over the flat parameter buffer.
+Every node is evaluated densely on the whole batch, exactly like the
+reference.
+"""
+import ctypes
+from types import SimpleNamespace as Ns
+
+import numpy as np
+import torch
+
+from lib import _cabi
+from lib.layer_types import (BatchNorm, Chain, CrossEntropyError, LinTrans, MultiscaleBatchNorm,
+                             MultiscaleConvMax, MultiscaleRect, Param, Rect, Select, Softmax, ToPyramid)
+from lib.net_types import n_leaves
+
+F32, BF16 = 0, 1
+HYP_LR, HYP_MU, HYP_TAU, HYP_EPS, HYP_KCPT, HYP_GSCALE, HYP_COUNT = 0, 1, 2, 3, 4, 5, 8
+STATS_CAP = 592          # 4 CTAs per SM worth of partial rows
+MAXS = 8
+
+
+def _ru(a, b):
+    return (a + b - 1) // b * b
+
+
+def _vp(t):
+    """device pointer of a tensor (or None) as c_void_p"""
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _is_chain(layer, types):
+    return (isinstance(layer, Chain) and len(layer.comps) == len(types)
+            and all(isinstance(c, t) for c, t in zip(layer.comps, types)))
+
+
+_PYR = [ToPyramid]
+_RCM = [MultiscaleConvMax, MultiscaleBatchNorm, MultiscaleRect]
+_REG = [Select, LinTrans, Softmax, CrossEntropyError]
+_RTR = [Select, LinTrans, BatchNorm, Rect, LinTrans, BatchNorm, Rect, LinTrans]
+
+
+class Geo:
+    """Padded-planes geometry of one scale (see csrc/common.cuh)."""
+
+    def __init__(self, B, H, W):
+        self.B, self.H, self.W = B, H, W
+        self.Wp = W + 1
+        self.S = (H + 1) * (W + 1)
+        self.rows = B * self.S
+        self.G = max(64, _ru(W + 2, 8))
+        self.P = _ru(self.G + self.rows + 128 + self.G, 8)
+
+    def args(self):
+        return (self.B, self.H, self.W, self.G, self.P)
+
+
+class Engine:
+    def __init__(self, net, precision='fp32', device=None, graphs=False, dist=False, impl=None,
+                 dry_run=False):
+        # dry_run: build plans on host memory without launching anything (used by
+        # the CPU test-suite to exercise the planner); it cannot execute.
+        self.dry = bool(dry_run)
+        if not self.dry and not torch.cuda.is_available():
+            raise RuntimeError('multipath-nn_b200 needs a CUDA device (sm_100a); there is no CPU fallback')
+        self.L = _cabi.lib()
+        self.net = net
+        if self.dry:
+            self.dev = torch.device('cpu')
+        else:
+            self.dev = torch.device('cuda', torch.cuda.current_device() if device is None else device)
+        assert precision in ('fp32', 'bf16')
+        self.dtype = F32 if precision == 'fp32' else BF16
+        self.tdtype = torch.float32 if precision == 'fp32' else torch.bfloat16
+        # stencil implementation: 0 = SIMT fp32-accumulate, 1 = tcgen05
+        self.impl = (1 if (precision == 'bf16' and self.L.mpnn_has_umma()) else 0) if impl is None else impl
+        # weight gradient: the tcgen05 variant is not wired yet -> SIMT fp32-accumulate
+        self.impl_w = 0
+        self.use_graphs = graphs
+        self.dist = dist
+        self.world = torch.distributed.get_world_size() if dist else 1
+        self.dynamic = bool(net.dynamic)
+        self.critic = type(net).__name__ == 'CriticNet'
+        self.stream = None
+        self._analyse()
+        self._alloc_params()
+        self._plans = {}
+        self._graphs = {}
+        self.hyp_host = torch.zeros(HYP_COUNT, dtype=torch.float32)
+        if not self.dry:
+            self.hyp_host = self.hyp_host.pin_memory()
+        self.hyp = torch.zeros(HYP_COUNT, dtype=torch.float32, device=self.dev)
+
+    # ------------------------------------------------------------------ #
+    # static analysis of the layer tree
+    # ------------------------------------------------------------------ #
+    def _analyse(self):
+        net = self.net
+        self.nodes = []
+
+        def visit(layer, parent, sink_idx):
+            nd = Ns(layer=layer, idx=len(self.nodes), parent=parent, sink_idx=sink_idx, kids=[],
+                    router=layer.router)
+            if _is_chain(layer, _PYR):
+                nd.kind = 'pyr'
+            elif _is_chain(layer, _RCM):
+                nd.kind = 'rcm'
+                if layer.comps[0].hypers.supp != 3:
+                    raise NotImplementedError('engine: MultiscaleConvMax supp=%r' % layer.comps[0].hypers.supp)
+            elif _is_chain(layer, _REG):
+                nd.kind = 'reg'
+                if layer.comps[0].hypers.i != -1:
+                    raise NotImplementedError('engine: LogReg must select the coarsest scale')
+            else:
+                raise NotImplementedError(
+                    'engine: tree node %r (%s) is not one of the hot-path compositions '
+                    '(ToPyramid | ConvMax+BN+Rect | Select+LinTrans+Softmax+CrossEntropy)'
+                    % (layer.name, [type(c).__name__ for c in layer.comps]))
+            if layer.router is not None:
+                if not _is_chain(layer.router, _RTR):
+                    raise NotImplementedError('engine: router of %r is not the FC-BN-ReLU x2 + FC chain' % layer.name)
+                if len(layer.sinks) < 2 or len(layer.sinks) > MAXS:
+                    raise NotImplementedError('engine: router with %d sinks' % len(layer.sinks))
+            elif len(layer.sinks) > 1:
+                raise ValueError('switch %r has no router' % layer.name)
+            self.nodes.append(nd)
+            if parent is not None:
+                self.nodes[parent].kids.append(nd.idx)
+            for i, s in enumerate(layer.sinks):
+                visit(s, nd.idx, i)
+        visit(net.root, None, 0)
+        if self.nodes[0].kind != 'pyr':
+            raise NotImplementedError('engine: the root must be the ToPyramid chain')
+        for nd in self.nodes:
+            if nd.kind == 'reg' and nd.kids:
+                raise NotImplementedError('engine: LogReg with sinks')
+            if nd.kind in ('rcm', 'reg') and self.nodes[nd.parent].kind == 'reg':
+                raise NotImplementedError('engine: node under a LogReg')
+            if nd.kind == 'pyr' and nd.idx != 0:
+                raise NotImplementedError('engine: nested ToPyramid')
+            if nd.kind == 'pyr' and (nd.router is not None):
+                raise NotImplementedError('engine: router on the ToPyramid node')
+        self.leaves = [nd for nd in self.nodes if not nd.kids]
+        self.switches = [nd for nd in self.nodes if len(nd.kids) > 1]
+        for s, nd in enumerate(self.switches):
+            nd.sw = s
+        for e, nd in enumerate(nd for nd in self.nodes if nd.kind == 'reg'):
+            nd.err = e
+        self.regs = [nd for nd in self.nodes if nd.kind == 'reg']
+        if not self.dynamic and self.switches:
+            raise NotImplementedError('engine: SRNet with switches')
+
+    # ------------------------------------------------------------------ #
+    # parameters: flat trainable buffer + flat state buffer (BN EMAs)
+    # ------------------------------------------------------------------ #
+    def _alloc_params(self):
+        net = self.net
+        hy = net.hypers
+        a_rtr = float(getattr(hy, 'α_rtr', 1.0)) if self.dynamic else 1.0
+        self.tparams, self.sparams = [], []
+        seg_start, seg_node, seg_mult, seg_l2 = [], [], [], []
+        off_t = off_s = 0
+
+        def walk(layer, node_idx, mult):
+            nonlocal off_t, off_s
+            if layer is None:
+                return
+            for key, p in vars(layer.params).items():
+                assert isinstance(p, Param)
+                if p.trainable:
+                    l2 = 0.0
+                    if isinstance(layer, LinTrans) and key == 'w':
+                        if getattr(layer.hypers, 'res', False):
+                            raise NotImplementedError('engine: LinTrans(res=True)')
+                        l2 = float(layer.hypers.k_l2)
+                    elif isinstance(layer, MultiscaleConvMax) and key.startswith('w_'):
+                        l2 = float(layer.hypers.k_l2)
+                    p._bind = (self, 'theta', off_t)
+                    self.tparams.append(p)
+                    seg_start.append(off_t); seg_node.append(node_idx)
+                    seg_mult.append(mult); seg_l2.append(l2)
+                    off_t += p.value.size
+                else:
+                    p._bind = (self, 'state', off_s)
+                    self.sparams.append(p)
+                    off_s += p.value.size
+            for c in layer.comps:
+                walk(c, node_idx, mult)
+        for nd in self.nodes:
+            walk(nd.layer, nd.idx, 1.0)
+            walk(nd.router, nd.idx, a_rtr)
+        self.n_theta, self.n_state = off_t, off_s
+        seg_start.append(off_t)
+        n_nodes = len(self.nodes)
+        dev = self.dev
+        self.theta = torch.zeros(off_t, dtype=torch.float32, device=dev)
+        # gradient buffer carries the per-node p_tr moments in its tail so that
+        # one all-reduce covers both (data-parallel TALR stays replica-consistent)
+        self.grad = torch.zeros(off_t + 2 * n_nodes, dtype=torch.float32, device=dev)
+        self.accum = torch.zeros(off_t, dtype=torch.float32, device=dev)
+        self.state = torch.zeros(max(off_s, 1), dtype=torch.float32, device=dev)
+        self.seg_start = torch.tensor(seg_start, dtype=torch.int32, device=dev)
+        self.seg_node = torch.tensor(seg_node, dtype=torch.int32, device=dev)
+        self.seg_mult = torch.tensor(seg_mult, dtype=torch.float32, device=dev)
+        self.seg_l2 = torch.tensor(seg_l2, dtype=torch.float32, device=dev)
+        self.n_seg = len(seg_node)
+        for p in self.tparams + self.sparams:
+            self.push_param(p)
+
+    def _buf(self, p):
+        kind, off = p._bind[1], p._bind[2]
+        return (self.theta if kind == 'theta' else self.state)[off:off + p.value.size]
+
+    def push_param(self, p):
+        self._buf(p).copy_(torch.from_numpy(p.value.reshape(-1)))
+
+    def fetch_param(self, p):
+        p.value = self._buf(p).cpu().numpy().reshape(p.value.shape).copy()
+
+    def tptr(self, p):
+        return ctypes.c_void_p(self.theta.data_ptr() + 4 * p._bind[2]) if p._bind[1] == 'theta' \
+            else ctypes.c_void_p(self.state.data_ptr() + 4 * p._bind[2])
+
+    def gptr(self, p):
+        assert p._bind[1] == 'theta'
+        return ctypes.c_void_p(self.grad.data_ptr() + 4 * p._bind[2])
+
+    def grads_numpy(self):
+        """{Param: gradient ndarray} of the last backward (before TALR)."""
+        g = self.grad.cpu().numpy()
+        return {p: g[p._bind[2]:p._bind[2] + p.value.size].reshape(p.value.shape).copy() for p in self.tparams}
+
+    # ------------------------------------------------------------------ #
+    # plan construction
+    # ------------------------------------------------------------------ #
+    def _plan(self, B, bn_train, need_bwd):
+        key = (B, bool(bn_train), bool(need_bwd))
+        if key not in self._plans:
+            self._plans[key] = _Plan(self, B, bn_train, need_bwd)
+        return self._plans[key]
+
+    # ------------------------------------------------------------------ #
+    # feeding
+    # ------------------------------------------------------------------ #
+    def _to_dev(self, v, shape, name):
+        if isinstance(v, torch.Tensor):
+            t = v
+            if t.dtype != torch.float32:
+                t = t.float()
+        else:
+            t = torch.from_numpy(np.ascontiguousarray(v, dtype=np.float32))
+        if tuple(t.shape) != tuple(shape):
+            raise ValueError('feed %s: shape %s, expected %s' % (name, tuple(t.shape), tuple(shape)))
+        return t
+
+    def _feed(self, plan, feed, train):
+        net = self.net
+        hy = net.hypers
+        x0 = feed[net.x0]
+        y = feed[net.y]
+        B = plan.B
+        plan.x0.copy_(self._to_dev(x0, (B,) + tuple(hy.x0_shape), 'x0'), non_blocking=True)
+        plan.y.copy_(self._to_dev(y, (B,) + tuple(hy.y_shape), 'y'), non_blocking=True)
+        h = self.hyp_host
+        h[HYP_LR] = float(feed.get(net.λ_lrn, hy.λ_lrn))
+        h[HYP_MU] = float(feed.get(net.μ_lrn, hy.μ_lrn))
+        h[HYP_GSCALE] = 1.0 / self.world
+        if self.dynamic:
+            h[HYP_TAU] = float(feed.get(net.τ, hy.τ))
+            h[HYP_EPS] = float(feed.get(net.ϵ, hy.ε))
+            if hy.dyn_k_cpt:
+                kc = np.asarray(feed[net.k_cpt], dtype=np.float32).reshape(-1)
+                if kc.size == 1:
+                    kc = np.full(B, kc[0], np.float32)      # train-adaptive-nets:102-105
+                if kc.size != B:
+                    raise ValueError('feed k_cpt: %d values for batch %d' % (kc.size, B))
+                plan.kcpt.copy_(torch.from_numpy(kc), non_blocking=True)
+                plan.kextra.copy_(torch.from_numpy(kc * np.float32(hy.α_cpt)), non_blocking=True)
+            else:
+                h[HYP_KCPT] = float(hy.k_cpt)
+        self.hyp.copy_(h, non_blocking=True)
+
+    def _batch_of(self, feed):
+        x0 = feed[self.net.x0]
+        return int(x0.shape[0])
+
+    # ------------------------------------------------------------------ #
+    # public steps
+    # ------------------------------------------------------------------ #
+    def _run(self, ops):
+        if self.dry:
+            raise RuntimeError('dry-run engine cannot execute: the hot path is CUDA-only')
+        self.stream = ctypes.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)
+        for op in ops:
+            op()
+
+    def train_step(self, feed, update=True):
+        """One `net.train.run(...)`: forward ('tr'), backward, TALR + momentum."""
+        B = self._batch_of(feed)
+        plan = self._plan(B, True, True)
+        with torch.cuda.device(self.dev):
+            self._feed(plan, feed, True)
+            self.run_resident(plan, update)
+
+    def run_resident(self, plan, update=True):
+        """Step on inputs already resident in plan.x0 / plan.y / self.hyp."""
+        if self.use_graphs and update:
+            g = self._graphs.get(id(plan))
+            if g is None:
+                g = self._capture(plan)
+            g.replay()
+            return
+        self._step_ops(plan, update)
+
+    def _step_ops(self, plan, update):
+        self._run(plan.pack_ops)
+        self._run(plan.fwd_ops)
+        self.grad.zero_()
+        self._run(plan.bwd_ops)
+        if update:
+            if self.dist:
+                torch.distributed.all_reduce(self.grad)
+            self._run(plan.opt_ops)
+
+    def _capture(self, plan):
+        # warm-up on a side stream (allocations, lazy module loads), then capture
+        s = torch.cuda.Stream(self.dev)
+        s.wait_stream(torch.cuda.current_stream(self.dev))
+        keep = (self.theta.clone(), self.accum.clone(), self.state.clone())
+        with torch.cuda.stream(s):
+            self._step_ops(plan, True)
+        torch.cuda.current_stream(self.dev).wait_stream(s)
+        torch.cuda.synchronize(self.dev)
+        self.theta.copy_(keep[0]); self.accum.copy_(keep[1]); self.state.copy_(keep[2])
+        g = torch.cuda.CUDAGraph()
+        before = self.L.launches
+        with torch.cuda.graph(g):
+            self._step_ops(plan, True)
+        plan.graph_launches = self.L.launches - before
+        self._graphs[id(plan)] = g
+        return g
+
+    def forward(self, feed, mode=None):
+        """Forward only; returns the plan (buffers hold the results)."""
+        net = self.net
+        mode = feed.get(net.mode, 'ev') if mode is None else mode
+        B = self._batch_of(feed)
+        plan = self._plan(B, mode == 'tr', False)
+        with torch.cuda.device(self.dev):
+            self._feed(plan, feed, False)
+            self._run(plan.pack_ops)
+            self._run(plan.fwd_ops)
+        return plan
+
+    def eval_stats(self, feed):
+        """state_tensors of train-nets:111-130 for one batch (numpy)."""
+        net = self.net
+        plan = self.forward(feed)
+        B = plan.B
+        torch.cuda.synchronize(self.dev)
+        y = plan.y.cpu().numpy().astype(np.float64)
+        if self.dynamic:
+            p_ev = plan.p_ev.cpu().numpy().astype(np.float64)
+            p_tr = plan.p_tr.cpu().numpy().astype(np.float64)
+        else:
+            p_ev = np.ones((len(self.nodes), B))
+            p_tr = None
+        out = {}
+        acc = np.zeros(B)
+        moc = np.zeros(B)
+        for nd in self.nodes:
+            ops = nd.layer.n_ops + (nd.router.n_ops if nd.router is not None else 0)
+            moc += p_ev[nd.idx] * ops
+        for nd in self.regs:
+            l = nd.layer
+            d_cor = plan.reg[nd.idx].d_cor.cpu().numpy().astype(np.float64)
+            c_err = plan.reg[nd.idx].c_err.cpu().numpy().astype(np.float64)
+            pe = p_ev[nd.idx]
+            acc += pe * d_cor
+            out[(l, 'p_cor')] = pe * d_cor
+            out[(l, 'p_inc')] = pe * (1 - d_cor)
+            out[(l, 'p_cor_by_cls')] = (pe * d_cor)[:, None] * y
+            out[(l, 'p_inc_by_cls')] = (pe * (1 - d_cor))[:, None] * y
+            if p_tr is not None:
+                out[(l, 'p_tr')] = p_tr[nd.idx]
+            out[(l, 'c_err')] = c_err
+        for nd in self.switches:
+            r = plan.rtr[nd.idx].R.cpu().numpy().astype(np.float64)
+            out[(nd.layer, 'x_rte')] = np.abs(r).mean(1)
+        out[(net, 'acc')] = acc
+        out[(net, 'moc')] = moc
+        return out
+
+    def debug_forward(self, feed, mode='tr'):
+        """Internal tensors of one forward for the parity tests (numpy, by node index)."""
+        plan = self.forward(feed, mode)
+        torch.cuda.synchronize(self.dev)
+        res = Ns(logits={}, c_err={}, d_cor={}, R={}, p_tr=None, p_ev=None, dec=None, plan=plan)
+        for nd in self.regs:
+            res.logits[nd.idx] = plan.reg[nd.idx].Z.cpu().numpy()
+            res.c_err[nd.idx] = plan.reg[nd.idx].c_err.cpu().numpy()
+            res.d_cor[nd.idx] = plan.reg[nd.idx].d_cor.cpu().numpy()
+        for nd in self.switches:
+            res.R[nd.idx] = plan.rtr[nd.idx].R.cpu().numpy()
+        if self.dynamic:
+            res.p_tr = plan.p_tr.cpu().numpy()
+            res.p_ev = plan.p_ev.cpu().numpy()
+            res.dec = plan.dec.cpu().numpy()
+        return res
+
+    def c_tot(self, plan):
+        """Value of the training objective for the plan's last forward+backward
+        (data term from the route kernel + L2 terms; logging / tests only)."""
+        B = plan.B
+        if self.dynamic:
+            data = float(plan.c_data.double().mean())
+            w = plan.p_tr.double().mean(1)
+        else:
+            data = float(sum(plan.reg[nd.idx].c_err.double().mean() for nd in self.regs))
+            w = torch.ones(len(self.nodes), dtype=torch.float64, device=self.dev)
+        mod = 0.0
+        seg_l2 = self.seg_l2.cpu().numpy(); seg_node = self.seg_node.cpu().numpy()
+        for s, p in enumerate(self.tparams):
+            if seg_l2[s] > 0:
+                mod += float(w[seg_node[s]]) * seg_l2[s] * float((self._buf(p).double() ** 2).sum())
+        return data + mod
+
+
+class _Plan:
+    """Buffers + launch list for one (batch size, BN mode, needs-backward)."""
+
+    def __init__(self, eng, B, bn_train, need_bwd):
+        self.eng, self.B, self.bn_train, self.need_bwd = eng, B, bn_train, need_bwd
+        self.pack_ops, self.fwd_ops, self.bwd_ops, self.opt_ops = [], [], [], []
+        self.graph_launches = 0
+        self._build()
+
+    # -- allocation helpers ------------------------------------------------ #
+    def planes(self, C, geo):
+        return torch.zeros((C // 8, geo.P, 8), dtype=self.eng.tdtype, device=self.eng.dev)
+
+    def f32(self, *shape):
+        return torch.zeros(shape, dtype=torch.float32, device=self.eng.dev)
+
+    def _build(self):
+        eng, L, B = self.eng, self.eng.L, self.B
+        net = eng.net
+        dt, impl = eng.dtype, eng.impl
+        dev = eng.dev
+        train, bwd = self.bn_train, self.need_bwd
+        H0, W0, C0 = net.hypers.x0_shape
+        n_cls = net.hypers.y_shape[0]
+        self.x0 = self.f32(B, H0, W0, C0)
+        self.y = self.f32(B, n_cls)
+        self.kcpt = self.f32(B)
+        self.kextra = self.f32(B)
+        cmax = 8
+        for nd in eng.nodes:
+            if nd.kind == 'rcm':
+                cmax = max(cmax, max(nd.layer.comps[0].hypers.n_chan))
+        self.partials = self.f32(STATS_CAP * 2 * cmax)
+        self.cnt = ctypes.c_int(0)
+        S = lambda: eng.stream
+        Balloc = _ru(B, 8)
+        self.node = {}
+        self.reg, self.rtr = {}, {}
+        cpad_q = 16 if dt == BF16 else 8
+        dyn_k = eng.dynamic and bool(net.hypers.dyn_k_cpt)
+
+        # ---------------- forward ---------------- #
+        for nd in eng.nodes:
+            lay = nd.layer
+            st = Ns()
+            self.node[nd.idx] = st
+            if nd.kind == 'pyr':
+                n_sc = lay.comps[0].hypers.n_scales
+                cpad = _ru(C0, cpad_q)
+                st.out = []
+                for i in range(n_sc):
+                    geo = Geo(B, H0 // 2 ** i, W0 // 2 ** i)
+                    t = self.planes(cpad, geo)
+                    st.out.append(Ns(t=t, C=cpad, Creal=C0, geo=geo, dact=None, writers=0))
+                    self.fwd_ops.append(lambda t=t, i=i, geo=geo: L.pack_input(
+                        _vp(self.x0), B, H0, W0, C0, 2 ** i, _vp(t), cpad, geo.G, geo.P, dt, S()))
+                st.needs_grad = False
+            elif nd.kind == 'rcm':
+                self._build_rcm_fwd(nd, st, Balloc)
+            elif nd.kind == 'reg':
+                par = self.node[nd.parent]
+                fc = lay.comps[1]
+                eps = float(lay.comps[3].hypers.ε)
+                r = Ns(Z=self.f32(B, n_cls), prob=self.f32(B, n_cls), c_err=self.f32(B), d_cor=self.f32(B),
+                       dZ=self.f32(B, n_cls) if bwd else None, fc=fc, eps=eps)
+                self.reg[nd.idx] = r
+                F = par.F
+                self.fwd_ops.append(lambda par=par, r=r, fc=fc, F=F: L.fc_fwd(
+                    _vp(par.feat), F, Balloc, B, eng.tptr(fc.params.w), eng.tptr(fc.params.b), None,
+                    n_cls, _vp(r.Z), dt, S()))
+                self.fwd_ops.append(lambda r=r: L.softmax_ce_fwd(
+                    _vp(r.Z), _vp(self.y), B, n_cls, r.eps, _vp(r.prob), _vp(r.c_err), _vp(r.d_cor), S()))
+            if nd.router is not None:
+                self._build_router_fwd(nd, Balloc, dyn_k)
+
+        # ---------------- routing ---------------- #
+        if eng.dynamic:
+            self._build_routing()
+
+        if not bwd:
+            return
+        # ---------------- backward ---------------- #
+        if eng.dynamic:
+            hy = net.hypers
+            self.bwd_ops.append(lambda: L.route_bwd(
+                _vp(self.t_parent), _vp(self.t_sink), _vp(self.t_nsinks), _vp(self.t_child), _vp(self.t_floor),
+                _vp(self.t_sw), _vp(self.t_ops), _vp(self.t_err), len(eng.nodes), _vp(self.R_tab), _vp(eng.hyp), B,
+                _vp(self.p_tr), _vp(self.p_ev), _vp(self.cerr_tab), _vp(self.dcor_tab),
+                _vp(self.kcpt) if dyn_k else None,
+                1 if eng.critic else 0, float(getattr(hy, 'k_dec', 0.0)), float(getattr(hy, 'k_cre', 0.0)),
+                1 if getattr(hy, 'optimistic', False) else 0, 1 if getattr(hy, 'use_cls_err', False) else 0,
+                _vp(self.dR_tab), _vp(self.route_scratch), _vp(self.c_data), S()))
+            n_theta = eng.n_theta
+            self.bwd_ops.append(lambda: L.node_moments(
+                _vp(self.p_tr), len(eng.nodes), B, ctypes.c_void_p(eng.grad.data_ptr() + 4 * n_theta), S()))
+        for nd in reversed(eng.nodes):
+            if nd.kind == 'reg':
+                r = self.reg[nd.idx]
+                par = self.node[nd.parent]
+                coef = (lambda nd=nd: ctypes.c_void_p(self.p_tr.data_ptr() + 4 * nd.idx * B)) if eng.dynamic \
+                    else (lambda: None)
+                self.bwd_ops.append(lambda r=r, coef=coef: L.softmax_ce_bwd(
+                    _vp(r.prob), _vp(self.y), B, n_cls, r.eps, coef(), 1.0 / B, _vp(r.dZ), S()))
+                self.bwd_ops.append(lambda r=r, par=par: L.fc_bwd_weight(
+                    _vp(par.feat), par.F, Balloc, B, None, _vp(r.dZ), n_cls,
+                    eng.gptr(r.fc.params.w), eng.gptr(r.fc.params.b), dt, S()))
+            if nd.router is not None:
+                self._build_router_bwd(nd, Balloc, dyn_k)
+            if nd.kind == 'rcm':
+                self._build_rcm_bwd(nd, Balloc)
+        # ---------------- optimiser ---------------- #
+        talr = 1 if (eng.dynamic and bool(net.hypers.talr)) else 0
+        stats_ptr = (lambda: ctypes.c_void_p(eng.grad.data_ptr() + 4 * eng.n_theta)) if eng.dynamic else (lambda: None)
+        self.opt_ops.append(lambda: L.talr_momentum_step(
+            _vp(eng.theta), _vp(eng.grad), _vp(eng.accum), eng.n_theta, _vp(eng.seg_start), _vp(eng.seg_node),
+            _vp(eng.seg_mult), _vp(eng.seg_l2), eng.n_seg, stats_ptr(), talr, _vp(eng.hyp), S()))
+
+    # -- conv stage -------------------------------------------------------- #
+    def _build_rcm_fwd(self, nd, st, Balloc):
+        eng, L, B = self.eng, self.eng.L, self.B
+        dt, impl = eng.dtype, eng.impl
+        S = lambda: eng.stream
+        lay = nd.layer
+        cm, mbn = lay.comps[0], lay.comps[1]
+        par = self.node[nd.parent]
+        n_chan = list(cm.hypers.n_chan)
+        n = len(n_chan)
+        pin = par.out[len(par.out) - n:]
+        st.pin = pin
+        st.needs_grad = True
+        st.out, st.sc = [], []
+        kid_rcm = [k for k in nd.kids if eng.nodes[k].kind == 'rcm']
+        has_heads = any(eng.nodes[k].kind == 'reg' for k in nd.kids) or nd.router is not None
+
+        def live(k):
+            for c in kid_rcm:
+                m = len(eng.nodes[c].layer.comps[0].hypers.n_chan)
+                if k >= n - m:
+                    return True
+            return k == n - 1 and has_heads
+        train, bwd = self.bn_train, self.need_bwd
+        for k in range(n):
+            src = pin[k]
+            geo = src.geo
+            N = n_chan[k]
+            K0 = src.C
+            K1 = n_chan[k - 1] if k > 0 else 0
+            sc = Ns(k=k, geo=geo, N=N, K0=K0, K0real=src.Creal, K1=K1, src=src, live=live(k),
+                    dpooled=None, geo_p=None)
+            sc.lin = self.planes(N, geo)
+            sc.act = self.planes(N, geo) if any(
+                k >= n - len(eng.nodes[c].layer.comps[0].hypers.n_chan) for c in kid_rcm) else None
+            sc.pooled = None
+            if k < n - 1:
+                sc.geo_p = pin[k + 1].geo
+                sc.pooled = self.planes(N, sc.geo_p)
+            sc.feat = None
+            if k == n - 1 and has_heads:
+                st.F = geo.H * geo.W * N
+                sc.feat = torch.zeros((st.F // 8, Balloc, 8), dtype=eng.tdtype, device=eng.dev)
+                st.feat = sc.feat
+            sc.Wf = torch.zeros((9, (K0 + K1) // 8, N, 8), dtype=eng.tdtype, device=eng.dev)
+            sc.ss = self.f32(2, N)
+            sc.mr = self.f32(2, N)
+            sc.bn = mbn.comps[k]
+            wh = getattr(cm.params, 'w_horz_%i' % k)
+            wv = getattr(cm.params, 'w_vert_%i' % (k - 1)) if k > 0 else None
+            bk = getattr(cm.params, 'b_%i' % k)
+            sc.wh, sc.wv, sc.bk = wh, wv, bk
+            if tuple(wh.shape[:2]) != (3, 3):
+                raise NotImplementedError('engine: conv window %s' % (wh.shape[:2],))
+            self.pack_ops.append(lambda sc=sc, wh=wh: L.pack_weights(
+                eng.tptr(wh), 9, sc.K0real, sc.N, 0, 0, sc.K0 + sc.K1, 0, sc.N, _vp(sc.Wf), dt, S()))
+            if wv is not None:
+                self.pack_ops.append(lambda sc=sc, wv=wv: L.pack_weights(
+                    eng.tptr(wv), 9, sc.K1, sc.N, 0, sc.K0, sc.K0 + sc.K1, 0, sc.N, _vp(sc.Wf), dt, S()))
+            prev = st.sc[k - 1] if k > 0 else None
+            use_stats = sc.live and train
+
+            def conv(sc=sc, prev=prev, use_stats=use_stats):
+                L.stencil_gemm(_vp(sc.src.t), sc.K0, _vp(prev.pooled) if prev is not None else None, sc.K1,
+                               _vp(sc.Wf), 9, eng.tptr(sc.bk), _vp(sc.lin), sc.N, 0, None, 0, 0,
+                               *sc.geo.args(), _vp(self.partials) if use_stats else None, STATS_CAP,
+                               ctypes.byref(self.cnt), dt, dt, impl, S())
+            self.fwd_ops.append(conv)
+            if sc.live:
+                bn = sc.bn
+
+                def fin(sc=sc, bn=bn, use_stats=use_stats):
+                    L.bn_finalize(_vp(self.partials), self.cnt.value if use_stats else 0, sc.N,
+                                  float(B * sc.geo.H * sc.geo.W), eng.tptr(bn.params.γ), eng.tptr(bn.params.β),
+                                  eng.tptr(bn.params.m_avg), eng.tptr(bn.params.v_avg),
+                                  float(bn.hypers.d), float(bn.hypers.ε), 1 if use_stats else 0,
+                                  _vp(sc.ss), _vp(sc.mr), S())
+                self.fwd_ops.append(fin)
+            if sc.live or sc.pooled is not None:
+                def post(sc=sc):
+                    L.bn_relu_pool_fwd(_vp(sc.lin), sc.N, *sc.geo.args(), _vp(sc.ss) if sc.live else None,
+                                       _vp(sc.act), _vp(sc.pooled), sc.geo_p.P if sc.pooled is not None else 0,
+                                       _vp(sc.feat), Balloc, dt, S())
+                self.fwd_ops.append(post)
+            st.sc.append(sc)
+            st.out.append(Ns(t=sc.act, C=N, Creal=N, geo=geo, dact=None, writers=0))
+
+    def _build_rcm_bwd(self, nd, Balloc):
+        eng, L, B = self.eng, self.eng.L, self.B
+        dt, impl = eng.dtype, eng.impl
+        S = lambda: eng.stream
+        st = self.node[nd.idx]
+        lay = nd.layer
+        cm = lay.comps[0]
+        n = len(st.sc)
+        par = self.node[nd.parent]
+        par_grad = par.needs_grad
+        # gradient of the heads wrt the flattened coarsest scale
+        heads = [k for k in nd.kids if eng.nodes[k].kind == 'reg']
+        st.dfeat = None
+        if heads or nd.router is not None:
+            if len(heads) > 1:
+                raise NotImplementedError('engine: more than one LogReg under one node')
+            st.dfeat = torch.zeros_like(st.feat)
+            pairs = []
+            if heads:
+                r = self.reg[heads[0]]
+                pairs.append((r.dZ, r.fc.params.w, r.dZ.shape[1]))
+            if nd.router is not None:
+                rt = self.rtr[nd.idx]
+                pairs.append((rt.dZ1, rt.fc1.params.w, 16))
+            p0 = pairs[0]
+            p1 = pairs[1] if len(pairs) > 1 else (None, None, 0)
+            self.bwd_ops.append(lambda p0=p0, p1=p1: L.fc_bwd_data(
+                _vp(p0[0]), eng.tptr(p0[1]), p0[2], _vp(p1[0]), eng.tptr(p1[1]) if p1[1] is not None else None,
+                p1[2], st.F, Balloc, B, _vp(st.dfeat), dt, S()))
+        for k in range(n - 1, -1, -1):
+            sc = st.sc[k]
+            geo = sc.geo
+            sc.dlin = self.planes(sc.N, geo)
+            dact = st.out[k].dact                    # written by child conv stages (already built)
+            dfeat = st.dfeat if (k == n - 1) else None
+            dpooled = sc.dpooled      # gradient wrt pooled(lin_k), set by scale k+1's dgrad below
+            live = sc.live and (dact is not None or dfeat is not None)
+            sc.sums = self.f32(2, sc.N)
+            if live:
+                bn = sc.bn
+
+                def red(sc=sc, dact=dact, dfeat=dfeat, bn=bn):
+                    L.bn_bwd_reduce(_vp(sc.lin), _vp(dact), _vp(dfeat), Balloc, _vp(sc.ss), _vp(sc.mr), sc.N,
+                                    *sc.geo.args(), _vp(self.partials), STATS_CAP, ctypes.byref(self.cnt), dt, S())
+                    L.bn_bwd_finalize(_vp(self.partials), self.cnt.value, sc.N, _vp(sc.sums),
+                                      eng.gptr(bn.params.γ), eng.gptr(bn.params.β), S())
+                self.bwd_ops.append(red)
+            if not live and dpooled is None:
+                raise RuntimeError('engine: scale %d of %r has no gradient path' % (k, lay.name))
+
+            def elt(sc=sc, dact=dact, dfeat=dfeat, dpooled=dpooled, live=live):
+                L.bn_relu_pool_bwd(_vp(sc.lin), _vp(dact), _vp(dfeat), Balloc, _vp(dpooled),
+                                   sc.geo_p.P if dpooled is not None else 0,
+                                   _vp(sc.ss) if live else None, _vp(sc.mr), _vp(sc.sums),
+                                   float(B * sc.geo.H * sc.geo.W), sc.N, *sc.geo.args(), _vp(sc.dlin), dt, S())
+            self.bwd_ops.append(elt)
+            prev = st.sc[k - 1] if k > 0 else None
+
+            def wgrad(sc=sc, prev=prev):
+                L.stencil_wgrad(_vp(sc.src.t), sc.K0, sc.K0real, eng.gptr(sc.wh),
+                                _vp(prev.pooled) if prev is not None else None, sc.K1, sc.K1,
+                                eng.gptr(sc.wv) if sc.wv is not None else None,
+                                _vp(sc.dlin), sc.N, sc.N, eng.gptr(sc.bk), 9, *sc.geo.args(), dt, eng.impl_w, S())
+            self.bwd_ops.append(wgrad)
+            # data gradient: towards the parent's activation (N0) and the pooled predecessor (N1)
+            N0 = sc.K0 if par_grad else 0
+            N1 = sc.K1
+            if N0 + N1 == 0:
+                continue
+            sc.Wd = torch.zeros((9, sc.N // 8, N0 + N1, 8), dtype=eng.tdtype, device=eng.dev)
+            if N0:
+                self.pack_ops.append(lambda sc=sc, N0=N0, N1=N1: L.pack_weights(
+                    eng.tptr(sc.wh), 9, sc.K0real, sc.N, 1, 0, sc.N, 0, N0 + N1, _vp(sc.Wd), dt, S()))
+            if N1:
+                self.pack_ops.append(lambda sc=sc, N0=N0, N1=N1: L.pack_weights(
+                    eng.tptr(sc.wv), 9, sc.K1, sc.N, 1, 0, sc.N, N0, N0 + N1, _vp(sc.Wd), dt, S()))
+            acc0 = 0
+            out0 = None
+            if N0:
+                slot = sc.src
+                if slot.dact is None:
+                    slot.dact = self.planes(slot.C, geo)
+                acc0 = 1 if slot.writers > 0 else 0
+                slot.writers += 1
+                out0 = slot.dact
+            if N1:
+                prev.dpooled = self.planes(sc.K1, geo)
+
+            def dgrad(sc=sc, out0=out0, N0=N0, N1=N1, acc0=acc0, prev=prev):
+                L.stencil_gemm(_vp(sc.dlin), sc.N, None, 0, _vp(sc.Wd), 9, None,
+                               _vp(out0), N0, acc0, _vp(prev.dpooled) if N1 else None, N1, 0,
+                               *sc.geo.args(), None, 0, None, dt, dt, impl, S())
+            self.bwd_ops.append(dgrad)
+
+    # -- router ------------------------------------------------------------ #
+    def _build_router_fwd(self, nd, Balloc, dyn_k):
+        eng, L, B = self.eng, self.eng.L, self.B
+        dt = eng.dtype
+        S = lambda: eng.stream
+        st = self.node[nd.idx]
+        c = nd.router.comps
+        fc1, bn1, fc2, bn2, fc3 = c[1], c[2], c[4], c[5], c[7]
+        if c[0].hypers.i != -1:
+            raise NotImplementedError('engine: router must select the coarsest scale')
+        ns = len(nd.kids)
+        if fc1.hypers.n_chan != 16 or fc2.hypers.n_chan != 16 or fc3.hypers.n_chan != ns:
+            raise NotImplementedError('engine: router widths')
+        bwd = self.need_bwd
+        rt = Ns(fc1=fc1, bn1=bn1, fc2=fc2, bn2=bn2, fc3=fc3, ns=ns,
+                Z1=self.f32(B, 16), Z2=self.f32(B, 16), R=self.f32(B, ns), save=self.f32(64),
+                dR=self.f32(B, ns) if bwd else None, dZ1=self.f32(B, 16) if bwd else None,
+                scratch=self.f32(2 * B * 16) if bwd else None)
+        self.rtr[nd.idx] = rt
+        train = 1 if self.bn_train else 0
+        self.fwd_ops.append(lambda: L.fc_fwd(
+            _vp(st.feat), st.F, Balloc, B, eng.tptr(fc1.params.w), eng.tptr(fc1.params.b),
+            _vp(self.kextra) if dyn_k else None, 16, _vp(rt.Z1), dt, S()))
+        P = lambda lay, k: eng.tptr(getattr(lay.params, k))
+        self.fwd_ops.append(lambda: L.router_tail_fwd(
+            _vp(rt.Z1), B, 16, P(bn1, 'γ'), P(bn1, 'β'), P(bn1, 'm_avg'), P(bn1, 'v_avg'),
+            P(fc2, 'w'), P(fc2, 'b'), P(bn2, 'γ'), P(bn2, 'β'), P(bn2, 'm_avg'), P(bn2, 'v_avg'),
+            P(fc3, 'w'), P(fc3, 'b'), ns, float(bn1.hypers.d), float(bn1.hypers.ε), train,
+            _vp(rt.Z2), _vp(rt.R), _vp(rt.save), S()))
+
+    def _build_router_bwd(self, nd, Balloc, dyn_k):
+        eng, L, B = self.eng, self.eng.L, self.B
+        dt = eng.dtype
+        S = lambda: eng.stream
+        st = self.node[nd.idx]
+        rt = self.rtr[nd.idx]
+        P = lambda lay, k: eng.tptr(getattr(lay.params, k))
+        Gp = lambda lay, k: eng.gptr(getattr(lay.params, k))
+        self.bwd_ops.append(lambda: L.router_tail_bwd(
+            _vp(rt.Z1), _vp(rt.Z2), _vp(rt.dR), B, 16, rt.ns,
+            P(rt.bn1, 'γ'), P(rt.bn1, 'β'), P(rt.fc2, 'w'), P(rt.bn2, 'γ'), P(rt.bn2, 'β'), P(rt.fc3, 'w'),
+            _vp(rt.save),
+            Gp(rt.bn1, 'γ'), Gp(rt.bn1, 'β'), Gp(rt.fc2, 'w'), Gp(rt.fc2, 'b'),
+            Gp(rt.bn2, 'γ'), Gp(rt.bn2, 'β'), Gp(rt.fc3, 'w'), Gp(rt.fc3, 'b'),
+            _vp(rt.dZ1), _vp(rt.scratch), S()))
+        self.bwd_ops.append(lambda: L.fc_bwd_weight(
+            _vp(st.feat), st.F, Balloc, B, _vp(self.kextra) if dyn_k else None, _vp(rt.dZ1), 16,
+            Gp(rt.fc1, 'w'), Gp(rt.fc1, 'b'), dt, S()))
+
+    # -- routing ----------------------------------------------------------- #
+    def _build_routing(self):
+        eng, L, B = self.eng, self.eng.L, self.B
+        S = lambda: eng.stream
+        dev = eng.dev
+        nodes = eng.nodes
+        nn = len(nodes)
+        root_leaves = n_leaves(eng.net.root)
+        ti = lambda v: torch.tensor(v, dtype=torch.int32, device=dev)
+        tf = lambda v: torch.tensor(v, dtype=torch.float32, device=dev)
+        self.t_parent = ti([nd.parent if nd.parent is not None else -1 for nd in nodes])
+        self.t_sink = ti([nd.sink_idx for nd in nodes])
+        self.t_nsinks = ti([len(nd.kids) for nd in nodes])
+        child = np.full((nn, MAXS), -1, np.int32)
+        for nd in nodes:
+            child[nd.idx, :len(nd.kids)] = nd.kids
+        self.t_child = ti(child)
+        self.t_floor = tf([n_leaves(nd.layer) / root_leaves for nd in nodes])
+        self.t_sw = ti([getattr(nd, 'sw', -1) if len(nd.kids) > 1 else -1 for nd in nodes])
+        self.t_ops = tf([float(nd.layer.n_ops + (nd.router.n_ops if nd.router is not None else 0)) for nd in nodes])
+        self.t_err = ti([nd.err if nd.kind == 'reg' else -1 for nd in nodes])
+        self.p_tr = self.f32(nn, B)
+        self.p_ev = self.f32(nn, B)
+        n_sw = max(len(eng.switches), 1)
+        self.dec = torch.zeros((n_sw, B), dtype=torch.int32, device=dev)
+        tp = lambda ts: torch.tensor([t.data_ptr() for t in ts] or [0], dtype=torch.int64, device=dev)
+        self.R_tab = tp([self.rtr[nd.idx].R for nd in eng.switches])
+        self.cerr_tab = tp([self.reg[nd.idx].c_err for nd in eng.regs])
+        self.dcor_tab = tp([self.reg[nd.idx].d_cor for nd in eng.regs])
+        self.fwd_ops.append(lambda: L.route_fwd(
+            _vp(self.t_parent), _vp(self.t_sink), _vp(self.t_nsinks), _vp(self.t_floor), _vp(self.t_sw), nn,
+            _vp(self.R_tab), _vp(eng.hyp), B, _vp(self.p_tr), _vp(self.p_ev), _vp(self.dec), S()))
+        if self.need_bwd:
+            self.dR_tab = tp([self.rtr[nd.idx].dR for nd in eng.switches])
+            self.route_scratch = self.f32(3 * nn * B)
+            self.c_data = self.f32(B)

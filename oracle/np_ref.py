@@ -126,9 +126,13 @@ def _leaves(rec):
     return 1 if not rec['sinks'] else sum(map(_leaves, rec['sinks']))
 
 
-def forward(record, x0, y, mode='ev', tau=None, k_cpt=None):
+def forward(record, x0, y, mode='ev', tau=None, k_cpt=None, frozen=None):
     """-> dict(c_tot, nodes{path: dict(p_tr, p_ev, c_err, d_cor, r, n_ops)}).
-    Follows net_types.py:85-97 (SR), :103-181 (actor), :187-284 (critic)."""
+    Follows net_types.py:85-97 (SR), :103-181 (actor), :187-284 (critic).
+
+    `frozen`: the `nodes` dict of a previous forward; its p_tr / c_ev / c_opt are
+    used wherever the reference applies tf.stop_gradient, so that finite
+    differences of c_tot reproduce the gradient TF would compute."""
     hy = record['hypers']
     kind = record['type']
     x0 = np.float64(x0); y = np.float64(y)
@@ -200,8 +204,9 @@ def forward(record, x0, y, mode='ev', tau=None, k_cpt=None):
             o['c_ev'] = base + sum((dec == i) * nodes[k]['c_ev'] for i, k in enumerate(kids))
             o['c_opt'] = base + np.min([nodes[k]['c_opt'] * one for k in kids], 0)
             key = 'c_opt' if hy.get('optimistic', False) else 'c_ev'
+            tgt = frozen if frozen is not None else nodes           # stop_gradient(target)
             o['c_cre'] = hy.get('k_cre', 1e-3) * sum(
-                (r[:, i] + nodes[k][key]) ** 2 for i, k in enumerate(kids))
+                (r[:, i] + tgt[k][key]) ** 2 for i, k in enumerate(kids))
 
     route('', one, one)
     tot = 0.0
@@ -209,10 +214,12 @@ def forward(record, x0, y, mode='ev', tau=None, k_cpt=None):
         o = nodes[pth]
         rmod = o['router']['c_mod'] if o['router'] else 0.0
         rops = o['router']['n_ops'] if o['router'] else 0
+        sg_p = frozen[pth]['p_tr'] if frozen is not None else o['p_tr']   # stop_gradient(p_tr)
         if critic:
-            tot += np.mean(o['p_tr'] * (o['c_err'] + o['c_cre'] + o['c_mod'] + rmod))
+            tot += np.mean(sg_p * (o['c_err'] + o['c_cre'] + o['c_mod'] + rmod))
         else:
-            tot += np.mean(o['p_tr'] * (o['c_err'] + k_cpt * (o['n_ops'] + rops) + o['c_mod'] + rmod))
+            tot += np.mean(o['p_tr'] * (o['c_err'] + k_cpt * (o['n_ops'] + rops)))
+            tot += np.mean(sg_p * (o['c_mod'] + rmod))
             if len(o['rec']['sinks']) > 1:
-                tot += np.mean(o['p_tr'] * hy.get('k_dec', 0.01) * (o['router']['x'] ** 2).sum(1))
+                tot += np.mean(sg_p * hy.get('k_dec', 0.01) * (o['router']['x'] ** 2).sum(1))
     return dict(c_tot=tot, nodes=nodes, order=order)

@@ -1,0 +1,458 @@
+"""Kernel-level parity (B200): every libmpnn_sm100 entry point, called through
+the C ABI, against NumPy / PyTorch-CPU restatements on seeded inputs."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import np_ref
+from util import Geo, from_planes, rel_err, to_planes
+
+pytestmark = pytest.mark.gpu
+
+F32, BF16 = 0, 1
+
+
+def L():
+    from lib import _cabi
+    return _cabi.lib()
+
+
+def vp(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def dev(a, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    return t if dtype is None else t.to(dtype)
+
+
+def bf16_round(a):
+    return torch.from_numpy(np.ascontiguousarray(a, np.float32)).to(torch.bfloat16).float().numpy()
+
+
+def pack_w(w_hwio, Ktot, k_off, Ntot, n_off, packed, mode, dt):
+    w = dev(w_hwio.astype(np.float32))
+    kh, kw, I, O = w_hwio.shape
+    L().pack_weights(vp(w), kh * kw, I, O, mode, k_off, Ktot, n_off, Ntot, vp(packed), dt, None)
+
+
+# --------------------------------------------------------------------------- #
+# tcgen05 bring-up: descriptor conventions
+# --------------------------------------------------------------------------- #
+def _blob_kmajor(M, K, rows_total, row_off, a):
+    """planes layout [K/8][rows_total][8] bf16 holding a[M][K] from row row_off"""
+    t = np.zeros((K // 8, rows_total, 8), np.float32)
+    for kg in range(K // 8):
+        t[kg, row_off:row_off + M] = a[:, kg * 8:(kg + 1) * 8]
+    return t
+
+
+@pytest.mark.parametrize('N,K,row_off', [(16, 16, 0), (32, 64, 0), (64, 32, 21), (128, 128, 7), (256, 16, 3)])
+def test_umma_kmajor_descriptors(N, K, row_off):
+    rng = np.random.default_rng(0)
+    a = bf16_round(rng.standard_normal((128, K)))
+    b = bf16_round(rng.standard_normal((N, K)))
+    rows = 128 + 40
+    A = dev(_blob_kmajor(128, K, rows, row_off, a), torch.bfloat16)
+    Bm = dev(_blob_kmajor(N, K, N, 0, b), torch.bfloat16)
+    D = torch.zeros((128, N), device='cuda')
+    L().umma_selftest(vp(A), A.numel() * 2, row_off * 16, vp(Bm), Bm.numel() * 2, vp(D), N, K, 0, 0,
+                      rows * 16, 128, N * 16, 128, None)
+    torch.cuda.synchronize()
+    ref = a.astype(np.float64) @ b.astype(np.float64).T
+    assert rel_err(D.cpu().numpy(), ref) < 1e-5
+
+
+@pytest.mark.parametrize('N,K', [(16, 32), (64, 128), (144, 64)])
+def test_umma_mnmajor_descriptors(N, K):
+    """MN-major operands (the wgrad orientation): element (m,k) of A lives at
+    plane m/8, row k -- SBO = plane stride, LBO = 128 B per 8 rows of K."""
+    rng = np.random.default_rng(1)
+    a = bf16_round(rng.standard_normal((128, K)))      # A[m][k]
+    b = bf16_round(rng.standard_normal((N, K)))        # B[n][k]
+    A = np.zeros((16, K, 8), np.float32)
+    for mg in range(16):
+        A[mg] = a[mg * 8:(mg + 1) * 8].T
+    Bm = np.zeros((N // 8, K, 8), np.float32)
+    for ng in range(N // 8):
+        Bm[ng] = b[ng * 8:(ng + 1) * 8].T
+    A = dev(A, torch.bfloat16); Bm = dev(Bm, torch.bfloat16)
+    D = torch.zeros((128, N), device='cuda')
+    L().umma_selftest(vp(A), A.numel() * 2, 0, vp(Bm), Bm.numel() * 2, vp(D), N, K, 1, 1,
+                      128, K * 16, 128, K * 16, None)
+    torch.cuda.synchronize()
+    ref = a.astype(np.float64) @ b.astype(np.float64).T
+    assert rel_err(D.cpu().numpy(), ref) < 1e-5
+
+
+# --------------------------------------------------------------------------- #
+# stencil GEMM (conv forward), SIMT and tcgen05
+# --------------------------------------------------------------------------- #
+def _conv_case(B, H, Cin, Cp, Cout, seed=0):
+    rng = np.random.default_rng(seed)
+    x = rng.standard_normal((B, H, H, Cin)).astype(np.float32)
+    xp = rng.standard_normal((B, H, H, Cp)).astype(np.float32) if Cp else None
+    wh = (rng.standard_normal((3, 3, Cin, Cout)) / np.sqrt(9 * Cin)).astype(np.float32)
+    wv = (rng.standard_normal((3, 3, Cp, Cout)) / np.sqrt(9 * Cp)).astype(np.float32) if Cp else None
+    bias = rng.standard_normal(Cout).astype(np.float32)
+    return x, xp, wh, wv, bias
+
+
+def _run_gemm(x, xp, wh, wv, bias, dt, impl, want_stats=True):
+    B, H, _, Cin = x.shape
+    Cout = wh.shape[3]
+    Cp = xp.shape[3] if xp is not None else 0
+    geo = Geo(B, H, H)
+    q = 16 if dt == BF16 else 8
+    K0 = (Cin + q - 1) // q * q
+    td = torch.float32 if dt == F32 else torch.bfloat16
+    A0 = dev(to_planes(x, geo, K0), td)
+    A1 = dev(to_planes(xp, geo), td) if xp is not None else None
+    Wp = torch.zeros((9, (K0 + Cp) // 8, Cout, 8), dtype=td, device='cuda')
+    pack_w(wh, K0 + Cp, 0, Cout, 0, Wp, 0, dt)
+    if wv is not None:
+        pack_w(wv, K0 + Cp, K0, Cout, 0, Wp, 0, dt)
+    out = torch.zeros((Cout // 8, geo.P, 8), dtype=td, device='cuda')
+    stats = torch.zeros(592 * 2 * Cout, device='cuda')
+    cnt = ctypes.c_int(0)
+    L().stencil_gemm(vp(A0), K0, vp(A1), Cp, vp(Wp), 9, vp(dev(bias)), vp(out), Cout, 0, None, 0, 0,
+                     B, H, H, geo.G, geo.P, vp(stats) if want_stats else None, 592, ctypes.byref(cnt),
+                     dt, dt, impl, None)
+    torch.cuda.synchronize()
+    y = from_planes(out.float().cpu().numpy(), geo, Cout)
+    st = stats.cpu().numpy()[:cnt.value * 2 * Cout].reshape(cnt.value, 2, Cout).sum(0) if want_stats else None
+    return y, st
+
+
+def _ref_conv(x, xp, wh, wv, bias, rounder=lambda a: a):
+    y = np_ref.conv3_same(np.float64(rounder(x)), np.float64(rounder(wh))) + bias
+    if xp is not None:
+        y = y + np_ref.conv3_same(np.float64(rounder(xp)), np.float64(rounder(wv)))
+    return y
+
+
+@pytest.mark.parametrize('B,H,Cin,Cp,Cout', [(3, 8, 3, 0, 16), (2, 16, 16, 16, 16), (5, 4, 32, 64, 64),
+                                              (2, 32, 16, 0, 32), (7, 4, 128, 0, 128)])
+def test_stencil_gemm_simt_fp32(B, H, Cin, Cp, Cout):
+    x, xp, wh, wv, bias = _conv_case(B, H, Cin, Cp, Cout)
+    y, st = _run_gemm(x, xp, wh, wv, bias, F32, 0)
+    ref = _ref_conv(x, xp, wh, wv, bias)
+    assert rel_err(y, ref) < 1e-5
+    np.testing.assert_allclose(st[0], ref.sum((0, 1, 2)), rtol=1e-4, atol=1e-3)
+    np.testing.assert_allclose(st[1], (ref ** 2).sum((0, 1, 2)), rtol=1e-4)
+
+
+@pytest.mark.parametrize('impl', [0, 1])
+@pytest.mark.parametrize('B,H,Cin,Cp,Cout', [(3, 8, 3, 0, 16), (2, 16, 16, 16, 16), (5, 4, 32, 64, 64),
+                                              (2, 32, 16, 0, 32), (7, 4, 128, 0, 128), (40, 4, 64, 64, 64),
+                                              (9, 8, 64, 0, 64), (130, 32, 16, 16, 16)])
+def test_stencil_gemm_bf16(impl, B, H, Cin, Cp, Cout):
+    x, xp, wh, wv, bias = _conv_case(B, H, Cin, Cp, Cout, seed=impl)
+    y, st = _run_gemm(x, xp, wh, wv, bias, BF16, impl)
+    ref = _ref_conv(x, xp, wh, wv, bias, bf16_round)     # exact products of bf16 operands
+    # output itself is stored as bf16: 2^-9 relative rounding
+    assert rel_err(y, ref) < 4e-3
+    np.testing.assert_allclose(st[0], ref.sum((0, 1, 2)), rtol=2e-3, atol=0.05 * np.sqrt(ref.size / Cout))
+    np.testing.assert_allclose(st[1], (ref ** 2).sum((0, 1, 2)), rtol=2e-3)
+
+
+@pytest.mark.parametrize('dt,impl', [(F32, 0), (BF16, 0), (BF16, 1)])
+def test_stencil_dgrad_split_outputs(dt, impl):
+    """dgrad = same kernel with transposed/flipped weights, columns split over two outputs"""
+    rng = np.random.default_rng(5)
+    B, H, Cin, Cp, Cout = 4, 8, 32, 16, 32
+    g = rng.standard_normal((B, H, H, Cout)).astype(np.float32)
+    wh = rng.standard_normal((3, 3, Cin, Cout)).astype(np.float32) / 10
+    wv = rng.standard_normal((3, 3, Cp, Cout)).astype(np.float32) / 10
+    geo = Geo(B, H, H)
+    td = torch.float32 if dt == F32 else torch.bfloat16
+    rd = (lambda a: a) if dt == F32 else bf16_round
+    G = dev(to_planes(g, geo), td)
+    Wd = torch.zeros((9, Cout // 8, Cin + Cp, 8), dtype=td, device='cuda')
+    pack_w(wh, Cout, 0, Cin + Cp, 0, Wd, 1, dt)
+    pack_w(wv, Cout, 0, Cin + Cp, Cin, Wd, 1, dt)
+    o0 = torch.zeros((Cin // 8, geo.P, 8), dtype=td, device='cuda')
+    o1 = torch.zeros((Cp // 8, geo.P, 8), dtype=td, device='cuda')
+    L().stencil_gemm(vp(G), Cout, None, 0, vp(Wd), 9, None, vp(o0), Cin, 0, vp(o1), Cp, 0,
+                     B, H, H, geo.G, geo.P, None, 0, None, dt, dt, impl, None)
+    torch.cuda.synchronize()
+    gt = torch.tensor(rd(g), dtype=torch.float64).permute(0, 3, 1, 2)
+    for w, o, C in ((wh, o0, Cin), (wv, o1, Cp)):
+        wt = torch.tensor(rd(w), dtype=torch.float64).permute(3, 2, 0, 1)      # OIHW
+        ref = torch.nn.functional.conv_transpose2d(gt, wt, padding=1).permute(0, 2, 3, 1).numpy()
+        assert rel_err(from_planes(o.float().cpu().numpy(), geo, C), ref) < (1e-5 if dt == F32 else 4e-3)
+
+
+@pytest.mark.parametrize('dt', [F32, BF16])
+def test_stencil_wgrad(dt):
+    rng = np.random.default_rng(6)
+    B, H, Cin, Cp, Cout = 6, 8, 3, 16, 32
+    x = rng.standard_normal((B, H, H, Cin)).astype(np.float32)
+    xp = rng.standard_normal((B, H, H, Cp)).astype(np.float32)
+    g = rng.standard_normal((B, H, H, Cout)).astype(np.float32)
+    geo = Geo(B, H, H)
+    q = 16 if dt == BF16 else 8
+    K0 = (Cin + q - 1) // q * q
+    td = torch.float32 if dt == F32 else torch.bfloat16
+    rd = (lambda a: a) if dt == F32 else bf16_round
+    A0 = dev(to_planes(x, geo, K0), td); A1 = dev(to_planes(xp, geo), td); G = dev(to_planes(g, geo), td)
+    dW0 = torch.zeros((9, Cin, Cout), device='cuda'); dW1 = torch.zeros((9, Cp, Cout), device='cuda')
+    db = torch.zeros(Cout, device='cuda')
+    L().stencil_wgrad(vp(A0), K0, Cin, vp(dW0), vp(A1), Cp, Cp, vp(dW1), vp(G), Cout, Cout, vp(db), 9,
+                      B, H, H, geo.G, geo.P, dt, 0, None)
+    torch.cuda.synchronize()
+    gt = torch.tensor(rd(g), dtype=torch.float64).permute(0, 3, 1, 2)
+    for xin, dW, C in ((x, dW0, Cin), (xp, dW1, Cp)):
+        xt = torch.tensor(rd(xin), dtype=torch.float64).permute(0, 3, 1, 2).requires_grad_(False)
+        w = torch.zeros((Cout, C, 3, 3), dtype=torch.float64, requires_grad=True)
+        (torch.nn.functional.conv2d(xt, w, padding=1) * gt).sum().backward()
+        ref = w.grad.permute(2, 3, 1, 0).reshape(9, C, Cout).numpy()
+        assert rel_err(dW.cpu().numpy(), ref) < 1e-4
+    np.testing.assert_allclose(db.cpu().numpy(), rd(g).sum((0, 1, 2)), rtol=1e-4, atol=1e-3)
+
+
+# --------------------------------------------------------------------------- #
+# BN + ReLU + pool
+# --------------------------------------------------------------------------- #
+@pytest.mark.parametrize('dt', [F32, BF16])
+@pytest.mark.parametrize('pool', [True, False])
+def test_bn_relu_pool_fwd_bwd(dt, pool):
+    rng = np.random.default_rng(7)
+    B, H, C = 5, 8 if pool else 4, 16
+    td = torch.float32 if dt == F32 else torch.bfloat16
+    rd = (lambda a: a) if dt == F32 else bf16_round
+    lin = rd(rng.standard_normal((B, H, H, C)).astype(np.float32) * 2 + 0.5)
+    gamma = rng.standard_normal(C).astype(np.float32); beta = rng.standard_normal(C).astype(np.float32) * 0.1
+    geo = Geo(B, H, H); gp = Geo(B, H // 2, H // 2)
+    LIN = dev(to_planes(lin, geo), td)
+    # statistics from exact per-channel sums (finalize path)
+    part = dev(np.stack([lin.sum((0, 1, 2)), (lin.astype(np.float64) ** 2).sum((0, 1, 2))]).astype(np.float32))
+    ss = torch.zeros((2, C), device='cuda'); mr = torch.zeros((2, C), device='cuda')
+    m_avg = torch.zeros(C, device='cuda'); v_avg = torch.ones(C, device='cuda')
+    L().bn_finalize(vp(part), 1, C, float(B * H * H), vp(dev(gamma)), vp(dev(beta)), vp(m_avg), vp(v_avg),
+                    0.9, 1e-6, 1, vp(ss), vp(mr), None)
+    act = torch.zeros_like(LIN)
+    pooled = torch.zeros((C // 8, gp.P, 8), dtype=td, device='cuda') if pool else None
+    Balloc = 8
+    feat = None if pool else torch.zeros((H * H * C // 8, Balloc, 8), dtype=td, device='cuda')
+    L().bn_relu_pool_fwd(vp(LIN), C, B, H, H, geo.G, geo.P, vp(ss), vp(act), vp(pooled), gp.P if pool else 0,
+                         vp(feat), Balloc, dt, None)
+    torch.cuda.synchronize()
+    xt = torch.tensor(lin, dtype=torch.float64, requires_grad=True)
+    m = xt.mean((0, 1, 2)); v = ((xt - m) ** 2).mean((0, 1, 2))
+    yt = torch.relu(torch.tensor(gamma, dtype=torch.float64) * (xt - m) / torch.sqrt(v + 1e-6)
+                    + torch.tensor(beta, dtype=torch.float64))
+    tol = 1e-4 if dt == F32 else 1e-2
+    assert rel_err(from_planes(act.float().cpu().numpy(), geo, C), yt.detach().numpy()) < tol
+    np.testing.assert_allclose(m_avg.cpu().numpy(), 0.1 * m.detach().numpy(), rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(v_avg.cpu().numpy(), 0.9 + 0.1 * v.detach().numpy(), rtol=1e-4)
+    if pool:
+        pt = torch.nn.functional.max_pool2d(xt.permute(0, 3, 1, 2), 2).permute(0, 2, 3, 1)
+        np.testing.assert_array_equal(from_planes(pooled.float().cpu().numpy(), gp, C), pt.detach().numpy())
+    else:
+        f = feat.float().cpu().numpy()          # [F/8][Balloc][8] -> (B, F)
+        flat = np.concatenate([f[i, :B] for i in range(f.shape[0])], 1)
+        assert rel_err(flat, yt.detach().numpy().reshape(B, -1)) < tol
+    # backward
+    dy = rd(rng.standard_normal((B, H, H, C)).astype(np.float32))
+    dp = rd(rng.standard_normal((B, H // 2, H // 2, C)).astype(np.float32)) if pool else None
+    df = None if pool else rd(rng.standard_normal((B, H, H, C)).astype(np.float32))
+    DY = dev(to_planes(dy, geo), td)
+    DP = dev(to_planes(dp, gp), td) if pool else None
+    DF = None
+    if df is not None:
+        t = np.zeros((H * H * C // 8, Balloc, 8), np.float32)
+        flat = df.reshape(B, -1)
+        for i in range(t.shape[0]):
+            t[i, :B] = flat[:, i * 8:(i + 1) * 8]
+        DF = dev(t, td)
+    parts = torch.zeros(592 * 2 * C, device='cuda'); cnt = ctypes.c_int(0)
+    L().bn_bwd_reduce(vp(LIN), vp(DY), vp(DF), Balloc, vp(ss), vp(mr), C, B, H, H, geo.G, geo.P,
+                      vp(parts), 592, ctypes.byref(cnt), dt, None)
+    sums = torch.zeros((2, C), device='cuda'); dg = torch.zeros(C, device='cuda'); dbt = torch.zeros(C, device='cuda')
+    L().bn_bwd_finalize(vp(parts), cnt.value, C, vp(sums), vp(dg), vp(dbt), None)
+    dlin = torch.zeros_like(LIN)
+    L().bn_relu_pool_bwd(vp(LIN), vp(DY), vp(DF), Balloc, vp(DP), gp.P if pool else 0, vp(ss), vp(mr), vp(sums),
+                         float(B * H * H), C, B, H, H, geo.G, geo.P, vp(dlin), dt, None)
+    torch.cuda.synchronize()
+    gtot = torch.tensor(dy, dtype=torch.float64) + (torch.tensor(df, dtype=torch.float64) if df is not None else 0)
+    loss = (yt * gtot).sum()
+    if pool:
+        loss = loss + (pt * torch.tensor(dp, dtype=torch.float64)).sum()
+    loss.backward()
+    assert rel_err(from_planes(dlin.float().cpu().numpy(), geo, C), xt.grad.numpy()) < (1e-4 if dt == F32 else 2e-2)
+
+
+# --------------------------------------------------------------------------- #
+# heads
+# --------------------------------------------------------------------------- #
+@pytest.mark.parametrize('dt', [F32, BF16])
+@pytest.mark.parametrize('B,F,n,extra', [(5, 256, 10, False), (37, 512, 16, True), (128, 2048, 2, False)])
+def test_fc_fwd_bwd(dt, B, F, n, extra):
+    rng = np.random.default_rng(8)
+    td = torch.float32 if dt == F32 else torch.bfloat16
+    rd = (lambda a: a) if dt == F32 else bf16_round
+    x = rd(rng.standard_normal((B, F)).astype(np.float32))
+    W = rng.standard_normal((F + (1 if extra else 0), n)).astype(np.float32) / 10
+    bias = rng.standard_normal(n).astype(np.float32)
+    ex = rng.standard_normal(B).astype(np.float32) if extra else None
+    Balloc = (B + 7) // 8 * 8
+    t = np.zeros((F // 8, Balloc, 8), np.float32)
+    for i in range(F // 8):
+        t[i, :B] = x[:, i * 8:(i + 1) * 8]
+    X = dev(t, td)
+    Z = torch.zeros((B, n), device='cuda')
+    Wd, EX = dev(W), (dev(ex) if extra else None)
+    L().fc_fwd(vp(X), F, Balloc, B, vp(Wd), vp(dev(bias)), vp(EX), n, vp(Z), dt, None)
+    xf = np.concatenate([x, ex[:, None]], 1) if extra else x
+    ref = xf.astype(np.float64) @ W + bias
+    torch.cuda.synchronize()
+    assert rel_err(Z.cpu().numpy(), ref) < 1e-5
+    dZ = rng.standard_normal((B, n)).astype(np.float32)
+    dZ2 = rng.standard_normal((B, 16)).astype(np.float32)
+    W2 = rng.standard_normal((F, 16)).astype(np.float32) / 10
+    dX = torch.zeros_like(X)
+    L().fc_bwd_data(vp(dev(dZ)), vp(Wd), n, vp(dev(dZ2)), vp(dev(W2)), 16, F, Balloc, B, vp(dX), dt, None)
+    torch.cuda.synchronize()
+    f = dX.float().cpu().numpy()
+    got = np.concatenate([f[i, :B] for i in range(F // 8)], 1)
+    refx = dZ.astype(np.float64) @ W[:F].T + dZ2.astype(np.float64) @ W2.T
+    assert rel_err(got, refx) < (1e-5 if dt == F32 else 4e-3)
+    dW = torch.zeros_like(Wd); db = torch.zeros(n, device='cuda')
+    L().fc_bwd_weight(vp(X), F, Balloc, B, vp(EX), vp(dev(dZ)), n, vp(dW), vp(db), dt, None)
+    torch.cuda.synchronize()
+    assert rel_err(dW.cpu().numpy(), xf.astype(np.float64).T @ dZ) < 1e-5
+    np.testing.assert_allclose(db.cpu().numpy(), dZ.sum(0), rtol=1e-4, atol=1e-4)
+
+
+def test_softmax_ce():
+    rng = np.random.default_rng(9)
+    B, n = 77, 10
+    z = rng.standard_normal((B, n)).astype(np.float32) * 3
+    z[0] = 0            # tie -> first index
+    y = np.eye(n, dtype=np.float32)[rng.integers(0, n, B)]
+    coef = rng.random(B).astype(np.float32)
+    Z, Y = dev(z), dev(y)
+    prob = torch.zeros_like(Z); ce = torch.zeros(B, device='cuda'); dc = torch.zeros(B, device='cuda')
+    L().softmax_ce_fwd(vp(Z), vp(Y), B, n, 1e-6, vp(prob), vp(ce), vp(dc), None)
+    dZ = torch.zeros_like(Z)
+    L().softmax_ce_bwd(vp(prob), vp(Y), B, n, 1e-6, vp(dev(coef)), 1.0 / B, vp(dZ), None)
+    torch.cuda.synchronize()
+    zt = torch.tensor(z, dtype=torch.float64, requires_grad=True)
+    p = torch.softmax(zt, 1)
+    c = -(torch.tensor(y, dtype=torch.float64) * torch.log(1e-6 / n + (1 - 1e-6) * p)).sum(1)
+    (c * torch.tensor(coef, dtype=torch.float64) / B).sum().backward()
+    np.testing.assert_allclose(ce.cpu().numpy(), c.detach().numpy(), rtol=1e-5, atol=1e-6)
+    assert rel_err(dZ.cpu().numpy(), zt.grad.numpy()) < 1e-5
+    from oracle.torch_ref import first_argmax
+    exp = (first_argmax(p.detach(), 1) == first_argmax(torch.tensor(y), 1)).float().numpy()
+    np.testing.assert_array_equal(dc.cpu().numpy(), exp)
+
+
+@pytest.mark.parametrize('B,ns', [(9, 2), (700, 3)])
+def test_router_tail(B, ns):
+    rng = np.random.default_rng(10)
+    C = 16
+    z1 = rng.standard_normal((B, C)).astype(np.float32)
+    P = {k: rng.standard_normal(s).astype(np.float32) * sc for k, s, sc in [
+        ('g1', C, 1), ('b1', C, .3), ('W2', (C, C), .3), ('c2', C, .1), ('g2', C, 1), ('b2', C, .3),
+        ('W3', (C, ns), .3), ('c3', ns, .1)]}
+    D = {k: dev(v) for k, v in P.items()}
+    m1 = torch.zeros(C, device='cuda'); v1 = torch.ones(C, device='cuda')
+    m2 = torch.zeros(C, device='cuda'); v2 = torch.ones(C, device='cuda')
+    Z1 = dev(z1); Z2 = torch.zeros((B, C), device='cuda'); R = torch.zeros((B, ns), device='cuda')
+    save = torch.zeros(64, device='cuda')
+    L().router_tail_fwd(vp(Z1), B, C, vp(D['g1']), vp(D['b1']), vp(m1), vp(v1), vp(D['W2']), vp(D['c2']),
+                        vp(D['g2']), vp(D['b2']), vp(m2), vp(v2), vp(D['W3']), vp(D['c3']), ns, 0.9, 1e-6, 1,
+                        vp(Z2), vp(R), vp(save), None)
+    T = {k: torch.tensor(v, dtype=torch.float64, requires_grad=True) for k, v in P.items()}
+    zt = torch.tensor(z1, dtype=torch.float64, requires_grad=True)
+
+    def bn(x, g, b):
+        m = x.mean(0); v = ((x - m) ** 2).mean(0)
+        return g * (x - m) / torch.sqrt(v + 1e-6) + b, m, v
+    h1, mm1, vv1 = bn(zt, T['g1'], T['b1'])
+    z2 = torch.relu(h1) @ T['W2'] + T['c2']
+    h2, mm2, vv2 = bn(z2, T['g2'], T['b2'])
+    r = torch.relu(h2) @ T['W3'] + T['c3']
+    torch.cuda.synchronize()
+    assert rel_err(R.cpu().numpy(), r.detach().numpy()) < 1e-4
+    np.testing.assert_allclose(v2.cpu().numpy(), 0.9 + 0.1 * vv2.detach().numpy(), rtol=1e-4)
+    dr = rng.standard_normal((B, ns)).astype(np.float32)
+    (r * torch.tensor(dr, dtype=torch.float64)).sum().backward()
+    G = {k: torch.zeros_like(D[k]) for k in P}
+    dZ1 = torch.zeros((B, C), device='cuda'); scratch = torch.zeros(2 * B * C, device='cuda')
+    L().router_tail_bwd(vp(Z1), vp(Z2), vp(dev(dr)), B, C, ns, vp(D['g1']), vp(D['b1']), vp(D['W2']),
+                        vp(D['g2']), vp(D['b2']), vp(D['W3']), vp(save),
+                        vp(G['g1']), vp(G['b1']), vp(G['W2']), vp(G['c2']), vp(G['g2']), vp(G['b2']),
+                        vp(G['W3']), vp(G['c3']), vp(dZ1), vp(scratch), None)
+    torch.cuda.synchronize()
+    assert rel_err(dZ1.cpu().numpy(), zt.grad.numpy()) < 2e-4
+    for k in P:
+        assert rel_err(G[k].cpu().numpy(), T[k].grad.numpy()) < 2e-4, k
+
+
+# --------------------------------------------------------------------------- #
+# compaction / gather / scatter / optimiser
+# --------------------------------------------------------------------------- #
+def test_compact_gather_scatter():
+    rng = np.random.default_rng(11)
+    nn, B = 5, 2500
+    pe = (rng.random((nn, B)) < np.array([1.0, 0.5, 0.02, 0.0, 0.9])[:, None]).astype(np.float32)
+    PE = dev(pe)
+    idx = torch.full((nn, B), -1, dtype=torch.int32, device='cuda'); cnt = torch.zeros(nn, dtype=torch.int32, device='cuda')
+    L().compact_paths(vp(PE), nn, B, vp(idx), vp(cnt), None)
+    torch.cuda.synchronize()
+    for i in range(nn):
+        want = np.nonzero(pe[i])[0]
+        assert int(cnt[i]) == len(want)
+        np.testing.assert_array_equal(idx[i, :len(want)].cpu().numpy(), want)      # bit-exact, order preserving
+    # gather images of node 1 and scatter them back
+    Bs, H, C = 64, 4, 16
+    x = rng.standard_normal((Bs, H, H, C)).astype(np.float32)
+    sel = np.sort(rng.choice(Bs, 20, replace=False)).astype(np.int32)
+    gs, gd = Geo(Bs, H, H), Geo(32, H, H)
+    for dt, td in ((F32, torch.float32), (BF16, torch.bfloat16)):
+        rd = (lambda a: a) if dt == F32 else bf16_round
+        X = dev(to_planes(rd(x), gs), td)
+        I = dev(sel); N = dev(np.array([len(sel)], np.int32))
+        Y = torch.zeros((C // 8, gd.P, 8), dtype=td, device='cuda')
+        L().gather_images(vp(X), Bs, gs.P, vp(I), vp(N), vp(Y), 32, gd.P, C, H, H, gs.G, dt, None)
+        torch.cuda.synchronize()
+        got = from_planes(Y.float().cpu().numpy(), gd, C)
+        np.testing.assert_array_equal(got[:len(sel)], rd(x)[sel])
+        Zt = torch.zeros_like(X)
+        L().scatter_add_images(vp(Y), 32, gd.P, vp(I), vp(N), vp(Zt), Bs, gs.P, C, H, H, gs.G, dt, None)
+        torch.cuda.synchronize()
+        back = from_planes(Zt.float().cpu().numpy(), gs, C)
+        exp = np.zeros_like(x); exp[sel] = rd(x)[sel]
+        np.testing.assert_array_equal(back, exp)
+
+
+def test_talr_momentum_step():
+    rng = np.random.default_rng(12)
+    sizes = [7, 100, 33, 1, 500]
+    n = sum(sizes)
+    th = rng.standard_normal(n).astype(np.float32); g = rng.standard_normal(n).astype(np.float32)
+    a = rng.standard_normal(n).astype(np.float32)
+    start = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
+    node = np.array([0, 1, 1, 2, 2], np.int32); mult = np.array([1, 1, 2, 1, .5], np.float32)
+    l2 = np.array([0, 1e-4, 0, 1e-4, 0], np.float32)
+    stats = np.array([[1.0, 1.0], [0.25, 0.4], [1e-6, 1e-3]], np.float32)
+    hyp = np.zeros(8, np.float32); hyp[0] = 0.1; hyp[1] = 0.9; hyp[5] = 0.5
+    TH, A = dev(th), dev(a)
+    # moments ride in the all-reduced tail: kernel multiplies them by gscale too
+    L().talr_momentum_step(vp(TH), vp(dev(g)), vp(A), n, vp(dev(start)), vp(dev(node)), vp(dev(mult)), vp(dev(l2)),
+                           5, vp(dev(stats / 0.5)), 1, vp(dev(hyp)), None)
+    torch.cuda.synchronize()
+    exp_th, exp_a = th.astype(np.float64).copy(), a.astype(np.float64).copy()
+    for s in range(5):
+        sl = slice(start[s], start[s + 1])
+        gg = g[sl] * 0.5 + 2 * l2[s] * stats[node[s], 1] * th[sl]
+        gg = gg * mult[s] / np.sqrt(stats[node[s], 0])
+        exp_a[sl] = 0.9 * a[sl] + gg
+        exp_th[sl] = th[sl] - 0.1 * exp_a[sl]
+    np.testing.assert_allclose(A.cpu().numpy(), exp_a, rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(TH.cpu().numpy(), exp_th, rtol=1e-5, atol=1e-6)

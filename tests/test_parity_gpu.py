@@ -1,0 +1,188 @@
+"""End-to-end parity on B200: the CUDA path (through net.train.run /
+net.eval_stats, i.e. the reference-facing API over the C ABI) against the CPU
+oracle on the same seeded inputs and byte-identical weights.
+
+Tolerances (north_star): fp32 mode -- logits, losses, gradients within 1e-3
+relative; routing decisions bit-exact wherever the oracle's decision margin
+exceeds 1e-4.  bf16 mode (stated here): logits / c_err within 3e-2 relative
+(L2 norm over the batch), gradients within 8e-2, decisions exact where the
+fp64 margin exceeds 5e-2.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle.torch_ref import OracleNet
+from util import batch, node_paths, randomize_routers, record_of, rel_err, tiny_net
+
+pytestmark = pytest.mark.gpu
+
+TOL = {'fp32': dict(fwd=1e-3, grad=1e-3, margin=1e-4, step=2e-3),
+       'bf16': dict(fwd=3e-2, grad=8e-2, margin=5e-2, step=8e-2)}
+
+
+def _nets(kind, hy, seed=0):
+    net = tiny_net(kind, seed=seed, **hy)
+    if kind != 'sr':
+        randomize_routers(net)
+    return net
+
+
+def _feed(net, x0, y, tau=0.7, kc=None, lr=None, mode=None):
+    f = {net.x0: x0, net.y: y}
+    if net.dynamic:
+        f[net.τ] = tau
+        if net.hypers.dyn_k_cpt:
+            f[net.k_cpt] = kc
+    if lr is not None:
+        f[net.λ_lrn] = lr
+    if mode is not None:
+        f[net.mode] = mode
+    return f
+
+
+CASES = [('sr', {}), ('ac', dict(k_cpt=4e-9)), ('cr', dict(k_cpt=4e-9)),
+         ('cr', dict(k_cpt=1e-8, optimistic=True)), ('cr', dict(k_cpt=1e-8, use_cls_err=True)),
+         ('actree', dict(k_cpt=2e-9)), ('ac', dict(dyn_k_cpt=True)), ('ac', dict(k_cpt=1e-8, talr=False))]
+
+
+@pytest.mark.parametrize('prec', ['fp32', 'bf16'])
+@pytest.mark.parametrize('kind,hy', CASES)
+def test_forward_and_gradients(kind, hy, prec):
+    tol = TOL[prec]
+    B = 24
+    net = _nets(kind, hy).configure(precision=prec)
+    rec = record_of(net)
+    x0, y = batch(B, seed=3)
+    kc = np.random.default_rng(3).choice([0.0, 1e-9, 6.4e-8], B).astype(np.float32) if hy.get('dyn_k_cpt') else None
+    o = OracleNet(rec, torch.float64)
+    out, g_ref = o.grads(x0, y, tau=0.7, k_cpt=kc)
+    eng = net._get_engine()
+    feed = _feed(net, x0, y, 0.7, kc)
+    eng.train_step(feed, update=False)
+    torch.cuda.synchronize()
+    plan = eng._plan(B, True, True)
+    paths = node_paths(net)
+    # ---- forward values
+    for nd in eng.regs:
+        path = paths[nd.idx][0]
+        ref = out.nodes[path]
+        z_ref = ref.comps[1].x.detach().numpy()
+        assert rel_err(plan.reg[nd.idx].Z.cpu().numpy(), z_ref) < tol['fwd'], ('logits', path)
+        assert rel_err(plan.reg[nd.idx].c_err.cpu().numpy(), ref.c_err.detach().numpy()) < tol['fwd'], ('c_err', path)
+    if net.dynamic:
+        p_tr = plan.p_tr.cpu().numpy(); p_ev = plan.p_ev.cpu().numpy(); dec = plan.dec.cpu().numpy()
+        for nd in eng.switches:
+            path = paths[nd.idx][0]
+            r_ref = out.nodes[path].router.x.detach().numpy()
+            r = plan.rtr[nd.idx].R.cpu().numpy()
+            assert rel_err(r, r_ref) < 5 * tol['fwd'], ('router logits', path)
+            srt = np.sort(r_ref, 1)
+            sure = (srt[:, -1] - srt[:, -2]) > tol['margin']
+            np.testing.assert_array_equal(dec[nd.sw][sure], r_ref.argmax(1)[sure])      # bit-exact decisions
+        for nd in eng.nodes:
+            path = paths[nd.idx][0]
+            assert rel_err(p_tr[nd.idx], out.nodes[path].p_tr.detach().numpy()) < 5 * tol['fwd'], ('p_tr', path)
+        leaves = [nd.idx for nd in eng.nodes if not nd.kids]
+        np.testing.assert_array_equal(p_ev[leaves].sum(0), 1.0)        # every example reaches exactly one leaf
+    # ---- objective
+    assert abs(eng.c_tot(plan) - float(out.c_tot.detach())) < tol['fwd'] * abs(float(out.c_tot.detach()))
+    # ---- gradients (before TALR), per parameter tensor; engine and oracle enumerate
+    # parameters in the same order (preorder nodes: layer params, comps, then router)
+    g = eng.grads_numpy()
+    assert len(eng.tparams) == len(o.trainable)
+    worst = 0.0
+    for p, (path, role, key, t) in zip(eng.tparams, o.trainable):
+        ref = g_ref[(path, role, key, id(t))].numpy()
+        assert ref.shape == g[p].shape, (path, role, key)
+        n = np.linalg.norm(ref)
+        if n < 1e-9:
+            assert np.linalg.norm(g[p]) < 1e-6, (path, role, key)
+            continue
+        err = np.linalg.norm(g[p] - ref) / n
+        worst = max(worst, err)
+        assert err < tol['grad'], (err, path, role, key)
+    print('worst gradient rel err', worst)
+
+
+@pytest.mark.parametrize('prec', ['fp32', 'bf16'])
+@pytest.mark.parametrize('kind,hy', [('sr', {}), ('ac', dict(k_cpt=4e-9)), ('cr', dict(k_cpt=4e-9))])
+def test_training_steps_track_the_oracle(kind, hy, prec):
+    """3 x net.train.run(...) with the reference's schedules: parameters and
+    BatchNorm EMAs follow the oracle."""
+    tol = TOL[prec]
+    B = 16
+    net = _nets(kind, hy, seed=1).configure(precision=prec)
+    rec = record_of(net)
+    o = OracleNet(rec, torch.float32)
+    for t in range(3):
+        x0, y = batch(B, seed=10 + t)
+        lr, tau = 0.05 / 2 ** t, 1.0 / 2 ** (t / 2)
+        net.train.run(_feed(net, x0, y, tau, lr=lr, mode='tr'))
+        o.train_step(x0, y, lr=lr, mu=0.9, tau=tau)
+    o.write_back()
+    from lib import serdes
+    got = serdes.encode_net(net)
+
+    def cmp(a, b, path):
+        for k in a['params']:
+            ra, rb = a['params'][k], b['params'][k]
+            if k in ('m_avg', 'v_avg') and np.array_equal(ra, [0, 1][k == 'v_avg'] + 0 * ra):
+                continue        # BN of a scale nothing consumes: never evaluated (TF prunes it too)
+            assert rel_err(ra, rb) < tol['step'], (path, a['type'], k, rel_err(ra, rb))
+        for i, (x, z) in enumerate(zip(a['comps'], b['comps'])):
+            cmp(x, z, path + '.c%d' % i)
+        if a['router'] is not None:
+            cmp(a['router'], b['router'], path + '.router')
+        for i, (x, z) in enumerate(zip(a['sinks'], b['sinks'])):
+            cmp(x, z, path + '/%d' % i)
+    cmp(got['root'], rec['root'], '')
+
+
+@pytest.mark.parametrize('kind,hy', [('sr', {}), ('ac', dict(k_cpt=4e-9)), ('cr', dict(k_cpt=4e-9))])
+def test_eval_stats_match_state_tensors(kind, hy):
+    """net.eval_stats == the reference's state_tensors (train-nets:111-130), incl. a ragged batch."""
+    net = _nets(kind, hy, seed=2).configure(precision='fp32')
+    rec = record_of(net)
+    o = OracleNet(rec, torch.float64)
+    paths = node_paths(net)
+    for B in (32, 5):
+        x0, y = batch(B, seed=B)
+        got = net.eval_stats(_feed(net, x0, y, 0.5))
+        ref, out = o.state(x0, y, tau=0.5)
+        np.testing.assert_allclose(got[(net, 'moc')], ref[('net', 'moc')], rtol=1e-6)
+        for path, l in paths:
+            for name in ('p_cor', 'p_inc', 'p_cor_by_cls', 'p_inc_by_cls', 'p_tr', 'c_err', 'x_rte'):
+                if (path, name) in ref:
+                    r = ref[(path, name)]
+                    a = got[(l, name)]
+                    if name in ('c_err', 'p_tr', 'x_rte'):
+                        assert rel_err(a, r) < 2e-3, (path, name)
+                    else:
+                        # p_ev-weighted stats are exact unless a decision sits inside the margin
+                        assert np.mean(np.abs(a - r) > 1e-6) <= 0.1, (path, name)
+
+
+def test_cuda_graph_replay_equals_eager():
+    B = 16
+    nets = [_nets('ac', dict(k_cpt=4e-9), seed=5).configure(precision='fp32', graphs=g) for g in (False, True)]
+    for t in range(3):
+        x0, y = batch(B, seed=20 + t)
+        for net in nets:
+            net.train.run(_feed(net, x0, y, 0.9, lr=0.05, mode='tr'))
+    torch.cuda.synchronize()
+    a, b = nets[0]._engine.theta.cpu().numpy(), nets[1]._engine.theta.cpu().numpy()
+    assert rel_err(b, a) < 1e-5
+
+
+def test_serdes_roundtrip_through_device(tmp_path):
+    from lib import serdes
+    net = _nets('ac', dict(k_cpt=4e-9), seed=6).configure(precision='fp32')
+    x0, y = batch(8)
+    net.train.run(_feed(net, x0, y, 1.0, lr=0.1, mode='tr'))
+    path = str(tmp_path / 'net.npy')
+    serdes.write_net(path, net)
+    net2 = serdes.read_net(path).configure(precision='fp32')
+    s1 = net.eval_stats(_feed(net, x0, y, 1.0)); s2 = net2.eval_stats(_feed(net2, x0, y, 1.0))
+    np.testing.assert_allclose(s1[(net, 'moc')], s2[(net2, 'moc')])
+    np.testing.assert_allclose(s1[(net, 'acc')], s2[(net2, 'acc')])

@@ -1,0 +1,133 @@
+"""Shared helpers for the test-suite: small nets, planes-layout emulation in
+NumPy (the layout of csrc/common.cuh), comparison helpers."""
+import copy
+
+import numpy as np
+
+from lib import layer_types as lt
+from lib import serdes
+from lib.layer_types import (BatchNorm, Chain, CrossEntropyError, LinTrans, MultiscaleBatchNorm,
+                             MultiscaleConvMax, MultiscaleRect, Rect, Select, Softmax, ToPyramid)
+from lib.net_types import ActorNet, CriticNet, SRNet
+
+K_L2 = 1e-4
+
+
+def _fc(n, s=1):
+    return LinTrans(n_chan=n, k_l2=K_L2, σ_w=s)
+
+
+def router(n_sinks):
+    if n_sinks < 2:
+        return None
+    return Chain(name='Router', comps=[Select(i=-1), _fc(16), BatchNorm(), Rect(), _fc(16), BatchNorm(),
+                                       Rect(), _fc(n_sinks, 0)])
+
+
+def pyr(n_scales, *sinks):
+    return Chain(name='ToPyramid', sinks=sinks, comps=[ToPyramid(n_scales=n_scales)])
+
+
+def rcm(n_chan, *sinks):
+    return Chain(name='ReConvMax', sinks=sinks, router=router(len(sinks)), comps=[
+        MultiscaleConvMax(n_chan=list(n_chan), supp=3, k_l2=K_L2, σ_w=1), MultiscaleBatchNorm(), MultiscaleRect()])
+
+
+def reg(n_cls):
+    return Chain(name='LogReg', comps=[Select(i=-1), _fc(n_cls), Softmax(), CrossEntropyError()])
+
+
+def tiny_net(kind='ac', n_cls=10, x0_shape=(16, 16, 3), seed=0, **hypers):
+    """16x16 input, 3-scale pyramid, stages [16,16,16] -> [16,16] -> [32];
+    'sr' is a chain, 'ac'/'cr' route at both inner stages, 'tree' has a 3-way switch."""
+    lt.seed(seed)
+    if kind == 'sr':
+        root = pyr(3, rcm([16, 16, 16], rcm([16, 16], rcm([32], reg(n_cls)))))
+        return SRNet(x0_shape=x0_shape, y_shape=(n_cls,), root=root)
+    cls = CriticNet if kind.startswith('cr') else ActorNet
+    if kind.endswith('tree'):
+        root = pyr(3, rcm([16, 16, 16], reg(n_cls),
+                          rcm([16, 16], reg(n_cls), rcm([32], reg(n_cls))),
+                          rcm([16, 16], reg(n_cls), rcm([32], reg(n_cls)))))
+    else:
+        root = pyr(3, rcm([16, 16, 16], reg(n_cls), rcm([16, 16], reg(n_cls), rcm([32], reg(n_cls)))))
+    return cls(x0_shape=x0_shape, y_shape=(n_cls,), root=root, **hypers)
+
+
+def randomize_routers(net, seed=1, scale=0.5):
+    """The reference zero-initialises the last router layer (all decisions tie
+    to sink 0); give it weights so parity tests see non-trivial routing."""
+    rng = np.random.default_rng(seed)
+    for l in net.layers:
+        if l.router is not None:
+            last = l.router.comps[-1]
+            last.params.w.assign((scale * rng.standard_normal(last.params.w.shape)).astype(np.float32))
+            last.params.b.assign((0.1 * rng.standard_normal(last.params.b.shape)).astype(np.float32))
+    return net
+
+
+def batch(B, x0_shape=(16, 16, 3), n_cls=10, seed=0):
+    rng = np.random.default_rng(seed)
+    x0 = rng.random((B,) + tuple(x0_shape)).astype(np.float32)
+    y = np.eye(n_cls, dtype=np.float32)[rng.integers(0, n_cls, B)]
+    return x0, y
+
+
+def record_of(net):
+    return copy.deepcopy(serdes.encode_net(net))
+
+
+def node_paths(net):
+    """preorder list of (path, layer) matching oracle path naming."""
+    out = []
+
+    def walk(l, path):
+        out.append((path, l))
+        for i, s in enumerate(l.sinks):
+            walk(s, (path + '/' if path else '') + str(i))
+    walk(net.root, '')
+    return out
+
+
+def rel_err(a, b):
+    a = np.asarray(a, np.float64); b = np.asarray(b, np.float64)
+    d = np.linalg.norm(a - b)
+    n = np.linalg.norm(b)
+    return d / n if n > 0 else d
+
+
+# ---- planes layout emulation ------------------------------------------------ #
+class Geo:
+    def __init__(self, B, H, W):
+        self.B, self.H, self.W = B, H, W
+        self.Wp = W + 1
+        self.S = (H + 1) * (W + 1)
+        self.rows = B * self.S
+        self.G = max(64, (W + 2 + 7) // 8 * 8)
+        self.P = (self.G + self.rows + 128 + self.G + 7) // 8 * 8
+
+
+def to_planes(x, geo, Cpad=None, dtype=np.float32):
+    """NHWC -> [Cpad/8][P][8] with zero pads/guards."""
+    B, H, W, C = x.shape
+    Cpad = C if Cpad is None else Cpad
+    t = np.zeros((Cpad // 8, geo.P, 8), dtype)
+    xp = np.zeros((B, H, W, Cpad), dtype)
+    xp[..., :C] = x
+    rows = (geo.G + np.arange(B)[:, None, None] * geo.S + (np.arange(H)[None, :, None] + 1) * geo.Wp
+            + (np.arange(W)[None, None, :] + 1))
+    for kg in range(Cpad // 8):
+        t[kg, rows.reshape(-1)] = xp[..., kg * 8:(kg + 1) * 8].reshape(-1, 8)
+    return t
+
+
+def from_planes(t, geo, C):
+    B, H, W = geo.B, geo.H, geo.W
+    rows = (geo.G + np.arange(B)[:, None, None] * geo.S + (np.arange(H)[None, :, None] + 1) * geo.Wp
+            + (np.arange(W)[None, None, :] + 1)).reshape(-1)
+    out = np.concatenate([t[kg, rows] for kg in range(t.shape[0])], 1)
+    return out.reshape(B, H, W, -1)[..., :C]
+
+
+def stencil_offsets(Wp):
+    return [(t // 3 - 1) * Wp + (t % 3 - 1) for t in range(9)]
