@@ -8,21 +8,37 @@
 
 #define RT_MAXS 8   // max sinks per switch
 
-__device__ __forceinline__ int route_softmax(const float* __restrict__ r, int ns, float tau, float* sm) {
-    float x[RT_MAXS];
+// softmax(r / tau) and the first-max argmax of r.  All loops are fully unrolled
+// over RT_MAXS with a `j < ns` predicate so the small arrays stay in registers
+// (statically indexed); callers must index `sm` the same way.
+__device__ __forceinline__ int route_softmax(const float* r, int ns, float tau, float (&sm)[RT_MAXS]) {
     float mx = -INFINITY, mr = -INFINITY;
     int dec = 0;
-    for (int j = 0; j < ns; ++j) {
-        float v = r[j];
-        if (v > mr) { mr = v; dec = j; }          // first maximal index (tf.argmax)
-        x[j] = v / tau;
-        mx = fmaxf(mx, x[j]);
+#pragma unroll
+    for (int j = 0; j < RT_MAXS; ++j) {
+        sm[j] = 0.f;
+        if (j < ns) {
+            float v = r[j];
+            if (v > mr) { mr = v; dec = j; }          // first maximal index (tf.argmax)
+            sm[j] = v / tau;
+            mx = fmaxf(mx, sm[j]);
+        }
     }
     float s = 0.f;
-    for (int j = 0; j < ns; ++j) { x[j] = expf(x[j] - mx); s += x[j]; }
-    float inv = 1.f / s;
-    for (int j = 0; j < ns; ++j) sm[j] = x[j] * inv;
+#pragma unroll
+    for (int j = 0; j < RT_MAXS; ++j)
+        if (j < ns) { sm[j] = expf(sm[j] - mx); s += sm[j]; }
+    const float inv = 1.f / s;
+#pragma unroll
+    for (int j = 0; j < RT_MAXS; ++j) sm[j] *= inv;
     return dec;
+}
+
+__device__ __forceinline__ float pick(const float (&v)[RT_MAXS], int idx) {
+    float out = 0.f;
+#pragma unroll
+    for (int j = 0; j < RT_MAXS; ++j) out = (j == idx) ? v[j] : out;
+    return out;
 }
 
 __global__ void route_fwd_kernel(const int* __restrict__ parent, const int* __restrict__ sink_idx,
@@ -44,7 +60,7 @@ __global__ void route_fwd_kernel(const int* __restrict__ parent, const int* __re
             int d = route_softmax(R[slot] + (size_t)b * ns, ns, tau, sm);
             int si = sink_idx[i];
             if (si == 0 && dec) dec[(size_t)slot * B + b] = d;
-            pt = (pt - eps * floor_[par]) * sm[si] + eps * floor_[i];
+            pt = (pt - eps * floor_[par]) * pick(sm, si) + eps * floor_[i];
             pe = pe * (d == si ? 1.f : 0.f);
         }
         p_tr[(size_t)i * B + b] = pt;
@@ -62,17 +78,17 @@ extern "C" int mpnn_route_fwd(const int* parent, const int* sink_idx, const int*
     return mpnn_check_launch("route_fwd");
 }
 
-__global__ void route_bwd_kernel(const int* __restrict__ parent, const int* __restrict__ sink_idx,
-                                 const int* __restrict__ n_sinks, const int* __restrict__ child,
-                                 const float* __restrict__ floor_, const int* __restrict__ sw,
-                                 const float* __restrict__ ops, const int* __restrict__ err, int n_nodes,
-                                 const float* const* __restrict__ R, const float* __restrict__ hyp, int B,
-                                 const float* __restrict__ p_tr, const float* __restrict__ p_ev,
-                                 const float* const* __restrict__ c_err, const float* const* __restrict__ d_cor,
-                                 const float* __restrict__ k_cpt,
+__global__ void route_bwd_kernel(const int* parent, const int* sink_idx,
+                                 const int* n_sinks, const int* child,
+                                 const float* floor_, const int* sw,
+                                 const float* ops, const int* err, int n_nodes,
+                                 const float* const* R, const float* hyp, int B,
+                                 const float* p_tr, const float* p_ev,
+                                 const float* const* c_err, const float* const* d_cor,
+                                 const float* k_cpt,
                                  int critic, float k_dec, float k_cre, int optimistic, int use_cls_err,
-                                 float* const* __restrict__ dR, float* __restrict__ scratch,
-                                 float* __restrict__ c_data) {
+                                 float* const* dR, float* scratch,
+                                 float* c_data) {
     int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
     const float invB = 1.f / (float)B;
@@ -96,7 +112,7 @@ __global__ void route_bwd_kernel(const int* __restrict__ parent, const int* __re
             if (ns >= 2) {
                 float sm[RT_MAXS];
                 route_softmax(R[sw[par]] + (size_t)b * ns, ns, tau, sm);
-                g *= sm[sink_idx[i]];
+                g *= pick(sm, sink_idx[i]);
             }
             gp[(size_t)par * B + b] += g;
         }
@@ -108,14 +124,19 @@ __global__ void route_bwd_kernel(const int* __restrict__ parent, const int* __re
             route_softmax(r, ns, tau, sm);
             float pt = p_tr[(size_t)i * B + b];
             float dot = 0.f, r2 = 0.f;
-            for (int j = 0; j < ns; ++j) {
-                gs[j] = gp[(size_t)child[i * RT_MAXS + j] * B + b] * (pt - eps * floor_[i]);
-                dot = fmaf(sm[j], gs[j], dot);
-                r2 = fmaf(r[j], r[j], r2);
+#pragma unroll
+            for (int j = 0; j < RT_MAXS; ++j) {
+                gs[j] = 0.f;
+                if (j < ns) {
+                    gs[j] = gp[(size_t)child[i * RT_MAXS + j] * B + b] * (pt - eps * floor_[i]);
+                    dot = fmaf(sm[j], gs[j], dot);
+                    r2 = fmaf(r[j], r[j], r2);
+                }
             }
             float* out = dR[sw[i]] + (size_t)b * ns;
-            for (int j = 0; j < ns; ++j)
-                out[j] = sm[j] * (gs[j] - dot) / tau + pt * k_dec * 2.f * r[j] * invB;
+#pragma unroll
+            for (int j = 0; j < RT_MAXS; ++j)
+                if (j < ns) out[j] = sm[j] * (gs[j] - dot) / tau + pt * k_dec * 2.f * r[j] * invB;
             total += pt * k_dec * r2;
         }
     } else {

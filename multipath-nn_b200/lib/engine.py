@@ -232,10 +232,24 @@ class Engine:
         assert p._bind[1] == 'theta'
         return ctypes.c_void_p(self.grad.data_ptr() + 4 * p._bind[2])
 
-    def grads_numpy(self):
-        """{Param: gradient ndarray} of the last backward (before TALR)."""
-        g = self.grad.cpu().numpy()
-        return {p: g[p._bind[2]:p._bind[2] + p.value.size].reshape(p.value.shape).copy() for p in self.tparams}
+    def grads_numpy(self, with_l2=False):
+        """{Param: gradient ndarray} of the last backward (before TALR).  The L2
+        (c_mod) term is applied inside the optimiser kernel; with_l2 adds it here
+        the same way (2 k_l2 mean(p_tr) theta) so the result is d c_tot / d theta."""
+        g = self.grad.cpu().numpy().astype(np.float64)
+        out = {}
+        if with_l2:
+            th = self.theta.cpu().numpy().astype(np.float64)
+            l2 = self.seg_l2.cpu().numpy(); node = self.seg_node.cpu().numpy()
+            stats = g[self.n_theta:].reshape(-1, 2)
+        for s, p in enumerate(self.tparams):
+            sl = slice(p._bind[2], p._bind[2] + p.value.size)
+            v = g[sl].copy()
+            if with_l2 and l2[s] > 0:
+                coef = stats[node[s], 1] if self.dynamic else 1.0
+                v += 2.0 * l2[s] * coef * th[sl]
+            out[p] = v.reshape(p.value.shape)
+        return out
 
     # ------------------------------------------------------------------ #
     # plan construction
@@ -442,6 +456,11 @@ class _Plan:
         self.graph_launches = 0
         self._build()
 
+    @staticmethod
+    def _tag(fn, kind, flops=0.0, nbytes=0.0):
+        """algorithmic work of one launch (bench.py roofline); untagged ops are 'misc'"""
+        fn.kind, fn.flops, fn.nbytes = kind, float(flops), float(nbytes)
+
     # -- allocation helpers ------------------------------------------------ #
     def planes(self, C, geo):
         return torch.zeros((C // 8, geo.P, 8), dtype=self.eng.tdtype, device=self.eng.dev)
@@ -617,6 +636,8 @@ class _Plan:
                                _vp(sc.Wf), 9, eng.tptr(sc.bk), _vp(sc.lin), sc.N, 0, None, 0, 0,
                                *sc.geo.args(), _vp(self.partials) if use_stats else None, STATS_CAP,
                                ctypes.byref(self.cnt), dt, dt, impl, S())
+            self._tag(conv, 'conv_fwd', flops=2.0 * B * sc.geo.H * sc.geo.W * 9 * (sc.K0real + sc.K1) * sc.N,
+                      nbytes=B * sc.geo.H * sc.geo.W * (sc.K0 + sc.K1 + sc.N) * (2 if dt == BF16 else 4))
             self.fwd_ops.append(conv)
             if sc.live:
                 bn = sc.bn
@@ -633,6 +654,7 @@ class _Plan:
                     L.bn_relu_pool_fwd(_vp(sc.lin), sc.N, *sc.geo.args(), _vp(sc.ss) if sc.live else None,
                                        _vp(sc.act), _vp(sc.pooled), sc.geo_p.P if sc.pooled is not None else 0,
                                        _vp(sc.feat), Balloc, dt, S())
+                self._tag(post, 'bn_fwd', nbytes=B * sc.geo.H * sc.geo.W * sc.N * (2 if dt == BF16 else 4) * (1 + (sc.act is not None) + 0.25 * (sc.pooled is not None) + (sc.feat is not None)))
                 self.fwd_ops.append(post)
             st.sc.append(sc)
             st.out.append(Ns(t=sc.act, C=N, Creal=N, geo=geo, dact=None, writers=0))
@@ -683,6 +705,7 @@ class _Plan:
                                     *sc.geo.args(), _vp(self.partials), STATS_CAP, ctypes.byref(self.cnt), dt, S())
                     L.bn_bwd_finalize(_vp(self.partials), self.cnt.value, sc.N, _vp(sc.sums),
                                       eng.gptr(bn.params.γ), eng.gptr(bn.params.β), S())
+                self._tag(red, 'bn_bwd_reduce', nbytes=B * sc.geo.H * sc.geo.W * sc.N * (2 if dt == BF16 else 4) * 2)
                 self.bwd_ops.append(red)
             if not live and dpooled is None:
                 raise RuntimeError('engine: scale %d of %r has no gradient path' % (k, lay.name))
@@ -692,6 +715,7 @@ class _Plan:
                                    sc.geo_p.P if dpooled is not None else 0,
                                    _vp(sc.ss) if live else None, _vp(sc.mr), _vp(sc.sums),
                                    float(B * sc.geo.H * sc.geo.W), sc.N, *sc.geo.args(), _vp(sc.dlin), dt, S())
+            self._tag(elt, 'bn_bwd', nbytes=B * sc.geo.H * sc.geo.W * sc.N * (2 if dt == BF16 else 4) * 3)
             self.bwd_ops.append(elt)
             prev = st.sc[k - 1] if k > 0 else None
 
@@ -700,6 +724,8 @@ class _Plan:
                                 _vp(prev.pooled) if prev is not None else None, sc.K1, sc.K1,
                                 eng.gptr(sc.wv) if sc.wv is not None else None,
                                 _vp(sc.dlin), sc.N, sc.N, eng.gptr(sc.bk), 9, *sc.geo.args(), dt, eng.impl_w, S())
+            self._tag(wgrad, 'conv_wgrad', flops=2.0 * B * sc.geo.H * sc.geo.W * 9 * (sc.K0real + sc.K1) * sc.N,
+                      nbytes=B * sc.geo.H * sc.geo.W * (sc.K0 + sc.K1 + sc.N) * (2 if dt == BF16 else 4))
             self.bwd_ops.append(wgrad)
             # data gradient: towards the parent's activation (N0) and the pooled predecessor (N1)
             N0 = sc.K0 if par_grad else 0
@@ -729,6 +755,8 @@ class _Plan:
                 L.stencil_gemm(_vp(sc.dlin), sc.N, None, 0, _vp(sc.Wd), 9, None,
                                _vp(out0), N0, acc0, _vp(prev.dpooled) if N1 else None, N1, 0,
                                *sc.geo.args(), None, 0, None, dt, dt, impl, S())
+            self._tag(dgrad, 'conv_dgrad', flops=2.0 * B * sc.geo.H * sc.geo.W * 9 * sc.N * (N0 + N1),
+                      nbytes=B * sc.geo.H * sc.geo.W * (sc.N + N0 + N1) * (2 if dt == BF16 else 4))
             self.bwd_ops.append(dgrad)
 
     # -- router ------------------------------------------------------------ #

@@ -98,6 +98,36 @@ def first_argmax(x, dim):
 
 
 # --------------------------------------------------------------------------- #
+# Optional emulation of bf16 STORAGE (quant='bf16'): the CUDA path keeps conv
+# operands / activations / activation gradients in bf16 and accumulates in
+# fp32.  Rounding only those tensors here gives an oracle "in the arithmetic
+# the device stores in", so kernel bugs are not masked by (or mistaken for)
+# the number format's own error.
+# --------------------------------------------------------------------------- #
+
+class _RoundBoth(torch.autograd.Function):
+    """value and incoming gradient rounded to bf16 (activations, lin, pooled)"""
+    @staticmethod
+    def forward(ctx, x):
+        return x.to(torch.bfloat16).to(x.dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.to(torch.bfloat16).to(g.dtype)
+
+
+class _RoundFwd(torch.autograd.Function):
+    """value rounded to bf16, gradient untouched (packed weights, input pyramid)"""
+    @staticmethod
+    def forward(ctx, x):
+        return x.to(torch.bfloat16).to(x.dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g
+
+
+# --------------------------------------------------------------------------- #
 # Layer interpreter
 # --------------------------------------------------------------------------- #
 
@@ -117,7 +147,9 @@ class OracleNet:
     dtype  : torch.float32 (reference precision) or torch.float64
     """
 
-    def __init__(self, record, dtype=torch.float32):
+    def __init__(self, record, dtype=torch.float32, quant=None):
+        assert quant in (None, 'bf16')
+        self.quant = quant
         self.rec = record
         self.kind = record['type']
         self.dtype = dtype
@@ -160,6 +192,12 @@ class OracleNet:
             for s in r['sinks']:
                 put(s)
         put(self.rec['root'])
+
+    def _q(self, x):
+        return _RoundBoth.apply(x) if self.quant else x
+
+    def _qf(self, x):
+        return _RoundFwd.apply(x) if self.quant else x
 
     # -- layer link rules -------------------------------------------------- #
     def _link(self, rec, x, y, mode):
@@ -213,7 +251,7 @@ class OracleNet:
             nd.x = x.amax(tuple(range(1, x.dim() - 1)))
         elif kind == 'ToPyramid':                   # layer_types.py:118-125
             h, w = x.shape[1:3]
-            nd.x = [tf_resize_legacy(x, h // 2 ** i, w // 2 ** i)
+            nd.x = [self._qf(tf_resize_legacy(x, h // 2 ** i, w // 2 ** i))
                     for i in range(hy.get('n_scales', 1))]
         elif kind == 'MultiscaleConvMax':           # layer_types.py:149-194
             n = len(hy['n_chan'])
@@ -223,21 +261,21 @@ class OracleNet:
             sq = 0.0
             for k in range(n):
                 wh = p['w_horz_%i' % k]
-                o = p['b_%i' % k] + tf_conv2d_same(xin[k], wh)
+                o = p['b_%i' % k] + tf_conv2d_same(xin[k], self._qf(wh))
                 sq = sq + (wh ** 2).sum()
                 ops = wh.numel()
                 if k > 0:
                     wv = p['w_vert_%i' % (k - 1)]
-                    o = o + tf_conv2d_same(tf_max_pool_same(out[k - 1], 2, 2), wv)
+                    o = o + tf_conv2d_same(self._q(tf_max_pool_same(out[k - 1], 2, 2)), self._qf(wv))
                     sq = sq + (wv ** 2).sum()
                     ops += wv.numel()
                 n_ops += int(o.shape[1] * o.shape[2]) * ops
-                out.append(o)
+                out.append(self._q(o))
             nd.x = out
             nd.c_mod = hy.get('k_l2', 0) * sq
             nd.n_ops = n_ops
         elif kind == 'MultiscaleRect':              # layer_types.py:196-199
-            nd.x = [torch.relu(v) for v in x]
+            nd.x = [self._q(torch.relu(v)) for v in x]
         elif kind == 'Select':                      # layer_types.py:201-206
             nd.x = x[hy.get('i', 0)]
         elif kind == 'BatchNorm':                   # layer_types.py:219-239
