@@ -238,16 +238,31 @@ def main():
     prof = {}
     if rank == 0:
         ops = plan.pack_ops + plan.fwd_ops + plan.bwd_ops + plan.opt_ops
+        # untagged launches are labelled by the C-ABI entry point they call
+        called = []
+        saved = {}
+        for name in L.protos:
+            short = name[5:]
+            try:
+                fn = getattr(L, short)
+            except AttributeError:
+                continue
+            saved[short] = fn
+            L.__dict__[short] = (lambda fn, short: (lambda *a: (called.append(short), fn(*a))[1]))(fn, short)
         for rep in range(3):
             evs = []
             eng.grad.zero_()
             eng.stream = __import__('ctypes').c_void_p(torch.cuda.current_stream(dev).cuda_stream)
             for op in ops:
                 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                del called[:]
                 a.record(); op(); b.record()
+                if not hasattr(op, 'kind'):
+                    op.kind = called[0] if called else 'misc'
                 evs.append((op, a, b))
             torch.cuda.synchronize(dev)
             if rep == 2:
+                L.__dict__.update(saved)
                 for op, a, b in evs:
                     k = getattr(op, 'kind', 'misc')
                     d = prof.setdefault(k, {'ms': 0.0, 'flops': 0.0, 'bytes': 0.0, 'n': 0})

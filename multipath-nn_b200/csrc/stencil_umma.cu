@@ -18,93 +18,12 @@
 // of tile i overlaps the MMAs of tile i+1.  Weights for the CTA's N-slice stay
 // resident in shared memory for the kernel's lifetime.
 #include "common.cuh"
+#include "umma.cuh"
 #include "../../include/mpnn.h"
 
 extern "C" int mpnn_has_umma(void) { return 1; }
 
 namespace {
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-    return (uint32_t)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred P1;\n"
-        "LAB_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-        "@P1 bra DONE;\n"
-        "bra LAB_WAIT;\n"
-        "DONE:\n"
-        "}" ::"r"(bar), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
-        "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
-}
-__device__ __forceinline__ void tc_ld16(uint32_t taddr, float v[16]) {
-    uint32_t r[16];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
-// shared-memory matrix descriptor, SWIZZLE_NONE ("interleaved") layout, sm_100 version bit
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) |
-           ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46);
-}
-// kind::f16 instruction descriptor: D=f32, A=B=bf16, M=128
-__device__ __forceinline__ uint32_t make_idesc(int N, int a_mn, int b_mn) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
-           ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
-}
-__device__ __forceinline__ uint32_t tmem_cols_pow2(int c) {
-    uint32_t n = 32;
-    while ((int)n < c) n <<= 1;
-    return n;
-}
-
-// sum over the 32 lanes of v[0..16): afterwards every lane holds the total of column (lane & 15)
-__device__ __forceinline__ float warp_colsum16(float v[16], int lane) {
-#pragma unroll
-    for (int s = 8; s >= 1; s >>= 1) {
-        const bool up = (lane & s) != 0;
-#pragma unroll
-        for (int i = 0; i < s; ++i) {
-            float send = up ? v[i] : v[i + s];
-            float keep = up ? v[i + s] : v[i];
-            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
-        }
-    }
-    return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 16);
-}
 
 struct GemmArgs {
     const __nv_bfloat16* A0; const __nv_bfloat16* A1; const __nv_bfloat16* Wp;
@@ -404,12 +323,6 @@ int mpnn_stencil_gemm_umma(const void* A0, int K0, const void* A1, int K1, const
     }
     stencil_gemm_umma_kernel<<<dim3(gx, split), kThreads, smem, st>>>(a);
     return mpnn_check_launch("stencil_gemm_umma");
-}
-
-int mpnn_stencil_wgrad_umma(const void*, int, int, float*, const void*, int, int, float*, const void*, int,
-                            int, float*, int, Geom, cudaStream_t) {
-    mpnn_set_error("stencil_wgrad: tcgen05 path not implemented yet (use impl=0)");
-    return MPNN_ERR_UNSUPPORTED;
 }
 
 extern "C" int mpnn_umma_selftest(const void* A, int a_bytes, int a_off, const void* Bm, int b_bytes,

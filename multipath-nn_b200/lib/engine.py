@@ -81,8 +81,9 @@ class Engine:
         self.tdtype = torch.float32 if precision == 'fp32' else torch.bfloat16
         # stencil implementation: 0 = SIMT fp32-accumulate, 1 = tcgen05
         self.impl = (1 if (precision == 'bf16' and self.L.mpnn_has_umma()) else 0) if impl is None else impl
-        # weight gradient: the tcgen05 variant is not wired yet -> SIMT fp32-accumulate
-        self.impl_w = 0
+        # weight gradient follows the conv implementation (per launch it drops back to the
+        # SIMT kernel when the shape exceeds what the tcgen05 wgrad tiles: K0+K1 > 128)
+        self.impl_w = self.impl
         self.use_graphs = graphs
         self.dist = dist
         self.world = torch.distributed.get_world_size() if dist else 1
@@ -723,7 +724,8 @@ class _Plan:
                 L.stencil_wgrad(_vp(sc.src.t), sc.K0, sc.K0real, eng.gptr(sc.wh),
                                 _vp(prev.pooled) if prev is not None else None, sc.K1, sc.K1,
                                 eng.gptr(sc.wv) if sc.wv is not None else None,
-                                _vp(sc.dlin), sc.N, sc.N, eng.gptr(sc.bk), 9, *sc.geo.args(), dt, eng.impl_w, S())
+                                _vp(sc.dlin), sc.N, sc.N, eng.gptr(sc.bk), 9, *sc.geo.args(), dt,
+                                eng.impl_w if (sc.K0 + sc.K1 <= 128 and sc.N <= 256) else 0, S())
             self._tag(wgrad, 'conv_wgrad', flops=2.0 * B * sc.geo.H * sc.geo.W * 9 * (sc.K0real + sc.K1) * sc.N,
                       nbytes=B * sc.geo.H * sc.geo.W * (sc.K0 + sc.K1 + sc.N) * (2 if dt == BF16 else 4))
             self.bwd_ops.append(wgrad)

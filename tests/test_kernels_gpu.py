@@ -76,13 +76,29 @@ def test_umma_kmajor_descriptors(N, K, row_off):
     assert rel_err(D.cpu().numpy(), ref) < 1e-5
 
 
-@pytest.mark.parametrize('N,K', [(16, 32), (64, 128), (144, 64)])
-def test_umma_mnmajor_descriptors(N, K):
+@pytest.mark.parametrize('N,K,row_off', [(16, 32, 0), (64, 128, 0), (144, 64, 0), (32, 64, 5), (16, 128, 35)])
+def test_umma_mnmajor_descriptors(N, K, row_off):
     """MN-major operands (the wgrad orientation): element (m,k) of A lives at
-    plane m/8, row k -- SBO = plane stride, LBO = 128 B per 8 rows of K."""
+    plane m/8, row k -- SBO = plane stride, LBO = 128 B per 8 rows of K.  row_off
+    shifts the start address by whole 16-byte rows (a convolution tap)."""
     rng = np.random.default_rng(1)
     a = bf16_round(rng.standard_normal((128, K)))      # A[m][k]
     b = bf16_round(rng.standard_normal((N, K)))        # B[n][k]
+    if row_off:
+        rows = K + 48
+        A = np.zeros((16, rows, 8), np.float32)
+        for mg in range(16):
+            A[mg, row_off:row_off + K] = a[mg * 8:(mg + 1) * 8].T
+        Bm = np.zeros((N // 8, K, 8), np.float32)
+        for ng in range(N // 8):
+            Bm[ng] = b[ng * 8:(ng + 1) * 8].T
+        A = dev(A, torch.bfloat16); Bm = dev(Bm, torch.bfloat16)
+        D = torch.zeros((128, N), device='cuda')
+        L().umma_selftest(vp(A), A.numel() * 2, row_off * 16, vp(Bm), Bm.numel() * 2, vp(D), N, K, 1, 1,
+                          128, rows * 16, 128, K * 16, None)
+        torch.cuda.synchronize()
+        assert rel_err(D.cpu().numpy(), a.astype(np.float64) @ b.astype(np.float64).T) < 1e-5
+        return
     A = np.zeros((16, K, 8), np.float32)
     for mg in range(16):
         A[mg] = a[mg * 8:(mg + 1) * 8].T
@@ -196,26 +212,33 @@ def test_stencil_dgrad_split_outputs(dt, impl):
         assert rel_err(from_planes(o.float().cpu().numpy(), geo, C), ref) < (1e-5 if dt == F32 else 4e-3)
 
 
-@pytest.mark.parametrize('dt', [F32, BF16])
-def test_stencil_wgrad(dt):
+@pytest.mark.parametrize('dt,impl,shape', [
+    (F32, 0, (6, 8, 3, 16, 32)), (BF16, 0, (6, 8, 3, 16, 32)), (BF16, 1, (6, 8, 3, 16, 32)),
+    (BF16, 1, (3, 32, 16, 16, 16)), (BF16, 1, (50, 4, 64, 64, 64)), (BF16, 1, (33, 4, 128, 0, 128)),
+    (BF16, 1, (9, 16, 32, 32, 32)), (BF16, 1, (700, 4, 32, 64, 64))])
+def test_stencil_wgrad(dt, impl, shape):
     rng = np.random.default_rng(6)
-    B, H, Cin, Cp, Cout = 6, 8, 3, 16, 32
+    B, H, Cin, Cp, Cout = shape
     x = rng.standard_normal((B, H, H, Cin)).astype(np.float32)
-    xp = rng.standard_normal((B, H, H, Cp)).astype(np.float32)
+    xp = rng.standard_normal((B, H, H, Cp)).astype(np.float32) if Cp else None
     g = rng.standard_normal((B, H, H, Cout)).astype(np.float32)
     geo = Geo(B, H, H)
     q = 16 if dt == BF16 else 8
     K0 = (Cin + q - 1) // q * q
     td = torch.float32 if dt == F32 else torch.bfloat16
     rd = (lambda a: a) if dt == F32 else bf16_round
-    A0 = dev(to_planes(x, geo, K0), td); A1 = dev(to_planes(xp, geo), td); G = dev(to_planes(g, geo), td)
-    dW0 = torch.zeros((9, Cin, Cout), device='cuda'); dW1 = torch.zeros((9, Cp, Cout), device='cuda')
+    A0 = dev(to_planes(x, geo, K0), td); G = dev(to_planes(g, geo), td)
+    A1 = dev(to_planes(xp, geo), td) if Cp else None
+    dW0 = torch.zeros((9, Cin, Cout), device='cuda')
+    dW1 = torch.zeros((9, Cp, Cout), device='cuda') if Cp else None
     db = torch.zeros(Cout, device='cuda')
     L().stencil_wgrad(vp(A0), K0, Cin, vp(dW0), vp(A1), Cp, Cp, vp(dW1), vp(G), Cout, Cout, vp(db), 9,
-                      B, H, H, geo.G, geo.P, dt, 0, None)
+                      B, H, H, geo.G, geo.P, dt, impl, None)
     torch.cuda.synchronize()
     gt = torch.tensor(rd(g), dtype=torch.float64).permute(0, 3, 1, 2)
     for xin, dW, C in ((x, dW0, Cin), (xp, dW1, Cp)):
+        if not C:
+            continue
         xt = torch.tensor(rd(xin), dtype=torch.float64).permute(0, 3, 1, 2).requires_grad_(False)
         w = torch.zeros((Cout, C, 3, 3), dtype=torch.float64, requires_grad=True)
         (torch.nn.functional.conv2d(xt, w, padding=1) * gt).sum().backward()
