@@ -300,6 +300,11 @@ def main():
                 extra = '%.0f GB/s' % (v['bytes'] / (v['ms'] * 1e-3) / 1e9)
             print('# %-14s n=%3d %8.3f ms  %5.1f%%  %s' % (k, v['n'], v['ms'], 100 * v['ms'] / tot_ms, extra),
                   file=sys.stderr)
+        for op, a, b in evs:
+            if getattr(op, 'desc', ''):
+                ms = a.elapsed_time(b)
+                print('#   %-11s %-18s %7.3f ms %7.1f TFLOP/s %7.0f GB/s' % (
+                    op.kind, op.desc, ms, op.flops / ms / 1e9, op.nbytes / ms / 1e6), file=sys.stderr)
 
     torch.set_num_threads(os.cpu_count() or 1)
     cpu_B = min(B, 256)

@@ -54,10 +54,23 @@ int mpnn_pack_weights(const float* w, int ntaps, int I, int O, int mode,
                       int k_off, int Ktot, int n_off, int Ntot,
                       void* packed, int dtype, void* stream);
 
+/* the same for a whole table of tensors in one launch (device array of descriptors);
+ * additionally mode 2: ((float*)packed)[n_off + o] = w[o], o < O (fp32 vector copy) */
+typedef struct {
+    const float* w; void* packed;
+    int ntaps, I, O, mode, k_off, Ktot, n_off, Ntot;
+} mpnn_pack_desc;
+int mpnn_pack_weights_batched(const mpnn_pack_desc* descs, int n, int blocks_per_desc,
+                              int dtype, void* stream);
+
 /* ---- stencil GEMM: tf.nn.conv2d SAME (lib/layer_types.py:106-107,181-185) */
 /* out[p][n] = bias[n] + sum_tap sum_k A[p+off(tap)][k] * Wp[tap][k][n]
  * A = concat(A0 (K0 ch), A1 (K1 ch)); columns [0,N0) go to out0, [N0,N0+N1)
  * to out1.  ntaps = 9 (3x3) or 1.  impl: 0 = fp32 SIMT, 1 = tcgen05 (bf16).
+ * out_dtype: 0 fp32 planes, 1 bf16 planes, 2 (tcgen05 only) fp32 ROW-MAJOR
+ *   out0[row][N0], out1[row][N1] with row = p - G -- used with ntaps = 1,
+ *   H = W = 0 (rows = B examples) for the fully-connected heads, whose wide K is
+ *   streamed through the pipeline in 32 KB slices.
  * stats (optional): per-CTA partial sums over VALID pixels of out:
  *   stats[cta][0][n] = sum, stats[cta][1][n] = sum of squares; returns the
  *   number of partial rows written through *n_parts (host pointer).
@@ -109,7 +122,8 @@ int mpnn_bn_relu_pool_bwd(const void* lin, const void* dAct, const void* dFeat, 
                           const void* dPooled, int Pp,
                           const float* ss, const float* mr, const float* sums, double count,
                           int C, int B, int H, int W, int G, int P,
-                          void* dLin, int dtype, void* stream);
+                          void* dLin, float* dbias /* += column sums of dLin, or NULL */,
+                          int dtype, void* stream);
 
 /* ---- heads: LinTrans / Softmax / CrossEntropyError (lib/layer_types.py:39-53,81-84,262-272) */
 /* Z[b][j] = sum_f X[f][b] W[f][j] (+ extra[b]*W[F][j]) + bias[j] */
@@ -124,11 +138,14 @@ int mpnn_fc_bwd_weight(const void* X, int F, int Balloc, int B, const float* ext
                        const float* dZ, int n, float* dW, float* db, int dtype, void* stream);
 /* prob = softmax(Z); c_err = -sum y log(eps/n + (1-eps) prob); d_cor = [argmax prob == argmax y]
  * (first maximal index). */
-int mpnn_softmax_ce_fwd(const float* Z, const float* y, int B, int n, float eps,
+int mpnn_softmax_ce_fwd(const float* Z, int ldz /* row stride of Z */, const float* y, int B, int n, float eps,
                         float* prob, float* c_err, float* d_cor, void* stream);
-/* dZ[b][j] = coef[b]*coef_scale * d c_err[b] / d Z[b][j]   (coef==NULL -> 1) */
+/* dZ[b][j] = coef[b]*coef_scale * d c_err[b] / d Z[b][j]   (coef==NULL -> 1).
+ * Outputs (each optional): dZ fp32 [B][n]; dZp two bf16 planes [2][Balloc][8]
+ * (columns >= n zero; operand of the tcgen05 head GEMMs); dbias += column sums. */
 int mpnn_softmax_ce_bwd(const float* prob, const float* y, int B, int n, float eps,
-                        const float* coef, float coef_scale, float* dZ, void* stream);
+                        const float* coef, float coef_scale, float* dZ,
+                        void* dZp, int Balloc, float* dbias, void* stream);
 
 /* Router tail (arch_and_hypers.py:45-49): BN -> ReLU -> FC(16) -> BN -> ReLU -> FC(ns)
  * applied to Z1 = output of the first router FC.  One CTA.
@@ -148,6 +165,35 @@ int mpnn_router_tail_bwd(const float* Z1, const float* Z2, const float* dR, int 
                          float* dg1, float* dbt1, float* dW2, float* dbias2,
                          float* dg2, float* dbt2, float* dW3, float* dbias3,
                          float* dZ1, float* scratch /* >= 2*B*C */, void* stream);
+
+/* All routers of a net in one launch (one CTA per router); descriptors are a
+ * DEVICE array.  Semantics per element as in the two functions above. */
+typedef struct {
+    const float* Z1; const float* g1; const float* b1; float* m1; float* v1;
+    const float* W2; const float* bias2; const float* g2; const float* b2; float* m2; float* v2;
+    const float* W3; const float* bias3; float* Z2; float* R; float* save;
+    int ns; int reserved;
+} mpnn_router_fwd_desc;
+int mpnn_router_tail_fwd_batched(const mpnn_router_fwd_desc* descs, int n, int B, int C,
+                                 float d, float eps, int train, void* stream);
+typedef struct {
+    const float* Z1; const float* Z2; const float* dR;
+    const float* g1; const float* b1; const float* W2; const float* g2; const float* b2;
+    const float* W3; const float* save;
+    float* dg1; float* dbt1; float* dW2; float* dbias2; float* dg2; float* dbt2; float* dW3; float* dbias3;
+    float* dZ1; float* scratch;
+    void* dZ1p;        /* optional: dZ1 also as two bf16 planes [2][Balloc][8] */
+    float* dbias1;     /* optional: += column sums of dZ1 (bias of the first router FC) */
+    int ns; int Balloc;
+} mpnn_router_bwd_desc;
+int mpnn_router_tail_bwd_batched(const mpnn_router_bwd_desc* descs, int n, int B, int C, void* stream);
+
+/* tcgen05 weight gradient of the heads sharing one feature matrix X
+ * ([F/8][Balloc][8] bf16; Balloc a multiple of 128), dZ as bf16 planes [N/8][Balloc][8]:
+ *   dWa[f][j] += sum_b X[f][b] dZ[b][j]            (f < Fa, j < na)   LogReg
+ *   dWb[f][j] += sum_b X[f][b] dZ[b][Nsplit + j]   (f < Fb, j < nb)   first router FC */
+int mpnn_fc_wgrad(const void* X, int F, int Balloc, int B, const void* dZ, int N, int Nsplit,
+                  float* dWa, int Fa, int na, float* dWb, int Fb, int nb, void* stream);
 
 /* ---- routing (lib/net_types.py:108-131,193-243) ------------------------ */
 /* Tree tables (device int/float arrays, nodes in preorder, node 0 = root):

@@ -11,15 +11,23 @@ __global__ void bn_finalize_kernel(const float* __restrict__ partials, int n_par
                                    float* __restrict__ m_avg, float* __restrict__ v_avg,
                                    float d, float eps, int train,
                                    float* __restrict__ ss, float* __restrict__ mr) {
-    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    // one warp per channel: lanes stride over the partial rows (fixed order -> deterministic)
+    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
     if (c >= C) return;
     float mean, var;
     if (train) {
         double s = 0.0, s2 = 0.0;
-        for (int i = 0; i < n_parts; ++i) {
+        for (int i = lane; i < n_parts; i += 32) {
             s += (double)partials[((size_t)i * 2) * C + c];
             s2 += (double)partials[((size_t)i * 2 + 1) * C + c];
         }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            s += __shfl_xor_sync(0xffffffffu, s, o);
+            s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+        }
+        if (lane != 0) return;
         double m = s / count;
         double v = s2 / count - m * m;
         if (v < 0.0) v = 0.0;
@@ -29,6 +37,7 @@ __global__ void bn_finalize_kernel(const float* __restrict__ partials, int n_par
             v_avg[c] = d * v_avg[c] + (1.f - d) * var;
         }
     } else {
+        if (lane != 0) return;
         mean = m_avg[c]; var = v_avg[c];
     }
     float rstd = 1.0f / sqrtf(var + eps);
@@ -43,7 +52,7 @@ extern "C" int mpnn_bn_finalize(const float* partials, int n_parts, int C, doubl
                                 const float* gamma, const float* beta, float* m_avg, float* v_avg,
                                 float d, float eps, int train, float* ss, float* mr, void* stream) {
     MPNN_REQUIRE(C > 0 && (train == 0 || (partials && n_parts > 0)), "bn_finalize: args");
-    bn_finalize_kernel<<<ceil_div(C, 128), 128, 0, (cudaStream_t)stream>>>(
+    bn_finalize_kernel<<<ceil_div(C, 4), 128, 0, (cudaStream_t)stream>>>(
         partials, n_parts, C, count, gamma, beta, m_avg, v_avg, d, eps, train, ss, mr);
     return mpnn_check_launch("bn_finalize");
 }
@@ -216,13 +225,20 @@ extern "C" int mpnn_bn_bwd_reduce(const void* lin, const void* dAct, const void*
 __global__ void bn_bwd_finalize_kernel(const float* __restrict__ partials, int n_parts, int C,
                                        float* __restrict__ sums, float* __restrict__ dgamma,
                                        float* __restrict__ dbeta) {
-    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);      // warp per channel
+    const int lane = threadIdx.x & 31;
     if (c >= C) return;
     double s0 = 0.0, s1 = 0.0;
-    for (int i = 0; i < n_parts; ++i) {
+    for (int i = lane; i < n_parts; i += 32) {
         s0 += (double)partials[((size_t)i * 2) * C + c];
         s1 += (double)partials[((size_t)i * 2 + 1) * C + c];
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    }
+    if (lane != 0) return;
     sums[c] = (float)s0;
     sums[C + c] = (float)s1;
     if (dgamma) dgamma[c] += (float)s1;
@@ -231,7 +247,7 @@ __global__ void bn_bwd_finalize_kernel(const float* __restrict__ partials, int n
 
 extern "C" int mpnn_bn_bwd_finalize(const float* partials, int n_parts, int C,
                                     float* sums, float* dgamma, float* dbeta, void* stream) {
-    bn_bwd_finalize_kernel<<<ceil_div(C, 128), 128, 0, (cudaStream_t)stream>>>(
+    bn_bwd_finalize_kernel<<<ceil_div(C, 4), 128, 0, (cudaStream_t)stream>>>(
         partials, n_parts, C, sums, dgamma, dbeta);
     return mpnn_check_launch("bn_bwd_finalize");
 }
@@ -242,27 +258,28 @@ __global__ void bn_relu_pool_bwd_kernel(const T* __restrict__ lin, const T* __re
                                         const T* __restrict__ dPooled, Geom gp,
                                         const float* __restrict__ ss, const float* __restrict__ mr,
                                         const float* __restrict__ sums, float inv_count,
-                                        int C, Geom g, T* __restrict__ dLin) {
-    const int KG = C / 8;
+                                        int C, Geom g, T* __restrict__ dLin, float* __restrict__ dbias) {
+    // grid: x strides over pixels (or 2x2 blocks), y = 8-channel plane
+    const int kg = blockIdx.y;
     const int HH = POOL ? g.H / 2 : g.H, WW = POOL ? g.W / 2 : g.W;
-    const long long total = (long long)KG * g.B * HH * WW;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-         i += (long long)gridDim.x * blockDim.x) {
-        int w = i % WW;
-        long long r = i / WW;
-        int h = r % HH; r /= HH;
-        int n = r % g.B;
-        int kg = r / g.B;
-        float a[8], c[8], mean[8], rstd[8], m0[8], m1[8];
-        if (ss) {
+    const int total = g.B * HH * WW;
+    float a[8], c[8], mean[8], rstd[8], m0[8], m1[8], bs[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                a[j] = __ldg(ss + kg * 8 + j); c[j] = __ldg(ss + C + kg * 8 + j);
-                mean[j] = __ldg(mr + kg * 8 + j); rstd[j] = __ldg(mr + C + kg * 8 + j);
-                m0[j] = __ldg(sums + kg * 8 + j) * inv_count;
-                m1[j] = __ldg(sums + C + kg * 8 + j) * inv_count;
-            }
+    for (int j = 0; j < 8; ++j) bs[j] = 0.f;
+    if (ss) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            a[j] = __ldg(ss + kg * 8 + j); c[j] = __ldg(ss + C + kg * 8 + j);
+            mean[j] = __ldg(mr + kg * 8 + j); rstd[j] = __ldg(mr + C + kg * 8 + j);
+            m0[j] = __ldg(sums + kg * 8 + j) * inv_count;
+            m1[j] = __ldg(sums + C + kg * 8 + j) * inv_count;
         }
+    }
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        int w = i % WW;
+        int r = i / WW;
+        int h = r % HH;
+        int n = r / HH;
         if (POOL) {
             float out[4][8], lv[4][8];
 #pragma unroll
@@ -295,13 +312,31 @@ __global__ void bn_relu_pool_bwd_kernel(const T* __restrict__ lin, const T* __re
             for (int k = 0; k < 4; ++k) {
                 int hh = 2 * h + (k >> 1), ww = 2 * w + (k & 1);
                 Row8<T>::store(plane_row(dLin, kg, g.P, row_of(g, n, hh, ww)), out[k]);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) bs[j] += out[k][j];
             }
         } else {
             float dy[8], xh[8], lv[8], out[8];
             bn_row_grad<T>(lin, dAct, dFeat, Balloc, C, g, kg, n, h, w, a, c, mean, rstd, dy, xh, lv);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) out[j] = a[j] * (dy[j] - m0[j] - xh[j] * m1[j]);
+            for (int j = 0; j < 8; ++j) { out[j] = a[j] * (dy[j] - m0[j] - xh[j] * m1[j]); bs[j] += out[j]; }
             Row8<T>::store(plane_row(dLin, kg, g.P, row_of(g, n, h, w)), out);
+        }
+    }
+    if (dbias) {
+        // conv bias gradient = column sums of dLin (layer_types.py:181-185: b_k is added before BN)
+        __shared__ float red[8][8];
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float t = warp_sum(bs[j]);
+            if (lane == 0) red[warp][j] = t;
+        }
+        __syncthreads();
+        if (threadIdx.x < 8) {
+            float t = 0.f;
+            for (int wv = 0; wv < 8; ++wv) t += red[wv][threadIdx.x];
+            atomicAdd(dbias + kg * 8 + threadIdx.x, t);
         }
     }
 }
@@ -310,7 +345,7 @@ extern "C" int mpnn_bn_relu_pool_bwd(const void* lin, const void* dAct, const vo
                                      const void* dPooled, int Pp,
                                      const float* ss, const float* mr, const float* sums, double count,
                                      int C, int B, int H, int W, int G, int P,
-                                     void* dLin, int dtype, void* stream) {
+                                     void* dLin, float* dbias, int dtype, void* stream) {
     MPNN_REQUIRE(C % 8 == 0, "bn_relu_pool_bwd: C=%d", C);
     MPNN_REQUIRE(ss || dPooled, "bn_relu_pool_bwd: nothing to do");
     MPNN_REQUIRE(!ss || (mr && sums), "bn_relu_pool_bwd: missing stats");
@@ -318,20 +353,23 @@ extern "C" int mpnn_bn_relu_pool_bwd(const void* lin, const void* dAct, const vo
     Geom gp = make_geom(B, H / 2, W / 2, G, Pp);
     const bool pool = dPooled != nullptr;
     MPNN_REQUIRE(!pool || (H % 2 == 0 && W % 2 == 0), "bn_relu_pool_bwd: odd size");
-    long long total = (long long)(C / 8) * B * (pool ? (H / 2) * (W / 2) : H * W);
-    int grid = (int)((total + 255) / 256);
-    if (grid > 148 * 16) grid = 148 * 16;
-    if (grid < 1) grid = 1;
+    long long total = (long long)B * (pool ? (H / 2) * (W / 2) : H * W);
+    int gx = (int)((total + 255) / 256);
+    int cap = 148 * 16 / (C / 8);
+    if (cap < 148) cap = 148;
+    if (gx > cap) gx = cap;
+    if (gx < 1) gx = 1;
+    dim3 grid(gx, C / 8);
     float inv = (float)(1.0 / count);
     cudaStream_t st = (cudaStream_t)stream;
     if (pool) {
         MPNN_DISPATCH_DTYPE(dtype, (bn_relu_pool_bwd_kernel<T, true><<<grid, 256, 0, st>>>(
             (const T*)lin, (const T*)dAct, (const T*)dFeat, Balloc, (const T*)dPooled, gp, ss, mr, sums,
-            inv, C, g, (T*)dLin)));
+            inv, C, g, (T*)dLin, dbias)));
     } else {
         MPNN_DISPATCH_DTYPE(dtype, (bn_relu_pool_bwd_kernel<T, false><<<grid, 256, 0, st>>>(
             (const T*)lin, (const T*)dAct, (const T*)dFeat, Balloc, (const T*)dPooled, gp, ss, mr, sums,
-            inv, C, g, (T*)dLin)));
+            inv, C, g, (T*)dLin, dbias)));
     }
     return mpnn_check_launch("bn_relu_pool_bwd");
 }

@@ -146,8 +146,8 @@ extern "C" int mpnn_fc_bwd_weight(const void* X, int F, int Balloc, int B, const
 
 // ------------------------------------------------------ softmax + CE forward
 #define CE_NMAX 32
-__global__ void softmax_ce_fwd_kernel(const float* __restrict__ Z, const float* __restrict__ y, int B, int n,
-                                      float eps, float* __restrict__ prob, float* __restrict__ c_err,
+__global__ void softmax_ce_fwd_kernel(const float* __restrict__ Z, int ldz, const float* __restrict__ y, int B,
+                                      int n, float eps, float* __restrict__ prob, float* __restrict__ c_err,
                                       float* __restrict__ d_cor) {
     int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
@@ -155,7 +155,7 @@ __global__ void softmax_ce_fwd_kernel(const float* __restrict__ Z, const float* 
     float mx = -INFINITY;
 #pragma unroll
     for (int j = 0; j < CE_NMAX; ++j)
-        if (j < n) { z[j] = Z[(size_t)b * n + j]; mx = fmaxf(mx, z[j]); }
+        if (j < n) { z[j] = Z[(size_t)b * ldz + j]; mx = fmaxf(mx, z[j]); }
     float sum = 0.f;
 #pragma unroll
     for (int j = 0; j < CE_NMAX; ++j)
@@ -178,38 +178,69 @@ __global__ void softmax_ce_fwd_kernel(const float* __restrict__ Z, const float* 
     d_cor[b] = am_p == am_y ? 1.f : 0.f;
 }
 
-extern "C" int mpnn_softmax_ce_fwd(const float* Z, const float* y, int B, int n, float eps,
+extern "C" int mpnn_softmax_ce_fwd(const float* Z, int ldz, const float* y, int B, int n, float eps,
                                    float* prob, float* c_err, float* d_cor, void* stream) {
-    MPNN_REQUIRE(n >= 1 && n <= CE_NMAX, "softmax_ce_fwd: n=%d", n);
-    softmax_ce_fwd_kernel<<<ceil_div(B, 128), 128, 0, (cudaStream_t)stream>>>(Z, y, B, n, eps, prob, c_err, d_cor);
+    MPNN_REQUIRE(n >= 1 && n <= CE_NMAX && ldz >= n, "softmax_ce_fwd: n=%d ldz=%d", n, ldz);
+    softmax_ce_fwd_kernel<<<ceil_div(B, 128), 128, 0, (cudaStream_t)stream>>>(Z, ldz, y, B, n, eps, prob, c_err, d_cor);
     return mpnn_check_launch("softmax_ce_fwd");
 }
 
-__global__ void softmax_ce_bwd_kernel(const float* __restrict__ prob, const float* __restrict__ y, int B, int n,
-                                      float eps, const float* __restrict__ coef, float coef_scale,
-                                      float* __restrict__ dZ) {
+// dZ in fp32 [B][n] and/or as two bf16 planes [2][Balloc][8] (columns >= n zero) for the
+// tcgen05 head GEMMs; dbias += column sums of dZ.
+__global__ void __launch_bounds__(128)
+softmax_ce_bwd_kernel(const float* __restrict__ prob, const float* __restrict__ y, int B, int n,
+                      float eps, const float* __restrict__ coef, float coef_scale,
+                      float* __restrict__ dZ, __nv_bfloat16* __restrict__ dZp, int Balloc,
+                      float* __restrict__ dbias) {
     int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= B) return;
-    float s[CE_NMAX], g[CE_NMAX];
-    float dot = 0.f;
+    float d[16];
 #pragma unroll
-    for (int j = 0; j < CE_NMAX; ++j)
-        if (j < n) {
-            s[j] = prob[(size_t)b * n + j];
-            float yy = y[(size_t)b * n + j];
-            g[j] = -yy * (1.f - eps) / (eps / n + (1.f - eps) * s[j]);
-            dot = fmaf(s[j], g[j], dot);
+    for (int j = 0; j < 16; ++j) d[j] = 0.f;
+    if (b < B) {
+        float s[CE_NMAX], g[CE_NMAX];
+        float dot = 0.f;
+#pragma unroll
+        for (int j = 0; j < CE_NMAX; ++j)
+            if (j < n) {
+                s[j] = prob[(size_t)b * n + j];
+                float yy = y[(size_t)b * n + j];
+                g[j] = -yy * (1.f - eps) / (eps / n + (1.f - eps) * s[j]);
+                dot = fmaf(s[j], g[j], dot);
+            }
+        float k = (coef ? coef[b] : 1.f) * coef_scale;
+#pragma unroll
+        for (int j = 0; j < CE_NMAX; ++j)
+            if (j < n) {
+                float v = k * s[j] * (g[j] - dot);
+                if (dZ) dZ[(size_t)b * n + j] = v;
+                if (j < 16) d[j] = v;
+            }
+        if (dZp) {
+            Row8<__nv_bfloat16>::store(plane_row(dZp, 0, Balloc, b), d);
+            Row8<__nv_bfloat16>::store(plane_row(dZp, 1, Balloc, b), d + 8);
         }
-    float k = (coef ? coef[b] : 1.f) * coef_scale;
+    }
+    if (dbias) {
+        __shared__ float red[4][16];
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll
-    for (int j = 0; j < CE_NMAX; ++j)
-        if (j < n) dZ[(size_t)b * n + j] = k * s[j] * (g[j] - dot);
+        for (int j = 0; j < 16; ++j) {
+            float t = warp_sum(d[j]);
+            if (lane == 0) red[warp][j] = t;
+        }
+        __syncthreads();
+        if (threadIdx.x < n && threadIdx.x < 16)
+            atomicAdd(dbias + threadIdx.x, red[0][threadIdx.x] + red[1][threadIdx.x] + red[2][threadIdx.x] + red[3][threadIdx.x]);
+    }
 }
 
 extern "C" int mpnn_softmax_ce_bwd(const float* prob, const float* y, int B, int n, float eps,
-                                   const float* coef, float coef_scale, float* dZ, void* stream) {
+                                   const float* coef, float coef_scale, float* dZ,
+                                   void* dZp, int Balloc, float* dbias, void* stream) {
     MPNN_REQUIRE(n >= 1 && n <= CE_NMAX, "softmax_ce_bwd: n=%d", n);
-    softmax_ce_bwd_kernel<<<ceil_div(B, 128), 128, 0, (cudaStream_t)stream>>>(prob, y, B, n, eps, coef, coef_scale, dZ);
+    MPNN_REQUIRE((!dZp && !dbias) || n <= 16, "softmax_ce_bwd: planes / bias output need n <= 16 (n=%d)", n);
+    softmax_ce_bwd_kernel<<<ceil_div(B, 128), 128, 0, (cudaStream_t)stream>>>(
+        prob, y, B, n, eps, coef, coef_scale, dZ, (__nv_bfloat16*)dZp, Balloc, dbias);
     return mpnn_check_launch("softmax_ce_bwd");
 }
 
@@ -245,8 +276,8 @@ __device__ void rt_channel_stats(const float* __restrict__ Zin, int B, float* me
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(RT_THREADS)
-router_tail_fwd_kernel(const float* Z1, int B,
+__device__ __forceinline__ void
+router_tail_fwd_body(const float* Z1, int B,
                        const float* __restrict__ g1, const float* __restrict__ b1, float* m1, float* v1,
                        const float* __restrict__ W2, const float* __restrict__ bias2,
                        const float* __restrict__ g2, const float* __restrict__ b2, float* m2, float* v2,
@@ -311,6 +342,29 @@ router_tail_fwd_kernel(const float* Z1, int B,
     }
 }
 
+__global__ void __launch_bounds__(RT_THREADS)
+router_tail_fwd_kernel(const float* Z1, int B, const float* g1, const float* b1, float* m1, float* v1,
+                       const float* W2, const float* bias2, const float* g2, const float* b2, float* m2,
+                       float* v2, const float* W3, const float* bias3, int ns, float d, float eps, int train,
+                       float* Z2, float* R, float* save) {
+    router_tail_fwd_body(Z1, B, g1, b1, m1, v1, W2, bias2, g2, b2, m2, v2, W3, bias3, ns, d, eps, train, Z2, R, save);
+}
+
+// every router of the net in one launch: one CTA per router
+__global__ void __launch_bounds__(RT_THREADS)
+router_tail_fwd_batched_kernel(const mpnn_router_fwd_desc* __restrict__ descs, int B, float d, float eps, int train) {
+    const mpnn_router_fwd_desc r = descs[blockIdx.x];
+    router_tail_fwd_body(r.Z1, B, r.g1, r.b1, r.m1, r.v1, r.W2, r.bias2, r.g2, r.b2, r.m2, r.v2, r.W3, r.bias3,
+                         r.ns, d, eps, train, r.Z2, r.R, r.save);
+}
+
+extern "C" int mpnn_router_tail_fwd_batched(const mpnn_router_fwd_desc* descs, int n, int B, int C,
+                                            float d, float eps, int train, void* stream) {
+    MPNN_REQUIRE(C == RT_C && n >= 1, "router_tail_fwd_batched: C=%d n=%d", C, n);
+    router_tail_fwd_batched_kernel<<<n, RT_THREADS, 0, (cudaStream_t)stream>>>(descs, B, d, eps, train);
+    return mpnn_check_launch("router_tail_fwd_batched");
+}
+
 extern "C" int mpnn_router_tail_fwd(const float* Z1, int B, int C,
                                     const float* g1, const float* b1, float* m1, float* v1,
                                     const float* W2, const float* bias2,
@@ -336,8 +390,8 @@ __device__ __forceinline__ void rt_block_add(const float (&v)[N], float* acc) {
     }
 }
 
-__global__ void __launch_bounds__(RT_THREADS)
-router_tail_bwd_kernel(const float* __restrict__ Z1, const float* __restrict__ Z2,
+__device__ __forceinline__ void
+router_tail_bwd_body(const float* __restrict__ Z1, const float* __restrict__ Z2,
                        const float* __restrict__ dR, int B, int ns,
                        const float* __restrict__ g1, const float* __restrict__ b1,
                        const float* __restrict__ W2,
@@ -345,7 +399,8 @@ router_tail_bwd_kernel(const float* __restrict__ Z1, const float* __restrict__ Z
                        const float* __restrict__ W3, const float* __restrict__ save,
                        float* dg1, float* dbt1, float* dW2, float* dbias2,
                        float* dg2, float* dbt2, float* dW3, float* dbias3,
-                       float* __restrict__ dZ1, float* __restrict__ scratch) {
+                       float* __restrict__ dZ1, float* __restrict__ scratch,
+                       __nv_bfloat16* __restrict__ dZ1p, int Balloc, float* dbias1) {
     __shared__ float sW2[RT_C * RT_C], sW3[RT_C * RT_NSMAX];
     __shared__ float a1[RT_C], c1[RT_C], a2[RT_C], c2[RT_C], mn1[RT_C], rs1[RT_C], mn2[RT_C], rs2[RT_C];
     __shared__ float sacc[2 * RT_C];
@@ -469,16 +524,58 @@ router_tail_bwd_kernel(const float* __restrict__ Z1, const float* __restrict__ Z
         __syncthreads();
     }
     if (tid < RT_C) { dbt1[tid] += sacc[tid]; dg1[tid] += sacc[RT_C + tid]; }
-    // Phase C: BN1 backward in place
+    // Phase C: BN1 backward in place (+ bf16 planes copy for the tcgen05 head GEMMs)
+    float bsum[RT_C];
+#pragma unroll
+    for (int i = 0; i < RT_C; ++i) bsum[i] = 0.f;
     for (int b = tid; b < B; b += RT_THREADS) {
+        float o[RT_C];
 #pragma unroll
         for (int i = 0; i < RT_C; ++i) {
             float z = Z1[(size_t)b * RT_C + i];
             float xh = (z - mn1[i]) * rs1[i];
             float dz = dZ1[(size_t)b * RT_C + i];
-            dZ1[(size_t)b * RT_C + i] = a1[i] * (dz - sacc[i] * invB - xh * sacc[RT_C + i] * invB);
+            dz = a1[i] * (dz - sacc[i] * invB - xh * sacc[RT_C + i] * invB);
+            dZ1[(size_t)b * RT_C + i] = dz;
+            o[i] = dz;
+            bsum[i] += dz;
+        }
+        if (dZ1p) {
+            Row8<__nv_bfloat16>::store(plane_row(dZ1p, 0, Balloc, b), o);
+            Row8<__nv_bfloat16>::store(plane_row(dZ1p, 1, Balloc, b), o + 8);
         }
     }
+    if (dbias1) {          // bias of the first router FC (zero up to rounding under train-mode BN)
+        __syncthreads();
+        if (tid < RT_C) sacc[tid] = 0.f;
+        __syncthreads();
+        rt_block_add<RT_C>(bsum, sacc);
+        __syncthreads();
+        if (tid < RT_C) dbias1[tid] += sacc[tid];
+    }
+}
+
+__global__ void __launch_bounds__(RT_THREADS)
+router_tail_bwd_kernel(const float* Z1, const float* Z2, const float* dR, int B, int ns,
+                       const float* g1, const float* b1, const float* W2, const float* g2, const float* b2,
+                       const float* W3, const float* save, float* dg1, float* dbt1, float* dW2, float* dbias2,
+                       float* dg2, float* dbt2, float* dW3, float* dbias3, float* dZ1, float* scratch) {
+    router_tail_bwd_body(Z1, Z2, dR, B, ns, g1, b1, W2, g2, b2, W3, save, dg1, dbt1, dW2, dbias2, dg2, dbt2,
+                         dW3, dbias3, dZ1, scratch, nullptr, 0, nullptr);
+}
+
+__global__ void __launch_bounds__(RT_THREADS)
+router_tail_bwd_batched_kernel(const mpnn_router_bwd_desc* __restrict__ descs, int B) {
+    const mpnn_router_bwd_desc r = descs[blockIdx.x];
+    router_tail_bwd_body(r.Z1, r.Z2, r.dR, B, r.ns, r.g1, r.b1, r.W2, r.g2, r.b2, r.W3, r.save, r.dg1, r.dbt1,
+                         r.dW2, r.dbias2, r.dg2, r.dbt2, r.dW3, r.dbias3, r.dZ1, r.scratch,
+                         (__nv_bfloat16*)r.dZ1p, r.Balloc, r.dbias1);
+}
+
+extern "C" int mpnn_router_tail_bwd_batched(const mpnn_router_bwd_desc* descs, int n, int B, int C, void* stream) {
+    MPNN_REQUIRE(C == RT_C && n >= 1, "router_tail_bwd_batched: C=%d n=%d", C, n);
+    router_tail_bwd_batched_kernel<<<n, RT_THREADS, 0, (cudaStream_t)stream>>>(descs, B);
+    return mpnn_check_launch("router_tail_bwd_batched");
 }
 
 extern "C" int mpnn_router_tail_bwd(const float* Z1, const float* Z2, const float* dR, int B, int C, int ns,

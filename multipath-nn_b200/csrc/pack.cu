@@ -92,6 +92,38 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, int ntaps, int 
     }
 }
 
+// all weight tensors of a step in ONE launch: blockIdx.y selects the descriptor
+template <typename T>
+__global__ void pack_weights_batched_kernel(const mpnn_pack_desc* __restrict__ descs) {
+    const mpnn_pack_desc d = descs[blockIdx.y];
+    const int total = d.ntaps * d.I * d.O;
+    if (d.mode == 2) {          // fp32 vector copy (bias vectors of fused heads)
+        float* pf = static_cast<float*>(d.packed);
+        for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < d.O; e += gridDim.x * blockDim.x)
+            pf[d.n_off + e] = __ldg(d.w + e);
+        return;
+    }
+    T* packed = static_cast<T*>(d.packed);
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+        int o = e % d.O;
+        int i = (e / d.O) % d.I;
+        int t = e / (d.O * d.I);
+        int k, n, tap;
+        if (d.mode == 0) { k = d.k_off + i; n = d.n_off + o; tap = t; }
+        else             { k = d.k_off + o; n = d.n_off + i; tap = d.ntaps - 1 - t; }
+        size_t dst = (((size_t)tap * (d.Ktot / 8) + (k >> 3)) * d.Ntot + n) * 8 + (k & 7);
+        packed[dst] = cvt_from_float<T>(__ldg(d.w + e));
+    }
+}
+
+extern "C" int mpnn_pack_weights_batched(const mpnn_pack_desc* descs, int n, int blocks_per_desc,
+                                         int dtype, void* stream) {
+    MPNN_REQUIRE(n >= 1 && n <= 65535 && blocks_per_desc >= 1, "pack_weights_batched: n=%d", n);
+    dim3 grid(blocks_per_desc, n);
+    MPNN_DISPATCH_DTYPE(dtype, (pack_weights_batched_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(descs)));
+    return mpnn_check_launch("pack_weights_batched");
+}
+
 extern "C" int mpnn_pack_weights(const float* w, int ntaps, int I, int O, int mode,
                                  int k_off, int Ktot, int n_off, int Ntot,
                                  void* packed, int dtype, void* stream) {

@@ -131,8 +131,9 @@ extern "C" int mpnn_stencil_gemm(const void* A0, int K0, const void* A1, int K1,
     MPNN_REQUIRE(N0 % 8 == 0 && N1 % 8 == 0 && N0 + N1 > 0, "stencil_gemm: N0=%d N1=%d", N0, N1);
     MPNN_REQUIRE(K1 == 0 || A1, "stencil_gemm: A1 null");
     Geom g = make_geom(B, H, W, G, P);
-    MPNN_REQUIRE(G >= g.Wp + 1, "stencil_gemm: front guard %d < %d", G, g.Wp + 1);
-    MPNN_REQUIRE(P >= G + g.rows + 128 + g.Wp + 1, "stencil_gemm: back guard too small (P=%d)", P);
+    const int halo = ntaps == 9 ? g.Wp + 1 : 0;
+    MPNN_REQUIRE(G >= halo, "stencil_gemm: front guard %d < %d", G, halo);
+    MPNN_REQUIRE(P >= G + ceil_div(g.rows, 128) * 128 + halo, "stencil_gemm: back guard too small (P=%d)", P);
     MPNN_REQUIRE(!stats || stats_cap > 0, "stencil_gemm: stats_cap");
     cudaStream_t st = (cudaStream_t)stream;
     if (impl == 1) {

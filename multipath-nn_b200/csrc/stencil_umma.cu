@@ -31,7 +31,10 @@ struct GemmArgs {
     void* out0; void* out1;
     float* stats;
     Geom g;
-    int K0, K1, N, N0, NB, ntaps, acc0, acc1, out_f32, n_tiles, nstage, rowsA, halo;
+    int K0, K1, N, N0, NB, ntaps, acc0, acc1, n_tiles, nstage, rowsA, halo;
+    int out_mode;      // 0: bf16 planes, 1: fp32 planes, 2: fp32 row-major [row][ld]
+    int ld0, ld1;      // leading dimensions of out0 / out1 in row-major mode
+    int KC, n_kc;      // planes per pipeline stage and stages per tile (K is streamed for wide FC inputs)
 };
 
 constexpr int kThreads = 192;
@@ -44,7 +47,7 @@ stencil_gemm_umma_kernel(const GemmArgs a) {
     const int NB = a.NB, n0 = blockIdx.y * NB;
     const uint32_t w_bytes = (uint32_t)a.ntaps * KG * NB * 16;
     const uint32_t PS = (uint32_t)a.rowsA * 16;          // plane stride inside a stage
-    const uint32_t stage_bytes = PS * KG;
+    const uint32_t stage_bytes = PS * a.KC;
     uint8_t* sW = smem;
     uint8_t* sA = smem + ((w_bytes + 127) & ~127u);
     uint64_t* bars = reinterpret_cast<uint64_t*>(sA + (size_t)a.nstage * stage_bytes);
@@ -81,17 +84,21 @@ stencil_gemm_umma_kernel(const GemmArgs a) {
                 bulk_g2s(smem_u32(sW) + (uint32_t)t * NB * 16,
                          a.Wp + ((size_t)t * a.N + n0) * 8, (uint32_t)NB * 16, wbar);
             int it = 0;
-            for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
-                const int s = it % a.nstage;
-                const uint32_t ph = (uint32_t)(it / a.nstage) & 1u;
-                mbar_wait(empty0 + 8 * s, ph ^ 1u);
-                mbar_expect_tx(full0 + 8 * s, stage_bytes);
+            for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
                 const size_t row0 = (size_t)(a.g.G + tile * 128 - a.halo);
-                const uint32_t dst = smem_u32(sA) + (uint32_t)s * stage_bytes;
-                for (int kg = 0; kg < KG; ++kg) {
-                    const __nv_bfloat16* src = kg < KG0 ? a.A0 + ((size_t)kg * a.g.P + row0) * 8
-                                                        : a.A1 + ((size_t)(kg - KG0) * a.g.P + row0) * 8;
-                    bulk_g2s(dst + (uint32_t)kg * PS, src, PS, full0 + 8 * s);
+                for (int ci = 0; ci < a.n_kc; ++ci, ++it) {
+                    const int s = it % a.nstage;
+                    const uint32_t ph = (uint32_t)(it / a.nstage) & 1u;
+                    const int kg0 = ci * a.KC, kgn = min(a.KC, KG - kg0);
+                    mbar_wait(empty0 + 8 * s, ph ^ 1u);
+                    mbar_expect_tx(full0 + 8 * s, PS * kgn);
+                    const uint32_t dst = smem_u32(sA) + (uint32_t)s * stage_bytes;
+                    for (int j = 0; j < kgn; ++j) {
+                        const int kg = kg0 + j;
+                        const __nv_bfloat16* src = kg < KG0 ? a.A0 + ((size_t)kg * a.g.P + row0) * 8
+                                                            : a.A1 + ((size_t)(kg - KG0) * a.g.P + row0) * 8;
+                        bulk_g2s(dst + (uint32_t)j * PS, src, PS, full0 + 8 * s);
+                    }
                 }
             }
         }
@@ -101,30 +108,34 @@ stencil_gemm_umma_kernel(const GemmArgs a) {
         if (lane == 0) {
             const uint32_t idesc = make_idesc(NB, 0, 0);
             mbar_wait(wbar, 0);
-            int it = 0;
-            for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
-                const int s = it % a.nstage;
-                const uint32_t ph = (uint32_t)(it / a.nstage) & 1u;
-                const int acc = it & 1;
-                const uint32_t aph = (uint32_t)(it >> 1) & 1u;
+            int it = 0, tl = 0;
+            for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++tl) {
+                const int acc = tl & 1;
+                const uint32_t aph = (uint32_t)(tl >> 1) & 1u;
                 mbar_wait(tempty0 + 8 * acc, aph ^ 1u);
-                mbar_wait(full0 + 8 * s, ph);
-                tc_fence_after();
-                const uint32_t abase = smem_u32(sA) + (uint32_t)s * stage_bytes;
                 const uint32_t wbase = smem_u32(sW);
                 const uint32_t dcol = tmem_base + (uint32_t)acc * NB;
                 uint32_t first = 0;
-                for (int tap = 0; tap < a.ntaps; ++tap) {
-                    const int off = a.ntaps == 9 ? (tap / 3 - 1) * a.g.Wp + (tap % 3 - 1) : 0;
-                    const uint32_t arow = abase + (uint32_t)(a.halo + off) * 16;
-                    for (int kk = 0; kk < KG; kk += 2) {
-                        const uint64_t ad = make_desc(arow + (uint32_t)kk * PS, PS, 128);
-                        const uint64_t bd = make_desc(wbase + (uint32_t)(tap * KG + kk) * NB * 16, (uint32_t)NB * 16, 128);
-                        tc_mma(dcol, ad, bd, idesc, first);
-                        first = 1;
+                for (int ci = 0; ci < a.n_kc; ++ci, ++it) {
+                    const int s = it % a.nstage;
+                    const uint32_t ph = (uint32_t)(it / a.nstage) & 1u;
+                    const int kg0 = ci * a.KC, kgn = min(a.KC, KG - kg0);
+                    mbar_wait(full0 + 8 * s, ph);
+                    tc_fence_after();
+                    const uint32_t abase = smem_u32(sA) + (uint32_t)s * stage_bytes;
+                    for (int tap = 0; tap < a.ntaps; ++tap) {
+                        const int off = a.ntaps == 9 ? (tap / 3 - 1) * a.g.Wp + (tap % 3 - 1) : 0;
+                        const uint32_t arow = abase + (uint32_t)(a.halo + off) * 16;
+                        for (int kk = 0; kk < kgn; kk += 2) {
+                            const uint64_t ad = make_desc(arow + (uint32_t)kk * PS, PS, 128);
+                            const uint64_t bd = make_desc(wbase + (uint32_t)(tap * KG + kg0 + kk) * NB * 16,
+                                                          (uint32_t)NB * 16, 128);
+                            tc_mma(dcol, ad, bd, idesc, first);
+                            first = 1;
+                        }
                     }
+                    tc_commit(empty0 + 8 * s);      // smem stage reusable once the MMAs retire
                 }
-                tc_commit(empty0 + 8 * s);          // smem stage reusable once the MMAs retire
                 tc_commit(tfull0 + 8 * acc);        // accumulator ready for the epilogue
             }
         }
@@ -164,7 +175,12 @@ stencil_gemm_umma_kernel(const GemmArgs a) {
                         float o[8];
 #pragma unroll
                         for (int i = 0; i < 8; ++i) o[i] = v[hh * 8 + i];
-                        if (a.out_f32) {
+                        if (a.out_mode == 2) {
+                            // fp32 row-major [row][ld]: logits of the fully-connected heads
+                            const int ld = cc < a.N0 ? a.ld0 : a.ld1;
+                            float* d = (float*)base + (size_t)q * ld + kgp * 8;
+                            Row8<float>::store(d, o);
+                        } else if (a.out_mode == 1) {
                             float* d = plane_row((float*)base, kgp, a.g.P, p);
                             if (accf) { float t[8]; Row8<float>::load(d, t);
 #pragma unroll
@@ -278,7 +294,13 @@ int mpnn_stencil_gemm_umma(const void* A0, int K0, const void* A1, int K1, const
     const int KG = (K0 + K1) / 8;
     const int halo = ntaps == 9 ? g.Wp + 1 : 0;
     const int rowsA = 128 + 2 * halo;
-    const size_t stage = (size_t)rowsA * 16 * KG;
+    // planes per pipeline stage: all of K when that is small (convs), else ~32 KB slices (wide FC inputs)
+    int KC = KG;
+    if ((size_t)rowsA * 16 * KG > 40 * 1024) {
+        KC = (int)((32 * 1024) / ((size_t)rowsA * 16)) & ~1;
+        if (KC < 2) KC = 2;
+    }
+    const size_t stage = (size_t)rowsA * 16 * KC;
     const size_t kMax = 227 * 1024 - 1024;
     int split = 0, nstage = 0, NB = 0;
     for (int s = 1; s <= 8; s *= 2) {
@@ -308,8 +330,11 @@ int mpnn_stencil_gemm_umma(const void* A0, int K0, const void* A1, int K1, const
     a.A0 = (const __nv_bfloat16*)A0; a.A1 = (const __nv_bfloat16*)A1; a.Wp = (const __nv_bfloat16*)Wp;
     a.bias = bias; a.out0 = out0; a.out1 = out1; a.stats = stats; a.g = g;
     a.K0 = K0; a.K1 = K1; a.N = N; a.N0 = N0; a.NB = NB; a.ntaps = ntaps; a.acc0 = acc0; a.acc1 = acc1;
-    a.out_f32 = out_dtype == MPNN_F32; a.n_tiles = ceil_div(g.rows, 128); a.nstage = nstage;
-    a.rowsA = rowsA; a.halo = halo;
+    a.out_mode = out_dtype == MPNN_BF16 ? 0 : (out_dtype == MPNN_F32 ? 1 : 2);
+    a.ld0 = N0; a.ld1 = N1;
+    a.n_tiles = ceil_div(g.rows, 128); a.nstage = nstage;
+    a.rowsA = rowsA; a.halo = halo; a.KC = KC; a.n_kc = ceil_div(KG, KC);
+    MPNN_REQUIRE(a.out_mode != 2 || (!acc0 && !acc1 && !stats), "stencil_gemm: row-major output cannot accumulate");
     int gx = 148 * per_sm / split;
     if (gx > a.n_tiles) gx = a.n_tiles;
     if (stats && gx > stats_cap) gx = stats_cap;

@@ -66,10 +66,11 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
     return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) |
            ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46);
 }
-// kind::f16 instruction descriptor: D=f32, A=B=bf16, M=128
-__device__ __forceinline__ uint32_t make_idesc(int N, int a_mn, int b_mn) {
+// kind::f16 instruction descriptor: D=f32, A=B=bf16, M=128 (or 64: D then lives in
+// lanes [0,16) of each 32-lane TMEM quadrant, row m -> lane 32*(m/16) + m%16)
+__device__ __forceinline__ uint32_t make_idesc(int N, int a_mn, int b_mn, int M = 128) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
-           ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
+           ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 __device__ __forceinline__ uint32_t tmem_cols_pow2(int c) {
     uint32_t n = 32;

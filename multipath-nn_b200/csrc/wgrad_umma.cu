@@ -6,30 +6,43 @@
 // ROWS of both operands: element (channel c, pixel p) sits at plane c/8, row p,
 // i.e. exactly the UMMA MN-major interleaved core-matrix layout (8 pixels x 16 B
 // contiguous per core matrix; LBO = 128 B between 8-pixel groups, SBO = plane
-// stride between 8-channel groups).  So both operands are staged with the same
-// one-bulk-copy-per-plane producer as the forward kernel and need no transpose:
-//   D_tap[m = input channel][n = output channel] += A_tap^T (MN-major, shifted
-//   start address per tap) x G (MN-major),  K = 16 pixels per tcgen05.mma.
-// Input channels go on M (padded to 128 by reading whatever follows the staged
-// planes -- rows of D are independent, rows >= K0+K1 are never read back), the
-// output channels on N, so the tensor time per tap is proportional to C_out.
+// stride between 8-channel groups).  Both operands are staged with one bulk
+// copy per plane and need no transpose:
+//   D[m = input channel][n = output channel] += A^T (MN-major, start address
+//   shifted by the tap's row offset) x G (MN-major),  K = 16 pixels per MMA.
 //
-// A CTA owns a group of TG taps (all nine when 9*N TMEM columns fit, else one
-// kernel row of three) and walks pixel chunks of 128 rows, accumulating in
-// TMEM across the whole walk; partial sums from different CTAs are combined
-// with fp32 red.global.add into the flat gradient buffer (which the optimiser
-// kernel consumes).
+// tcgen05.mma always fetches M >= 64 operand rows from shared memory, and for
+// thin layers (16..32 input channels) that fetch -- not the tensor pipe, not HBM
+// -- is the bottleneck (128 B/clk/SM).  Two measures keep the rows useful:
+//   * M = 64 instead of 128 whenever the stacked rows fit in 64;
+//   * "dw stacking" (CP = 3) for K0+K1 <= 40: each plane is staged three times,
+//     shifted by dw = -1, 0, +1 rows, as consecutive 8-row groups of M, so ONE
+//     MMA per kernel row dh covers three taps (rows m = (plane*3 + dw)*8 + c).
+// Without stacking (CP = 1) a CTA owns TG taps (9, or 3 when 9*N exceeds the
+// 512 TMEM columns) and issues one MMA per tap.
+//
+// A CTA walks pixel chunks of 128 rows accumulating in TMEM across the whole
+// walk; partial sums from different CTAs are combined with fp32
+// red.global.add into the flat gradient buffer the optimiser kernel consumes.
 #include "common.cuh"
 #include "umma.cuh"
 #include "../../include/mpnn.h"
 
 namespace {
 
+// destination of one (row segment, column segment) block of the accumulator
+struct WDst { float* p; int ld, rows, cols; };
+
 struct WgradArgs {
     const __nv_bfloat16* A0; const __nv_bfloat16* A1; const __nv_bfloat16* Gd;
-    float* dW0; float* dW1;
+    WDst dst[2][2];        // [row segment: k < K0 | k >= K0][column segment: n < Nsplit | n >= Nsplit]
     Geom g;
-    int K0, K1, K0real, K1real, N, Nreal, ntaps, TG, n_chunks, nstage, rowsA, halo;
+    int K0, K1, N, Nsplit, ntaps;
+    int CP;        // staged copies per plane: 1, or 3 (dw stacking)
+    int NM;        // MMAs per 16-pixel step per CTA (taps, or kernel rows when stacked)
+    int M;         // 64 or 128
+    int n_chunks, nstage, rowsA, halo;
+    int vec4;      // gradient rows are 16-byte aligned: use vector reductions
 };
 
 constexpr int kWThreads = 192;
@@ -39,17 +52,19 @@ __global__ void __launch_bounds__(kWThreads, 1)
 stencil_wgrad_umma_kernel(const WgradArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int KG = (a.K0 + a.K1) >> 3, KG0 = a.K0 >> 3, NG = a.N >> 3;
-    const uint32_t PSA = (uint32_t)a.rowsA * 16;         // plane stride of the A stage
+    const int KGall = (a.K0 + a.K1) >> 3, KG0 = a.K0 >> 3, NG = a.N >> 3;
+    const int kgb = blockIdx.z * 16;                     // first plane of this CTA's M block
+    const int KG = min(16, KGall - kgb);                 // planes staged by this CTA
+    const uint32_t PSA = (uint32_t)a.rowsA * 16;         // stride between 8-row groups of the A stage
     const uint32_t PSG = (uint32_t)kChunk * 16;          // plane stride of the G stage
-    const uint32_t stageA = PSA * KG, stageG = PSG * NG;
+    const uint32_t stageA = PSA * KG * a.CP, stageG = PSG * NG;
     uint8_t* sA = smem;
     uint8_t* sG = smem + (size_t)a.nstage * stageA;
     uint64_t* bars = reinterpret_cast<uint64_t*>(sG + (size_t)a.nstage * stageG);
     const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * a.nstage, done = empty0 + 8 * a.nstage;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * a.nstage + 1);
-    const int tap0 = blockIdx.y * a.TG;
-    const uint32_t ncols = tmem_cols_pow2(a.TG * a.N);
+    const int t0 = blockIdx.y * a.NM;                    // first tap (CP=1) / kernel row (CP=3) of this CTA
+    const uint32_t ncols = tmem_cols_pow2(a.NM * a.N);
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < a.nstage; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
@@ -65,7 +80,6 @@ stencil_wgrad_umma_kernel(const WgradArgs a) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const bool has_work = (int)blockIdx.x < a.n_chunks;
 
     if (warp == 0) {
         if (lane == 0) {
@@ -79,9 +93,14 @@ stencil_wgrad_umma_kernel(const WgradArgs a) {
                 const uint32_t dA = smem_u32(sA) + (uint32_t)s * stageA;
                 const uint32_t dG = smem_u32(sG) + (uint32_t)s * stageG;
                 for (int kg = 0; kg < KG; ++kg) {
-                    const __nv_bfloat16* src = kg < KG0 ? a.A0 + ((size_t)kg * a.g.P + p0 - a.halo) * 8
-                                                        : a.A1 + ((size_t)(kg - KG0) * a.g.P + p0 - a.halo) * 8;
-                    bulk_g2s(dA + (uint32_t)kg * PSA, src, PSA, full0 + 8 * s);
+                    const int kga = kgb + kg;
+                    const __nv_bfloat16* pl = kga < KG0 ? a.A0 + (size_t)kga * a.g.P * 8
+                                                        : a.A1 + (size_t)(kga - KG0) * a.g.P * 8;
+                    for (int cp = 0; cp < a.CP; ++cp) {
+                        // CP=3: copy cp holds the plane shifted by dw = cp-1 rows
+                        const size_t row0 = p0 - a.halo + (a.CP == 3 ? cp - 1 : 0);
+                        bulk_g2s(dA + (uint32_t)(kg * a.CP + cp) * PSA, pl + row0 * 8, PSA, full0 + 8 * s);
+                    }
                 }
                 for (int ng = 0; ng < NG; ++ng)
                     bulk_g2s(dG + (uint32_t)ng * PSG, a.Gd + ((size_t)ng * a.g.P + p0) * 8, PSG, full0 + 8 * s);
@@ -89,8 +108,8 @@ stencil_wgrad_umma_kernel(const WgradArgs a) {
         }
         __syncwarp();
     } else if (warp == 1) {
-        if (lane == 0 && has_work) {
-            const uint32_t idesc = make_idesc(a.N, 1, 1);        // both operands MN-major
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc(a.N, 1, 1, a.M);   // both operands MN-major
             int it = 0;
             for (int c = blockIdx.x; c < a.n_chunks; c += gridDim.x, ++it) {
                 const int s = it % a.nstage;
@@ -99,9 +118,10 @@ stencil_wgrad_umma_kernel(const WgradArgs a) {
                 tc_fence_after();
                 const uint32_t aB = smem_u32(sA) + (uint32_t)s * stageA;
                 const uint32_t gB = smem_u32(sG) + (uint32_t)s * stageG;
-                for (int t = 0; t < a.TG; ++t) {
-                    const int tap = tap0 + t;
-                    const int off = a.ntaps == 9 ? (tap / 3 - 1) * a.g.Wp + (tap % 3 - 1) : 0;
+                for (int t = 0; t < a.NM; ++t) {
+                    int off;                                  // row shift of this MMA's A operand
+                    if (a.CP == 3) off = (t0 + t - 1) * a.g.Wp;
+                    else off = a.ntaps == 9 ? ((t0 + t) / 3 - 1) * a.g.Wp + ((t0 + t) % 3 - 1) : 0;
                     const uint32_t arow = aB + (uint32_t)(a.halo + off) * 16;
                     const uint32_t dcol = tmem_base + (uint32_t)t * a.N;
                     for (int ks = 0; ks < kChunk / 16; ++ks) {
@@ -115,26 +135,42 @@ stencil_wgrad_umma_kernel(const WgradArgs a) {
             tc_commit(done);
         }
         __syncwarp();
-    } else if (has_work) {
-        // epilogue: TMEM row m = input channel, columns = (tap, output channel)
+    } else {
+        // epilogue: TMEM row m = stacked input-channel row, columns = (MMA index, output channel)
         const int quad = warp & 3;
-        const int m = quad * 32 + lane;
+        const int m = a.M == 64 ? quad * 16 + lane : quad * 32 + lane;
+        const bool row_ok = a.M == 64 ? lane < 16 : true;
         mbar_wait(done, 0);
         tc_fence_after();
-        const bool in0 = m < a.K0real;
-        const bool in1 = m >= a.K0 && (m - a.K0) < a.K1real;
-        for (int t = 0; t < a.TG; ++t) {
-            const int tap = tap0 + t;
-            float* dst = nullptr;
-            if (in0) dst = a.dW0 + ((size_t)tap * a.K0real + m) * a.Nreal;
-            else if (in1) dst = a.dW1 + ((size_t)tap * a.K1real + (m - a.K0)) * a.Nreal;
+        const int grp = m >> 3, cc = m & 7;
+        const int kg = a.CP == 3 ? grp / 3 : grp;
+        const int dwi = a.CP == 3 ? grp % 3 : 0;
+        const int k = (kgb + kg) * 8 + cc;               // input channel in the concatenated K space
+        const int rs = k >= a.K0 ? 1 : 0;
+        const int kr = rs ? k - a.K0 : k;
+        const bool row_live = row_ok && kg < KG;
+        for (int t = 0; t < a.NM; ++t) {
+            const int tap = a.CP == 3 ? (t0 + t) * 3 + dwi : t0 + t;
             for (int c = 0; c < a.N; c += 16) {
                 float v[16];
                 tc_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(t * a.N + c), v);
-                if (dst) {
+                const int cs = c >= a.Nsplit ? 1 : 0;
+                const WDst d = a.dst[rs][cs];
+                const int n = cs ? c - a.Nsplit : c;
+                if (row_live && d.p && kr < d.rows) {
+                    float* dst = d.p + ((size_t)tap * d.rows + kr) * d.ld + n;
+                    if (a.vec4 && (d.ld & 3) == 0) {
+                        // one 16-byte red.global.add.v4.f32 per 4 columns (sm_90+)
 #pragma unroll
-                    for (int i = 0; i < 16; ++i)
-                        if (c + i < a.Nreal) atomicAdd(dst + c + i, v[i]);
+                        for (int i = 0; i < 16; i += 4)
+                            if (n + i < d.cols)
+                                atomicAdd(reinterpret_cast<float4*>(dst + i),
+                                          make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]));
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i)
+                            if (n + i < d.cols) atomicAdd(dst + i, v[i]);
+                    }
                 }
             }
         }
@@ -177,41 +213,46 @@ colsum_planes_kernel(const __nv_bfloat16* __restrict__ Gd, Geom g, int Nreal, fl
 
 }  // namespace
 
-int mpnn_stencil_wgrad_umma(const void* A0, int K0, int K0real, float* dW0, const void* A1, int K1,
-                            int K1real, float* dW1, const void* Gd, int N, int Nreal, float* dbias,
-                            int ntaps, Geom g, cudaStream_t st) {
-    MPNN_REQUIRE(K0 % 16 == 0 && K1 % 16 == 0 && N % 16 == 0, "stencil_wgrad(tcgen05): K0=%d K1=%d N=%d", K0, K1, N);
-    MPNN_REQUIRE(K0 + K1 <= 128 && N <= 256, "stencil_wgrad(tcgen05): K=%d > 128 or N=%d > 256", K0 + K1, N);
-    const int KG = (K0 + K1) / 8, NG = N / 8;
-    const int halo = ntaps == 9 ? g.Wp + 1 : 0;
-    const int rowsA = kChunk + 2 * halo;
-    int TG = ntaps;                                  // taps per CTA, bounded by 512 TMEM columns
-    if (TG * N > 512) TG = ntaps == 9 ? 3 : 1;
-    MPNN_REQUIRE(TG * N <= 512 && ntaps % TG == 0, "stencil_wgrad(tcgen05): N=%d too wide", N);
-    const size_t stageA = (size_t)rowsA * 16 * KG, stageG = (size_t)kChunk * 16 * NG;
+// shared launcher: fills the tiling fields of `a` (operands / destinations / K0,K1,N,Nsplit,ntaps,g set by caller)
+static int launch_wgrad(WgradArgs& a, const float* dbias_src_unused, cudaStream_t st) {
+    const int KGall = (a.K0 + a.K1) / 8, NG = a.N / 8;
+    const int mblocks = ceil_div(KGall, 16);
+    const int KG = KGall < 16 ? KGall : 16;          // planes per CTA (largest block)
+    a.CP = (a.ntaps == 9 && mblocks == 1 && 3 * KG <= 16) ? 3 : 1;
+    a.M = KG * a.CP <= 8 ? 64 : 128;
+    const int n_units = a.CP == 3 ? 3 : a.ntaps;     // MMAs per 16-pixel step over all CTAs of a chunk
+    a.NM = n_units;
+    if (a.NM * a.N > 512) a.NM = a.ntaps == 9 ? 3 : 1;
+    MPNN_REQUIRE(a.NM * a.N <= 512 && n_units % a.NM == 0, "wgrad(tcgen05): N=%d too wide", a.N);
+    a.halo = a.ntaps == 9 ? (a.CP == 3 ? a.g.Wp : a.g.Wp + 1) : 0;
+    a.rowsA = kChunk + 2 * a.halo;
+    const size_t stageA = (size_t)a.rowsA * 16 * KG * a.CP, stageG = (size_t)kChunk * 16 * NG;
     const size_t kMax = 227 * 1024 - 1024;
     int nstage = (int)((kMax - 256) / (stageA + stageG));
     if (nstage > 4) nstage = 4;
-    MPNN_REQUIRE(nstage >= 2, "stencil_wgrad(tcgen05): K=%d N=%d does not fit shared memory", K0 + K1, N);
+    MPNN_REQUIRE(nstage >= 2, "wgrad(tcgen05): K=%d N=%d does not fit shared memory", a.K0 + a.K1, a.N);
     size_t smem = (size_t)nstage * (stageA + stageG) + 256;
-    // the M=128 descriptor reads 16 planes from the start of an A stage: keep that inside the allocation
-    const size_t reach = (size_t)(nstage - 1) * stageA + (size_t)16 * rowsA * 16 + 64;
+    // the descriptor reads M/8 groups from the start of an A stage: keep that inside the allocation
+    const size_t reach = (size_t)(nstage - 1) * stageA + (size_t)(a.M / 8) * a.rowsA * 16 + 64;
     if (smem < reach) smem = reach;
-    MPNN_REQUIRE(smem <= kMax + 1024, "stencil_wgrad(tcgen05): shared memory reach %zu", smem);
+    MPNN_REQUIRE(smem <= kMax + 1024, "wgrad(tcgen05): shared memory reach %zu", smem);
     int ncols = 32;
-    while (ncols < TG * N) ncols <<= 1;
+    while (ncols < a.NM * a.N) ncols <<= 1;
     int per_sm = (int)((227 * 1024) / (smem + 1024));
     if (per_sm > 512 / ncols) per_sm = 512 / ncols;
     if (per_sm > 4) per_sm = 4;
     if (per_sm < 1) per_sm = 1;
-    WgradArgs a;
-    a.A0 = (const __nv_bfloat16*)A0; a.A1 = (const __nv_bfloat16*)A1; a.Gd = (const __nv_bfloat16*)Gd;
-    a.dW0 = dW0; a.dW1 = dW1; a.g = g; a.K0 = K0; a.K1 = K1; a.K0real = K0real; a.K1real = K1real;
-    a.N = N; a.Nreal = Nreal; a.ntaps = ntaps; a.TG = TG; a.n_chunks = ceil_div(g.rows, kChunk);
-    a.nstage = nstage; a.rowsA = rowsA; a.halo = halo;
-    const int groups = ntaps / TG;
-    int gx = 148 * per_sm / groups;
-    if (gx > a.n_chunks) gx = a.n_chunks;
+    a.n_chunks = ceil_div(a.g.rows, kChunk);
+    a.nstage = nstage;
+    a.vec4 = 1;
+    for (int r = 0; r < 2; ++r)
+        for (int c = 0; c < 2; ++c)
+            if (a.dst[r][c].p && ((uintptr_t)a.dst[r][c].p % 16 != 0)) a.vec4 = 0;
+    const int groups = n_units / a.NM;
+    int gx = 148 * per_sm / (groups * mblocks);
+    // every CTA ends with a full-size reduction of its accumulators into dW: give each
+    // at least 8 chunks of pixels so that the reduction traffic stays small next to the MMAs
+    if (gx > ceil_div(a.n_chunks, 8)) gx = ceil_div(a.n_chunks, 8);
     if (gx < 1) gx = 1;
     static bool attr_set = false;
     if (!attr_set) {
@@ -220,15 +261,49 @@ int mpnn_stencil_wgrad_umma(const void* A0, int K0, int K0real, float* dW0, cons
         if (e != cudaSuccess) { mpnn_set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return MPNN_ERR_CUDA; }
         attr_set = true;
     }
-    stencil_wgrad_umma_kernel<<<dim3(gx, groups), kWThreads, smem, st>>>(a);
-    int rc = mpnn_check_launch("stencil_wgrad_umma");
+    stencil_wgrad_umma_kernel<<<dim3(gx, groups, mblocks), kWThreads, smem, st>>>(a);
+    return mpnn_check_launch("stencil_wgrad_umma");
+}
+
+int mpnn_stencil_wgrad_umma(const void* A0, int K0, int K0real, float* dW0, const void* A1, int K1,
+                            int K1real, float* dW1, const void* Gd, int N, int Nreal, float* dbias,
+                            int ntaps, Geom g, cudaStream_t st) {
+    MPNN_REQUIRE(K0 % 16 == 0 && K1 % 16 == 0 && N % 16 == 0, "stencil_wgrad(tcgen05): K0=%d K1=%d N=%d", K0, K1, N);
+    MPNN_REQUIRE(N <= 256, "stencil_wgrad(tcgen05): N=%d > 256", N);
+    WgradArgs a;
+    a.A0 = (const __nv_bfloat16*)A0; a.A1 = (const __nv_bfloat16*)A1; a.Gd = (const __nv_bfloat16*)Gd;
+    a.g = g; a.K0 = K0; a.K1 = K1; a.N = N; a.Nsplit = N; a.ntaps = ntaps;
+    a.dst[0][0] = WDst{dW0, Nreal, K0real, Nreal};
+    a.dst[1][0] = WDst{dW1, Nreal, K1real, Nreal};
+    a.dst[0][1] = WDst{nullptr, 0, 0, 0};
+    a.dst[1][1] = WDst{nullptr, 0, 0, 0};
+    int rc = launch_wgrad(a, nullptr, st);
     if (rc) return rc;
     if (dbias) {
         int bx = ceil_div(g.rows, 256 * 8);
         if (bx > 148) bx = 148;
         if (bx < 1) bx = 1;
-        colsum_planes_kernel<<<dim3(bx, NG), 256, 0, st>>>((const __nv_bfloat16*)Gd, g, Nreal, dbias);
+        colsum_planes_kernel<<<dim3(bx, N / 8), 256, 0, st>>>((const __nv_bfloat16*)Gd, g, Nreal, dbias);
         rc = mpnn_check_launch("colsum_planes");
     }
     return rc;
+}
+
+// Weight gradient of the fully-connected heads sharing one feature matrix X:
+//   dWa[f][j] += sum_b X[f][b] * dZ[b][j]            (j <  na, f < Fa)   -- LogReg
+//   dWb[f][j] += sum_b X[f][b] * dZ[b][Nsplit + j]   (j <  nb, f < Fb)   -- first router FC
+// X: feature planes [F/8][Balloc][8] bf16, dZ: planes [N/8][Balloc][8] bf16.
+extern "C" int mpnn_fc_wgrad(const void* X, int F, int Balloc, int B, const void* dZ, int N, int Nsplit,
+                             float* dWa, int Fa, int na, float* dWb, int Fb, int nb, void* stream) {
+    MPNN_REQUIRE(F % 16 == 0 && N % 16 == 0 && Nsplit % 16 == 0 && N <= 256, "fc_wgrad: F=%d N=%d Nsplit=%d", F, N, Nsplit);
+    MPNN_REQUIRE(Balloc >= ceil_div(B, kChunk) * kChunk, "fc_wgrad: Balloc=%d must cover whole 128-row chunks", Balloc);
+    WgradArgs a;
+    a.A0 = (const __nv_bfloat16*)X; a.A1 = nullptr; a.Gd = (const __nv_bfloat16*)dZ;
+    a.g = make_geom(B, 0, 0, 0, Balloc);
+    a.K0 = F; a.K1 = 0; a.N = N; a.Nsplit = Nsplit; a.ntaps = 1;
+    a.dst[0][0] = WDst{dWa, na, Fa, na};
+    a.dst[0][1] = WDst{dWb, nb, Fb, nb};
+    a.dst[1][0] = WDst{nullptr, 0, 0, 0};
+    a.dst[1][1] = WDst{nullptr, 0, 0, 0};
+    return launch_wgrad(a, nullptr, (cudaStream_t)stream);
 }

@@ -27,6 +27,20 @@ STATS_CAP = 592          # 4 CTAs per SM worth of partial rows
 MAXS = 8
 
 
+def _struct(ptrs, ints):
+    """numpy dtype mirroring a C struct of pointers followed by ints (include/mpnn.h)"""
+    return np.dtype([(k, '<u8') for k in ptrs] + [(k, '<i4') for k in ints], align=True)
+
+
+_PACK = _struct(['w', 'packed'], ['ntaps', 'I', 'O', 'mode', 'k_off', 'Ktot', 'n_off', 'Ntot'])
+_RT_FWD = _struct(['Z1', 'g1', 'b1', 'm1', 'v1', 'W2', 'bias2', 'g2', 'b2', 'm2', 'v2', 'W3', 'bias3',
+                   'Z2', 'R', 'save'], ['ns', 'reserved'])
+_RT_BWD = _struct(['Z1', 'Z2', 'dR', 'g1', 'b1', 'W2', 'g2', 'b2', 'W3', 'save', 'dg1', 'dbt1', 'dW2',
+                   'dbias2', 'dg2', 'dbt2', 'dW3', 'dbias3', 'dZ1', 'scratch', 'dZ1p', 'dbias1'],
+                  ['ns', 'Balloc'])
+assert _PACK.itemsize == 48 and _RT_FWD.itemsize == 136 and _RT_BWD.itemsize == 184
+
+
 def _ru(a, b):
     return (a + b - 1) // b * b
 
@@ -183,6 +197,7 @@ class Engine:
                         l2 = float(layer.hypers.k_l2)
                     elif isinstance(layer, MultiscaleConvMax) and key.startswith('w_'):
                         l2 = float(layer.hypers.k_l2)
+                    off_t = _ru(off_t, 4)          # 16-byte aligned: vector reductions into the gradient
                     p._bind = (self, 'theta', off_t)
                     self.tparams.append(p)
                     seg_start.append(off_t); seg_node.append(node_idx)
@@ -298,6 +313,8 @@ class Engine:
                     raise ValueError('feed k_cpt: %d values for batch %d' % (kc.size, B))
                 plan.kcpt.copy_(torch.from_numpy(kc), non_blocking=True)
                 plan.kextra.copy_(torch.from_numpy(kc * np.float32(hy.α_cpt)), non_blocking=True)
+                for col in plan.kplanes:          # tcgen05 heads: the feature is one more input column
+                    col[:B].copy_(plan.kextra)
             else:
                 h[HYP_KCPT] = float(hy.k_cpt)
         self.hyp.copy_(h, non_blocking=True)
@@ -458,9 +475,9 @@ class _Plan:
         self._build()
 
     @staticmethod
-    def _tag(fn, kind, flops=0.0, nbytes=0.0):
+    def _tag(fn, kind, flops=0.0, nbytes=0.0, desc=''):
         """algorithmic work of one launch (bench.py roofline); untagged ops are 'misc'"""
-        fn.kind, fn.flops, fn.nbytes = kind, float(flops), float(nbytes)
+        fn.kind, fn.flops, fn.nbytes, fn.desc = kind, float(flops), float(nbytes), desc
 
     # -- allocation helpers ------------------------------------------------ #
     def planes(self, C, geo):
@@ -488,9 +505,14 @@ class _Plan:
         self.partials = self.f32(STATS_CAP * 2 * cmax)
         self.cnt = ctypes.c_int(0)
         S = lambda: eng.stream
-        Balloc = _ru(B, 8)
+        # fully-connected heads on the tensor cores (bf16/tcgen05 mode): one GEMM per conv stage
+        # computes the LogReg logits and the first router layer from the shared feature matrix
+        self.umma_heads = eng.impl == 1 and n_cls <= 16
+        Balloc = _ru(B, 128) if self.umma_heads else _ru(B, 8)
+        self.Balloc = Balloc
         self.node = {}
-        self.reg, self.rtr = {}, {}
+        self.reg, self.rtr, self.heads = {}, {}, {}
+        self.pack_list, self.rt_fwd, self.keep, self.kplanes = [], [], [], []
         cpad_q = 16 if dt == BF16 else 8
         dyn_k = eng.dynamic and bool(net.hypers.dyn_k_cpt)
 
@@ -516,23 +538,39 @@ class _Plan:
                 par = self.node[nd.parent]
                 fc = lay.comps[1]
                 eps = float(lay.comps[3].hypers.ε)
-                r = Ns(Z=self.f32(B, n_cls), prob=self.f32(B, n_cls), c_err=self.f32(B), d_cor=self.f32(B),
-                       dZ=self.f32(B, n_cls) if bwd else None, fc=fc, eps=eps)
+                if self.umma_heads:
+                    hd = self.heads[nd.parent]          # logits come from the parent's head GEMM
+                    r = Ns(Zbuf=hd.Z16, Z=hd.Z16[:, :n_cls], ldz=16, prob=self.f32(B, n_cls),
+                           c_err=self.f32(B), d_cor=self.f32(B), dZ=None, fc=fc, eps=eps)
+                else:
+                    zb = self.f32(B, n_cls)
+                    r = Ns(Zbuf=zb, Z=zb, ldz=n_cls, prob=self.f32(B, n_cls), c_err=self.f32(B),
+                           d_cor=self.f32(B), dZ=self.f32(B, n_cls) if bwd else None, fc=fc, eps=eps)
+                    F = par.F
+                    self.fwd_ops.append(lambda par=par, r=r, fc=fc, F=F: L.fc_fwd(
+                        _vp(par.feat), F, Balloc, B, eng.tptr(fc.params.w), eng.tptr(fc.params.b), None,
+                        n_cls, _vp(r.Zbuf), dt, S()))
                 self.reg[nd.idx] = r
-                F = par.F
-                self.fwd_ops.append(lambda par=par, r=r, fc=fc, F=F: L.fc_fwd(
-                    _vp(par.feat), F, Balloc, B, eng.tptr(fc.params.w), eng.tptr(fc.params.b), None,
-                    n_cls, _vp(r.Z), dt, S()))
                 self.fwd_ops.append(lambda r=r: L.softmax_ce_fwd(
-                    _vp(r.Z), _vp(self.y), B, n_cls, r.eps, _vp(r.prob), _vp(r.c_err), _vp(r.d_cor), S()))
+                    _vp(r.Zbuf), r.ldz, _vp(self.y), B, n_cls, r.eps, _vp(r.prob), _vp(r.c_err), _vp(r.d_cor), S()))
             if nd.router is not None:
-                self._build_router_fwd(nd, Balloc, dyn_k)
+                self._build_router_fwd(nd, Balloc, dyn_k, emit_fc=not self.umma_heads)
+            if nd.kind == 'rcm' and self.umma_heads and getattr(st, 'feat', None) is not None:
+                self._build_heads_fwd(nd, st, dyn_k)
 
-        # ---------------- routing ---------------- #
+        # ---------------- routers (all tails in one launch), routing ---------------- #
+        if self.rt_fwd:
+            bn0 = self.rtr[eng.switches[0].idx].bn1
+            tab = self._desc_table(_RT_FWD, self.rt_fwd)
+            self.keep.append(tab)
+            self.fwd_ops.append(lambda: L.router_tail_fwd_batched(
+                _vp(tab), len(self.rt_fwd), B, 16, float(bn0.hypers.d), float(bn0.hypers.ε),
+                1 if self.bn_train else 0, S()))
         if eng.dynamic:
             self._build_routing()
 
         if not bwd:
+            self._finish_pack()
             return
         # ---------------- backward ---------------- #
         if eng.dynamic:
@@ -548,18 +586,31 @@ class _Plan:
             n_theta = eng.n_theta
             self.bwd_ops.append(lambda: L.node_moments(
                 _vp(self.p_tr), len(eng.nodes), B, ctypes.c_void_p(eng.grad.data_ptr() + 4 * n_theta), S()))
+            if eng.switches:
+                # every dR is known right after route_bwd: all router tails backward in one launch
+                rows = [self._router_bwd_desc(nd) for nd in eng.switches]
+                tabb = self._desc_table(_RT_BWD, rows)
+                self.keep.append(tabb)
+                self.bwd_ops.append(lambda: L.router_tail_bwd_batched(_vp(tabb), len(rows), B, 16, S()))
         for nd in reversed(eng.nodes):
             if nd.kind == 'reg':
                 r = self.reg[nd.idx]
                 par = self.node[nd.parent]
                 coef = (lambda nd=nd: ctypes.c_void_p(self.p_tr.data_ptr() + 4 * nd.idx * B)) if eng.dynamic \
                     else (lambda: None)
-                self.bwd_ops.append(lambda r=r, coef=coef: L.softmax_ce_bwd(
-                    _vp(r.prob), _vp(self.y), B, n_cls, r.eps, coef(), 1.0 / B, _vp(r.dZ), S()))
-                self.bwd_ops.append(lambda r=r, par=par: L.fc_bwd_weight(
-                    _vp(par.feat), par.F, Balloc, B, None, _vp(r.dZ), n_cls,
-                    eng.gptr(r.fc.params.w), eng.gptr(r.fc.params.b), dt, S()))
-            if nd.router is not None:
+                if self.umma_heads:
+                    hd = self.heads[nd.parent]
+                    dzp = ctypes.c_void_p(hd.dZ.data_ptr() + (hd.leaf_off // 8) * Balloc * 16)
+                    self.bwd_ops.append(lambda r=r, coef=coef, dzp=dzp: L.softmax_ce_bwd(
+                        _vp(r.prob), _vp(self.y), B, n_cls, r.eps, coef(), 1.0 / B, None,
+                        dzp, Balloc, eng.gptr(r.fc.params.b), S()))
+                else:
+                    self.bwd_ops.append(lambda r=r, coef=coef: L.softmax_ce_bwd(
+                        _vp(r.prob), _vp(self.y), B, n_cls, r.eps, coef(), 1.0 / B, _vp(r.dZ), None, 0, None, S()))
+                    self.bwd_ops.append(lambda r=r, par=par: L.fc_bwd_weight(
+                        _vp(par.feat), par.F, Balloc, B, None, _vp(r.dZ), n_cls,
+                        eng.gptr(r.fc.params.w), eng.gptr(r.fc.params.b), dt, S()))
+            if nd.router is not None and not self.umma_heads:
                 self._build_router_bwd(nd, Balloc, dyn_k)
             if nd.kind == 'rcm':
                 self._build_rcm_bwd(nd, Balloc)
@@ -569,6 +620,125 @@ class _Plan:
         self.opt_ops.append(lambda: L.talr_momentum_step(
             _vp(eng.theta), _vp(eng.grad), _vp(eng.accum), eng.n_theta, _vp(eng.seg_start), _vp(eng.seg_node),
             _vp(eng.seg_mult), _vp(eng.seg_l2), eng.n_seg, stats_ptr(), talr, _vp(eng.hyp), S()))
+        self._finish_pack()
+
+    # -- descriptor tables (device arrays of C structs, see include/mpnn.h) -- #
+    def _desc_table(self, dtype, rows):
+        arr = np.zeros(len(rows), dtype=dtype)
+        for i, row in enumerate(rows):
+            for k, v in row.items():
+                if isinstance(v, ctypes.c_void_p):
+                    v = v.value or 0
+                elif isinstance(v, torch.Tensor):
+                    v = v.data_ptr()
+                arr[i][k] = 0 if v is None else v
+        return torch.from_numpy(arr.view(np.uint8).copy()).to(self.eng.dev)
+
+    def _finish_pack(self):
+        """one launch packs every conv weight tensor of the step (fwd + dgrad operands)"""
+        if not self.pack_list:
+            return
+        eng, L = self.eng, self.eng.L
+        tab = self._desc_table(_PACK, self.pack_list)
+        self.keep.append(tab)
+        n = len(self.pack_list)
+        self.pack_ops.append(lambda: L.pack_weights_batched(_vp(tab), n, 32, eng.dtype, eng.stream))
+
+    def _pack(self, param, packed, I, O, mode, k_off, Ktot, n_off, Ntot, ntaps=9):
+        """mode 0: forward operand, 1: dgrad operand (transposed, taps flipped), 2: fp32 vector copy"""
+        self.pack_list.append(dict(w=self.eng.tptr(param), packed=packed, ntaps=ntaps, I=I, O=O, mode=mode,
+                                   k_off=k_off, Ktot=Ktot, n_off=n_off, Ntot=Ntot))
+
+    # -- fully-connected heads on the tensor cores ---------------------------- #
+    def _build_heads_fwd(self, nd, st, dyn_k):
+        """One tcgen05 GEMM per conv stage: [LogReg logits | first router layer] = X @ [W_leaf | W_r1] + b
+        (lib/layer_types.py:39-53 twice, sharing the flattened coarsest scale X)."""
+        eng, L, B, Balloc = self.eng, self.eng.L, self.B, self.Balloc
+        S = lambda: eng.stream
+        n_cls = eng.net.hypers.y_shape[0]
+        leaves = [k for k in nd.kids if eng.nodes[k].kind == 'reg']
+        if len(leaves) > 1:
+            raise NotImplementedError('engine: more than one LogReg under one node')
+        rt = self.rtr.get(nd.idx)
+        hd = Ns(leaf_off=0 if leaves else None, r_off=(16 if leaves else 0) if rt is not None else None)
+        hd.N = 16 * (bool(leaves) + (rt is not None))
+        F, Fext = st.F, st.Fext
+        hd.Z16 = self.f32(B, 16) if leaves else None
+        hd.Wfc = torch.zeros((1, Fext // 8, hd.N, 8), dtype=eng.tdtype, device=eng.dev)
+        hd.bias = self.f32(hd.N)
+        hd.dZ = torch.zeros((hd.N // 8, Balloc, 8), dtype=eng.tdtype, device=eng.dev) if self.need_bwd else None
+        if leaves:
+            fc = eng.nodes[leaves[0]].layer.comps[1]
+            hd.fc_leaf = fc
+            self._pack(fc.params.w, hd.Wfc, F, n_cls, 0, 0, Fext, hd.leaf_off, hd.N, ntaps=1)
+            self._pack(fc.params.b, hd.bias, 1, n_cls, 2, 0, 8, hd.leaf_off, hd.N, ntaps=1)
+        if rt is not None:
+            rows = F + (1 if dyn_k else 0)
+            self._pack(rt.fc1.params.w, hd.Wfc, rows, 16, 0, 0, Fext, hd.r_off, hd.N, ntaps=1)
+            self._pack(rt.fc1.params.b, hd.bias, 1, 16, 2, 0, 8, hd.r_off, hd.N, ntaps=1)
+        outs = [(hd.Z16, 16)] if leaves else []
+        if rt is not None:
+            outs.append((rt.Z1, 16))
+        outs.append((None, 0))
+        (o0, n0), (o1, n1) = outs[0], outs[1]
+        self.heads[nd.idx] = hd
+
+        def gemm():
+            L.stencil_gemm(_vp(st.feat), Fext, None, 0, _vp(hd.Wfc), 1, _vp(hd.bias), _vp(o0), n0, 0, _vp(o1), n1, 0,
+                           B, 0, 0, 0, Balloc, None, 0, None, BF16, 2, 1, S())
+        self._tag(gemm, 'fc_fwd', desc='F%d N%d' % (Fext, hd.N), flops=2.0 * B * F * hd.N, nbytes=B * F * 2)
+        self.fwd_ops.append(gemm)
+
+    def _build_heads_bwd(self, nd, st, dyn_k):
+        eng, L, B, Balloc = self.eng, self.eng.L, self.B, self.Balloc
+        S = lambda: eng.stream
+        n_cls = eng.net.hypers.y_shape[0]
+        hd = self.heads[nd.idx]
+        rt = self.rtr.get(nd.idx)
+        F, Fext = st.F, st.Fext
+        leaf = getattr(hd, 'fc_leaf', None)
+        # weight gradients of both heads in one launch
+        a = (eng.gptr(leaf.params.w), F, n_cls) if leaf is not None else (None, 0, 0)
+        b = (eng.gptr(rt.fc1.params.w), F + (1 if dyn_k else 0), 16) if rt is not None else (None, 0, 0)
+        if leaf is None:
+            a, b = b, (None, 0, 0)
+
+        def wgrad():
+            L.fc_wgrad(_vp(st.feat), Fext, Balloc, B, _vp(hd.dZ), hd.N, 16, a[0], a[1], a[2], b[0], b[1], b[2], S())
+        self._tag(wgrad, 'fc_wgrad', desc='F%d N%d' % (Fext, hd.N), flops=2.0 * B * F * hd.N, nbytes=B * F * 2)
+        self.bwd_ops.append(wgrad)
+        # data gradient towards the flattened coarsest scale
+        hd.Wfd = torch.zeros((1, hd.N // 8, F, 8), dtype=eng.tdtype, device=eng.dev)
+        if leaf is not None:
+            self._pack(leaf.params.w, hd.Wfd, F, n_cls, 1, hd.leaf_off, hd.N, 0, F, ntaps=1)
+        if rt is not None:
+            self._pack(rt.fc1.params.w, hd.Wfd, F, 16, 1, hd.r_off, hd.N, 0, F, ntaps=1)
+        st.dfeat = torch.zeros((F // 8, Balloc, 8), dtype=eng.tdtype, device=eng.dev)
+
+        def dgrad():
+            L.stencil_gemm(_vp(hd.dZ), hd.N, None, 0, _vp(hd.Wfd), 1, None, _vp(st.dfeat), F, 0, None, 0, 0,
+                           B, 0, 0, 0, Balloc, None, 0, None, BF16, BF16, 1, S())
+        self._tag(dgrad, 'fc_dgrad', desc='N%d F%d' % (hd.N, F), flops=2.0 * B * F * hd.N, nbytes=B * F * 2)
+        self.bwd_ops.append(dgrad)
+
+    def _router_bwd_desc(self, nd):
+        eng = self.eng
+        rt = self.rtr[nd.idx]
+        P = lambda lay, k: eng.tptr(getattr(lay.params, k))
+        Gp = lambda lay, k: eng.gptr(getattr(lay.params, k))
+        return dict(Z1=rt.Z1, Z2=rt.Z2, dR=rt.dR, g1=P(rt.bn1, 'γ'), b1=P(rt.bn1, 'β'), W2=P(rt.fc2, 'w'),
+                    g2=P(rt.bn2, 'γ'), b2=P(rt.bn2, 'β'), W3=P(rt.fc3, 'w'), save=rt.save,
+                    dg1=Gp(rt.bn1, 'γ'), dbt1=Gp(rt.bn1, 'β'), dW2=Gp(rt.fc2, 'w'), dbias2=Gp(rt.fc2, 'b'),
+                    dg2=Gp(rt.bn2, 'γ'), dbt2=Gp(rt.bn2, 'β'), dW3=Gp(rt.fc3, 'w'), dbias3=Gp(rt.fc3, 'b'),
+                    dZ1=rt.dZ1, scratch=rt.scratch, ns=rt.ns, Balloc=self.Balloc,
+                    dZ1p=self._router_planes(nd), dbias1=Gp(rt.fc1, 'b') if self.umma_heads else None)
+
+    def _router_planes(self, nd):
+        """bf16 planes slot of dZ1 inside the node's head-gradient operand (tcgen05 heads only)"""
+        if not self.umma_heads:
+            return None
+        hd = self.heads[nd.idx]
+        return ctypes.c_void_p(hd.dZ.data_ptr() + (hd.r_off // 8) * self.Balloc * 16)
 
     # -- conv stage -------------------------------------------------------- #
     def _build_rcm_fwd(self, nd, st, Balloc):
@@ -612,8 +782,15 @@ class _Plan:
             sc.feat = None
             if k == n - 1 and has_heads:
                 st.F = geo.H * geo.W * N
-                sc.feat = torch.zeros((st.F // 8, Balloc, 8), dtype=eng.tdtype, device=eng.dev)
+                # tcgen05 heads with a per-example k_cpt feature (net_types.py:149-160): the feature
+                # alpha_cpt*k_cpt lives in channel 0 of one extra (16-aligned) pair of planes
+                ext = 16 if (self.umma_heads and nd.router is not None and eng.dynamic
+                             and bool(eng.net.hypers.dyn_k_cpt)) else 0
+                st.Fext = st.F + ext
+                sc.feat = torch.zeros((st.Fext // 8, Balloc, 8), dtype=eng.tdtype, device=eng.dev)
                 st.feat = sc.feat
+                if ext:
+                    self.kplanes.append(sc.feat[st.F // 8, :, 0])
             sc.Wf = torch.zeros((9, (K0 + K1) // 8, N, 8), dtype=eng.tdtype, device=eng.dev)
             sc.ss = self.f32(2, N)
             sc.mr = self.f32(2, N)
@@ -624,11 +801,9 @@ class _Plan:
             sc.wh, sc.wv, sc.bk = wh, wv, bk
             if tuple(wh.shape[:2]) != (3, 3):
                 raise NotImplementedError('engine: conv window %s' % (wh.shape[:2],))
-            self.pack_ops.append(lambda sc=sc, wh=wh: L.pack_weights(
-                eng.tptr(wh), 9, sc.K0real, sc.N, 0, 0, sc.K0 + sc.K1, 0, sc.N, _vp(sc.Wf), dt, S()))
+            self._pack(wh, sc.Wf, sc.K0real, sc.N, 0, 0, sc.K0 + sc.K1, 0, sc.N)
             if wv is not None:
-                self.pack_ops.append(lambda sc=sc, wv=wv: L.pack_weights(
-                    eng.tptr(wv), 9, sc.K1, sc.N, 0, sc.K0, sc.K0 + sc.K1, 0, sc.N, _vp(sc.Wf), dt, S()))
+                self._pack(wv, sc.Wf, sc.K1, sc.N, 0, sc.K0, sc.K0 + sc.K1, 0, sc.N)
             prev = st.sc[k - 1] if k > 0 else None
             use_stats = sc.live and train
 
@@ -637,7 +812,7 @@ class _Plan:
                                _vp(sc.Wf), 9, eng.tptr(sc.bk), _vp(sc.lin), sc.N, 0, None, 0, 0,
                                *sc.geo.args(), _vp(self.partials) if use_stats else None, STATS_CAP,
                                ctypes.byref(self.cnt), dt, dt, impl, S())
-            self._tag(conv, 'conv_fwd', flops=2.0 * B * sc.geo.H * sc.geo.W * 9 * (sc.K0real + sc.K1) * sc.N,
+            self._tag(conv, 'conv_fwd', desc='H%d K%d+%d N%d' % (sc.geo.H, sc.K0, sc.K1, sc.N), flops=2.0 * B * sc.geo.H * sc.geo.W * 9 * (sc.K0real + sc.K1) * sc.N,
                       nbytes=B * sc.geo.H * sc.geo.W * (sc.K0 + sc.K1 + sc.N) * (2 if dt == BF16 else 4))
             self.fwd_ops.append(conv)
             if sc.live:
@@ -673,7 +848,9 @@ class _Plan:
         # gradient of the heads wrt the flattened coarsest scale
         heads = [k for k in nd.kids if eng.nodes[k].kind == 'reg']
         st.dfeat = None
-        if heads or nd.router is not None:
+        if (heads or nd.router is not None) and self.umma_heads:
+            self._build_heads_bwd(nd, st, eng.dynamic and bool(eng.net.hypers.dyn_k_cpt))
+        elif heads or nd.router is not None:
             if len(heads) > 1:
                 raise NotImplementedError('engine: more than one LogReg under one node')
             st.dfeat = torch.zeros_like(st.feat)
@@ -715,7 +892,8 @@ class _Plan:
                 L.bn_relu_pool_bwd(_vp(sc.lin), _vp(dact), _vp(dfeat), Balloc, _vp(dpooled),
                                    sc.geo_p.P if dpooled is not None else 0,
                                    _vp(sc.ss) if live else None, _vp(sc.mr), _vp(sc.sums),
-                                   float(B * sc.geo.H * sc.geo.W), sc.N, *sc.geo.args(), _vp(sc.dlin), dt, S())
+                                   float(B * sc.geo.H * sc.geo.W), sc.N, *sc.geo.args(), _vp(sc.dlin),
+                                   eng.gptr(sc.bk), dt, S())
             self._tag(elt, 'bn_bwd', nbytes=B * sc.geo.H * sc.geo.W * sc.N * (2 if dt == BF16 else 4) * 3)
             self.bwd_ops.append(elt)
             prev = st.sc[k - 1] if k > 0 else None
@@ -724,9 +902,9 @@ class _Plan:
                 L.stencil_wgrad(_vp(sc.src.t), sc.K0, sc.K0real, eng.gptr(sc.wh),
                                 _vp(prev.pooled) if prev is not None else None, sc.K1, sc.K1,
                                 eng.gptr(sc.wv) if sc.wv is not None else None,
-                                _vp(sc.dlin), sc.N, sc.N, eng.gptr(sc.bk), 9, *sc.geo.args(), dt,
+                                _vp(sc.dlin), sc.N, sc.N, None, 9, *sc.geo.args(), dt,   # db: see bn_relu_pool_bwd
                                 eng.impl_w if (sc.K0 + sc.K1 <= 128 and sc.N <= 256) else 0, S())
-            self._tag(wgrad, 'conv_wgrad', flops=2.0 * B * sc.geo.H * sc.geo.W * 9 * (sc.K0real + sc.K1) * sc.N,
+            self._tag(wgrad, 'conv_wgrad', desc='H%d K%d+%d N%d' % (sc.geo.H, sc.K0, sc.K1, sc.N), flops=2.0 * B * sc.geo.H * sc.geo.W * 9 * (sc.K0real + sc.K1) * sc.N,
                       nbytes=B * sc.geo.H * sc.geo.W * (sc.K0 + sc.K1 + sc.N) * (2 if dt == BF16 else 4))
             self.bwd_ops.append(wgrad)
             # data gradient: towards the parent's activation (N0) and the pooled predecessor (N1)
@@ -736,11 +914,9 @@ class _Plan:
                 continue
             sc.Wd = torch.zeros((9, sc.N // 8, N0 + N1, 8), dtype=eng.tdtype, device=eng.dev)
             if N0:
-                self.pack_ops.append(lambda sc=sc, N0=N0, N1=N1: L.pack_weights(
-                    eng.tptr(sc.wh), 9, sc.K0real, sc.N, 1, 0, sc.N, 0, N0 + N1, _vp(sc.Wd), dt, S()))
+                self._pack(sc.wh, sc.Wd, sc.K0real, sc.N, 1, 0, sc.N, 0, N0 + N1)
             if N1:
-                self.pack_ops.append(lambda sc=sc, N0=N0, N1=N1: L.pack_weights(
-                    eng.tptr(sc.wv), 9, sc.K1, sc.N, 1, 0, sc.N, N0, N0 + N1, _vp(sc.Wd), dt, S()))
+                self._pack(sc.wv, sc.Wd, sc.K1, sc.N, 1, 0, sc.N, N0, N0 + N1)
             acc0 = 0
             out0 = None
             if N0:
@@ -757,12 +933,12 @@ class _Plan:
                 L.stencil_gemm(_vp(sc.dlin), sc.N, None, 0, _vp(sc.Wd), 9, None,
                                _vp(out0), N0, acc0, _vp(prev.dpooled) if N1 else None, N1, 0,
                                *sc.geo.args(), None, 0, None, dt, dt, impl, S())
-            self._tag(dgrad, 'conv_dgrad', flops=2.0 * B * sc.geo.H * sc.geo.W * 9 * sc.N * (N0 + N1),
+            self._tag(dgrad, 'conv_dgrad', desc='H%d K%d N%d+%d' % (sc.geo.H, sc.N, N0, N1), flops=2.0 * B * sc.geo.H * sc.geo.W * 9 * sc.N * (N0 + N1),
                       nbytes=B * sc.geo.H * sc.geo.W * (sc.N + N0 + N1) * (2 if dt == BF16 else 4))
             self.bwd_ops.append(dgrad)
 
     # -- router ------------------------------------------------------------ #
-    def _build_router_fwd(self, nd, Balloc, dyn_k):
+    def _build_router_fwd(self, nd, Balloc, dyn_k, emit_fc=True):
         eng, L, B = self.eng, self.eng.L, self.B
         dt = eng.dtype
         S = lambda: eng.stream
@@ -780,16 +956,16 @@ class _Plan:
                 dR=self.f32(B, ns) if bwd else None, dZ1=self.f32(B, 16) if bwd else None,
                 scratch=self.f32(2 * B * 16) if bwd else None)
         self.rtr[nd.idx] = rt
-        train = 1 if self.bn_train else 0
-        self.fwd_ops.append(lambda: L.fc_fwd(
-            _vp(st.feat), st.F, Balloc, B, eng.tptr(fc1.params.w), eng.tptr(fc1.params.b),
-            _vp(self.kextra) if dyn_k else None, 16, _vp(rt.Z1), dt, S()))
+        if emit_fc:
+            self.fwd_ops.append(lambda: L.fc_fwd(
+                _vp(st.feat), st.F, Balloc, B, eng.tptr(fc1.params.w), eng.tptr(fc1.params.b),
+                _vp(self.kextra) if dyn_k else None, 16, _vp(rt.Z1), dt, S()))
         P = lambda lay, k: eng.tptr(getattr(lay.params, k))
-        self.fwd_ops.append(lambda: L.router_tail_fwd(
-            _vp(rt.Z1), B, 16, P(bn1, 'γ'), P(bn1, 'β'), P(bn1, 'm_avg'), P(bn1, 'v_avg'),
-            P(fc2, 'w'), P(fc2, 'b'), P(bn2, 'γ'), P(bn2, 'β'), P(bn2, 'm_avg'), P(bn2, 'v_avg'),
-            P(fc3, 'w'), P(fc3, 'b'), ns, float(bn1.hypers.d), float(bn1.hypers.ε), train,
-            _vp(rt.Z2), _vp(rt.R), _vp(rt.save), S()))
+        # the tails of all routers run as ONE launch after the conv pipeline (see _build)
+        self.rt_fwd.append(dict(
+            Z1=rt.Z1, g1=P(bn1, 'γ'), b1=P(bn1, 'β'), m1=P(bn1, 'm_avg'), v1=P(bn1, 'v_avg'),
+            W2=P(fc2, 'w'), bias2=P(fc2, 'b'), g2=P(bn2, 'γ'), b2=P(bn2, 'β'), m2=P(bn2, 'm_avg'),
+            v2=P(bn2, 'v_avg'), W3=P(fc3, 'w'), bias3=P(fc3, 'b'), Z2=rt.Z2, R=rt.R, save=rt.save, ns=ns))
 
     def _build_router_bwd(self, nd, Balloc, dyn_k):
         eng, L, B = self.eng, self.eng.L, self.B
@@ -797,15 +973,8 @@ class _Plan:
         S = lambda: eng.stream
         st = self.node[nd.idx]
         rt = self.rtr[nd.idx]
-        P = lambda lay, k: eng.tptr(getattr(lay.params, k))
         Gp = lambda lay, k: eng.gptr(getattr(lay.params, k))
-        self.bwd_ops.append(lambda: L.router_tail_bwd(
-            _vp(rt.Z1), _vp(rt.Z2), _vp(rt.dR), B, 16, rt.ns,
-            P(rt.bn1, 'γ'), P(rt.bn1, 'β'), P(rt.fc2, 'w'), P(rt.bn2, 'γ'), P(rt.bn2, 'β'), P(rt.fc3, 'w'),
-            _vp(rt.save),
-            Gp(rt.bn1, 'γ'), Gp(rt.bn1, 'β'), Gp(rt.fc2, 'w'), Gp(rt.fc2, 'b'),
-            Gp(rt.bn2, 'γ'), Gp(rt.bn2, 'β'), Gp(rt.fc3, 'w'), Gp(rt.fc3, 'b'),
-            _vp(rt.dZ1), _vp(rt.scratch), S()))
+        # (the tail itself ran in the batched launch right after route_bwd)
         self.bwd_ops.append(lambda: L.fc_bwd_weight(
             _vp(st.feat), st.F, Balloc, B, _vp(self.kextra) if dyn_k else None, _vp(rt.dZ1), 16,
             Gp(rt.fc1, 'w'), Gp(rt.fc1, 'b'), dt, S()))

@@ -308,9 +308,13 @@ def test_bn_relu_pool_fwd_bwd(dt, pool):
     sums = torch.zeros((2, C), device='cuda'); dg = torch.zeros(C, device='cuda'); dbt = torch.zeros(C, device='cuda')
     L().bn_bwd_finalize(vp(parts), cnt.value, C, vp(sums), vp(dg), vp(dbt), None)
     dlin = torch.zeros_like(LIN)
+    dbias = torch.zeros(C, device='cuda')
     L().bn_relu_pool_bwd(vp(LIN), vp(DY), vp(DF), Balloc, vp(DP), gp.P if pool else 0, vp(ss), vp(mr), vp(sums),
-                         float(B * H * H), C, B, H, H, geo.G, geo.P, vp(dlin), dt, None)
+                         float(B * H * H), C, B, H, H, geo.G, geo.P, vp(dlin), vp(dbias), dt, None)
     torch.cuda.synchronize()
+    got_dlin = from_planes(dlin.float().cpu().numpy(), geo, C)
+    np.testing.assert_allclose(dbias.cpu().numpy(), got_dlin.sum((0, 1, 2)), rtol=2e-2,
+                               atol=2e-3 if dt == F32 else 0.2)     # dLin itself is bf16-rounded
     gtot = torch.tensor(dy, dtype=torch.float64) + (torch.tensor(df, dtype=torch.float64) if df is not None else 0)
     loss = (yt * gtot).sum()
     if pool:
@@ -370,10 +374,17 @@ def test_softmax_ce():
     coef = rng.random(B).astype(np.float32)
     Z, Y = dev(z), dev(y)
     prob = torch.zeros_like(Z); ce = torch.zeros(B, device='cuda'); dc = torch.zeros(B, device='cuda')
-    L().softmax_ce_fwd(vp(Z), vp(Y), B, n, 1e-6, vp(prob), vp(ce), vp(dc), None)
+    L().softmax_ce_fwd(vp(Z), n, vp(Y), B, n, 1e-6, vp(prob), vp(ce), vp(dc), None)
     dZ = torch.zeros_like(Z)
-    L().softmax_ce_bwd(vp(prob), vp(Y), B, n, 1e-6, vp(dev(coef)), 1.0 / B, vp(dZ), None)
+    Balloc = 128
+    dZp = torch.zeros((2, Balloc, 8), dtype=torch.bfloat16, device='cuda')
+    dbias = torch.zeros(n, device='cuda')
+    L().softmax_ce_bwd(vp(prob), vp(Y), B, n, 1e-6, vp(dev(coef)), 1.0 / B, vp(dZ), vp(dZp), Balloc, vp(dbias), None)
     torch.cuda.synchronize()
+    planes = dZp.float().cpu().numpy()
+    got_p = np.concatenate([planes[0, :B], planes[1, :B]], 1)
+    assert rel_err(got_p[:, :n], dZ.cpu().numpy()) < 4e-3 and np.all(got_p[:, n:] == 0) and np.all(planes[:, B:] == 0)
+    np.testing.assert_allclose(dbias.cpu().numpy(), dZ.cpu().numpy().sum(0), rtol=1e-4, atol=1e-6)
     zt = torch.tensor(z, dtype=torch.float64, requires_grad=True)
     p = torch.softmax(zt, 1)
     c = -(torch.tensor(y, dtype=torch.float64) * torch.log(1e-6 / n + (1 - 1e-6) * p)).sum(1)
@@ -569,3 +580,71 @@ def test_route_fwd_bwd(kind, hy):
     for nd in eng.switches:
         got = plan.rtr[nd.idx].dR.cpu().numpy()
         assert rel_err(got, Rt[nd.idx].grad.numpy()) < 1e-4, nd.idx
+
+
+# --------------------------------------------------------------------------- #
+# fully-connected heads on the tensor cores (ntaps = 1, K streamed in slices)
+# --------------------------------------------------------------------------- #
+@pytest.mark.parametrize('B,F,n_cls,dyn', [(40, 256, 10, False), (300, 2048, 10, True), (129, 512, 2, False)])
+def test_fc_heads_umma(B, F, n_cls, dyn):
+    rng = np.random.default_rng(14)
+    Balloc = (B + 127) // 128 * 128
+    Fext = F + (16 if dyn else 0)
+    x = bf16_round(rng.standard_normal((B, F)).astype(np.float32))
+    kx = bf16_round(rng.random(B).astype(np.float32)) if dyn else None
+    Wl = (rng.standard_normal((F, n_cls)) / 10).astype(np.float32)
+    Wr = (rng.standard_normal((F + (1 if dyn else 0), 16)) / 10).astype(np.float32)
+    bl = rng.standard_normal(n_cls).astype(np.float32); br = rng.standard_normal(16).astype(np.float32)
+    X = np.zeros((Fext // 8, Balloc, 8), np.float32)
+    for i in range(F // 8):
+        X[i, :B] = x[:, i * 8:(i + 1) * 8]
+    if dyn:
+        X[F // 8, :B, 0] = kx
+    X = dev(X, torch.bfloat16)
+    # pack [W_leaf | W_r1] and the bias vector with the batched packer
+    Wfc = torch.zeros((1, Fext // 8, 32, 8), dtype=torch.bfloat16, device='cuda')
+    bias = torch.zeros(32, device='cuda')
+    dWl, dWr, dbl, dbr = dev(Wl), dev(Wr), dev(bl), dev(br)
+    desc = np.zeros(4, dtype=np.dtype([('w', '<u8'), ('packed', '<u8')] + [(k, '<i4') for k in (
+        'ntaps', 'I', 'O', 'mode', 'k_off', 'Ktot', 'n_off', 'Ntot')], align=True))
+    desc[0] = (dWl.data_ptr(), Wfc.data_ptr(), 1, F, n_cls, 0, 0, Fext, 0, 32)
+    desc[1] = (dWr.data_ptr(), Wfc.data_ptr(), 1, Wr.shape[0], 16, 0, 0, Fext, 16, 32)
+    desc[2] = (dbl.data_ptr(), bias.data_ptr(), 1, 1, n_cls, 2, 0, 8, 0, 32)
+    desc[3] = (dbr.data_ptr(), bias.data_ptr(), 1, 1, 16, 2, 0, 8, 16, 32)
+    D = dev(desc.view(np.uint8))
+    L().pack_weights_batched(vp(D), 4, 8, BF16, None)
+    Z16 = torch.zeros((B, 16), device='cuda'); Z1 = torch.zeros((B, 16), device='cuda')
+    L().stencil_gemm(vp(X), Fext, None, 0, vp(Wfc), 1, vp(bias), vp(Z16), 16, 0, vp(Z1), 16, 0,
+                     B, 0, 0, 0, Balloc, None, 0, None, BF16, 2, 1, None)
+    torch.cuda.synchronize()
+    xf = np.concatenate([x, kx[:, None]], 1) if dyn else x
+    ref_l = x.astype(np.float64) @ bf16_round(Wl) + bl
+    ref_r = xf.astype(np.float64) @ bf16_round(Wr) + br
+    assert rel_err(Z16.cpu().numpy()[:, :n_cls], ref_l) < 1e-4
+    assert rel_err(Z1.cpu().numpy(), ref_r) < 1e-4
+    # backward: dZ planes [4][Balloc][8]
+    dz = bf16_round(rng.standard_normal((B, 32)).astype(np.float32))
+    dz[:, n_cls:16] = 0
+    P = np.zeros((4, Balloc, 8), np.float32)
+    for i in range(4):
+        P[i, :B] = dz[:, i * 8:(i + 1) * 8]
+    P = dev(P, torch.bfloat16)
+    gWl = torch.zeros_like(dWl); gWr = torch.zeros_like(dWr)
+    L().fc_wgrad(vp(X), Fext, Balloc, B, vp(P), 32, 16, vp(gWl), F, n_cls, vp(gWr), Wr.shape[0], 16, None)
+    torch.cuda.synchronize()
+    assert rel_err(gWl.cpu().numpy(), x.astype(np.float64).T @ dz[:, :n_cls]) < 1e-4
+    assert rel_err(gWr.cpu().numpy(), xf.astype(np.float64).T @ dz[:, 16:]) < 1e-4
+    Wfd = torch.zeros((1, 4, F, 8), dtype=torch.bfloat16, device='cuda')
+    desc2 = desc[:2].copy()
+    desc2[0] = (dWl.data_ptr(), Wfd.data_ptr(), 1, F, n_cls, 1, 0, 32, 0, F)
+    desc2[1] = (dWr.data_ptr(), Wfd.data_ptr(), 1, F, 16, 1, 16, 32, 0, F)
+    D2 = dev(desc2.view(np.uint8))
+    L().pack_weights_batched(vp(D2), 2, 8, BF16, None)
+    dX = torch.zeros((F // 8, Balloc, 8), dtype=torch.bfloat16, device='cuda')
+    L().stencil_gemm(vp(P), 32, None, 0, vp(Wfd), 1, None, vp(dX), F, 0, None, 0, 0,
+                     B, 0, 0, 0, Balloc, None, 0, None, BF16, BF16, 1, None)
+    torch.cuda.synchronize()
+    f = dX.float().cpu().numpy()
+    got = np.concatenate([f[i, :B] for i in range(F // 8)], 1)
+    ref = dz[:, :n_cls].astype(np.float64) @ bf16_round(Wl).T + dz[:, 16:].astype(np.float64) @ bf16_round(Wr[:F]).T
+    assert rel_err(got, ref) < 4e-3

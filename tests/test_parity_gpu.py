@@ -27,7 +27,9 @@ from util import batch, node_paths, randomize_routers, record_of, rel_err, tiny_
 pytestmark = pytest.mark.gpu
 
 TOL = {'fp32': dict(fwd=1e-3, grad=1e-3, margin=1e-4, step=2e-3),
-       'bf16': dict(fwd=3e-2, grad=1.5e-1, margin=5e-2, step=1e-1)}
+       # 'step': zero-initialised parameters (biases, beta) after 3 steps ARE accumulated gradients,
+       # i.e. sums with heavy cancellation of bf16-rounded terms -- noise-dominated in bf16
+       'bf16': dict(fwd=3e-2, grad=1.5e-1, margin=5e-2, step=3.5e-1)}
 
 
 def _nets(kind, hy, seed=0):
