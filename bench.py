@@ -154,7 +154,7 @@ def main():
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=5)
-    ap.add_argument('--batch', type=int, default=int(os.environ.get('MPNN_BENCH_BATCH', 1024)),
+    ap.add_argument('--batch', type=int, default=int(os.environ.get('MPNN_BENCH_BATCH', 2048)),
                     help='examples per GPU per step (reference trains at 128; see DESIGN.md)')
     ap.add_argument('--precision', default=os.environ.get('MPNN_PRECISION', 'bf16'))
     ap.add_argument('--impl', default='ours')

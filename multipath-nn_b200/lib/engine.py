@@ -358,7 +358,8 @@ class Engine:
         self._run(plan.bwd_ops)
         if update:
             if self.dist:
-                torch.distributed.all_reduce(self.grad)
+                from lib.parallel import allreduce_flat_
+                allreduce_flat_(self.grad)       # gradients + TALR moments, one collective per step
             self._run(plan.opt_ops)
 
     def _capture(self, plan):

@@ -1,0 +1,137 @@
+"""CPU-only tests of the host side: the reference-facing API surface, the file
+formats, the planner (dry run) and the C ABI's symbol table.  No GPU compute."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import arch_and_hypers as ah
+from lib import _cabi, desc, layer_types, net_types, serdes
+from lib.data import Dataset, synthetic_archive
+from lib.net_types import params_list_rec
+from util import record_of, tiny_net
+
+
+def _n_params(net):
+    return sum(p.value.size for l in net.layers
+               for p in list(params_list_rec(l)) + list(params_list_rec(l.router)) if p.trainable)
+
+
+def test_architecture_counts_match_survey():
+    """680,798 / 531,594 trainable parameters, 20,699,872 / 20,551,424 MAC per image."""
+    ac = ah.ac_chain(k_cpt=1e-9)((32, 32, 3), (10,))
+    sr = ah.sr_chain(8)((32, 32, 3), (10,))
+    assert _n_params(ac) == 680798 and _n_params(sr) == 531594
+    assert sum(l.n_ops + (l.router.n_ops if l.router else 0) for l in ac.layers) == 20699872
+    assert sum(l.n_ops for l in sr.layers) == 20551424
+    assert len(list(ac.layers)) == 17 and len(list(ac.leaves)) == 8 and len(list(ac.switches)) == 7
+    # router last layer is zero-initialised (sigma_w = 0): all decisions tie to sink 0 at init
+    for l in ac.switches:
+        assert not l.router.comps[-1].params.w.value.any()
+
+
+def test_tree_constructors_work():
+    """the reference's *-tree constructors raise NameError; here they build"""
+    net = ah.ac_tree(k_cpt=1e-9)((32, 32, 3), (10,))
+    assert len(list(net.leaves)) > 8 and max(len(l.sinks) for l in net.layers) == 3
+
+
+def test_hyper_keys_follow_python_identifier_normalisation():
+    """`ϵ` (U+03F5) in the reference's source becomes the attribute / record key U+03B5"""
+    net = tiny_net('ac', k_cpt=1e-9)
+    assert 'ε' in vars(net.hypers) and 'ϵ' not in vars(net.hypers)
+    rec = serdes.encode_net(net)
+    assert set(rec) == {'type', 'root', 'hypers', 'params'}
+    assert {'σ_w', 'k_l2', 'n_chan', 'res'} <= set(rec['root']['sinks'][0]['router']['comps'][1]['hypers'])
+
+
+@pytest.mark.parametrize('kind', ['sr', 'ac', 'cr', 'actree'])
+def test_serdes_roundtrip(kind, tmp_path):
+    net = tiny_net(kind, **({} if kind == 'sr' else dict(k_cpt=2e-9)))
+    path = str(tmp_path / 'net.npy')
+    serdes.write_net(path, net)
+    raw = np.load(path, allow_pickle=True)
+    assert raw.shape == () and raw.dtype == object          # np.save of a dict: 0-d object array
+    net2 = serdes.read_net(path)
+
+    def same(a, b):
+        assert a['type'] == b['type'] and a['name'] == b['name'] and a['hypers'] == b['hypers']
+        assert list(a['params']) == list(b['params'])
+        for k in a['params']:
+            assert a['params'][k].dtype == np.float32
+            np.testing.assert_array_equal(a['params'][k], b['params'][k])
+        for x, y in zip(a['comps'] + a['sinks'], b['comps'] + b['sinks']):
+            same(x, y)
+        if a['router'] is not None:
+            same(a['router'], b['router'])
+    ra, rb = serdes.encode_net(net), serdes.encode_net(net2)
+    assert ra['type'] == rb['type'] and ra['hypers'] == rb['hypers']
+    same(ra['root'], rb['root'])
+    # parameter key order of the conv layer follows the reference (layer_types.py:174-179)
+    keys = list(ra['root']['sinks'][0]['comps'][0]['params'])
+    assert keys == ['w_horz_0', 'w_horz_1', 'w_horz_2', 'w_vert_0', 'w_vert_1', 'b_0', 'b_1', 'b_2']
+
+
+def test_net_desc_schema_and_rendering():
+    """nested dict {type, stats_tr, stats_ts, root{name, stats_*, sinks}} and the log text (desc.py:24-79)"""
+    net = tiny_net('ac', k_cpt=1e-9)
+    st = desc.state_tensors(net)
+    leaves = list(net.leaves)
+    assert (net, 'acc') in st and (net, 'moc') in st and (leaves[0], 'p_cor_by_cls') in st
+    fake = {k: (0.5 if k[1] not in ('p_cor_by_cls', 'p_inc_by_cls') else [0.1] * 10) for k in st}
+    d = {'type': 'ActorNet', 'stats_tr': {k: v for (t, k), v in fake.items() if t is net},
+         'stats_ts': {k: v for (t, k), v in fake.items() if t is net},
+         'root': desc.layer_desc(net.root, fake, fake)}
+    assert d['root']['name'] == 'ToPyramid' and d['root']['sinks'][0]['name'] == 'ReConvMax'
+    assert d['root']['sinks'][0]['sinks'][0]['name'] == 'LogReg'          # sinks[0] = classifier leaf
+    text = desc.render_net_desc(d, 'nets/x/0000.npy — Epoch 1')
+    assert text.startswith('┌') and 'Training Set:' in text and '[ActorNet] (acc=0.5; moc=0.5)' in text
+    assert '↳ LogReg (c_err=0.5; p_cor=0.5; p_inc=0.5; p_tr=0.5)' in text
+
+
+def test_dataset_schema_and_augmentation():
+    ds = Dataset(archive=synthetic_archive(64, 32, (32, 32, 3), 10, seed=0), seed=1)
+    assert ds.x0_shape == (32, 32, 3) and ds.y_shape == (10,)
+    x, y = ds.augmented_training_batch(16)
+    assert x.dtype == np.float64 and x.shape == (16, 32, 32, 3) and y.shape == (16, 10)
+    sizes = [len(a) for a, _ in ds.training_set(24)]
+    assert sizes == [24, 24, 16]                                        # ragged tail (data.py:42-47)
+
+
+def test_cabi_exports_every_declared_symbol():
+    protos = _cabi.parse_header()
+    assert len(protos) >= 25 and 'mpnn_stencil_gemm' in protos and 'mpnn_route_fwd' in protos
+    lib = ctypes.CDLL(_cabi.LIB_PATH)
+    for name in protos:
+        assert hasattr(lib, name), name
+    assert _cabi.lib().mpnn_version() >= 100 and _cabi.lib().mpnn_has_umma() == 1
+
+
+def test_no_cpu_fallback():
+    """the product path refuses to run without a CUDA device"""
+    if torch.cuda.is_available():
+        pytest.skip('GPU present')
+    net = tiny_net('sr')
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        net.train.run({net.x0: np.zeros((2, 16, 16, 3), np.float32), net.y: np.eye(10, dtype=np.float32)[:2]})
+
+
+@pytest.mark.parametrize('kind,prec,impl', [('sr', 'fp32', 0), ('ac', 'bf16', 1), ('cr', 'bf16', 1), ('actree', 'fp32', 0)])
+def test_planner_dry_run(kind, prec, impl):
+    from lib.engine import Engine
+    net = tiny_net(kind, **({} if kind == 'sr' else dict(k_cpt=2e-9)))
+    eng = Engine(net, precision=prec, impl=impl, dry_run=True)
+    plan = eng._plan(12, True, True)
+    assert len(plan.pack_ops) == 1 and plan.fwd_ops and plan.bwd_ops and len(plan.opt_ops) == 1
+    assert eng.n_theta >= _n_params(net)
+    kinds = [getattr(op, 'kind', '') for op in plan.fwd_ops + plan.bwd_ops]
+    assert kinds.count('conv_fwd') == 6 * (2 if kind == 'actree' else 1) - (3 if kind == 'actree' else 0)
+    assert kinds.count('conv_wgrad') == kinds.count('conv_fwd')
+    with pytest.raises(RuntimeError, match='CUDA-only'):
+        eng._run(plan.fwd_ops)
+    with pytest.raises(NotImplementedError):
+        from lib.layer_types import Chain, Rect
+        from lib.net_types import SRNet
+        Engine(SRNet(x0_shape=(16, 16, 3), y_shape=(10,), root=Chain(comps=[Rect()])), dry_run=True)
