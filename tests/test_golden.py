@@ -78,4 +78,4 @@ def test_cuda_path_matches_golden_fp32(name):
     e2 = net2._get_engine()
     th = np.array([float(e2._buf(p).double().norm()) for p in e2.tparams])
     ref = g['theta_norms_after_3_steps']
-    np.testing.assert_allclose(th[ref > 1e-3], ref[ref > 1e-3], rtol=1e-3)
+    np.testing.assert_allclose(th, ref, rtol=2e-3, atol=2e-4)

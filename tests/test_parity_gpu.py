@@ -29,7 +29,7 @@ pytestmark = pytest.mark.gpu
 TOL = {'fp32': dict(fwd=1e-3, grad=1e-3, margin=1e-4, step=2e-3),
        # 'step': zero-initialised parameters (biases, beta) after 3 steps ARE accumulated gradients,
        # i.e. sums with heavy cancellation of bf16-rounded terms -- noise-dominated in bf16
-       'bf16': dict(fwd=3e-2, grad=1.5e-1, margin=5e-2, step=3.5e-1)}
+       'bf16': dict(fwd=3e-2, grad=1.5e-1, margin=5e-2, step=1e-1)}
 
 
 def _nets(kind, hy, seed=0):
@@ -150,6 +150,11 @@ def test_training_steps_track_the_oracle(kind, hy, prec):
             # absolute floor: biases in front of train-mode BN have zero gradient, so
             # both sides stay at ~0 and only rounding noise distinguishes them
             d = np.linalg.norm(np.float64(ra) - rb) / max(np.linalg.norm(rb), 1e-3 * np.sqrt(rb.size))
+            if prec == 'bf16' and (k in ('b', 'β') or k.startswith('b_')):
+                # zero-initialised parameters after 3 steps ARE accumulated gradients (sums with
+                # heavy cancellation of bf16-rounded terms): judged as a group below
+                zero_init.append((np.float64(ra).ravel(), np.float64(rb).ravel()))
+                continue
             assert d < tol['step'], (path, a['type'], k, d)
         for i, (x, z) in enumerate(zip(a['comps'], b['comps'])):
             cmp(x, z, path + '.c%d' % i)
@@ -157,7 +162,11 @@ def test_training_steps_track_the_oracle(kind, hy, prec):
             cmp(a['router'], b['router'], path + '.router')
         for i, (x, z) in enumerate(zip(a['sinks'], b['sinks'])):
             cmp(x, z, path + '/%d' % i)
+    zero_init = []
     cmp(got['root'], rec['root'], '')
+    if zero_init and prec == 'bf16':
+        a = np.concatenate([p[0] for p in zero_init]); b = np.concatenate([p[1] for p in zero_init])
+        assert rel_err(a, b) < 0.5
 
 
 @pytest.mark.parametrize('kind,hy', [('sr', {}), ('ac', dict(k_cpt=4e-9)), ('cr', dict(k_cpt=4e-9))])
