@@ -173,7 +173,8 @@ def main():
     dev = torch.device('cuda', local)
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
-        dist.init_process_group('nccl', device_id=dev)
+        import datetime
+        dist.init_process_group('nccl', device_id=dev, timeout=datetime.timedelta(seconds=180))
     B = args.batch
     net = make_net().configure(precision=args.precision, graphs=not args.no_graphs, dist=world > 1)
     eng = net._get_engine()
@@ -192,10 +193,16 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    # ---------------- warm-up (also captures the CUDA graph) ---------------- #
+    def note(msg):
+        if os.environ.get('MPNN_BENCH_VERBOSE'):
+            print('[bench rank %d] %s' % (rank, msg), file=sys.stderr, flush=True)
+
+    # ---------------- warm-up (also captures the CUDA graphs) --------------- #
+    note('warm-up')
     for t in range(args.warmup):
         net.train.run(feed(t))
     barrier()
+    note('warm-up done')
 
     # ---------------- device-resident timing -> value ---------------------- #
     clocks = Clocks(local)
@@ -212,6 +219,7 @@ def main():
         ev[t][1].record()
     barrier()
     launches = (plan.graph_launches * args.steps) if eng.use_graphs else (L.launches - l0)
+    note('device timing done')
     dev_ms = sum(a.elapsed_time(b) for a, b in ev)
     tt = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -233,6 +241,7 @@ def main():
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     e2e_s = float(tt.item())
     clk = clocks.stop() if rank == 0 else None
+    note('e2e done')
 
     # ---------------- per-kernel profile (eager, CUDA events per launch) ---- #
     prof = {}

@@ -347,38 +347,49 @@ class Engine:
             g = self._graphs.get(id(plan))
             if g is None:
                 g = self._capture(plan)
-            g.replay()
+            g[0].replay()                        # pack + forward + backward
+            if self.dist:
+                self._allreduce()                # the one collective of the step, between the two graphs
+            g[1].replay()                        # TALR + momentum
             return
-        self._step_ops(plan, update)
+        self._compute_ops(plan)
+        if update:
+            if self.dist:
+                self._allreduce()
+            self._run(plan.opt_ops)
 
-    def _step_ops(self, plan, update):
+    def _allreduce(self):
+        from lib.parallel import allreduce_flat_
+        allreduce_flat_(self.grad)               # [gradients | TALR moments]
+
+    def _compute_ops(self, plan):
         self._run(plan.pack_ops)
         self._run(plan.fwd_ops)
         self.grad.zero_()
         self._run(plan.bwd_ops)
-        if update:
-            if self.dist:
-                from lib.parallel import allreduce_flat_
-                allreduce_flat_(self.grad)       # gradients + TALR moments, one collective per step
-            self._run(plan.opt_ops)
 
     def _capture(self, plan):
-        # warm-up on a side stream (allocations, lazy module loads), then capture
+        """Two CUDA graphs per plan (compute | optimiser).  The NCCL all-reduce is issued eagerly
+        between them: it is a single launch, and keeping it out of stream capture avoids any
+        interaction between capture and the process group's watchdog."""
         s = torch.cuda.Stream(self.dev)
         s.wait_stream(torch.cuda.current_stream(self.dev))
         keep = (self.theta.clone(), self.accum.clone(), self.state.clone())
-        with torch.cuda.stream(s):
-            self._step_ops(plan, True)
+        with torch.cuda.stream(s):               # warm-up: allocations, lazy module loads
+            self._compute_ops(plan)
+            self._run(plan.opt_ops)
         torch.cuda.current_stream(self.dev).wait_stream(s)
         torch.cuda.synchronize(self.dev)
         self.theta.copy_(keep[0]); self.accum.copy_(keep[1]); self.state.copy_(keep[2])
-        g = torch.cuda.CUDAGraph()
+        g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
         before = self.L.launches
-        with torch.cuda.graph(g):
-            self._step_ops(plan, True)
+        with torch.cuda.graph(g1):
+            self._compute_ops(plan)
+        with torch.cuda.graph(g2):
+            self._run(plan.opt_ops)
         plan.graph_launches = self.L.launches - before
-        self._graphs[id(plan)] = g
-        return g
+        self._graphs[id(plan)] = (g1, g2)
+        return self._graphs[id(plan)]
 
     def forward(self, feed, mode=None):
         """Forward only; returns the plan (buffers hold the results)."""
