@@ -112,8 +112,9 @@ int mpnn_bn_bwd_reduce(const void* lin, const void* dAct, const void* dFeat, int
                        const float* ss, const float* mr, int C,
                        int B, int H, int W, int G, int P,
                        float* partials, int cap, int* n_parts, int dtype, void* stream);
-/* sums[0][c] = sum dy', sums[1][c] = sum dy'*xhat; dgamma += sums1, dbeta += sums0 */
-int mpnn_bn_bwd_finalize(const float* partials, int n_parts, int C,
+/* partials (from bn_bwd_reduce) hold sum dy' and sum dy'*x per channel;
+ * sums[0][c] = sum dy', sums[1][c] = sum dy'*xhat; dgamma += sums1, dbeta += sums0 */
+int mpnn_bn_bwd_finalize(const float* partials, int n_parts, int C, const float* mr,
                          float* sums, float* dgamma, float* dbeta, void* stream);
 /* backward, pass 2: dLin = ss0*(dy' - mean(dy') - xhat*mean(dy'*xhat))
  *                        + unpool(dPooled)   [argmax recomputed from lin]

@@ -1,0 +1,266 @@
+// BatchNorm (+ReLU, +2x2 max-pool) backward on padded-planes tensors.
+// Reference: TF autodiff of lib/layer_types.py:109-110 (pool), :196-199 (ReLU),
+// :219-249 (train-mode BN: gradient flows through the batch moments).
+//
+//   y = relu(a*x + c),  a = gamma*rstd,  c = beta - mean*a,  xhat = (x - mean)*rstd
+//   dy' = dy * [a*x + c > 0]
+//   dx  = a*(dy' - mean(dy') - xhat*mean(dy'*xhat))  + unpool(dPooled)
+//       = a*dy' + p*x + q,   p = -a*rstd*m1,  q = -a*m0 + a*rstd*mean*m1     (m0,m1 = batch means)
+// Both kernels are pure HBM streams, so they are written for occupancy: per-thread
+// state is four 8-vectors of constants plus the rows in flight (<= 64 registers).
+#include "common.cuh"
+#include "../../include/mpnn.h"
+
+// incoming gradient of one pixel row: dAct + dFeat (either may be absent)
+template <typename T>
+__device__ __forceinline__ void load_dy(const T* __restrict__ dAct, const T* __restrict__ dFeat, int Balloc,
+                                        int KG, const Geom& g, int kg, int n, int h, int w, int p, float d[8]) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) d[j] = 0.f;
+    if (dAct) Row8<T>::load(plane_row(dAct, kg, g.P, p), d);
+    if (dFeat) {
+        float d2[8];
+        Row8<T>::load(plane_row(dFeat, (h * g.W + w) * KG + kg, Balloc, n), d2);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) d[j] += d2[j];
+    }
+}
+
+// pass 1: per-CTA partial sums of dy' and dy'*x (the xhat form is recovered in finalize)
+template <typename T>
+__global__ void __launch_bounds__(256, 4)
+bn_bwd_reduce_kernel(const T* __restrict__ lin, const T* __restrict__ dAct, const T* __restrict__ dFeat,
+                     int Balloc, const float* __restrict__ ss, int C, Geom g, float* __restrict__ partials) {
+    const int kg = blockIdx.y, KG = C / 8;
+    float a[8], c[8], s0[8], s1[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        a[j] = ss[kg * 8 + j]; c[j] = ss[C + kg * 8 + j];
+        s0[j] = 0.f; s1[j] = 0.f;
+    }
+    const int total = g.B * g.H * g.W;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int w = i % g.W;
+        const int r = i / g.W;
+        const int h = r % g.H;
+        const int n = r / g.H;
+        const int p = row_of(g, n, h, w);
+        float lv[8], d[8];
+        Row8<T>::load(plane_row(lin, kg, g.P, p), lv);
+        load_dy<T>(dAct, dFeat, Balloc, KG, g, kg, n, h, w, p, d);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float dy = fmaf(a[j], lv[j], c[j]) > 0.f ? d[j] : 0.f;
+            s0[j] += dy;
+            s1[j] = fmaf(dy, lv[j], s1[j]);
+        }
+    }
+    __shared__ float red[8][16];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        float t0 = warp_sum(s0[j]), t1 = warp_sum(s1[j]);
+        if (lane == 0) { red[warp][j] = t0; red[warp][8 + j] = t1; }
+    }
+    __syncthreads();
+    if (threadIdx.x < 16) {
+        float t = 0.f;
+#pragma unroll
+        for (int wv = 0; wv < 8; ++wv) t += red[wv][threadIdx.x];
+        const int which = threadIdx.x / 8, j = threadIdx.x % 8;
+        partials[((size_t)blockIdx.x * 2 + which) * C + kg * 8 + j] = t;
+    }
+}
+
+extern "C" int mpnn_bn_bwd_reduce(const void* lin, const void* dAct, const void* dFeat, int Balloc,
+                                  const float* ss, const float* mr, int C,
+                                  int B, int H, int W, int G, int P,
+                                  float* partials, int cap, int* n_parts, int dtype, void* stream) {
+    MPNN_REQUIRE(C % 8 == 0 && cap > 0 && ss && mr, "bn_bwd_reduce: args");
+    Geom g = make_geom(B, H, W, G, P);
+    int total = B * H * W;
+    int gx = ceil_div(total, 256 * 4);
+    int lim = 148 * 8 / (C / 8);
+    if (lim < 74) lim = 74;
+    if (gx > lim) gx = lim;
+    if (gx > cap) gx = cap;
+    if (gx < 1) gx = 1;
+    if (n_parts) *n_parts = gx;
+    dim3 grid(gx, C / 8);
+    MPNN_DISPATCH_DTYPE(dtype, (bn_bwd_reduce_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(
+        (const T*)lin, (const T*)dAct, (const T*)dFeat, Balloc, ss, C, g, partials)));
+    return mpnn_check_launch("bn_bwd_reduce");
+}
+
+// partials hold sum(dy') and sum(dy'*x); sums[0] = sum dy', sums[1] = sum dy'*xhat
+__global__ void bn_bwd_finalize_kernel(const float* __restrict__ partials, int n_parts, int C,
+                                       const float* __restrict__ mr, float* __restrict__ sums,
+                                       float* __restrict__ dgamma, float* __restrict__ dbeta) {
+    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);      // warp per channel
+    const int lane = threadIdx.x & 31;
+    if (c >= C) return;
+    double s0 = 0.0, s1 = 0.0;
+    for (int i = lane; i < n_parts; i += 32) {
+        s0 += (double)partials[((size_t)i * 2) * C + c];
+        s1 += (double)partials[((size_t)i * 2 + 1) * C + c];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    }
+    if (lane != 0) return;
+    const double mean = mr[c], rstd = mr[C + c];
+    const double sx = rstd * (s1 - mean * s0);           // sum dy'*xhat
+    sums[c] = (float)s0;
+    sums[C + c] = (float)sx;
+    if (dgamma) dgamma[c] += (float)sx;
+    if (dbeta) dbeta[c] += (float)s0;
+}
+
+extern "C" int mpnn_bn_bwd_finalize(const float* partials, int n_parts, int C, const float* mr,
+                                    float* sums, float* dgamma, float* dbeta, void* stream) {
+    bn_bwd_finalize_kernel<<<ceil_div(C, 4), 128, 0, (cudaStream_t)stream>>>(
+        partials, n_parts, C, mr, sums, dgamma, dbeta);
+    return mpnn_check_launch("bn_bwd_finalize");
+}
+
+// pass 2
+template <typename T, bool POOL>
+__global__ void __launch_bounds__(256, POOL ? 3 : 4)
+bn_relu_pool_bwd_kernel(const T* __restrict__ lin, const T* __restrict__ dAct,
+                        const T* __restrict__ dFeat, int Balloc,
+                        const T* __restrict__ dPooled, Geom gp,
+                        const float* __restrict__ ss, const float* __restrict__ mr,
+                        const float* __restrict__ sums, float inv_count,
+                        int C, Geom g, T* __restrict__ dLin, float* __restrict__ dbias) {
+    // grid: x strides over pixels (or 2x2 blocks), y = 8-channel plane
+    const int kg = blockIdx.y, KG = C / 8;
+    const int HH = POOL ? g.H / 2 : g.H, WW = POOL ? g.W / 2 : g.W;
+    const int total = g.B * HH * WW;
+    float a[8], c[8], pp[8], qq[8], bs[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { bs[j] = 0.f; a[j] = 0.f; c[j] = 0.f; pp[j] = 0.f; qq[j] = 0.f; }
+    if (ss) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            a[j] = __ldg(ss + kg * 8 + j); c[j] = __ldg(ss + C + kg * 8 + j);
+            const float mean = __ldg(mr + kg * 8 + j), rstd = __ldg(mr + C + kg * 8 + j);
+            const float m0 = __ldg(sums + kg * 8 + j) * inv_count, m1 = __ldg(sums + C + kg * 8 + j) * inv_count;
+            pp[j] = -a[j] * rstd * m1;
+            qq[j] = -a[j] * m0 + a[j] * rstd * mean * m1;
+        }
+    }
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int w = i % WW;
+        const int r = i / WW;
+        const int h = r % HH;
+        const int n = r / HH;
+        if (POOL) {
+            // which of the 2x2 pixels holds the (first) maximum, per channel: 2 bits each
+            unsigned best = 0;
+            float dp[8];
+            if (dPooled) {
+                float bv[8];
+                Row8<T>::load(plane_row(lin, kg, g.P, row_of(g, n, 2 * h, 2 * w)), bv);
+#pragma unroll
+                for (int k = 1; k < 4; ++k) {
+                    float v[8];
+                    Row8<T>::load(plane_row(lin, kg, g.P, row_of(g, n, 2 * h + (k >> 1), 2 * w + (k & 1))), v);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        if (v[j] > bv[j]) { bv[j] = v[j]; best = (best & ~(3u << (2 * j))) | ((unsigned)k << (2 * j)); }
+                }
+                Row8<T>::load(plane_row(dPooled, kg, gp.P, row_of(gp, n, h, w)), dp);
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int hh = 2 * h + (k >> 1), ww = 2 * w + (k & 1);
+                const int p = row_of(g, n, hh, ww);
+                float out[8];
+                if (ss) {
+                    float lv[8], d[8];
+                    Row8<T>::load(plane_row(lin, kg, g.P, p), lv);      // L1 hit: read above for the argmax
+                    load_dy<T>(dAct, dFeat, Balloc, KG, g, kg, n, hh, ww, p, d);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float dy = fmaf(a[j], lv[j], c[j]) > 0.f ? d[j] : 0.f;
+                        out[j] = fmaf(a[j], dy, fmaf(pp[j], lv[j], qq[j]));
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) out[j] = 0.f;
+                }
+                if (dPooled) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        if (((best >> (2 * j)) & 3u) == (unsigned)k) out[j] += dp[j];
+                }
+                Row8<T>::store(plane_row(dLin, kg, g.P, p), out);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) bs[j] += out[j];
+            }
+        } else {
+            const int p = row_of(g, n, h, w);
+            float lv[8], d[8], out[8];
+            Row8<T>::load(plane_row(lin, kg, g.P, p), lv);
+            load_dy<T>(dAct, dFeat, Balloc, KG, g, kg, n, h, w, p, d);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float dy = fmaf(a[j], lv[j], c[j]) > 0.f ? d[j] : 0.f;
+                out[j] = fmaf(a[j], dy, fmaf(pp[j], lv[j], qq[j]));
+                bs[j] += out[j];
+            }
+            Row8<T>::store(plane_row(dLin, kg, g.P, p), out);
+        }
+    }
+    if (dbias) {
+        // conv bias gradient = column sums of dLin (layer_types.py:181-185: b_k is added before BN)
+        __shared__ float red[8][8];
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float t = warp_sum(bs[j]);
+            if (lane == 0) red[warp][j] = t;
+        }
+        __syncthreads();
+        if (threadIdx.x < 8) {
+            float t = 0.f;
+            for (int wv = 0; wv < 8; ++wv) t += red[wv][threadIdx.x];
+            atomicAdd(dbias + kg * 8 + threadIdx.x, t);
+        }
+    }
+}
+
+extern "C" int mpnn_bn_relu_pool_bwd(const void* lin, const void* dAct, const void* dFeat, int Balloc,
+                                     const void* dPooled, int Pp,
+                                     const float* ss, const float* mr, const float* sums, double count,
+                                     int C, int B, int H, int W, int G, int P,
+                                     void* dLin, float* dbias, int dtype, void* stream) {
+    MPNN_REQUIRE(C % 8 == 0, "bn_relu_pool_bwd: C=%d", C);
+    MPNN_REQUIRE(ss || dPooled, "bn_relu_pool_bwd: nothing to do");
+    MPNN_REQUIRE(!ss || (mr && sums), "bn_relu_pool_bwd: missing stats");
+    Geom g = make_geom(B, H, W, G, P);
+    Geom gp = make_geom(B, H / 2, W / 2, G, Pp);
+    const bool pool = dPooled != nullptr;
+    MPNN_REQUIRE(!pool || (H % 2 == 0 && W % 2 == 0), "bn_relu_pool_bwd: odd size");
+    long long total = (long long)B * (pool ? (H / 2) * (W / 2) : H * W);
+    int gx = (int)((total + 255) / 256);
+    int cap = 148 * 16 / (C / 8);
+    if (cap < 148) cap = 148;
+    if (gx > cap) gx = cap;
+    if (gx < 1) gx = 1;
+    dim3 grid(gx, C / 8);
+    float inv = (float)(1.0 / count);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (pool) {
+        MPNN_DISPATCH_DTYPE(dtype, (bn_relu_pool_bwd_kernel<T, true><<<grid, 256, 0, st>>>(
+            (const T*)lin, (const T*)dAct, (const T*)dFeat, Balloc, (const T*)dPooled, gp, ss, mr, sums,
+            inv, C, g, (T*)dLin, dbias)));
+    } else {
+        MPNN_DISPATCH_DTYPE(dtype, (bn_relu_pool_bwd_kernel<T, false><<<grid, 256, 0, st>>>(
+            (const T*)lin, (const T*)dAct, (const T*)dFeat, Balloc, (const T*)dPooled, gp, ss, mr, sums,
+            inv, C, g, (T*)dLin, dbias)));
+    }
+    return mpnn_check_launch("bn_relu_pool_bwd");
+}

@@ -36,6 +36,7 @@ struct Geom {
     int Wp, S;           // W+1, (H+1)*(W+1)
     int rows;            // B*S  (logical rows after the guard)
     int P;               // allocated rows per plane
+    uint32_t mS, mWp;    // floor(2^32/S)+1, floor(2^32/Wp)+1: division by multiply-high
 };
 
 static inline Geom make_geom(int B, int H, int W, int G, int P) {
@@ -43,16 +44,21 @@ static inline Geom make_geom(int B, int H, int W, int G, int P) {
     g.B = B; g.H = H; g.W = W; g.G = G;
     g.Wp = W + 1; g.S = (H + 1) * (W + 1);
     g.rows = B * g.S; g.P = P;
+    g.mS = g.S > 1 ? (uint32_t)((1ull << 32) / (uint64_t)g.S) + 1u : 0xFFFFFFFFu;
+    g.mWp = g.Wp > 1 ? (uint32_t)((1ull << 32) / (uint64_t)g.Wp) + 1u : 0xFFFFFFFFu;
     return g;
 }
 
 // row index (relative to the guard) -> validity; also yields n,h,w
 __device__ __forceinline__ bool row_valid(const Geom& g, int q, int& n, int& h, int& w) {
     if (q < 0 || q >= g.rows) return false;
-    n = q / g.S;
+    // __umulhi(q, m) with m = floor(2^32/d)+1 is q/d or q/d+1 for any q < 2^32: one fix-up, no division
+    n = (int)__umulhi((uint32_t)q, g.mS);
     int r = q - n * g.S;
-    int hr = r / g.Wp;
+    if (r < 0) { r += g.S; --n; } else if (r >= g.S) { r -= g.S; ++n; }   // second arm: degenerate S == 1 only
+    int hr = (int)__umulhi((uint32_t)r, g.mWp);
     int wc = r - hr * g.Wp;
+    if (wc < 0) { wc += g.Wp; --hr; } else if (wc >= g.Wp) { wc -= g.Wp; ++hr; }
     h = hr - 1; w = wc - 1;
     return hr >= 1 && wc >= 1;
 }

@@ -17,6 +17,7 @@
 // stages ring-buffered with mbarriers, two TMEM accumulators so the epilogue
 // of tile i overlaps the MMAs of tile i+1.  Weights for the CTA's N-slice stay
 // resident in shared memory for the kernel's lifetime.
+#include <cstdlib>
 #include "common.cuh"
 #include "umma.cuh"
 #include "../../include/mpnn.h"
@@ -35,16 +36,30 @@ struct GemmArgs {
     int out_mode;      // 0: bf16 planes, 1: fp32 planes, 2: fp32 row-major [row][ld]
     int ld0, ld1;      // leading dimensions of out0 / out1 in row-major mode
     int KC, n_kc;      // planes per pipeline stage and stages per tile (K is streamed for wide FC inputs)
+    int dbg;           // tuning aid (MPNN_TUNE_DBG): 1 skip MMAs, 2 skip stores, 4 skip loads, 8 skip tcgen05.ld
 };
 
 constexpr int kThreads = 192;
 
-__global__ void __launch_bounds__(kThreads, 1)
+__device__ __forceinline__ void tc_ld16_issue(uint32_t taddr, uint32_t r[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+}
+
+// NBT = compile-time N-slice width for the hot conv shapes (16, 32): the epilogue is
+// fully unrolled and the BN moments stay in per-thread registers across all tiles of
+// the CTA (one warp reduction at kernel end instead of one per tile).  NBT = 0 is the
+// generic width (any multiple of 16 up to 256) with a per-tile warp reduction.
+template <int NBT>
+__global__ void __launch_bounds__(kThreads, NBT == 16 ? 4 : (NBT == 32 ? 3 : 1))
 stencil_gemm_umma_kernel(const GemmArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int KG = (a.K0 + a.K1) >> 3, KG0 = a.K0 >> 3;
-    const int NB = a.NB, n0 = blockIdx.y * NB;
+    const int NB = NBT ? NBT : a.NB, n0 = blockIdx.y * NB;
     const uint32_t w_bytes = (uint32_t)a.ntaps * KG * NB * 16;
     const uint32_t PS = (uint32_t)a.rowsA * 16;          // plane stride inside a stage
     const uint32_t stage_bytes = PS * a.KC;
@@ -54,8 +69,9 @@ stencil_gemm_umma_kernel(const GemmArgs a) {
     // bars: full[nstage], empty[nstage], tfull[2], tempty[2], wbar
     const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * a.nstage;
     const uint32_t tfull0 = empty0 + 8 * a.nstage, tempty0 = tfull0 + 16, wbar = tempty0 + 16;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * a.nstage + 5);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * a.nstage + 6);   // 16-byte aligned
     float* sstat = reinterpret_cast<float*>(tmem_slot + 4);      // [4 warps][2][NB]
+    float* sbias = sstat + 4 * 2 * NB;                           // [NB]
     const uint32_t ncols = tmem_cols_pow2(2 * NB);
 
     if (threadIdx.x == 0) {
@@ -69,12 +85,19 @@ stencil_gemm_umma_kernel(const GemmArgs a) {
                      ::"r"(smem_u32(tmem_slot)), "r"(ncols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    if (a.stats && threadIdx.x >= 64)
-        for (int i = threadIdx.x - 64; i < 4 * 2 * NB; i += 128) sstat[i] = 0.f;
+    if (threadIdx.x >= 64) {
+        if (a.stats)
+            for (int i = threadIdx.x - 64; i < 4 * 2 * NB; i += 128) sstat[i] = 0.f;
+        for (int i = threadIdx.x - 64; i < NB; i += 128) sbias[i] = a.bias ? a.bias[n0 + i] : 0.f;
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    const bool spin = (a.dbg & 16) != 0;
+    auto mbar_wait = [spin](uint32_t bar, uint32_t parity) {
+        if (spin) mbar_wait_spin(bar, parity); else ::mbar_wait(bar, parity);
+    };
 
     if (warp == 0) {
         // ------------------------------------------------ producer
@@ -83,22 +106,29 @@ stencil_gemm_umma_kernel(const GemmArgs a) {
             for (int t = 0; t < a.ntaps * KG; ++t)
                 bulk_g2s(smem_u32(sW) + (uint32_t)t * NB * 16,
                          a.Wp + ((size_t)t * a.N + n0) * 8, (uint32_t)NB * 16, wbar);
-            int it = 0;
+            // the single-thread issue loops are the per-CTA critical path: no divisions, no
+            // 64-bit address rebuilds inside them (ring slot / phase are running counters)
+            int s = 0; uint32_t ph = 0;
+            const __nv_bfloat16* src0 = a.A0 + (size_t)(a.g.G - a.halo) * 8;
+            const __nv_bfloat16* src1 = a.A1 ? a.A1 + (size_t)(a.g.G - a.halo) * 8 : nullptr;
+            const size_t plane = (size_t)a.g.P * 8;
             for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
-                const size_t row0 = (size_t)(a.g.G + tile * 128 - a.halo);
-                for (int ci = 0; ci < a.n_kc; ++ci, ++it) {
-                    const int s = it % a.nstage;
-                    const uint32_t ph = (uint32_t)(it / a.nstage) & 1u;
+                const size_t toff = (size_t)tile * (128 * 8);
+                for (int ci = 0; ci < a.n_kc; ++ci) {
                     const int kg0 = ci * a.KC, kgn = min(a.KC, KG - kg0);
                     mbar_wait(empty0 + 8 * s, ph ^ 1u);
-                    mbar_expect_tx(full0 + 8 * s, PS * kgn);
-                    const uint32_t dst = smem_u32(sA) + (uint32_t)s * stage_bytes;
-                    for (int j = 0; j < kgn; ++j) {
-                        const int kg = kg0 + j;
-                        const __nv_bfloat16* src = kg < KG0 ? a.A0 + ((size_t)kg * a.g.P + row0) * 8
-                                                            : a.A1 + ((size_t)(kg - KG0) * a.g.P + row0) * 8;
-                        bulk_g2s(dst + (uint32_t)j * PS, src, PS, full0 + 8 * s);
+                    if (a.dbg & 4) mbar_arrive(full0 + 8 * s);
+                    else {
+                        mbar_expect_tx(full0 + 8 * s, PS * kgn);
+                        const uint32_t dst = smem_u32(sA) + (uint32_t)s * stage_bytes;
+                        for (int j = 0; j < kgn; ++j) {
+                            const int kg = kg0 + j;
+                            const __nv_bfloat16* src = kg < KG0 ? src0 + kg * plane + toff
+                                                                : src1 + (kg - KG0) * plane + toff;
+                            bulk_g2s(dst + (uint32_t)j * PS, src, PS, full0 + 8 * s);
+                        }
                     }
+                    if (++s == a.nstage) { s = 0; ph ^= 1u; }
                 }
             }
         }
@@ -107,34 +137,51 @@ stencil_gemm_umma_kernel(const GemmArgs a) {
         // ------------------------------------------------ MMA issuer
         if (lane == 0) {
             const uint32_t idesc = make_idesc(NB, 0, 0);
+            // descriptors: hi word (SBO = 128 B, version) is constant; the lo word is
+            // (address >> 4) | (LBO >> 4) << 16, so a tap shift of `off` rows (16 B each)
+            // or a K step is one 32-bit add
+            const uint32_t d_hi = (128u >> 4) | (1u << 14);
+            const uint32_t a_lo0 = (((smem_u32(sA) + (uint32_t)a.halo * 16) & 0x3FFFFu) >> 4) | ((PS >> 4) << 16);
+            const uint32_t b_lo0 = ((smem_u32(sW) & 0x3FFFFu) >> 4) | ((uint32_t)NB << 16);
+            const uint32_t a_stage = stage_bytes >> 4, a_kstep = 2 * (PS >> 4), b_kstep = 2 * (uint32_t)NB;
+            const uint32_t b_tap = (uint32_t)KG * NB;
+            const int Wp = a.g.Wp;
             mbar_wait(wbar, 0);
-            int it = 0, tl = 0;
+            int s = 0, tl = 0; uint32_t ph = 0;
             for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++tl) {
                 const int acc = tl & 1;
                 const uint32_t aph = (uint32_t)(tl >> 1) & 1u;
                 mbar_wait(tempty0 + 8 * acc, aph ^ 1u);
-                const uint32_t wbase = smem_u32(sW);
                 const uint32_t dcol = tmem_base + (uint32_t)acc * NB;
                 uint32_t first = 0;
-                for (int ci = 0; ci < a.n_kc; ++ci, ++it) {
-                    const int s = it % a.nstage;
-                    const uint32_t ph = (uint32_t)(it / a.nstage) & 1u;
+                for (int ci = 0; ci < a.n_kc; ++ci) {
                     const int kg0 = ci * a.KC, kgn = min(a.KC, KG - kg0);
                     mbar_wait(full0 + 8 * s, ph);
                     tc_fence_after();
-                    const uint32_t abase = smem_u32(sA) + (uint32_t)s * stage_bytes;
-                    for (int tap = 0; tap < a.ntaps; ++tap) {
-                        const int off = a.ntaps == 9 ? (tap / 3 - 1) * a.g.Wp + (tap % 3 - 1) : 0;
-                        const uint32_t arow = abase + (uint32_t)(a.halo + off) * 16;
-                        for (int kk = 0; kk < kgn; kk += 2) {
-                            const uint64_t ad = make_desc(arow + (uint32_t)kk * PS, PS, 128);
-                            const uint64_t bd = make_desc(wbase + (uint32_t)(tap * KG + kg0 + kk) * NB * 16,
-                                                          (uint32_t)NB * 16, 128);
-                            tc_mma(dcol, ad, bd, idesc, first);
-                            first = 1;
+                    const uint32_t a_lo = a_lo0 + (uint32_t)s * a_stage;
+                    const uint32_t b_lo = b_lo0 + (uint32_t)kg0 * NB;
+                    if (!(a.dbg & 1)) {
+                        if (a.ntaps == 9) {
+#pragma unroll
+                            for (int tap = 0; tap < 9; ++tap) {
+                                const uint32_t at = a_lo + (uint32_t)((tap / 3 - 1) * Wp + (tap % 3 - 1));
+                                const uint32_t bt = b_lo + (uint32_t)tap * b_tap;
+                                for (int kk = 0, ka = 0, kb = 0; kk < kgn; kk += 2, ka += a_kstep, kb += b_kstep) {
+                                    tc_mma(dcol, ((uint64_t)d_hi << 32) | (at + ka), ((uint64_t)d_hi << 32) | (bt + kb),
+                                           idesc, first);
+                                    first = 1;
+                                }
+                            }
+                        } else {
+                            for (int kk = 0, ka = 0, kb = 0; kk < kgn; kk += 2, ka += a_kstep, kb += b_kstep) {
+                                tc_mma(dcol, ((uint64_t)d_hi << 32) | (a_lo + ka), ((uint64_t)d_hi << 32) | (b_lo + kb),
+                                       idesc, first);
+                                first = 1;
+                            }
                         }
                     }
                     tc_commit(empty0 + 8 * s);      // smem stage reusable once the MMAs retire
+                    if (++s == a.nstage) { s = 0; ph ^= 1u; }
                 }
                 tc_commit(tfull0 + 8 * acc);        // accumulator ready for the epilogue
             }
@@ -145,57 +192,55 @@ stencil_gemm_umma_kernel(const GemmArgs a) {
         const int quad = warp & 3;                       // TMEM lane quadrant this warp may read
         const int m = quad * 32 + lane;
         float* wstat = sstat + (size_t)(warp - 2) * 2 * NB;
-        int it = 0;
-        for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
-            const int acc = it & 1;
-            const uint32_t aph = (uint32_t)(it >> 1) & 1u;
-            mbar_wait(tfull0 + 8 * acc, aph);
-            tc_fence_after();
-            const int q = tile * 128 + m;
-            const int p = a.g.G + q;
-            int n_, h_, w_;
-            const bool valid = row_valid(a.g, q, n_, h_, w_);
-            const bool inrange = q < a.g.rows;
-            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)acc * NB;
-            for (int c = 0; c < NB; c += 16) {
-                float v[16];
-                tc_ld16(taddr + c, v);
-                const int col = n0 + c;
-                if (a.bias) {
+        constexpr int NR = NBT ? NBT : 1;
+        float r1[NR], r2[NR];                            // running BN moments of this thread's rows (NBT path)
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) v[i] += __ldg(a.bias + col + i);
-                }
-                if (inrange) {
+        for (int i = 0; i < NR; ++i) { r1[i] = 0.f; r2[i] = 0.f; }
+        // one 16-column chunk: bias, store (bf16 / fp32 planes or fp32 row-major), moments
+        auto finish_chunk = [&](int c, float (&v)[16], int q, int p, bool inrange, bool valid, float* a1, float* a2) {
+            const float4* b4 = reinterpret_cast<const float4*>(sbias + c);
 #pragma unroll
-                    for (int hh = 0; hh < 2; ++hh) {
-                        const int cc = col + hh * 8;
-                        void* base; int accf, kgp;
-                        if (cc < a.N0) { base = a.out0; accf = a.acc0; kgp = cc >> 3; }
-                        else { base = a.out1; accf = a.acc1; kgp = (cc - a.N0) >> 3; }
-                        float o[8];
+            for (int i = 0; i < 4; ++i) {
+                const float4 b = b4[i];
+                v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+            }
+            const int col = n0 + c;
+            if (inrange) {
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) o[i] = v[hh * 8 + i];
-                        if (a.out_mode == 2) {
-                            // fp32 row-major [row][ld]: logits of the fully-connected heads
-                            const int ld = cc < a.N0 ? a.ld0 : a.ld1;
-                            float* d = (float*)base + (size_t)q * ld + kgp * 8;
-                            Row8<float>::store(d, o);
-                        } else if (a.out_mode == 1) {
-                            float* d = plane_row((float*)base, kgp, a.g.P, p);
-                            if (accf) { float t[8]; Row8<float>::load(d, t);
+                for (int hh = 0; hh < 2; ++hh) {
+                    const int cc = col + hh * 8;
+                    void* base; int accf, kgp;
+                    if (cc < a.N0) { base = a.out0; accf = a.acc0; kgp = cc >> 3; }
+                    else { base = a.out1; accf = a.acc1; kgp = (cc - a.N0) >> 3; }
+                    float o[8];
 #pragma unroll
-                                for (int i = 0; i < 8; ++i) o[i] += t[i]; }
-                            Row8<float>::store(d, o);
-                        } else {
-                            __nv_bfloat16* d = plane_row((__nv_bfloat16*)base, kgp, a.g.P, p);
-                            if (accf) { float t[8]; Row8<__nv_bfloat16>::load(d, t);
+                    for (int i = 0; i < 8; ++i) o[i] = v[hh * 8 + i];
+                    if (a.out_mode == 0) {
+                        __nv_bfloat16* d = plane_row((__nv_bfloat16*)base, kgp, a.g.P, p);
+                        if (accf) { float t[8]; Row8<__nv_bfloat16>::load(d, t);
 #pragma unroll
-                                for (int i = 0; i < 8; ++i) o[i] += t[i]; }
-                            Row8<__nv_bfloat16>::store(d, o);
-                        }
+                            for (int i = 0; i < 8; ++i) o[i] += t[i]; }
+                        Row8<__nv_bfloat16>::store(d, o);
+                    } else if (a.out_mode == 1) {
+                        float* d = plane_row((float*)base, kgp, a.g.P, p);
+                        if (accf) { float t[8]; Row8<float>::load(d, t);
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) o[i] += t[i]; }
+                        Row8<float>::store(d, o);
+                    } else {
+                        // fp32 row-major [row][ld]: logits of the fully-connected heads
+                        const int ld = cc < a.N0 ? a.ld0 : a.ld1;
+                        Row8<float>::store((float*)base + (size_t)q * ld + kgp * 8, o);
                     }
                 }
-                if (a.stats) {
+            }
+            if (a.stats) {
+                if (NBT) {
+                    if (valid) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) { a1[i] += v[i]; a2[i] = fmaf(v[i], v[i], a2[i]); }
+                    }
+                } else {
                     float s1[16], s2[16];
 #pragma unroll
                     for (int i = 0; i < 16; ++i) { s1[i] = valid ? v[i] : 0.f; s2[i] = s1[i] * s1[i]; }
@@ -204,9 +249,49 @@ stencil_gemm_umma_kernel(const GemmArgs a) {
                     if (lane < 16) { wstat[c + lane] += t1; wstat[NB + c + lane] += t2; }
                 }
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
+        };
+        int it = 0;
+        for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
+            const int acc = it & 1;
+            const uint32_t aph = (uint32_t)(it >> 1) & 1u;
+            const int q = tile * 128 + m;
+            const int p = a.g.G + q;
+            int n_, h_, w_;
+            const bool valid = a.stats ? row_valid(a.g, q, n_, h_, w_) : false;
+            const bool inrange = q < a.g.rows && !(a.dbg & 2);
+            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)acc * NB;
+            mbar_wait(tfull0 + 8 * acc, aph);
+            tc_fence_after();
+            if (NBT) {
+#pragma unroll
+                for (int ci = 0; ci < NR / 16; ++ci) {
+                    float v[16];
+                    tc_ld16(taddr + ci * 16, v);
+                    if (ci == NR / 16 - 1) {             // accumulator drained: hand it back before the math
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
+                    }
+                    finish_chunk(ci * 16, v, q, p, inrange, valid, r1 + (NBT ? ci * 16 : 0), r2 + (NBT ? ci * 16 : 0));
+                }
+            } else {
+                for (int c = 0; c < NB; c += 16) {
+                    float v[16];
+                    tc_ld16(taddr + c, v);
+                    finish_chunk(c, v, q, p, inrange, valid, r1, r2);
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
+            }
+        }
+        if (NBT && a.stats) {
+#pragma unroll
+            for (int ci = 0; ci < NR / 16; ++ci) {
+                float t1 = warp_colsum16(r1 + (NBT ? ci * 16 : 0), lane);
+                float t2 = warp_colsum16(r2 + (NBT ? ci * 16 : 0), lane);
+                if (lane < 16) { wstat[ci * 16 + lane] = t1; wstat[NB + ci * 16 + lane] = t2; }
+            }
         }
     }
     tc_fence_before();
@@ -291,8 +376,14 @@ int mpnn_stencil_gemm_umma(const void* A0, int K0, const void* A1, int K1, const
     const int N = N0 + N1;
     MPNN_REQUIRE(K0 % 16 == 0 && K1 % 16 == 0, "stencil_gemm(tcgen05): K0=%d K1=%d must be multiples of 16", K0, K1);
     MPNN_REQUIRE(N % 16 == 0 && N0 % 16 == 0, "stencil_gemm(tcgen05): N0=%d N1=%d must be multiples of 16", N0, N1);
+    MPNN_REQUIRE(ntaps == 1 || ntaps == 9, "stencil_gemm(tcgen05): ntaps=%d (1 or 9)", ntaps);
     const int KG = (K0 + K1) / 8;
-    const int halo = ntaps == 9 ? g.Wp + 1 : 0;
+    static const int tune_halo8 = getenv("MPNN_TUNE_HALO8") ? atoi(getenv("MPNN_TUNE_HALO8")) : 0;
+    static const int tune_per_sm = getenv("MPNN_TUNE_PER_SM") ? atoi(getenv("MPNN_TUNE_PER_SM")) : 0;
+    static const int tune_nstage = getenv("MPNN_TUNE_NSTAGE") ? atoi(getenv("MPNN_TUNE_NSTAGE")) : 0;
+    static const int tune_dbg = getenv("MPNN_TUNE_DBG") ? atoi(getenv("MPNN_TUNE_DBG")) : 0;
+    int halo = ntaps == 9 ? g.Wp + 1 : 0;
+    if (tune_halo8) halo = (halo + 7) & ~7;
     const int rowsA = 128 + 2 * halo;
     // planes per pipeline stage: all of K when that is small (convs), else ~32 KB slices (wide FC inputs)
     int KC = KG;
@@ -308,25 +399,29 @@ int mpnn_stencil_gemm_umma(const void* A0, int K0, const void* A1, int K1, const
         NB = N / s;
         if (NB > 256) continue;
         size_t w = ((size_t)ntaps * KG * NB * 16 + 127) & ~(size_t)127;
-        size_t fixed = w + 256 + (size_t)4 * 2 * NB * 4;
+        size_t fixed = w + 256 + (size_t)9 * NB * 4;
         if (fixed + 2 * stage <= kMax) {
             split = s;
             nstage = (int)((kMax - fixed) / stage);
             if (nstage > 4) nstage = 4;
+            if (tune_nstage && nstage > tune_nstage) nstage = tune_nstage;
             break;
         }
     }
     MPNN_REQUIRE(split > 0, "stencil_gemm(tcgen05): K=%d N=%d does not fit shared memory", K0 + K1, N);
     size_t w = ((size_t)ntaps * KG * NB * 16 + 127) & ~(size_t)127;
-    size_t smem = w + (size_t)nstage * stage + 256 + (size_t)4 * 2 * NB * 4;
+    size_t smem = w + (size_t)nstage * stage + 256 + (size_t)9 * NB * 4;
     // CTAs per SM by shared memory and by TMEM columns (alloc blocks when exhausted)
     int ncols = 32;
     while (ncols < 2 * NB) ncols <<= 1;
     int per_sm = (int)((227 * 1024) / (smem + 1024));
     if (per_sm > 512 / ncols) per_sm = 512 / ncols;
     if (per_sm > 4) per_sm = 4;
+    if (NB == 32 && per_sm > 3) per_sm = 3;       // register budget of the <32> instantiation
+    if (tune_per_sm && per_sm > tune_per_sm) per_sm = tune_per_sm;
     if (per_sm < 1) per_sm = 1;
     GemmArgs a;
+    a.dbg = tune_dbg;
     a.A0 = (const __nv_bfloat16*)A0; a.A1 = (const __nv_bfloat16*)A1; a.Wp = (const __nv_bfloat16*)Wp;
     a.bias = bias; a.out0 = out0; a.out1 = out1; a.stats = stats; a.g = g;
     a.K0 = K0; a.K1 = K1; a.N = N; a.N0 = N0; a.NB = NB; a.ntaps = ntaps; a.acc0 = acc0; a.acc1 = acc1;
@@ -340,13 +435,18 @@ int mpnn_stencil_gemm_umma(const void* A0, int K0, const void* A1, int K1, const
     if (stats && gx > stats_cap) gx = stats_cap;
     if (gx < 1) gx = 1;
     if (n_parts) *n_parts = stats ? gx : 0;
-    static size_t attr_set = 0;
-    if (smem > attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(stencil_gemm_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMax + 1024);
-        if (e != cudaSuccess) { mpnn_set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return MPNN_ERR_CUDA; }
-        attr_set = kMax + 1024;
+    void (*kern)(const GemmArgs) = NB == 16 ? stencil_gemm_umma_kernel<16>
+                                 : NB == 32 ? stencil_gemm_umma_kernel<32> : stencil_gemm_umma_kernel<0>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        void (*all[3])(const GemmArgs) = {stencil_gemm_umma_kernel<0>, stencil_gemm_umma_kernel<16>, stencil_gemm_umma_kernel<32>};
+        for (int i = 0; i < 3; ++i) {
+            cudaError_t e = cudaFuncSetAttribute(all[i], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMax + 1024);
+            if (e != cudaSuccess) { mpnn_set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return MPNN_ERR_CUDA; }
+        }
+        attr_set = true;
     }
-    stencil_gemm_umma_kernel<<<dim3(gx, split), kThreads, smem, st>>>(a);
+    kern<<<dim3(gx, split), kThreads, smem, st>>>(a);
     return mpnn_check_launch("stencil_gemm_umma");
 }
 

@@ -83,54 +83,64 @@ stencil_wgrad_umma_kernel(const WgradArgs a) {
 
     if (warp == 0) {
         if (lane == 0) {
-            int it = 0;
-            for (int c = blockIdx.x; c < a.n_chunks; c += gridDim.x, ++it) {
-                const int s = it % a.nstage;
-                const uint32_t ph = (uint32_t)(it / a.nstage) & 1u;
+            // issue loops are single-thread critical paths: running ring counters, hoisted bases
+            int s = 0; uint32_t ph = 0;
+            const size_t plane = (size_t)a.g.P * 8;
+            for (int c = blockIdx.x; c < a.n_chunks; c += gridDim.x) {
                 mbar_wait(empty0 + 8 * s, ph ^ 1u);
                 mbar_expect_tx(full0 + 8 * s, stageA + stageG);
                 const size_t p0 = (size_t)a.g.G + (size_t)c * kChunk;
-                const uint32_t dA = smem_u32(sA) + (uint32_t)s * stageA;
-                const uint32_t dG = smem_u32(sG) + (uint32_t)s * stageG;
+                uint32_t dA = smem_u32(sA) + (uint32_t)s * stageA;
+                uint32_t dG = smem_u32(sG) + (uint32_t)s * stageG;
                 for (int kg = 0; kg < KG; ++kg) {
                     const int kga = kgb + kg;
-                    const __nv_bfloat16* pl = kga < KG0 ? a.A0 + (size_t)kga * a.g.P * 8
-                                                        : a.A1 + (size_t)(kga - KG0) * a.g.P * 8;
-                    for (int cp = 0; cp < a.CP; ++cp) {
-                        // CP=3: copy cp holds the plane shifted by dw = cp-1 rows
-                        const size_t row0 = p0 - a.halo + (a.CP == 3 ? cp - 1 : 0);
-                        bulk_g2s(dA + (uint32_t)(kg * a.CP + cp) * PSA, pl + row0 * 8, PSA, full0 + 8 * s);
+                    const __nv_bfloat16* pl = (kga < KG0 ? a.A0 + kga * plane : a.A1 + (kga - KG0) * plane)
+                                              + (p0 - a.halo) * 8;
+                    if (a.CP == 3) {
+                        // copy cp holds the plane shifted by dw = cp-1 rows
+                        bulk_g2s(dA, pl - 8, PSA, full0 + 8 * s);
+                        bulk_g2s(dA + PSA, pl, PSA, full0 + 8 * s);
+                        bulk_g2s(dA + 2 * PSA, pl + 8, PSA, full0 + 8 * s);
+                        dA += 3 * PSA;
+                    } else {
+                        bulk_g2s(dA, pl, PSA, full0 + 8 * s);
+                        dA += PSA;
                     }
                 }
-                for (int ng = 0; ng < NG; ++ng)
-                    bulk_g2s(dG + (uint32_t)ng * PSG, a.Gd + ((size_t)ng * a.g.P + p0) * 8, PSG, full0 + 8 * s);
+                const __nv_bfloat16* gp = a.Gd + p0 * 8;
+                for (int ng = 0; ng < NG; ++ng, gp += plane, dG += PSG) bulk_g2s(dG, gp, PSG, full0 + 8 * s);
+                if (++s == a.nstage) { s = 0; ph ^= 1u; }
             }
         }
         __syncwarp();
     } else if (warp == 1) {
         if (lane == 0) {
             const uint32_t idesc = make_idesc(a.N, 1, 1, a.M);   // both operands MN-major
-            int it = 0;
-            for (int c = blockIdx.x; c < a.n_chunks; c += gridDim.x, ++it) {
-                const int s = it % a.nstage;
-                const uint32_t ph = (uint32_t)(it / a.nstage) & 1u;
+            // descriptor lo word = (address >> 4) | (LBO = 128 B) << 16; hi = SBO (plane stride) | version
+            const uint32_t a_hi = (PSA >> 4) | (1u << 14), g_hi = (PSG >> 4) | (1u << 14);
+            const uint32_t a_lo0 = (((smem_u32(sA) + (uint32_t)a.halo * 16) & 0x3FFFFu) >> 4) | (8u << 16);
+            const uint32_t g_lo0 = ((smem_u32(sG) & 0x3FFFFu) >> 4) | (8u << 16);
+            const uint32_t a_stage = stageA >> 4, g_stage = stageG >> 4;
+            int s = 0; uint32_t ph = 0, accum = 0;
+            for (int c = blockIdx.x; c < a.n_chunks; c += gridDim.x) {
                 mbar_wait(full0 + 8 * s, ph);
                 tc_fence_after();
-                const uint32_t aB = smem_u32(sA) + (uint32_t)s * stageA;
-                const uint32_t gB = smem_u32(sG) + (uint32_t)s * stageG;
+                const uint32_t aB = a_lo0 + (uint32_t)s * a_stage;
+                const uint32_t gB = g_lo0 + (uint32_t)s * g_stage;
                 for (int t = 0; t < a.NM; ++t) {
-                    int off;                                  // row shift of this MMA's A operand
+                    int off;                                  // row shift (16 B units) of this MMA's A operand
                     if (a.CP == 3) off = (t0 + t - 1) * a.g.Wp;
                     else off = a.ntaps == 9 ? ((t0 + t) / 3 - 1) * a.g.Wp + ((t0 + t) % 3 - 1) : 0;
-                    const uint32_t arow = aB + (uint32_t)(a.halo + off) * 16;
+                    const uint32_t arow = aB + (uint32_t)off;
                     const uint32_t dcol = tmem_base + (uint32_t)t * a.N;
-                    for (int ks = 0; ks < kChunk / 16; ++ks) {
-                        const uint64_t ad = make_desc(arow + (uint32_t)ks * 256, 128, PSA);
-                        const uint64_t bd = make_desc(gB + (uint32_t)ks * 256, 128, PSG);
-                        tc_mma(dcol, ad, bd, idesc, (it | ks) != 0);
-                    }
+#pragma unroll
+                    for (int ks = 0; ks < kChunk / 16; ++ks)   // 16 pixels = 256 B per K step
+                        tc_mma(dcol, ((uint64_t)a_hi << 32) | (arow + ks * 16), ((uint64_t)g_hi << 32) | (gB + ks * 16),
+                               idesc, accum | (uint32_t)ks);
                 }
+                accum = 1;
                 tc_commit(empty0 + 8 * s);
+                if (++s == a.nstage) { s = 0; ph ^= 1u; }
             }
             tc_commit(done);
         }

@@ -893,7 +893,7 @@ class _Plan:
                 def red(sc=sc, dact=dact, dfeat=dfeat, bn=bn):
                     L.bn_bwd_reduce(_vp(sc.lin), _vp(dact), _vp(dfeat), Balloc, _vp(sc.ss), _vp(sc.mr), sc.N,
                                     *sc.geo.args(), _vp(self.partials), STATS_CAP, ctypes.byref(self.cnt), dt, S())
-                    L.bn_bwd_finalize(_vp(self.partials), self.cnt.value, sc.N, _vp(sc.sums),
+                    L.bn_bwd_finalize(_vp(self.partials), self.cnt.value, sc.N, _vp(sc.mr), _vp(sc.sums),
                                       eng.gptr(bn.params.γ), eng.gptr(bn.params.β), S())
                 self._tag(red, 'bn_bwd_reduce', nbytes=B * sc.geo.H * sc.geo.W * sc.N * (2 if dt == BF16 else 4) * 2)
                 self.bwd_ops.append(red)

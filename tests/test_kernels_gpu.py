@@ -306,7 +306,7 @@ def test_bn_relu_pool_fwd_bwd(dt, pool):
     L().bn_bwd_reduce(vp(LIN), vp(DY), vp(DF), Balloc, vp(ss), vp(mr), C, B, H, H, geo.G, geo.P,
                       vp(parts), 592, ctypes.byref(cnt), dt, None)
     sums = torch.zeros((2, C), device='cuda'); dg = torch.zeros(C, device='cuda'); dbt = torch.zeros(C, device='cuda')
-    L().bn_bwd_finalize(vp(parts), cnt.value, C, vp(sums), vp(dg), vp(dbt), None)
+    L().bn_bwd_finalize(vp(parts), cnt.value, C, vp(mr), vp(sums), vp(dg), vp(dbt), None)
     dlin = torch.zeros_like(LIN)
     dbias = torch.zeros(C, device='cuda')
     L().bn_relu_pool_bwd(vp(LIN), vp(DY), vp(DF), Balloc, vp(DP), gp.P if pool else 0, vp(ss), vp(mr), vp(sums),
