@@ -11,6 +11,7 @@ Every node is evaluated densely on the whole batch, exactly like the
 reference.
 """
 import ctypes
+import os
 from types import SimpleNamespace as Ns
 
 import numpy as np
@@ -108,9 +109,17 @@ class Engine:
         self._alloc_params()
         self._plans = {}
         self._graphs = {}
-        self.hyp_host = torch.zeros(HYP_COUNT, dtype=torch.float32)
+        self._side = None
+        self.multistream = os.environ.get('MPNN_MULTISTREAM', '1') != '0'
+        # per-step scalars travel host->device asynchronously from pinned memory; a ring of slots
+        # (each guarded by an event) keeps step t+1's values from overwriting step t's before its
+        # copy has executed
+        self._hyp_ring = [torch.zeros(HYP_COUNT, dtype=torch.float32) for _ in range(1 if self.dry else 16)]
         if not self.dry:
-            self.hyp_host = self.hyp_host.pin_memory()
+            self._hyp_ring = [t.pin_memory() for t in self._hyp_ring]
+        self._hyp_ev = [None] * len(self._hyp_ring)
+        self._hyp_i = 0
+        self.hyp_host = self._hyp_ring[0]
         self.hyp = torch.zeros(HYP_COUNT, dtype=torch.float32, device=self.dev)
 
     # ------------------------------------------------------------------ #
@@ -298,7 +307,10 @@ class Engine:
         B = plan.B
         plan.x0.copy_(self._to_dev(x0, (B,) + tuple(hy.x0_shape), 'x0'), non_blocking=True)
         plan.y.copy_(self._to_dev(y, (B,) + tuple(hy.y_shape), 'y'), non_blocking=True)
-        h = self.hyp_host
+        i = self._hyp_i = (self._hyp_i + 1) % len(self._hyp_ring)
+        if self._hyp_ev[i] is not None:
+            self._hyp_ev[i].synchronize()
+        h = self.hyp_host = self._hyp_ring[i]
         h[HYP_LR] = float(feed.get(net.λ_lrn, hy.λ_lrn))
         h[HYP_MU] = float(feed.get(net.μ_lrn, hy.μ_lrn))
         h[HYP_GSCALE] = 1.0 / self.world
@@ -318,6 +330,9 @@ class Engine:
             else:
                 h[HYP_KCPT] = float(hy.k_cpt)
         self.hyp.copy_(h, non_blocking=True)
+        if self._hyp_ev[i] is None:
+            self._hyp_ev[i] = torch.cuda.Event()
+        self._hyp_ev[i].record()
 
     def _batch_of(self, feed):
         x0 = feed[self.net.x0]
@@ -329,9 +344,29 @@ class Engine:
     def _run(self, ops):
         if self.dry:
             raise RuntimeError('dry-run engine cannot execute: the hot path is CUDA-only')
-        self.stream = ctypes.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)
+        main = torch.cuda.current_stream(self.dev)
+        main_p = self.stream = ctypes.c_void_p(main.cuda_stream)
+        if not self.multistream:
+            for op in ops:
+                op()
+            return
+        # weight-gradient launches only feed the optimiser: they fork onto a second stream and
+        # overlap the BN-backward / data-gradient chain (fork/join also holds under graph capture)
+        if self._side is None:
+            self._side = torch.cuda.Stream(self.dev)
+        side_p = ctypes.c_void_p(self._side.cuda_stream)
+        forked = False
         for op in ops:
-            op()
+            if getattr(op, 'side', False):
+                self._side.wait_stream(main)
+                self.stream = side_p
+                op()
+                self.stream = main_p
+                forked = True
+            else:
+                op()
+        if forked:
+            main.wait_stream(self._side)
 
     def train_step(self, feed, update=True):
         """One `net.train.run(...)`: forward ('tr'), backward, TALR + momentum."""
@@ -490,6 +525,7 @@ class _Plan:
     def _tag(fn, kind, flops=0.0, nbytes=0.0, desc=''):
         """algorithmic work of one launch (bench.py roofline); untagged ops are 'misc'"""
         fn.kind, fn.flops, fn.nbytes, fn.desc = kind, float(flops), float(nbytes), desc
+        fn.side = kind in ('conv_wgrad', 'fc_wgrad')
 
     # -- allocation helpers ------------------------------------------------ #
     def planes(self, C, geo):
