@@ -564,19 +564,7 @@ router_tail_bwd_kernel(const float* Z1, const float* Z2, const float* dR, int B,
                          dW3, dbias3, dZ1, scratch, nullptr, 0, nullptr);
 }
 
-__global__ void __launch_bounds__(RT_THREADS)
-router_tail_bwd_batched_kernel(const mpnn_router_bwd_desc* __restrict__ descs, int B) {
-    const mpnn_router_bwd_desc r = descs[blockIdx.x];
-    router_tail_bwd_body(r.Z1, r.Z2, r.dR, B, r.ns, r.g1, r.b1, r.W2, r.g2, r.b2, r.W3, r.save, r.dg1, r.dbt1,
-                         r.dW2, r.dbias2, r.dg2, r.dbt2, r.dW3, r.dbias3, r.dZ1, r.scratch,
-                         (__nv_bfloat16*)r.dZ1p, r.Balloc, r.dbias1);
-}
-
-extern "C" int mpnn_router_tail_bwd_batched(const mpnn_router_bwd_desc* descs, int n, int B, int C, void* stream) {
-    MPNN_REQUIRE(C == RT_C && n >= 1, "router_tail_bwd_batched: C=%d n=%d", C, n);
-    router_tail_bwd_batched_kernel<<<n, RT_THREADS, 0, (cudaStream_t)stream>>>(descs, B);
-    return mpnn_check_launch("router_tail_bwd_batched");
-}
+// (the batched variant -- every router in one launch -- lives in router_bwd.cu)
 
 extern "C" int mpnn_router_tail_bwd(const float* Z1, const float* Z2, const float* dR, int B, int C, int ns,
                                     const float* g1, const float* b1, const float* W2,

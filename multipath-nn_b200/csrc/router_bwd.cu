@@ -1,0 +1,229 @@
+// Backward of every router tail of the net in ONE launch, one 8-CTA thread-block
+// cluster per router (reference: lib/net_types.py router() = FC16-BN-ReLU-FC16-
+// BN-ReLU-FC(n_sinks); TF autodiff through train-mode batch norm).
+//
+// Train-mode BN makes the backward a chain of two batch-wide reductions
+//   (BN2 sums) -> (BN1 sums) -> dZ1,
+// which a single CTA can only walk serially over the whole batch.  Here the
+// batch is split over the 8 CTAs of a cluster; each CTA reduces its slice, the
+// slices are combined through distributed shared memory (fixed rank order, so
+// the BN statistics are deterministic) and cluster.sync() separates the phases.
+// The two small weight gradients (16x16, 16xns) are accumulated per CTA from
+// shared-memory tiles and added to the flat gradient buffer with fp32 atomics.
+#include <cooperative_groups.h>
+#include "common.cuh"
+#include "../../include/mpnn.h"
+
+namespace cg = cooperative_groups;
+
+namespace {
+
+constexpr int C = 16;            // router width
+constexpr int NSMAX = 8;         // max sinks
+constexpr int T = 256;           // threads per CTA = rows per tile
+constexpr int CL = 8;            // CTAs per cluster
+constexpr int LD = C + 1;        // padded tile row
+
+__device__ __forceinline__ void block_add(const float* v, int n, float* acc) {
+    const int lane = threadIdx.x & 31;
+    for (int i = 0; i < n; ++i) {
+        float t = warp_sum(v[i]);
+        if (lane == 0) atomicAdd(acc + i, t);
+    }
+}
+
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(T)
+router_tail_bwd_cluster_kernel(const mpnn_router_bwd_desc* __restrict__ descs, int B) {
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (int)cluster.block_rank();
+    const mpnn_router_bwd_desc r = descs[blockIdx.x / CL];
+    const int ns = r.ns, tid = threadIdx.x;
+
+    __shared__ float sW2[C * C], sW3[C * NSMAX];
+    __shared__ float a1[C], c1[C], a2[C], c2[C], mn1[C], rs1[C], mn2[C], rs2[C];
+    __shared__ float tH[T * LD], tD[T * LD], tR[T * (NSMAX + 1)];
+    __shared__ float part[T];
+    __shared__ float sum2[2 * C], sum1[2 * C];      // this CTA's BN2 / BN1 partial sums (read by the cluster)
+    __shared__ float tot2[2 * C], tot1[2 * C];      // cluster totals
+    __shared__ float sb1[C];
+
+    sW2[tid] = r.W2[tid];
+    if (tid < C * ns) sW3[tid] = r.W3[tid];
+    if (tid < C) {
+        mn1[tid] = r.save[tid]; rs1[tid] = r.save[C + tid];
+        mn2[tid] = r.save[2 * C + tid]; rs2[tid] = r.save[3 * C + tid];
+        a1[tid] = r.g1[tid] * rs1[tid]; c1[tid] = r.b1[tid] - mn1[tid] * a1[tid];
+        a2[tid] = r.g2[tid] * rs2[tid]; c2[tid] = r.b2[tid] - mn2[tid] * a2[tid];
+        sb1[tid] = 0.f;
+    }
+    if (tid < 2 * C) { sum2[tid] = 0.f; sum1[tid] = 0.f; }
+    __syncthreads();
+
+    const int Bc = (B + CL - 1) / CL;
+    const int b_lo = rank * Bc, b_hi = min(B, b_lo + Bc);
+    const float invB = 1.f / (float)B;
+
+    // forward recompute of one row up to dL/d(BN2 output): h2, masked dz, xhat2
+    auto row_top = [&](int b, float* h2, float* dz, float* xh, float* dr) {
+        for (int k = 0; k < NSMAX; ++k) dr[k] = k < ns ? r.dR[(size_t)b * ns + k] : 0.f;
+#pragma unroll
+        for (int i = 0; i < C; ++i) {
+            const float z = r.Z2[(size_t)b * C + i];
+            const float h = fmaxf(fmaf(a2[i], z, c2[i]), 0.f);
+            float dh = 0.f;
+            for (int k = 0; k < ns; ++k) dh = fmaf(dr[k], sW3[i * ns + k], dh);
+            h2[i] = h;
+            dz[i] = h > 0.f ? dh : 0.f;
+            xh[i] = (z - mn2[i]) * rs2[i];
+        }
+    };
+
+    // ---- phase A: FC3 / ReLU2 backward, BN2 sums, dW3, dbias3 --------------------
+    {
+        float s01[2 * C];
+#pragma unroll
+        for (int i = 0; i < 2 * C; ++i) s01[i] = 0.f;
+        const int q = tid >> 7, t = tid & 127, gi = t >> 3, gk = t & 7;     // (row phase, i, k)
+        float acc = 0.f, accb = 0.f;
+        for (int base = b_lo; base < b_hi; base += T) {
+            const int b = base + tid;
+            float h2[C], dz[C], xh[C], dr[NSMAX];
+            if (b < b_hi) {
+                row_top(b, h2, dz, xh, dr);
+#pragma unroll
+                for (int i = 0; i < C; ++i) { s01[i] += dz[i]; s01[C + i] += dz[i] * xh[i]; }
+            } else {
+#pragma unroll
+                for (int i = 0; i < C; ++i) h2[i] = 0.f;
+#pragma unroll
+                for (int k = 0; k < NSMAX; ++k) dr[k] = 0.f;
+            }
+#pragma unroll
+            for (int i = 0; i < C; ++i) tH[tid * LD + i] = h2[i];
+#pragma unroll
+            for (int k = 0; k < NSMAX; ++k) tR[tid * (NSMAX + 1) + k] = dr[k];
+            __syncthreads();
+            for (int row = q; row < T; row += 2) {
+                const float drv = tR[row * (NSMAX + 1) + gk];
+                acc = fmaf(tH[row * LD + gi], drv, acc);
+                accb += drv;
+            }
+            __syncthreads();
+        }
+        part[tid] = acc;
+        __syncthreads();
+        if (tid < 128 && gk < ns) atomicAdd(r.dW3 + gi * ns + gk, part[tid] + part[tid + 128]);
+        __syncthreads();
+        part[tid] = accb;
+        __syncthreads();
+        if (tid < 128 && gi == 0 && gk < ns) atomicAdd(r.dbias3 + gk, part[tid] + part[tid + 128]);
+        block_add(s01, 2 * C, sum2);
+    }
+    cluster.sync();
+    if (tid < 2 * C) {
+        float t = 0.f;
+        for (int k = 0; k < CL; ++k) t += cluster.map_shared_rank(sum2, k)[tid];
+        tot2[tid] = t;
+        if (rank == 0) {
+            if (tid < C) r.dbt2[tid] += t; else r.dg2[tid - C] += t;
+        }
+    }
+    __syncthreads();
+
+    // ---- phase B: BN2 / FC2 / ReLU1 backward, BN1 sums, dW2, dbias2 ----------------
+    {
+        float s01[2 * C];
+#pragma unroll
+        for (int i = 0; i < 2 * C; ++i) s01[i] = 0.f;
+        const int gi = tid >> 4, gj = tid & 15;
+        float acc = 0.f, accb = 0.f;
+        for (int base = b_lo; base < b_hi; base += T) {
+            const int b = base + tid;
+            float h[C], dz2[C];
+            if (b < b_hi) {
+                float dz[C], xh[C], dr[NSMAX];
+                row_top(b, h, dz, xh, dr);
+#pragma unroll
+                for (int j = 0; j < C; ++j)
+                    dz2[j] = a2[j] * (dz[j] - tot2[j] * invB - xh[j] * tot2[C + j] * invB);
+#pragma unroll
+                for (int i = 0; i < C; ++i) {
+                    const float z = r.Z1[(size_t)b * C + i];
+                    const float h1 = fmaxf(fmaf(a1[i], z, c1[i]), 0.f);
+                    float dh = 0.f;
+#pragma unroll
+                    for (int j = 0; j < C; ++j) dh = fmaf(dz2[j], sW2[i * C + j], dh);
+                    const float d1 = h1 > 0.f ? dh : 0.f;
+                    const float x1 = (z - mn1[i]) * rs1[i];
+                    h[i] = h1;
+                    r.dZ1[(size_t)b * C + i] = d1;
+                    s01[i] += d1; s01[C + i] += d1 * x1;
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < C; ++i) { h[i] = 0.f; dz2[i] = 0.f; }
+            }
+#pragma unroll
+            for (int i = 0; i < C; ++i) { tH[tid * LD + i] = h[i]; tD[tid * LD + i] = dz2[i]; }
+            __syncthreads();
+            for (int row = 0; row < T; ++row) {
+                const float dv = tD[row * LD + gj];
+                acc = fmaf(tH[row * LD + gi], dv, acc);
+                accb += dv;
+            }
+            __syncthreads();
+        }
+        atomicAdd(r.dW2 + tid, acc);
+        if (gi == 0) atomicAdd(r.dbias2 + gj, accb);
+        block_add(s01, 2 * C, sum1);
+    }
+    cluster.sync();
+    if (tid < 2 * C) {
+        float t = 0.f;
+        for (int k = 0; k < CL; ++k) t += cluster.map_shared_rank(sum1, k)[tid];
+        tot1[tid] = t;
+        if (rank == 0) {
+            if (tid < C) r.dbt1[tid] += t; else r.dg1[tid - C] += t;
+        }
+    }
+    __syncthreads();
+
+    // ---- phase C: BN1 backward in place (+ bf16 planes copy for the tcgen05 head GEMMs) ---
+    {
+        float bsum[C];
+#pragma unroll
+        for (int i = 0; i < C; ++i) bsum[i] = 0.f;
+        for (int b = b_lo + tid; b < b_hi; b += T) {
+            float o[C];
+#pragma unroll
+            for (int i = 0; i < C; ++i) {
+                const float z = r.Z1[(size_t)b * C + i];
+                const float x1 = (z - mn1[i]) * rs1[i];
+                float d = r.dZ1[(size_t)b * C + i];
+                d = a1[i] * (d - tot1[i] * invB - x1 * tot1[C + i] * invB);
+                r.dZ1[(size_t)b * C + i] = d;
+                o[i] = d;
+                bsum[i] += d;
+            }
+            if (r.dZ1p) {
+                __nv_bfloat16* pl = (__nv_bfloat16*)r.dZ1p;
+                Row8<__nv_bfloat16>::store(plane_row(pl, 0, r.Balloc, b), o);
+                Row8<__nv_bfloat16>::store(plane_row(pl, 1, r.Balloc, b), o + 8);
+            }
+        }
+        if (r.dbias1) {      // bias of the first router FC (zero up to rounding under train-mode BN)
+            block_add(bsum, C, sb1);
+            __syncthreads();
+            if (tid < C) atomicAdd(r.dbias1 + tid, sb1[tid]);
+        }
+    }
+    cluster.sync();          // keep this CTA's shared memory alive until every peer has read it
+}
+
+}  // namespace
+
+extern "C" int mpnn_router_tail_bwd_batched(const mpnn_router_bwd_desc* descs, int n, int B, int Cw, void* stream) {
+    MPNN_REQUIRE(Cw == C && n >= 1, "router_tail_bwd_batched: C=%d n=%d", Cw, n);
+    router_tail_bwd_cluster_kernel<<<n * CL, T, 0, (cudaStream_t)stream>>>(descs, B);
+    return mpnn_check_launch("router_tail_bwd_batched");
+}

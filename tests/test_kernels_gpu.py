@@ -442,6 +442,61 @@ def test_router_tail(B, ns):
         assert rel_err(G[k].cpu().numpy(), T[k].grad.numpy()) < 2e-4, k
 
 
+@pytest.mark.parametrize('B', [24, 1000, 2048 + 77])
+def test_router_tail_bwd_batched_matches_single(B):
+    """The one-launch cluster kernel (8 CTAs per router, DSMEM reductions) against the
+    single-CTA kernel validated above; routers of different fan-out in the same launch."""
+    from lib.engine import _RT_BWD
+    rng = np.random.default_rng(12)
+    C = 16
+    Balloc = -(-B // 128) * 128
+    cases, rows = [], []
+    for ns in (2, 5, 8):
+        z1 = rng.standard_normal((B, C)).astype(np.float32)
+        P = {k: dev(rng.standard_normal(sh).astype(np.float32) * sc) for k, sh, sc in [
+            ('g1', C, 1), ('b1', C, .3), ('W2', (C, C), .3), ('c2', C, .1), ('g2', C, 1), ('b2', C, .3),
+            ('W3', (C, ns), .3), ('c3', ns, .1)]}
+        st = [torch.zeros(C, device='cuda'), torch.ones(C, device='cuda'), torch.zeros(C, device='cuda'),
+              torch.ones(C, device='cuda')]
+        Z1 = dev(z1); Z2 = torch.zeros((B, C), device='cuda'); R = torch.zeros((B, ns), device='cuda')
+        save = torch.zeros(64, device='cuda')
+        L().router_tail_fwd(vp(Z1), B, C, vp(P['g1']), vp(P['b1']), vp(st[0]), vp(st[1]), vp(P['W2']), vp(P['c2']),
+                            vp(P['g2']), vp(P['b2']), vp(st[2]), vp(st[3]), vp(P['W3']), vp(P['c3']), ns, 0.9, 1e-6, 1,
+                            vp(Z2), vp(R), vp(save), None)
+        dR = dev(rng.standard_normal((B, ns)).astype(np.float32))
+        ref = {k: torch.zeros_like(P[k]) for k in P}
+        ref['dZ1'] = torch.zeros((B, C), device='cuda')
+        scratch = torch.zeros(2 * B * C, device='cuda')
+        L().router_tail_bwd(vp(Z1), vp(Z2), vp(dR), B, C, ns, vp(P['g1']), vp(P['b1']), vp(P['W2']),
+                            vp(P['g2']), vp(P['b2']), vp(P['W3']), vp(save),
+                            vp(ref['g1']), vp(ref['b1']), vp(ref['W2']), vp(ref['c2']), vp(ref['g2']), vp(ref['b2']),
+                            vp(ref['W3']), vp(ref['c3']), vp(ref['dZ1']), vp(scratch), None)
+        got = {k: torch.zeros_like(P[k]) for k in P}
+        got['dZ1'] = torch.zeros((B, C), device='cuda')
+        got['dZ1p'] = torch.zeros((2, Balloc, 8), dtype=torch.bfloat16, device='cuda')
+        got['c1'] = torch.zeros(C, device='cuda')
+        ptr = lambda t: t.data_ptr()
+        rows.append((ptr(Z1), ptr(Z2), ptr(dR), ptr(P['g1']), ptr(P['b1']), ptr(P['W2']), ptr(P['g2']), ptr(P['b2']),
+                     ptr(P['W3']), ptr(save), ptr(got['g1']), ptr(got['b1']), ptr(got['W2']), ptr(got['c2']),
+                     ptr(got['g2']), ptr(got['b2']), ptr(got['W3']), ptr(got['c3']), ptr(got['dZ1']), 0,
+                     ptr(got['dZ1p']), ptr(got['c1']), ns, Balloc))
+        cases.append((ref, got, (Z2, R, save, scratch, st)))     # keep every buffer alive until the batched launch
+    table = dev(np.frombuffer(np.array(rows, dtype=_RT_BWD).tobytes(), np.uint8).copy(), torch.uint8)
+    L().router_tail_bwd_batched(vp(table), len(rows), B, C, None)
+    torch.cuda.synchronize()
+    for ref, got, _ in cases:
+        for k in ref:
+            a, b = got[k].cpu().numpy(), ref[k].cpu().numpy()
+            if k == 'c2':          # zero gradient (bias in front of train-mode BN): both are rounding noise
+                assert np.abs(a).max() < 1e-4 * np.abs(ref['c3'].cpu().numpy()).max()
+                continue
+            assert rel_err(a, b) < 2e-5, (k, [(kk, float(rel_err(got[kk].cpu().numpy(), ref[kk].cpu().numpy()))) for kk in ref])
+        planes = got['dZ1p'].float().cpu().numpy()
+        flat = np.concatenate([planes[0, :B], planes[1, :B]], 1)
+        assert rel_err(flat, ref['dZ1'].cpu().numpy()) < 4e-3 and np.all(planes[:, B:] == 0)
+        assert np.abs(got['c1'].cpu().numpy()).max() < 1e-3      # column sums of dZ1 vanish under train-mode BN
+
+
 # --------------------------------------------------------------------------- #
 # compaction / gather / scatter / optimiser
 # --------------------------------------------------------------------------- #
