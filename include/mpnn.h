@@ -82,6 +82,26 @@ int mpnn_stencil_gemm(const void* A0, int K0, const void* A1, int K1,
                       float* stats, int stats_cap, int* n_parts,
                       int dtype, int out_dtype, int impl, void* stream);
 
+/* Train-mode BatchNorm statistics fused into their producer ("last CTA finalises").
+ * acc: [2*C + 1] doubles, zeroed ONCE at allocation (the kernels leave it zeroed):
+ * every CTA adds its partial sums with fp64 atomics and draws a ticket; the last
+ * one converts the totals into ss = (gamma*rstd, beta - mean*gamma*rstd),
+ * mr = (mean, rstd), updates the running averages (lib/layer_types.py:219-249)
+ * and resets acc.  Replaces stats + mpnn_bn_finalize on the training path. */
+typedef struct {
+    double* acc;
+    const float* gamma; const float* beta;
+    float* m_avg; float* v_avg;      /* running moments (may be NULL) */
+    float* ss; float* mr;            /* outputs, [2][C] each */
+    double count;                    /* B*H*W */
+    float d; float eps;
+} mpnn_bn_fuse;
+/* mpnn_stencil_gemm (9 taps, single output, no accumulate) + fused BN statistics of `out` */
+int mpnn_conv_bn_stats(const void* A0, int K0, const void* A1, int K1,
+                       const void* Wp, const float* bias, void* out, int N,
+                       int B, int H, int W, int G, int P, const mpnn_bn_fuse* bn,
+                       int dtype, int impl, void* stream);
+
 /* weight gradient of the above:
  *   dW0[tap][k][n] += sum_p A0[p+off][k] * Gd[p][n]   (k < K0real, n < Nreal)
  *   dW1 likewise for A1;  dbias[n] += sum_p Gd[p][n]
@@ -112,6 +132,13 @@ int mpnn_bn_bwd_reduce(const void* lin, const void* dAct, const void* dFeat, int
                        const float* ss, const float* mr, int C,
                        int B, int H, int W, int G, int P,
                        float* partials, int cap, int* n_parts, int dtype, void* stream);
+/* the same reduction with the finalisation fused (last CTA): writes sums[2][C] and adds
+ * dgamma / dbeta; acc as in mpnn_bn_fuse.  Replaces bn_bwd_reduce + bn_bwd_finalize. */
+typedef struct { double* acc; float* sums; float* dgamma; float* dbeta; } mpnn_bn_bwd_fuse;
+int mpnn_bn_bwd_reduce_fused(const void* lin, const void* dAct, const void* dFeat, int Balloc,
+                             const float* ss, const float* mr, int C,
+                             int B, int H, int W, int G, int P,
+                             const mpnn_bn_bwd_fuse* f, int dtype, void* stream);
 /* partials (from bn_bwd_reduce) hold sum dy' and sum dy'*x per channel;
  * sums[0][c] = sum dy', sums[1][c] = sum dy'*xhat; dgamma += sums1, dbeta += sums0 */
 int mpnn_bn_bwd_finalize(const float* partials, int n_parts, int C, const float* mr,

@@ -10,6 +10,7 @@
 // state is four 8-vectors of constants plus the rows in flight (<= 64 registers).
 #include "common.cuh"
 #include "../../include/mpnn.h"
+#include "bn_fuse.cuh"
 
 // incoming gradient of one pixel row: dAct + dFeat (either may be absent)
 template <typename T>
@@ -30,7 +31,8 @@ __device__ __forceinline__ void load_dy(const T* __restrict__ dAct, const T* __r
 template <typename T>
 __global__ void __launch_bounds__(256, 4)
 bn_bwd_reduce_kernel(const T* __restrict__ lin, const T* __restrict__ dAct, const T* __restrict__ dFeat,
-                     int Balloc, const float* __restrict__ ss, int C, Geom g, float* __restrict__ partials) {
+                     int Balloc, const float* __restrict__ ss, int C, Geom g, float* __restrict__ partials,
+                     const float* __restrict__ mr, const mpnn_bn_bwd_fuse f) {
     const int kg = blockIdx.y, KG = C / 8;
     float a[8], c[8], s0[8], s1[8];
 #pragma unroll
@@ -63,33 +65,76 @@ bn_bwd_reduce_kernel(const T* __restrict__ lin, const T* __restrict__ dAct, cons
         if (lane == 0) { red[warp][j] = t0; red[warp][8 + j] = t1; }
     }
     __syncthreads();
-    if (threadIdx.x < 16) {
+    if (partials && threadIdx.x < 16) {
         float t = 0.f;
 #pragma unroll
         for (int wv = 0; wv < 8; ++wv) t += red[wv][threadIdx.x];
         const int which = threadIdx.x / 8, j = threadIdx.x % 8;
         partials[((size_t)blockIdx.x * 2 + which) * C + kg * 8 + j] = t;
     }
+    if (f.acc) {
+        // fused finalisation (see bn_fuse.cuh): totals of dy' and dy'*x -> sums in the xhat form
+        const bool last = mpnn_acc_and_ticket(f.acc, C, kg * 8, 8, gridDim.x * gridDim.y, [&](int i) {
+            float t = 0.f;
+#pragma unroll
+            for (int wv = 0; wv < 8; ++wv) t += red[wv][i];
+            return t; });
+        if (last) {
+            for (int c = threadIdx.x; c < C; c += blockDim.x) {
+                const double t0 = __ldcg(f.acc + c), t1 = __ldcg(f.acc + C + c);
+                f.acc[c] = 0.0; f.acc[C + c] = 0.0;
+                const double mean = mr[c], rstd = mr[C + c];
+                const double sx = rstd * (t1 - mean * t0);           // sum dy'*xhat
+                f.sums[c] = (float)t0;
+                f.sums[C + c] = (float)sx;
+                if (f.dgamma) f.dgamma[c] += (float)sx;
+                if (f.dbeta) f.dbeta[c] += (float)t0;
+            }
+            if (threadIdx.x == 0) *reinterpret_cast<unsigned*>(f.acc + 2 * C) = 0u;
+        }
+    }
 }
 
-extern "C" int mpnn_bn_bwd_reduce(const void* lin, const void* dAct, const void* dFeat, int Balloc,
-                                  const float* ss, const float* mr, int C,
-                                  int B, int H, int W, int G, int P,
-                                  float* partials, int cap, int* n_parts, int dtype, void* stream) {
-    MPNN_REQUIRE(C % 8 == 0 && cap > 0 && ss && mr, "bn_bwd_reduce: args");
+static int bn_bwd_reduce_impl(const void* lin, const void* dAct, const void* dFeat, int Balloc,
+                              const float* ss, const float* mr, int C,
+                              int B, int H, int W, int G, int P,
+                              float* partials, int cap, int* n_parts, const mpnn_bn_bwd_fuse* fp,
+                              int dtype, void* stream) {
+    MPNN_REQUIRE(C % 8 == 0 && ss && mr && (fp || cap > 0), "bn_bwd_reduce: args");
+    MPNN_REQUIRE(!fp || (fp->acc && fp->sums), "bn_bwd_reduce_fused: incomplete mpnn_bn_bwd_fuse");
     Geom g = make_geom(B, H, W, G, P);
     int total = B * H * W;
     int gx = ceil_div(total, 256 * 4);
     int lim = 148 * 8 / (C / 8);
     if (lim < 74) lim = 74;
     if (gx > lim) gx = lim;
-    if (gx > cap) gx = cap;
+    if (partials && gx > cap) gx = cap;
     if (gx < 1) gx = 1;
     if (n_parts) *n_parts = gx;
+    mpnn_bn_bwd_fuse f = {};
+    if (fp) f = *fp;
     dim3 grid(gx, C / 8);
     MPNN_DISPATCH_DTYPE(dtype, (bn_bwd_reduce_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(
-        (const T*)lin, (const T*)dAct, (const T*)dFeat, Balloc, ss, C, g, partials)));
+        (const T*)lin, (const T*)dAct, (const T*)dFeat, Balloc, ss, C, g, partials, mr, f)));
     return mpnn_check_launch("bn_bwd_reduce");
+}
+
+extern "C" int mpnn_bn_bwd_reduce(const void* lin, const void* dAct, const void* dFeat, int Balloc,
+                                  const float* ss, const float* mr, int C,
+                                  int B, int H, int W, int G, int P,
+                                  float* partials, int cap, int* n_parts, int dtype, void* stream) {
+    MPNN_REQUIRE(partials, "bn_bwd_reduce: partials is NULL");
+    return bn_bwd_reduce_impl(lin, dAct, dFeat, Balloc, ss, mr, C, B, H, W, G, P, partials, cap, n_parts,
+                              nullptr, dtype, stream);
+}
+
+extern "C" int mpnn_bn_bwd_reduce_fused(const void* lin, const void* dAct, const void* dFeat, int Balloc,
+                                        const float* ss, const float* mr, int C,
+                                        int B, int H, int W, int G, int P,
+                                        const mpnn_bn_bwd_fuse* f, int dtype, void* stream) {
+    MPNN_REQUIRE(f, "bn_bwd_reduce_fused: f is NULL");
+    return bn_bwd_reduce_impl(lin, dAct, dFeat, Balloc, ss, mr, C, B, H, W, G, P, nullptr, 0, nullptr, f,
+                              dtype, stream);
 }
 
 // partials hold sum(dy') and sum(dy'*x); sums[0] = sum dy', sums[1] = sum dy'*xhat

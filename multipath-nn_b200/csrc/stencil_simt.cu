@@ -4,10 +4,12 @@
 // stencil_umma.cu and is selected with impl=1.
 #include "common.cuh"
 #include "../../include/mpnn.h"
+#include "bn_fuse.cuh"
 
 int mpnn_stencil_gemm_umma(const void* A0, int K0, const void* A1, int K1, const void* Wp, int ntaps,
                            const float* bias, void* out0, int N0, int acc0, void* out1, int N1, int acc1,
-                           Geom g, float* stats, int stats_cap, int* n_parts, int out_dtype, cudaStream_t st);
+                           Geom g, float* stats, int stats_cap, int* n_parts, int out_dtype,
+                           const mpnn_bn_fuse* bn, cudaStream_t st);
 int mpnn_stencil_wgrad_umma(const void* A0, int K0, int K0real, float* dW0, const void* A1, int K1,
                             int K1real, float* dW1, const void* Gd, int N, int Nreal, float* dbias,
                             int ntaps, Geom g, cudaStream_t st);
@@ -21,7 +23,7 @@ __global__ void __launch_bounds__(128)
 stencil_gemm_simt(const T* __restrict__ A0, int K0, const T* __restrict__ A1, int K1,
                   const T* __restrict__ Wp, int ntaps, const float* __restrict__ bias,
                   TO* __restrict__ out0, int N0, int acc0, TO* __restrict__ out1, int N1, int acc1,
-                  Geom g, int n_tiles, float* __restrict__ stats) {
+                  Geom g, int n_tiles, float* __restrict__ stats, const mpnn_bn_fuse bn) {
     const int N = N0 + N1;
     const int n0 = blockIdx.y * NB;
     const int KG0 = K0 / 8, KG = (K0 + K1) / 8;
@@ -72,12 +74,12 @@ stencil_gemm_simt(const T* __restrict__ A0, int K0, const T* __restrict__ A1, in
                 Row8<TO>::store(dst, v);
             }
         }
-        if (stats && valid) {
+        if ((stats || bn.acc) && valid) {
 #pragma unroll
             for (int j = 0; j < NB; ++j) { ssum[j] += acc[j]; ssq[j] += acc[j] * acc[j]; }
         }
     }
-    if (stats) {
+    if (stats || bn.acc) {
         __shared__ float red[4][2 * NB];
         const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll
@@ -86,10 +88,15 @@ stencil_gemm_simt(const T* __restrict__ A0, int K0, const T* __restrict__ A1, in
             if (lane == 0) { red[warp][j] = s; red[warp][NB + j] = s2; }
         }
         __syncthreads();
-        if (threadIdx.x < 2 * NB) {
+        if (stats && threadIdx.x < 2 * NB) {
             float t = red[0][threadIdx.x] + red[1][threadIdx.x] + red[2][threadIdx.x] + red[3][threadIdx.x];
             int which = threadIdx.x / NB, j = threadIdx.x % NB;
             stats[((size_t)blockIdx.x * 2 + which) * N + n0 + j] = t;
+        }
+        if (bn.acc) {
+            const bool last = mpnn_acc_and_ticket(bn.acc, N, n0, NB, gridDim.x * gridDim.y,
+                                                  [&](int i) { return red[0][i] + red[1][i] + red[2][i] + red[3][i]; });
+            if (last) mpnn_bn_fwd_finalize_last(bn, N);
         }
     }
 }
@@ -97,35 +104,39 @@ stencil_gemm_simt(const T* __restrict__ A0, int K0, const T* __restrict__ A1, in
 template <typename T, typename TO>
 static int launch_gemm_simt(const void* A0, int K0, const void* A1, int K1, const void* Wp, int ntaps,
                             const float* bias, void* out0, int N0, int acc0, void* out1, int N1, int acc1,
-                            Geom g, float* stats, int stats_cap, int* n_parts, cudaStream_t st) {
+                            Geom g, float* stats, int stats_cap, int* n_parts, const mpnn_bn_fuse* bnp,
+                            cudaStream_t st) {
     const int N = N0 + N1;
+    mpnn_bn_fuse bn = {};
+    if (bnp) bn = *bnp;
     const int n_tiles = ceil_div(g.rows, 128);
     int gx = n_tiles;
     if (stats) { if (gx > stats_cap) gx = stats_cap; }
+    else if (bnp) { if (gx > 148 * 4) gx = 148 * 4; }
     else if (gx > 148 * 32) gx = 148 * 32;
     if (n_parts) *n_parts = stats ? gx : 0;
     if (N % 32 == 0 && N0 % 32 == 0) {
         dim3 grid(gx, N / 32);
         stencil_gemm_simt<T, TO, 32><<<grid, 128, 0, st>>>((const T*)A0, K0, (const T*)A1, K1, (const T*)Wp,
-            ntaps, bias, (TO*)out0, N0, acc0, (TO*)out1, N1, acc1, g, n_tiles, stats);
+            ntaps, bias, (TO*)out0, N0, acc0, (TO*)out1, N1, acc1, g, n_tiles, stats, bn);
     } else if (N % 16 == 0 && N0 % 16 == 0) {
         dim3 grid(gx, N / 16);
         stencil_gemm_simt<T, TO, 16><<<grid, 128, 0, st>>>((const T*)A0, K0, (const T*)A1, K1, (const T*)Wp,
-            ntaps, bias, (TO*)out0, N0, acc0, (TO*)out1, N1, acc1, g, n_tiles, stats);
+            ntaps, bias, (TO*)out0, N0, acc0, (TO*)out1, N1, acc1, g, n_tiles, stats, bn);
     } else {
         dim3 grid(gx, N / 8);
         stencil_gemm_simt<T, TO, 8><<<grid, 128, 0, st>>>((const T*)A0, K0, (const T*)A1, K1, (const T*)Wp,
-            ntaps, bias, (TO*)out0, N0, acc0, (TO*)out1, N1, acc1, g, n_tiles, stats);
+            ntaps, bias, (TO*)out0, N0, acc0, (TO*)out1, N1, acc1, g, n_tiles, stats, bn);
     }
     return mpnn_check_launch("stencil_gemm_simt");
 }
 
-extern "C" int mpnn_stencil_gemm(const void* A0, int K0, const void* A1, int K1,
-                                 const void* Wp, int ntaps, const float* bias,
-                                 void* out0, int N0, int acc0, void* out1, int N1, int acc1,
-                                 int B, int H, int W, int G, int P,
-                                 float* stats, int stats_cap, int* n_parts,
-                                 int dtype, int out_dtype, int impl, void* stream) {
+static int stencil_gemm_impl(const void* A0, int K0, const void* A1, int K1,
+                             const void* Wp, int ntaps, const float* bias,
+                             void* out0, int N0, int acc0, void* out1, int N1, int acc1,
+                             int B, int H, int W, int G, int P,
+                             float* stats, int stats_cap, int* n_parts, const mpnn_bn_fuse* bn,
+                             int dtype, int out_dtype, int impl, void* stream) {
     MPNN_REQUIRE(ntaps == 9 || ntaps == 1, "stencil_gemm: ntaps=%d", ntaps);
     MPNN_REQUIRE(K0 % 8 == 0 && K1 % 8 == 0 && K0 > 0, "stencil_gemm: K0=%d K1=%d", K0, K1);
     MPNN_REQUIRE(N0 % 8 == 0 && N1 % 8 == 0 && N0 + N1 > 0, "stencil_gemm: N0=%d N1=%d", N0, N1);
@@ -135,20 +146,41 @@ extern "C" int mpnn_stencil_gemm(const void* A0, int K0, const void* A1, int K1,
     MPNN_REQUIRE(G >= halo, "stencil_gemm: front guard %d < %d", G, halo);
     MPNN_REQUIRE(P >= G + ceil_div(g.rows, 128) * 128 + halo, "stencil_gemm: back guard too small (P=%d)", P);
     MPNN_REQUIRE(!stats || stats_cap > 0, "stencil_gemm: stats_cap");
+    MPNN_REQUIRE(!bn || (bn->acc && bn->gamma && bn->beta && bn->ss && bn->mr && bn->count > 0),
+                 "conv_bn_stats: incomplete mpnn_bn_fuse");
     cudaStream_t st = (cudaStream_t)stream;
     if (impl == 1) {
         MPNN_REQUIRE(dtype == MPNN_BF16, "stencil_gemm: tcgen05 path needs bf16 operands");
         return mpnn_stencil_gemm_umma(A0, K0, A1, K1, Wp, ntaps, bias, out0, N0, acc0, out1, N1, acc1,
-                                      g, stats, stats_cap, n_parts, out_dtype, st);
+                                      g, stats, stats_cap, n_parts, out_dtype, bn, st);
     }
 #define GO(T, TO) return launch_gemm_simt<T, TO>(A0, K0, A1, K1, Wp, ntaps, bias, out0, N0, acc0, out1, N1, \
-                                                 acc1, g, stats, stats_cap, n_parts, st)
+                                                 acc1, g, stats, stats_cap, n_parts, bn, st)
     if (dtype == MPNN_F32 && out_dtype == MPNN_F32) GO(float, float);
     if (dtype == MPNN_BF16 && out_dtype == MPNN_BF16) GO(__nv_bfloat16, __nv_bfloat16);
     if (dtype == MPNN_BF16 && out_dtype == MPNN_F32) GO(__nv_bfloat16, float);
 #undef GO
     mpnn_set_error("stencil_gemm: dtype combo %d/%d", dtype, out_dtype);
     return MPNN_ERR_ARG;
+}
+
+extern "C" int mpnn_stencil_gemm(const void* A0, int K0, const void* A1, int K1,
+                                 const void* Wp, int ntaps, const float* bias,
+                                 void* out0, int N0, int acc0, void* out1, int N1, int acc1,
+                                 int B, int H, int W, int G, int P,
+                                 float* stats, int stats_cap, int* n_parts,
+                                 int dtype, int out_dtype, int impl, void* stream) {
+    return stencil_gemm_impl(A0, K0, A1, K1, Wp, ntaps, bias, out0, N0, acc0, out1, N1, acc1, B, H, W, G, P,
+                             stats, stats_cap, n_parts, nullptr, dtype, out_dtype, impl, stream);
+}
+
+extern "C" int mpnn_conv_bn_stats(const void* A0, int K0, const void* A1, int K1,
+                                  const void* Wp, const float* bias, void* out, int N,
+                                  int B, int H, int W, int G, int P, const mpnn_bn_fuse* bn,
+                                  int dtype, int impl, void* stream) {
+    MPNN_REQUIRE(bn, "conv_bn_stats: bn is NULL");
+    return stencil_gemm_impl(A0, K0, A1, K1, Wp, 9, bias, out, N, 0, nullptr, 0, 0, B, H, W, G, P,
+                             nullptr, 0, nullptr, bn, dtype, dtype, impl, stream);
 }
 
 // --------------------------------------------------------------------------- //

@@ -21,6 +21,7 @@
 #include "common.cuh"
 #include "umma.cuh"
 #include "../../include/mpnn.h"
+#include "bn_fuse.cuh"
 
 extern "C" int mpnn_has_umma(void) { return 1; }
 
@@ -36,6 +37,7 @@ struct GemmArgs {
     int out_mode;      // 0: bf16 planes, 1: fp32 planes, 2: fp32 row-major [row][ld]
     int ld0, ld1;      // leading dimensions of out0 / out1 in row-major mode
     int KC, n_kc;      // planes per pipeline stage and stages per tile (K is streamed for wide FC inputs)
+    mpnn_bn_fuse bn;   // bn.acc != NULL: fused BN statistics (last CTA finalises)
     int dbg;           // tuning aid (MPNN_TUNE_DBG): 1 skip MMAs, 2 skip stores, 4 skip loads, 8 skip tcgen05.ld
 };
 
@@ -85,8 +87,9 @@ stencil_gemm_umma_kernel(const GemmArgs a) {
                      ::"r"(smem_u32(tmem_slot)), "r"(ncols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+    const bool want_stats = a.stats != nullptr || a.bn.acc != nullptr;
     if (threadIdx.x >= 64) {
-        if (a.stats)
+        if (want_stats)
             for (int i = threadIdx.x - 64; i < 4 * 2 * NB; i += 128) sstat[i] = 0.f;
         for (int i = threadIdx.x - 64; i < NB; i += 128) sbias[i] = a.bias ? a.bias[n0 + i] : 0.f;
     }
@@ -234,7 +237,7 @@ stencil_gemm_umma_kernel(const GemmArgs a) {
                     }
                 }
             }
-            if (a.stats) {
+            if (want_stats) {
                 if (NBT) {
                     if (valid) {
 #pragma unroll
@@ -257,7 +260,7 @@ stencil_gemm_umma_kernel(const GemmArgs a) {
             const int q = tile * 128 + m;
             const int p = a.g.G + q;
             int n_, h_, w_;
-            const bool valid = a.stats ? row_valid(a.g, q, n_, h_, w_) : false;
+            const bool valid = want_stats ? row_valid(a.g, q, n_, h_, w_) : false;
             const bool inrange = q < a.g.rows && !(a.dbg & 2);
             const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)acc * NB;
             mbar_wait(tfull0 + 8 * acc, aph);
@@ -285,7 +288,7 @@ stencil_gemm_umma_kernel(const GemmArgs a) {
                 if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
             }
         }
-        if (NBT && a.stats) {
+        if (NBT && want_stats) {
 #pragma unroll
             for (int ci = 0; ci < NR / 16; ++ci) {
                 float t1 = warp_colsum16(r1 + (NBT ? ci * 16 : 0), lane);
@@ -303,6 +306,11 @@ stencil_gemm_umma_kernel(const GemmArgs a) {
             for (int w = 0; w < 4; ++w) t += sstat[(size_t)w * 2 * NB + which * NB + j];
             a.stats[((size_t)blockIdx.x * 2 + which) * a.N + n0 + j] = t;
         }
+    }
+    if (a.bn.acc) {
+        const bool last = mpnn_acc_and_ticket(a.bn.acc, a.N, n0, NB, gridDim.x * gridDim.y, [&](int i) {
+            return sstat[i] + sstat[2 * NB + i] + sstat[4 * NB + i] + sstat[6 * NB + i]; });
+        if (last) mpnn_bn_fwd_finalize_last(a.bn, a.N);
     }
     if (warp == 1) {
         tc_fence_after();
@@ -372,7 +380,8 @@ umma_selftest_kernel(const uint8_t* __restrict__ A, int a_bytes, int a_off, cons
 
 int mpnn_stencil_gemm_umma(const void* A0, int K0, const void* A1, int K1, const void* Wp, int ntaps,
                            const float* bias, void* out0, int N0, int acc0, void* out1, int N1, int acc1,
-                           Geom g, float* stats, int stats_cap, int* n_parts, int out_dtype, cudaStream_t st) {
+                           Geom g, float* stats, int stats_cap, int* n_parts, int out_dtype,
+                           const mpnn_bn_fuse* bn, cudaStream_t st) {
     const int N = N0 + N1;
     MPNN_REQUIRE(K0 % 16 == 0 && K1 % 16 == 0, "stencil_gemm(tcgen05): K0=%d K1=%d must be multiples of 16", K0, K1);
     MPNN_REQUIRE(N % 16 == 0 && N0 % 16 == 0, "stencil_gemm(tcgen05): N0=%d N1=%d must be multiples of 16", N0, N1);
@@ -422,6 +431,8 @@ int mpnn_stencil_gemm_umma(const void* A0, int K0, const void* A1, int K1, const
     if (per_sm < 1) per_sm = 1;
     GemmArgs a;
     a.dbg = tune_dbg;
+    a.bn = mpnn_bn_fuse{};
+    if (bn) a.bn = *bn;
     a.A0 = (const __nv_bfloat16*)A0; a.A1 = (const __nv_bfloat16*)A1; a.Wp = (const __nv_bfloat16*)Wp;
     a.bias = bias; a.out0 = out0; a.out1 = out1; a.stats = stats; a.g = g;
     a.K0 = K0; a.K1 = K1; a.N = N; a.N0 = N0; a.NB = NB; a.ntaps = ntaps; a.acc0 = acc0; a.acc1 = acc1;
@@ -429,7 +440,7 @@ int mpnn_stencil_gemm_umma(const void* A0, int K0, const void* A1, int K1, const
     a.ld0 = N0; a.ld1 = N1;
     a.n_tiles = ceil_div(g.rows, 128); a.nstage = nstage;
     a.rowsA = rowsA; a.halo = halo; a.KC = KC; a.n_kc = ceil_div(KG, KC);
-    MPNN_REQUIRE(a.out_mode != 2 || (!acc0 && !acc1 && !stats), "stencil_gemm: row-major output cannot accumulate");
+    MPNN_REQUIRE(a.out_mode != 2 || (!acc0 && !acc1 && !stats && !bn), "stencil_gemm: row-major output cannot accumulate");
     int gx = 148 * per_sm / split;
     if (gx > a.n_tiles) gx = a.n_tiles;
     if (stats && gx > stats_cap) gx = stats_cap;
@@ -441,7 +452,7 @@ int mpnn_stencil_gemm_umma(const void* A0, int K0, const void* A1, int K1, const
     if (!attr_set) {
         void (*all[3])(const GemmArgs) = {stencil_gemm_umma_kernel<0>, stencil_gemm_umma_kernel<16>, stencil_gemm_umma_kernel<32>};
         for (int i = 0; i < 3; ++i) {
-            cudaError_t e = cudaFuncSetAttribute(all[i], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMax + 1024);
+            cudaError_t e = cudaFuncSetAttribute(all[i], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMax);   // + static smem stays under 227 KB
             if (e != cudaSuccess) { mpnn_set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return MPNN_ERR_CUDA; }
         }
         attr_set = true;

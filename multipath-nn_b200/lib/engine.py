@@ -39,7 +39,19 @@ _RT_FWD = _struct(['Z1', 'g1', 'b1', 'm1', 'v1', 'W2', 'bias2', 'g2', 'b2', 'm2'
 _RT_BWD = _struct(['Z1', 'Z2', 'dR', 'g1', 'b1', 'W2', 'g2', 'b2', 'W3', 'save', 'dg1', 'dbt1', 'dW2',
                    'dbias2', 'dg2', 'dbt2', 'dW3', 'dbias3', 'dZ1', 'scratch', 'dZ1p', 'dbias1'],
                   ['ns', 'Balloc'])
+_BN_FUSE = np.dtype([(k, '<u8') for k in ('acc', 'gamma', 'beta', 'm_avg', 'v_avg', 'ss', 'mr')]
+                    + [('count', '<f8'), ('d', '<f4'), ('eps', '<f4')], align=True)
+_BN_BWD_FUSE = _struct(['acc', 'sums', 'dgamma', 'dbeta'], [])
 assert _PACK.itemsize == 48 and _RT_FWD.itemsize == 136 and _RT_BWD.itemsize == 184
+assert _BN_FUSE.itemsize == 72 and _BN_BWD_FUSE.itemsize == 32
+
+
+def _host_struct(dtype, **fields):
+    """one C struct in host memory (numpy record); pointers given as c_void_p / int / None"""
+    rec = np.zeros(1, dtype)
+    for k, v in fields.items():
+        rec[k] = (v.value or 0) if isinstance(v, ctypes.c_void_p) else (0 if v is None else v)
+    return rec
 
 
 def _ru(a, b):
@@ -855,23 +867,37 @@ class _Plan:
             prev = st.sc[k - 1] if k > 0 else None
             use_stats = sc.live and train
 
-            def conv(sc=sc, prev=prev, use_stats=use_stats):
-                L.stencil_gemm(_vp(sc.src.t), sc.K0, _vp(prev.pooled) if prev is not None else None, sc.K1,
-                               _vp(sc.Wf), 9, eng.tptr(sc.bk), _vp(sc.lin), sc.N, 0, None, 0, 0,
-                               *sc.geo.args(), _vp(self.partials) if use_stats else None, STATS_CAP,
-                               ctypes.byref(self.cnt), dt, dt, impl, S())
+            if use_stats:
+                # train-mode BN statistics ride on the conv launch (last CTA finalises): no bn_finalize
+                bn = sc.bn
+                sc.acc = torch.zeros(2 * N + 1, dtype=torch.float64, device=eng.dev)
+                sc.bnf = _host_struct(_BN_FUSE, acc=_vp(sc.acc), gamma=eng.tptr(bn.params.γ), beta=eng.tptr(bn.params.β),
+                                      m_avg=eng.tptr(bn.params.m_avg), v_avg=eng.tptr(bn.params.v_avg),
+                                      ss=_vp(sc.ss), mr=_vp(sc.mr), count=float(B * geo.H * geo.W),
+                                      d=float(bn.hypers.d), eps=float(bn.hypers.ε))
+
+                def conv(sc=sc, prev=prev):
+                    L.conv_bn_stats(_vp(sc.src.t), sc.K0, _vp(prev.pooled) if prev is not None else None, sc.K1,
+                                    _vp(sc.Wf), eng.tptr(sc.bk), _vp(sc.lin), sc.N, *sc.geo.args(),
+                                    ctypes.c_void_p(sc.bnf.ctypes.data), dt, impl, S())
+            else:
+                def conv(sc=sc, prev=prev):
+                    L.stencil_gemm(_vp(sc.src.t), sc.K0, _vp(prev.pooled) if prev is not None else None, sc.K1,
+                                   _vp(sc.Wf), 9, eng.tptr(sc.bk), _vp(sc.lin), sc.N, 0, None, 0, 0,
+                                   *sc.geo.args(), None, 0, None, dt, dt, impl, S())
             self._tag(conv, 'conv_fwd', desc='H%d K%d+%d N%d' % (sc.geo.H, sc.K0, sc.K1, sc.N), flops=2.0 * B * sc.geo.H * sc.geo.W * 9 * (sc.K0real + sc.K1) * sc.N,
                       nbytes=B * sc.geo.H * sc.geo.W * (sc.K0 + sc.K1 + sc.N) * (2 if dt == BF16 else 4))
             self.fwd_ops.append(conv)
-            if sc.live:
+            if sc.live and not use_stats:
                 bn = sc.bn
 
-                def fin(sc=sc, bn=bn, use_stats=use_stats):
-                    L.bn_finalize(_vp(self.partials), self.cnt.value if use_stats else 0, sc.N,
+                def fin(sc=sc, bn=bn):             # inference: scale/shift from the running moments
+                    L.bn_finalize(None, 0, sc.N,
                                   float(B * sc.geo.H * sc.geo.W), eng.tptr(bn.params.γ), eng.tptr(bn.params.β),
                                   eng.tptr(bn.params.m_avg), eng.tptr(bn.params.v_avg),
-                                  float(bn.hypers.d), float(bn.hypers.ε), 1 if use_stats else 0,
+                                  float(bn.hypers.d), float(bn.hypers.ε), 0,
                                   _vp(sc.ss), _vp(sc.mr), S())
+                self._tag(fin, 'bn_finalize')
                 self.fwd_ops.append(fin)
             if sc.live or sc.pooled is not None:
                 def post(sc=sc):
@@ -926,11 +952,14 @@ class _Plan:
             if live:
                 bn = sc.bn
 
-                def red(sc=sc, dact=dact, dfeat=dfeat, bn=bn):
-                    L.bn_bwd_reduce(_vp(sc.lin), _vp(dact), _vp(dfeat), Balloc, _vp(sc.ss), _vp(sc.mr), sc.N,
-                                    *sc.geo.args(), _vp(self.partials), STATS_CAP, ctypes.byref(self.cnt), dt, S())
-                    L.bn_bwd_finalize(_vp(self.partials), self.cnt.value, sc.N, _vp(sc.mr), _vp(sc.sums),
-                                      eng.gptr(bn.params.γ), eng.gptr(bn.params.β), S())
+                if getattr(sc, 'acc', None) is None:
+                    sc.acc = torch.zeros(2 * sc.N + 1, dtype=torch.float64, device=eng.dev)
+                sc.bnb = _host_struct(_BN_BWD_FUSE, acc=_vp(sc.acc), sums=_vp(sc.sums),
+                                      dgamma=eng.gptr(bn.params.γ), dbeta=eng.gptr(bn.params.β))
+
+                def red(sc=sc, dact=dact, dfeat=dfeat):
+                    L.bn_bwd_reduce_fused(_vp(sc.lin), _vp(dact), _vp(dfeat), Balloc, _vp(sc.ss), _vp(sc.mr), sc.N,
+                                          *sc.geo.args(), ctypes.c_void_p(sc.bnb.ctypes.data), dt, S())
                 self._tag(red, 'bn_bwd_reduce', nbytes=B * sc.geo.H * sc.geo.W * sc.N * (2 if dt == BF16 else 4) * 2)
                 self.bwd_ops.append(red)
             if not live and dpooled is None:

@@ -326,6 +326,66 @@ def test_bn_relu_pool_fwd_bwd(dt, pool):
 # --------------------------------------------------------------------------- #
 # heads
 # --------------------------------------------------------------------------- #
+@pytest.mark.parametrize('dt,impl', [(F32, 0), (BF16, 0), (BF16, 1)])
+@pytest.mark.parametrize('B,H,K0,K1,N', [(3, 8, 16, 0, 16), (40, 16, 16, 16, 32), (7, 4, 64, 32, 64), (300, 8, 16, 0, 16)])
+def test_fused_bn_statistics_match_the_two_launch_path(dt, impl, B, H, K0, K1, N):
+    """conv_bn_stats / bn_bwd_reduce_fused ("last CTA finalises", fp64 atomics) against
+    stencil_gemm + bn_finalize and bn_bwd_reduce + bn_bwd_finalize; run twice to check that
+    the accumulator cleans itself."""
+    from lib.engine import _BN_BWD_FUSE, _BN_FUSE, _host_struct
+    rng = np.random.default_rng(21)
+    td = torch.float32 if dt == F32 else torch.bfloat16
+    geo = Geo(B, H, H)
+    mk = lambda C: dev(to_planes(rng.standard_normal((B, H, H, C)).astype(np.float32), geo), td)
+    A0, A1 = mk(K0), (mk(K1) if K1 else None)
+    Wp = dev(rng.standard_normal((9, (K0 + K1) // 8, N, 8)).astype(np.float32) * 0.1, td)
+    bias = dev(rng.standard_normal(N).astype(np.float32))
+    gamma, beta = dev(rng.standard_normal(N).astype(np.float32)), dev(rng.standard_normal(N).astype(np.float32))
+    count = float(B * H * H)
+    # two-launch path
+    out_a = torch.zeros((N // 8, geo.P, 8), dtype=td, device='cuda')
+    parts = torch.zeros(592 * 2 * N, device='cuda'); cnt = ctypes.c_int(0)
+    L().stencil_gemm(vp(A0), K0, vp(A1), K1, vp(Wp), 9, vp(bias), vp(out_a), N, 0, None, 0, 0, B, H, H, geo.G, geo.P,
+                     vp(parts), 592, ctypes.byref(cnt), dt, dt, impl, None)
+    ss_a, mr_a = torch.zeros((2, N), device='cuda'), torch.zeros((2, N), device='cuda')
+    ma_a, va_a = torch.zeros(N, device='cuda'), torch.ones(N, device='cuda')
+    L().bn_finalize(vp(parts), cnt.value, N, count, vp(gamma), vp(beta), vp(ma_a), vp(va_a), 0.9, 1e-6, 1,
+                    vp(ss_a), vp(mr_a), None)
+    # fused path (twice)
+    acc = torch.zeros(2 * N + 1, dtype=torch.float64, device='cuda')
+    ss_b, mr_b = torch.zeros((2, N), device='cuda'), torch.zeros((2, N), device='cuda')
+    ma_b, va_b = torch.zeros(N, device='cuda'), torch.ones(N, device='cuda')
+    out_b = torch.zeros_like(out_a)
+    f = _host_struct(_BN_FUSE, acc=vp(acc), gamma=vp(gamma), beta=vp(beta), m_avg=vp(ma_b), v_avg=vp(va_b),
+                     ss=vp(ss_b), mr=vp(mr_b), count=count, d=0.9, eps=1e-6)
+    for rep in range(2):
+        ma_b.zero_(); va_b.fill_(1.0)
+        L().conv_bn_stats(vp(A0), K0, vp(A1), K1, vp(Wp), vp(bias), vp(out_b), N, B, H, H, geo.G, geo.P,
+                          ctypes.c_void_p(f.ctypes.data), dt, impl, None)
+        torch.cuda.synchronize()
+        assert torch.equal(out_a, out_b)
+        assert float(acc.abs().max()) == 0.0                       # self-cleaned (ticket included)
+        for a, b in ((ss_a, ss_b), (mr_a, mr_b), (ma_a, ma_b), (va_a, va_b)):
+            np.testing.assert_allclose(b.cpu().numpy(), a.cpu().numpy(), rtol=2e-5, atol=2e-6)
+    # backward reduction
+    DY = mk(N)
+    sums_a = torch.zeros((2, N), device='cuda'); dg_a = torch.zeros(N, device='cuda'); db_a = torch.zeros(N, device='cuda')
+    L().bn_bwd_reduce(vp(out_a), vp(DY), None, 0, vp(ss_a), vp(mr_a), N, B, H, H, geo.G, geo.P,
+                      vp(parts), 592, ctypes.byref(cnt), dt, None)
+    L().bn_bwd_finalize(vp(parts), cnt.value, N, vp(mr_a), vp(sums_a), vp(dg_a), vp(db_a), None)
+    sums_b = torch.zeros((2, N), device='cuda'); dg_b = torch.zeros(N, device='cuda'); db_b = torch.zeros(N, device='cuda')
+    fb = _host_struct(_BN_BWD_FUSE, acc=vp(acc), sums=vp(sums_b), dgamma=vp(dg_b), dbeta=vp(db_b))
+    for rep in range(2):
+        dg_b.zero_(); db_b.zero_()
+        L().bn_bwd_reduce_fused(vp(out_a), vp(DY), None, 0, vp(ss_a), vp(mr_a), N, B, H, H, geo.G, geo.P,
+                                ctypes.c_void_p(fb.ctypes.data), dt, None)
+        torch.cuda.synchronize()
+        assert float(acc.abs().max()) == 0.0
+        scale = float(sums_a.abs().max())
+        for a, b in ((sums_a, sums_b), (dg_a, dg_b), (db_a, db_b)):
+            np.testing.assert_allclose(b.cpu().numpy(), a.cpu().numpy(), rtol=2e-5, atol=2e-6 * scale)
+
+
 @pytest.mark.parametrize('dt', [F32, BF16])
 @pytest.mark.parametrize('B,F,n,extra', [(5, 256, 10, False), (37, 512, 16, True), (128, 2048, 2, False)])
 def test_fc_fwd_bwd(dt, B, F, n, extra):
