@@ -121,7 +121,7 @@ class Engine:
         self._alloc_params()
         self._plans = {}
         self._graphs = {}
-        self._side = None
+        self._lanes = None
         self.multistream = os.environ.get('MPNN_MULTISTREAM', '1') != '0'
         # per-step scalars travel host->device asynchronously from pinned memory; a ring of slots
         # (each guarded by an event) keeps step t+1's values from overwriting step t's before its
@@ -362,23 +362,31 @@ class Engine:
             for op in ops:
                 op()
             return
-        # weight-gradient launches only feed the optimiser: they fork onto a second stream and
-        # overlap the BN-backward / data-gradient chain (fork/join also holds under graph capture)
-        if self._side is None:
-            self._side = torch.cuda.Stream(self.dev)
-        side_p = ctypes.c_void_p(self._side.cuda_stream)
-        forked = False
+        # Lanes.  0: the dependent chain (conv / BN / data gradients).  1: classifier and router
+        # heads, which only feed the losses (forward) or start from them (backward).  2: weight
+        # gradients, which only feed the optimiser.  Lane 1/2 launches fork onto their own streams
+        # and overlap the chain; cross-lane edges are explicit (op.deps -> events) and every lane
+        # joins the main stream at the end of the list, so the pattern is also valid under capture.
+        if self._lanes is None:
+            self._lanes = [None, torch.cuda.Stream(self.dev), torch.cuda.Stream(self.dev)]
+        used = set()
         for op in ops:
-            if getattr(op, 'side', False):
-                self._side.wait_stream(main)
-                self.stream = side_p
-                op()
-                self.stream = main_p
-                forked = True
-            else:
-                op()
-        if forked:
-            main.wait_stream(self._side)
+            lane = getattr(op, 'lane', 0)
+            st = main if lane == 0 else self._lanes[lane]
+            if lane and (lane not in used or getattr(op, 'fork', False)):
+                st.wait_stream(main)              # first use / fork point: everything issued on main so far
+                used.add(lane)
+            for d in getattr(op, 'deps', ()):
+                if getattr(d, 'lane', 0) != lane and getattr(d, '_ev', None) is not None:
+                    st.wait_event(d._ev)
+            self.stream = main_p if lane == 0 else ctypes.c_void_p(st.cuda_stream)
+            op()
+            if getattr(op, 'signal', False):
+                op._ev = torch.cuda.Event()
+                op._ev.record(st)
+        self.stream = main_p
+        for lane in used:
+            main.wait_stream(self._lanes[lane])
 
     def train_step(self, feed, update=True):
         """One `net.train.run(...)`: forward ('tr'), backward, TALR + momentum."""
@@ -537,7 +545,17 @@ class _Plan:
     def _tag(fn, kind, flops=0.0, nbytes=0.0, desc=''):
         """algorithmic work of one launch (bench.py roofline); untagged ops are 'misc'"""
         fn.kind, fn.flops, fn.nbytes, fn.desc = kind, float(flops), float(nbytes), desc
-        fn.side = kind in ('conv_wgrad', 'fc_wgrad')
+        if kind == 'conv_wgrad':
+            fn.lane, fn.fork = 2, True          # reads dLin produced just before it on the main lane
+
+    @staticmethod
+    def _after(op, *deps):
+        """op must run after deps (ops possibly on other lanes)"""
+        deps = [d for d in deps if d is not None]
+        op.deps = list(getattr(op, 'deps', ())) + deps
+        for d in deps:
+            d.signal = True
+        return op
 
     # -- allocation helpers ------------------------------------------------ #
     def planes(self, C, geo):
@@ -573,6 +591,7 @@ class _Plan:
         self.node = {}
         self.reg, self.rtr, self.heads = {}, {}, {}
         self.pack_list, self.rt_fwd, self.keep, self.kplanes = [], [], [], []
+        self.last_head_op = None
         cpad_q = 16 if dt == BF16 else 8
         dyn_k = eng.dynamic and bool(net.hypers.dyn_k_cpt)
 
@@ -611,8 +630,12 @@ class _Plan:
                         _vp(par.feat), F, Balloc, B, eng.tptr(fc.params.w), eng.tptr(fc.params.b), None,
                         n_cls, _vp(r.Zbuf), dt, S()))
                 self.reg[nd.idx] = r
-                self.fwd_ops.append(lambda r=r: L.softmax_ce_fwd(
-                    _vp(r.Zbuf), r.ldz, _vp(self.y), B, n_cls, r.eps, _vp(r.prob), _vp(r.c_err), _vp(r.d_cor), S()))
+                ce = lambda r=r: L.softmax_ce_fwd(
+                    _vp(r.Zbuf), r.ldz, _vp(self.y), B, n_cls, r.eps, _vp(r.prob), _vp(r.c_err), _vp(r.d_cor), S())
+                if self.umma_heads:
+                    ce.lane = 1                       # follows its head GEMM on the heads lane
+                    self.last_head_op = ce
+                self.fwd_ops.append(ce)
             if nd.router is not None:
                 self._build_router_fwd(nd, Balloc, dyn_k, emit_fc=not self.umma_heads)
             if nd.kind == 'rcm' and self.umma_heads and getattr(st, 'feat', None) is not None:
@@ -623,9 +646,10 @@ class _Plan:
             bn0 = self.rtr[eng.switches[0].idx].bn1
             tab = self._desc_table(_RT_FWD, self.rt_fwd)
             self.keep.append(tab)
-            self.fwd_ops.append(lambda: L.router_tail_fwd_batched(
+            tails = lambda: L.router_tail_fwd_batched(
                 _vp(tab), len(self.rt_fwd), B, 16, float(bn0.hypers.d), float(bn0.hypers.ε),
-                1 if self.bn_train else 0, S()))
+                1 if self.bn_train else 0, S())
+            self.fwd_ops.append(self._after(tails, self.last_head_op))   # needs every head GEMM / loss
         if eng.dynamic:
             self._build_routing()
 
@@ -652,6 +676,7 @@ class _Plan:
                 tabb = self._desc_table(_RT_BWD, rows)
                 self.keep.append(tabb)
                 self.bwd_ops.append(lambda: L.router_tail_bwd_batched(_vp(tabb), len(rows), B, 16, S()))
+        self.bwd_head_dep = self.bwd_ops[-1] if self.bwd_ops else None     # routing gradients are complete
         for nd in reversed(eng.nodes):
             if nd.kind == 'reg':
                 r = self.reg[nd.idx]
@@ -661,9 +686,11 @@ class _Plan:
                 if self.umma_heads:
                     hd = self.heads[nd.parent]
                     dzp = ctypes.c_void_p(hd.dZ.data_ptr() + (hd.leaf_off // 8) * Balloc * 16)
-                    self.bwd_ops.append(lambda r=r, coef=coef, dzp=dzp: L.softmax_ce_bwd(
+                    ceb = lambda r=r, coef=coef, dzp=dzp: L.softmax_ce_bwd(
                         _vp(r.prob), _vp(self.y), B, n_cls, r.eps, coef(), 1.0 / B, None,
-                        dzp, Balloc, eng.gptr(r.fc.params.b), S()))
+                        dzp, Balloc, eng.gptr(r.fc.params.b), S())
+                    ceb.lane = 1
+                    self.bwd_ops.append(self._after(ceb, self.bwd_head_dep))
                 else:
                     self.bwd_ops.append(lambda r=r, coef=coef: L.softmax_ce_bwd(
                         _vp(r.prob), _vp(self.y), B, n_cls, r.eps, coef(), 1.0 / B, _vp(r.dZ), None, 0, None, S()))
@@ -747,6 +774,9 @@ class _Plan:
             L.stencil_gemm(_vp(st.feat), Fext, None, 0, _vp(hd.Wfc), 1, _vp(hd.bias), _vp(o0), n0, 0, _vp(o1), n1, 0,
                            B, 0, 0, 0, Balloc, None, 0, None, BF16, 2, 1, S())
         self._tag(gemm, 'fc_fwd', desc='F%d N%d' % (Fext, hd.N), flops=2.0 * B * F * hd.N, nbytes=B * F * 2)
+        gemm.lane = 1
+        self._after(gemm, getattr(st, 'feat_op', None))
+        self.last_head_op = gemm
         self.fwd_ops.append(gemm)
 
     def _build_heads_bwd(self, nd, st, dyn_k):
@@ -766,7 +796,8 @@ class _Plan:
         def wgrad():
             L.fc_wgrad(_vp(st.feat), Fext, Balloc, B, _vp(hd.dZ), hd.N, 16, a[0], a[1], a[2], b[0], b[1], b[2], S())
         self._tag(wgrad, 'fc_wgrad', desc='F%d N%d' % (Fext, hd.N), flops=2.0 * B * F * hd.N, nbytes=B * F * 2)
-        self.bwd_ops.append(wgrad)
+        wgrad.lane = 1
+        self.bwd_ops.append(self._after(wgrad, self.bwd_head_dep))
         # data gradient towards the flattened coarsest scale
         hd.Wfd = torch.zeros((1, hd.N // 8, F, 8), dtype=eng.tdtype, device=eng.dev)
         if leaf is not None:
@@ -779,6 +810,8 @@ class _Plan:
             L.stencil_gemm(_vp(hd.dZ), hd.N, None, 0, _vp(hd.Wfd), 1, None, _vp(st.dfeat), F, 0, None, 0, 0,
                            B, 0, 0, 0, Balloc, None, 0, None, BF16, BF16, 1, S())
         self._tag(dgrad, 'fc_dgrad', desc='N%d F%d' % (hd.N, F), flops=2.0 * B * F * hd.N, nbytes=B * F * 2)
+        dgrad.lane = 1
+        st.dfeat_op = dgrad                          # the conv chain of this node waits for it
         self.bwd_ops.append(dgrad)
 
     def _router_bwd_desc(self, nd):
@@ -906,6 +939,8 @@ class _Plan:
                                        _vp(sc.feat), Balloc, dt, S())
                 self._tag(post, 'bn_fwd', nbytes=B * sc.geo.H * sc.geo.W * sc.N * (2 if dt == BF16 else 4) * (1 + (sc.act is not None) + 0.25 * (sc.pooled is not None) + (sc.feat is not None)))
                 self.fwd_ops.append(post)
+                if sc.feat is not None:
+                    st.feat_op = post
             st.sc.append(sc)
             st.out.append(Ns(t=sc.act, C=N, Creal=N, geo=geo, dact=None, writers=0))
 
@@ -961,6 +996,8 @@ class _Plan:
                     L.bn_bwd_reduce_fused(_vp(sc.lin), _vp(dact), _vp(dfeat), Balloc, _vp(sc.ss), _vp(sc.mr), sc.N,
                                           *sc.geo.args(), ctypes.c_void_p(sc.bnb.ctypes.data), dt, S())
                 self._tag(red, 'bn_bwd_reduce', nbytes=B * sc.geo.H * sc.geo.W * sc.N * (2 if dt == BF16 else 4) * 2)
+                if dfeat is not None:
+                    self._after(red, getattr(st, 'dfeat_op', None))
                 self.bwd_ops.append(red)
             if not live and dpooled is None:
                 raise RuntimeError('engine: scale %d of %r has no gradient path' % (k, lay.name))
@@ -972,6 +1009,8 @@ class _Plan:
                                    float(B * sc.geo.H * sc.geo.W), sc.N, *sc.geo.args(), _vp(sc.dlin),
                                    eng.gptr(sc.bk), dt, S())
             self._tag(elt, 'bn_bwd', nbytes=B * sc.geo.H * sc.geo.W * sc.N * (2 if dt == BF16 else 4) * 3)
+            if dfeat is not None:
+                self._after(elt, getattr(st, 'dfeat_op', None))
             self.bwd_ops.append(elt)
             prev = st.sc[k - 1] if k > 0 else None
 
