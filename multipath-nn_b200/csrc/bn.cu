@@ -58,47 +58,61 @@ extern "C" int mpnn_bn_finalize(const float* partials, int n_parts, int C, doubl
 }
 
 // ------------------------------------------------------------------ forward
+// One thread per (plane kg, image n, row pair h2, full-resolution column w) when pooling,
+// per pixel otherwise: consecutive lanes touch consecutive 16/32-byte rows, so every
+// load and store instruction is fully coalesced; the 2x2 maximum is taken in-thread
+// over the row pair and across the lane pair (w, w^1) with one shuffle per channel.
+// grid.y = plane, so the per-channel constants are loaded once per thread.
 template <typename T, bool POOL>
-__global__ void bn_relu_pool_fwd_kernel(const T* __restrict__ lin, int C, Geom g,
-                                        const float* __restrict__ ss, T* __restrict__ act,
-                                        T* __restrict__ pooled, Geom gp,
-                                        T* __restrict__ feat, int Balloc) {
-    const int KG = C / 8;
-    const int HH = POOL ? g.H / 2 : g.H, WW = POOL ? g.W / 2 : g.W;
-    const long long total = (long long)KG * g.B * HH * WW;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-         i += (long long)gridDim.x * blockDim.x) {
-        int w = i % WW;
-        long long r = i / WW;
-        int h = r % HH; r /= HH;
-        int n = r % g.B;
-        int kg = r / g.B;
-        float a[8], c[8];
-        if (ss && (act || feat)) {
+__global__ void __launch_bounds__(256)
+bn_relu_pool_fwd_kernel(const T* __restrict__ lin, int C, Geom g,
+                        const float* __restrict__ ss, T* __restrict__ act,
+                        T* __restrict__ pooled, Geom gp,
+                        T* __restrict__ feat, int Balloc) {
+    const int KG = C / 8, kg = blockIdx.y;
+    const int HH = POOL ? g.H / 2 : g.H;
+    const unsigned total = (unsigned)g.B * HH * g.W;          // host guarantees < 2^31
+    float a[8], c[8];
+    const bool affine = ss && (act || feat);
+    if (affine) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) { a[j] = __ldg(ss + kg * 8 + j); c[j] = __ldg(ss + C + kg * 8 + j); }
-        }
+        for (int j = 0; j < 8; ++j) { a[j] = __ldg(ss + kg * 8 + j); c[j] = __ldg(ss + C + kg * 8 + j); }
+    }
+    const unsigned lane = threadIdx.x & 31;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i - lane < total; i += gridDim.x * blockDim.x) {
+        const bool ok = i < total;
+        const unsigned ii = ok ? i : 0;
+        const int w = ii % (unsigned)g.W;
+        const unsigned r = ii / (unsigned)g.W;
+        const int h = r % (unsigned)HH;
+        const int n = r / (unsigned)HH;
         if (POOL) {
-            float mx[8];
+            const int p0 = row_of(g, n, 2 * h, w), p1 = p0 + g.Wp;
+            float v0[8], v1[8], mx[8];
+            if (ok) {
+                Row8<T>::load(plane_row(lin, kg, g.P, p0), v0);
+                Row8<T>::load(plane_row(lin, kg, g.P, p1), v1);
+            } else {
 #pragma unroll
-            for (int dy = 0; dy < 2; ++dy)
+                for (int j = 0; j < 8; ++j) { v0[j] = 0.f; v1[j] = 0.f; }
+            }
+            if (ok && act && ss) {
+                float o[8];
 #pragma unroll
-                for (int dx = 0; dx < 2; ++dx) {
-                    int p = row_of(g, n, 2 * h + dy, 2 * w + dx);
-                    float v[8];
-                    Row8<T>::load(plane_row(lin, kg, g.P, p), v);
+                for (int j = 0; j < 8; ++j) o[j] = fmaxf(fmaf(a[j], v0[j], c[j]), 0.f);
+                Row8<T>::store(plane_row(act, kg, g.P, p0), o);
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) mx[j] = (dy == 0 && dx == 0) ? v[j] : fmaxf(mx[j], v[j]);
-                    if (act && ss) {
-                        float o[8];
+                for (int j = 0; j < 8; ++j) o[j] = fmaxf(fmaf(a[j], v1[j], c[j]), 0.f);
+                Row8<T>::store(plane_row(act, kg, g.P, p1), o);
+            }
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) o[j] = fmaxf(fmaf(a[j], v[j], c[j]), 0.f);
-                        Row8<T>::store(plane_row(act, kg, g.P, p), o);
-                    }
-                }
-            Row8<T>::store(plane_row(pooled, kg, gp.P, row_of(gp, n, h, w)), mx);
-        } else {
-            int p = row_of(g, n, h, w);
+            for (int j = 0; j < 8; ++j) {
+                mx[j] = fmaxf(v0[j], v1[j]);
+                mx[j] = fmaxf(mx[j], __shfl_xor_sync(0xffffffffu, mx[j], 1));
+            }
+            if (ok && !(w & 1)) Row8<T>::store(plane_row(pooled, kg, gp.P, row_of(gp, n, h, w >> 1)), mx);
+        } else if (ok) {
+            const int p = row_of(g, n, h, w);
             float v[8], o[8];
             Row8<T>::load(plane_row(lin, kg, g.P, p), v);
 #pragma unroll
@@ -118,10 +132,14 @@ extern "C" int mpnn_bn_relu_pool_fwd(const void* lin, int C, int B, int H, int W
     MPNN_REQUIRE(!pooled || (H % 2 == 0 && W % 2 == 0), "bn_relu_pool_fwd: odd size");
     Geom g = make_geom(B, H, W, G, P);
     Geom gp = make_geom(B, H / 2, W / 2, G, Pp);
-    long long total = (long long)(C / 8) * B * (pooled ? (H / 2) * (W / 2) : H * W);
-    int grid = (int)((total + 255) / 256);
-    if (grid > 148 * 16) grid = 148 * 16;
-    if (grid < 1) grid = 1;
+    long long total = (long long)B * (pooled ? (H / 2) * W : H * W);
+    MPNN_REQUIRE(total < (1ll << 31), "bn_relu_pool_fwd: too many pixels");
+    int gx = (int)((total + 255) / 256);
+    int cap = 148 * 16 / (C / 8);
+    if (cap < 148) cap = 148;
+    if (gx > cap) gx = cap;
+    if (gx < 1) gx = 1;
+    dim3 grid(gx, C / 8);
     cudaStream_t st = (cudaStream_t)stream;
     if (pooled) {
         MPNN_DISPATCH_DTYPE(dtype, (bn_relu_pool_fwd_kernel<T, true><<<grid, 256, 0, st>>>(

@@ -362,19 +362,24 @@ class Engine:
             for op in ops:
                 op()
             return
-        # Lanes.  0: the dependent chain (conv / BN / data gradients).  1: classifier and router
-        # heads, which only feed the losses (forward) or start from them (backward).  2: weight
-        # gradients, which only feed the optimiser.  Lane 1/2 launches fork onto their own streams
-        # and overlap the chain; cross-lane edges are explicit (op.deps -> events) and every lane
-        # joins the main stream at the end of the list, so the pattern is also valid under capture.
+        # Lanes (one CUDA stream each).  0: input packing, routing, optimiser.  1: classifier and
+        # router heads, which only feed the losses (forward) or start from them (backward).
+        # 2: weight gradients, which only feed the optimiser.  3+k: the conv / BN / data-gradient
+        # ops of pyramid scale k -- layer L at scale k depends on layer L-1 at scale k (same lane)
+        # and on layer L at scale k-1 (pooled input; the neighbouring lane), so the scales advance
+        # as a wavefront and the small, latency-bound coarse-scale launches hide behind the large
+        # fine-scale ones.  Cross-lane edges are explicit (op.deps -> events); every lane forks
+        # from and joins the main stream inside one op list, so the pattern is valid under capture.
         if self._lanes is None:
-            self._lanes = [None, torch.cuda.Stream(self.dev), torch.cuda.Stream(self.dev)]
+            self._lanes = {}
         used = set()
         for op in ops:
             lane = getattr(op, 'lane', 0)
+            if lane and lane not in self._lanes:
+                self._lanes[lane] = torch.cuda.Stream(self.dev)
             st = main if lane == 0 else self._lanes[lane]
-            if lane and (lane not in used or getattr(op, 'fork', False)):
-                st.wait_stream(main)              # first use / fork point: everything issued on main so far
+            if lane and lane not in used:
+                st.wait_stream(main)              # first use: everything issued on main so far
                 used.add(lane)
             for d in getattr(op, 'deps', ()):
                 if getattr(d, 'lane', 0) != lane and getattr(d, '_ev', None) is not None:
@@ -546,7 +551,7 @@ class _Plan:
         """algorithmic work of one launch (bench.py roofline); untagged ops are 'misc'"""
         fn.kind, fn.flops, fn.nbytes, fn.desc = kind, float(flops), float(nbytes), desc
         if kind == 'conv_wgrad':
-            fn.lane, fn.fork = 2, True          # reads dLin produced just before it on the main lane
+            fn.lane = 2
 
     @staticmethod
     def _after(op, *deps):
@@ -608,8 +613,10 @@ class _Plan:
                     geo = Geo(B, H0 // 2 ** i, W0 // 2 ** i)
                     t = self.planes(cpad, geo)
                     st.out.append(Ns(t=t, C=cpad, Creal=C0, geo=geo, dact=None, writers=0))
-                    self.fwd_ops.append(lambda t=t, i=i, geo=geo: L.pack_input(
-                        _vp(self.x0), B, H0, W0, C0, 2 ** i, _vp(t), cpad, geo.G, geo.P, dt, S()))
+                    pk = lambda t=t, i=i, geo=geo: L.pack_input(
+                        _vp(self.x0), B, H0, W0, C0, 2 ** i, _vp(t), cpad, geo.G, geo.P, dt, S())
+                    pk.lane = 3 + i
+                    self.fwd_ops.append(pk)
                 st.needs_grad = False
             elif nd.kind == 'rcm':
                 self._build_rcm_fwd(nd, st, Balloc)
@@ -626,9 +633,10 @@ class _Plan:
                     r = Ns(Zbuf=zb, Z=zb, ldz=n_cls, prob=self.f32(B, n_cls), c_err=self.f32(B),
                            d_cor=self.f32(B), dZ=self.f32(B, n_cls) if bwd else None, fc=fc, eps=eps)
                     F = par.F
-                    self.fwd_ops.append(lambda par=par, r=r, fc=fc, F=F: L.fc_fwd(
+                    fcf = lambda par=par, r=r, fc=fc, F=F: L.fc_fwd(
                         _vp(par.feat), F, Balloc, B, eng.tptr(fc.params.w), eng.tptr(fc.params.b), None,
-                        n_cls, _vp(r.Zbuf), dt, S()))
+                        n_cls, _vp(r.Zbuf), dt, S())
+                    self.fwd_ops.append(self._after(fcf, getattr(par, 'feat_op', None)))
                 self.reg[nd.idx] = r
                 ce = lambda r=r: L.softmax_ce_fwd(
                     _vp(r.Zbuf), r.ldz, _vp(self.y), B, n_cls, r.eps, _vp(r.prob), _vp(r.c_err), _vp(r.d_cor), S())
@@ -920,6 +928,9 @@ class _Plan:
                                    *sc.geo.args(), None, 0, None, dt, dt, impl, S())
             self._tag(conv, 'conv_fwd', desc='H%d K%d+%d N%d' % (sc.geo.H, sc.K0, sc.K1, sc.N), flops=2.0 * B * sc.geo.H * sc.geo.W * 9 * (sc.K0real + sc.K1) * sc.N,
                       nbytes=B * sc.geo.H * sc.geo.W * (sc.K0 + sc.K1 + sc.N) * (2 if dt == BF16 else 4))
+            sc.lane = 3 + int(round(np.log2(eng.net.hypers.x0_shape[0] / geo.H)))
+            conv.lane = sc.lane
+            self._after(conv, getattr(prev, 'post_op', None) if prev is not None else None)   # pooled input
             self.fwd_ops.append(conv)
             if sc.live and not use_stats:
                 bn = sc.bn
@@ -931,6 +942,7 @@ class _Plan:
                                   float(bn.hypers.d), float(bn.hypers.ε), 0,
                                   _vp(sc.ss), _vp(sc.mr), S())
                 self._tag(fin, 'bn_finalize')
+                fin.lane = sc.lane
                 self.fwd_ops.append(fin)
             if sc.live or sc.pooled is not None:
                 def post(sc=sc):
@@ -938,6 +950,8 @@ class _Plan:
                                        _vp(sc.act), _vp(sc.pooled), sc.geo_p.P if sc.pooled is not None else 0,
                                        _vp(sc.feat), Balloc, dt, S())
                 self._tag(post, 'bn_fwd', nbytes=B * sc.geo.H * sc.geo.W * sc.N * (2 if dt == BF16 else 4) * (1 + (sc.act is not None) + 0.25 * (sc.pooled is not None) + (sc.feat is not None)))
+                post.lane = sc.lane
+                sc.post_op = post
                 self.fwd_ops.append(post)
                 if sc.feat is not None:
                     st.feat_op = post
@@ -972,9 +986,11 @@ class _Plan:
                 pairs.append((rt.dZ1, rt.fc1.params.w, 16))
             p0 = pairs[0]
             p1 = pairs[1] if len(pairs) > 1 else (None, None, 0)
-            self.bwd_ops.append(lambda p0=p0, p1=p1: L.fc_bwd_data(
+            fbd = lambda p0=p0, p1=p1: L.fc_bwd_data(
                 _vp(p0[0]), eng.tptr(p0[1]), p0[2], _vp(p1[0]), eng.tptr(p1[1]) if p1[1] is not None else None,
-                p1[2], st.F, Balloc, B, _vp(st.dfeat), dt, S()))
+                p1[2], st.F, Balloc, B, _vp(st.dfeat), dt, S())
+            st.dfeat_op = fbd
+            self.bwd_ops.append(fbd)
         for k in range(n - 1, -1, -1):
             sc = st.sc[k]
             geo = sc.geo
@@ -996,6 +1012,7 @@ class _Plan:
                     L.bn_bwd_reduce_fused(_vp(sc.lin), _vp(dact), _vp(dfeat), Balloc, _vp(sc.ss), _vp(sc.mr), sc.N,
                                           *sc.geo.args(), ctypes.c_void_p(sc.bnb.ctypes.data), dt, S())
                 self._tag(red, 'bn_bwd_reduce', nbytes=B * sc.geo.H * sc.geo.W * sc.N * (2 if dt == BF16 else 4) * 2)
+                red.lane = sc.lane
                 if dfeat is not None:
                     self._after(red, getattr(st, 'dfeat_op', None))
                 self.bwd_ops.append(red)
@@ -1009,8 +1026,10 @@ class _Plan:
                                    float(B * sc.geo.H * sc.geo.W), sc.N, *sc.geo.args(), _vp(sc.dlin),
                                    eng.gptr(sc.bk), dt, S())
             self._tag(elt, 'bn_bwd', nbytes=B * sc.geo.H * sc.geo.W * sc.N * (2 if dt == BF16 else 4) * 3)
+            elt.lane = sc.lane
             if dfeat is not None:
                 self._after(elt, getattr(st, 'dfeat_op', None))
+            self._after(elt, getattr(sc, 'dpooled_op', None))      # written by scale k+1's data gradient
             self.bwd_ops.append(elt)
             prev = st.sc[k - 1] if k > 0 else None
 
@@ -1022,7 +1041,7 @@ class _Plan:
                                 eng.impl_w if (sc.K0 + sc.K1 <= 128 and sc.N <= 256) else 0, S())
             self._tag(wgrad, 'conv_wgrad', desc='H%d K%d+%d N%d' % (sc.geo.H, sc.K0, sc.K1, sc.N), flops=2.0 * B * sc.geo.H * sc.geo.W * 9 * (sc.K0real + sc.K1) * sc.N,
                       nbytes=B * sc.geo.H * sc.geo.W * (sc.K0 + sc.K1 + sc.N) * (2 if dt == BF16 else 4))
-            self.bwd_ops.append(wgrad)
+            self.bwd_ops.append(self._after(wgrad, elt))
             # data gradient: towards the parent's activation (N0) and the pooled predecessor (N1)
             N0 = sc.K0 if par_grad else 0
             N1 = sc.K1
@@ -1051,6 +1070,9 @@ class _Plan:
                                *sc.geo.args(), None, 0, None, dt, dt, impl, S())
             self._tag(dgrad, 'conv_dgrad', desc='H%d K%d N%d+%d' % (sc.geo.H, sc.N, N0, N1), flops=2.0 * B * sc.geo.H * sc.geo.W * 9 * sc.N * (N0 + N1),
                       nbytes=B * sc.geo.H * sc.geo.W * (sc.N + N0 + N1) * (2 if dt == BF16 else 4))
+            dgrad.lane = sc.lane
+            if N1:
+                prev.dpooled_op = dgrad
             self.bwd_ops.append(dgrad)
 
     # -- router ------------------------------------------------------------ #
@@ -1073,9 +1095,10 @@ class _Plan:
                 scratch=self.f32(2 * B * 16) if bwd else None)
         self.rtr[nd.idx] = rt
         if emit_fc:
-            self.fwd_ops.append(lambda: L.fc_fwd(
+            fcr = lambda: L.fc_fwd(
                 _vp(st.feat), st.F, Balloc, B, eng.tptr(fc1.params.w), eng.tptr(fc1.params.b),
-                _vp(self.kextra) if dyn_k else None, 16, _vp(rt.Z1), dt, S()))
+                _vp(self.kextra) if dyn_k else None, 16, _vp(rt.Z1), dt, S())
+            self.fwd_ops.append(self._after(fcr, getattr(st, 'feat_op', None)))
         P = lambda lay, k: eng.tptr(getattr(lay.params, k))
         # the tails of all routers run as ONE launch after the conv pipeline (see _build)
         self.rt_fwd.append(dict(
