@@ -9,14 +9,15 @@ from util import Geo
 L = _cabi.lib()
 vp = lambda t: None if t is None else ctypes.c_void_p(t.data_ptr())
 B = int(os.environ.get('B', 2048))
-flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')
+flush = torch.zeros(256 << 20, dtype=torch.uint8, device='cuda')
+flush_sink = torch.zeros((), dtype=torch.int64, device='cuda')
 
 
 def timeit(fn, reps=10):
     fn(); torch.cuda.synchronize()
     ts = []
     for _ in range(reps):
-        flush.zero_()
+        flush_sink.copy_(flush.view(torch.int32)[::1].sum(dtype=torch.int64))
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record(); fn(); b.record(); torch.cuda.synchronize()
         ts.append(a.elapsed_time(b))
@@ -78,6 +79,9 @@ if __name__ == '__main__':
         conv_case(32, 16, 0, 16)
         conv_case(16, 32, 0, 32)
         conv_case(8, 64, 0, 64)
+    if what == 'nsweep':
+        for n in (16, 32, 48, 64, 96):
+            conv_case(32, 16, 0, n, stats=False)
     if what in ('all', 'wgrad'):
         wgrad_case(32, 16, 0, 16)
         wgrad_case(16, 16, 16, 16)
