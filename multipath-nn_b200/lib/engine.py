@@ -122,6 +122,7 @@ class Engine:
         self._plans = {}
         self._graphs = {}
         self._lanes = None
+        self._copy_stream, self._stage, self._stage_i = None, {}, 0
         self.multistream = os.environ.get('MPNN_MULTISTREAM', '1') != '0'
         # per-step scalars travel host->device asynchronously from pinned memory; a ring of slots
         # (each guarded by an event) keeps step t+1's values from overwriting step t's before its
@@ -317,8 +318,8 @@ class Engine:
         x0 = feed[net.x0]
         y = feed[net.y]
         B = plan.B
-        plan.x0.copy_(self._to_dev(x0, (B,) + tuple(hy.x0_shape), 'x0'), non_blocking=True)
-        plan.y.copy_(self._to_dev(y, (B,) + tuple(hy.y_shape), 'y'), non_blocking=True)
+        self._upload(plan, self._to_dev(x0, (B,) + tuple(hy.x0_shape), 'x0'),
+                     self._to_dev(y, (B,) + tuple(hy.y_shape), 'y'))
         i = self._hyp_i = (self._hyp_i + 1) % len(self._hyp_ring)
         if self._hyp_ev[i] is not None:
             self._hyp_ev[i].synchronize()
@@ -345,6 +346,39 @@ class Engine:
         if self._hyp_ev[i] is None:
             self._hyp_ev[i] = torch.cuda.Event()
         self._hyp_ev[i].record()
+
+    def _upload(self, plan, x0, y):
+        """Host batch -> plan.x0 / plan.y.  Host tensors go through a double-buffered device
+        staging slot on a copy stream, so the PCIe transfer of step t+1 overlaps the kernels of
+        step t; the step itself starts with a device-to-device copy out of the slot."""
+        if x0.is_cuda and y.is_cuda:
+            plan.x0.copy_(x0, non_blocking=True)
+            plan.y.copy_(y, non_blocking=True)
+            return
+        main = torch.cuda.current_stream(self.dev)
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(self.dev)
+        slots = self._stage.get(plan.B)
+        if slots is None:
+            slots = self._stage[plan.B] = [Ns(x=torch.empty_like(plan.x0), y=torch.empty_like(plan.y),
+                                              ready=torch.cuda.Event(), consumed=None, src=None)
+                                           for _ in range(2)]
+        self._stage_i ^= 1
+        sl = slots[self._stage_i]
+        cs = self._copy_stream
+        if sl.consumed is not None:
+            cs.wait_event(sl.consumed)             # the step that read this slot two uploads ago
+        with torch.cuda.stream(cs):
+            sl.src = (x0, y)                       # keep pinned sources alive until the slot is reused
+            sl.x.copy_(x0, non_blocking=True)
+            sl.y.copy_(y, non_blocking=True)
+            sl.ready.record(cs)
+        main.wait_event(sl.ready)
+        plan.x0.copy_(sl.x, non_blocking=True)
+        plan.y.copy_(sl.y, non_blocking=True)
+        if sl.consumed is None:
+            sl.consumed = torch.cuda.Event()
+        sl.consumed.record(main)
 
     def _batch_of(self, feed):
         x0 = feed[self.net.x0]
