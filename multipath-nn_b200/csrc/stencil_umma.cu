@@ -102,9 +102,14 @@ stencil_gemm_umma_kernel(const GemmArgs a) {
         // ------------------------------------------------ producer
         if (lane == 0) {
             mbar_expect_tx(wbar, w_bytes);
-            for (int t = 0; t < a.ntaps * KG; ++t)
-                bulk_g2s(smem_u32(sW) + (uint32_t)t * NB * 16,
-                         a.Wp + ((size_t)t * a.N + n0) * 8, (uint32_t)NB * 16, wbar);
+            if (NB == a.N) {
+                // unsplit N: the packed weights [tap][K/8][N][8] are one contiguous block
+                bulk_g2s(smem_u32(sW), a.Wp, w_bytes, wbar);
+            } else {
+                for (int t = 0; t < a.ntaps * KG; ++t)
+                    bulk_g2s(smem_u32(sW) + (uint32_t)t * NB * 16,
+                             a.Wp + ((size_t)t * a.N + n0) * 8, (uint32_t)NB * 16, wbar);
+            }
             // the single-thread issue loops are the per-CTA critical path: no divisions, no
             // 64-bit address rebuilds inside them (ring slot / phase are running counters)
             int s = 0; uint32_t ph = 0;
