@@ -99,16 +99,17 @@ stencil_gemm_umma_kernel(const GemmArgs a) {
     };
 
     if (warp == 0) {
-        // ------------------------------------------------ producer
-        if (lane == 0) {
-            mbar_expect_tx(wbar, w_bytes);
+        // ------------------------------------------------ producer (whole warp, one elected lane issues)
+        {
+            const bool leader = elect_one();
+            if (leader) mbar_expect_tx(wbar, w_bytes);
             if (NB == a.N) {
                 // unsplit N: the packed weights [tap][K/8][N][8] are one contiguous block
-                bulk_g2s(smem_u32(sW), a.Wp, w_bytes, wbar);
+                if (leader) bulk_g2s(smem_u32(sW), a.Wp, w_bytes, wbar);
             } else {
                 for (int t = 0; t < a.ntaps * KG; ++t)
-                    bulk_g2s(smem_u32(sW) + (uint32_t)t * NB * 16,
-                             a.Wp + ((size_t)t * a.N + n0) * 8, (uint32_t)NB * 16, wbar);
+                    if (leader) bulk_g2s(smem_u32(sW) + (uint32_t)t * NB * 16,
+                                         a.Wp + ((size_t)t * a.N + n0) * 8, (uint32_t)NB * 16, wbar);
             }
             // the single-thread issue loops are the per-CTA critical path: no divisions, no
             // 64-bit address rebuilds inside them (ring slot / phase are running counters)
@@ -121,16 +122,16 @@ stencil_gemm_umma_kernel(const GemmArgs a) {
                 for (int ci = 0; ci < a.n_kc; ++ci) {
                     const int kg0 = ci * a.KC, kgn = min(a.KC, KG - kg0);
                     mbar_wait(empty0 + 8 * s, ph ^ 1u);
-                    stamp((tile - blockIdx.x) / gridDim.x, 0);
-                    if (a.dbg & 4) mbar_arrive(full0 + 8 * s);
+                    if (leader) stamp((tile - blockIdx.x) / gridDim.x, 0);
+                    if (a.dbg & 4) { if (leader) mbar_arrive(full0 + 8 * s); }
                     else {
-                        mbar_expect_tx(full0 + 8 * s, PS * kgn);
+                        if (leader) mbar_expect_tx(full0 + 8 * s, PS * kgn);
                         const uint32_t dst = smem_u32(sA) + (uint32_t)s * stage_bytes;
                         for (int j = 0; j < kgn; ++j) {
                             const int kg = kg0 + j;
                             const __nv_bfloat16* src = kg < KG0 ? src0 + kg * plane + toff
                                                                 : src1 + (kg - KG0) * plane + toff;
-                            bulk_g2s(dst + (uint32_t)j * PS, src, PS, full0 + 8 * s);
+                            if (leader) bulk_g2s(dst + (uint32_t)j * PS, src, PS, full0 + 8 * s);
                         }
                     }
                     if (++s == a.nstage) { s = 0; ph ^= 1u; }
@@ -139,8 +140,9 @@ stencil_gemm_umma_kernel(const GemmArgs a) {
         }
         __syncwarp();
     } else if (warp == 1) {
-        // ------------------------------------------------ MMA issuer
-        if (lane == 0) {
+        // ------------------------------------------------ MMA issuer (whole warp, one elected lane issues)
+        {
+            const bool leader = elect_one();
             const uint32_t idesc = make_idesc(NB, 0, 0);
             // descriptors: hi word (SBO = 128 B, version) is constant; the lo word is
             // (address >> 4) | (LBO >> 4) << 16, so a tap shift of `off` rows (16 B each)
@@ -157,14 +159,14 @@ stencil_gemm_umma_kernel(const GemmArgs a) {
                 const int acc = tl & 1;
                 const uint32_t aph = (uint32_t)(tl >> 1) & 1u;
                 mbar_wait(tempty0 + 8 * acc, aph ^ 1u);
-                stamp(tl, 1);
+                if (leader) stamp(tl, 1);
                 const uint32_t dcol = tmem_base + (uint32_t)acc * NB;
                 uint32_t first = 0;
                 for (int ci = 0; ci < a.n_kc; ++ci) {
                     const int kg0 = ci * a.KC, kgn = min(a.KC, KG - kg0);
                     mbar_wait(full0 + 8 * s, ph);
                     tc_fence_after();
-                    stamp(tl, 2);
+                    if (leader) stamp(tl, 2);
                     const uint32_t a_lo = a_lo0 + (uint32_t)s * a_stage;
                     const uint32_t b_lo = b_lo0 + (uint32_t)kg0 * NB;
                     if (!(a.dbg & 1)) {
@@ -174,24 +176,23 @@ stencil_gemm_umma_kernel(const GemmArgs a) {
                                 const uint32_t at = a_lo + (uint32_t)((tap / 3 - 1) * Wp + (tap % 3 - 1));
                                 const uint32_t bt = b_lo + (uint32_t)tap * b_tap;
                                 for (int kk = 0, ka = 0, kb = 0; kk < kgn; kk += 2, ka += a_kstep, kb += b_kstep) {
-                                    tc_mma(dcol, ((uint64_t)d_hi << 32) | (at + ka), ((uint64_t)d_hi << 32) | (bt + kb),
-                                           idesc, first);
+                                    if (leader) tc_mma(dcol, ((uint64_t)d_hi << 32) | (at + ka),
+                                                       ((uint64_t)d_hi << 32) | (bt + kb), idesc, first);
                                     first = 1;
                                 }
                             }
                         } else {
                             for (int kk = 0, ka = 0, kb = 0; kk < kgn; kk += 2, ka += a_kstep, kb += b_kstep) {
-                                tc_mma(dcol, ((uint64_t)d_hi << 32) | (a_lo + ka), ((uint64_t)d_hi << 32) | (b_lo + kb),
-                                       idesc, first);
+                                if (leader) tc_mma(dcol, ((uint64_t)d_hi << 32) | (a_lo + ka),
+                                                   ((uint64_t)d_hi << 32) | (b_lo + kb), idesc, first);
                                 first = 1;
                             }
                         }
                     }
-                    tc_commit(empty0 + 8 * s);      // smem stage reusable once the MMAs retire
+                    if (leader) tc_commit(empty0 + 8 * s);      // smem stage reusable once the MMAs retire
                     if (++s == a.nstage) { s = 0; ph ^= 1u; }
                 }
-                tc_commit(tfull0 + 8 * acc);        // accumulator ready for the epilogue
-                stamp(tl, 3);
+                if (leader) { tc_commit(tfull0 + 8 * acc); stamp(tl, 3); }   // accumulator ready for the epilogue
             }
         }
         __syncwarp();

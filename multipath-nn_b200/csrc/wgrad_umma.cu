@@ -82,13 +82,15 @@ stencil_wgrad_umma_kernel(const WgradArgs a) {
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        if (lane == 0) {
-            // issue loops are single-thread critical paths: running ring counters, hoisted bases
+        {
+            // issue loops run with the whole warp in uniform control flow, one elected lane issuing
+            // (see elect_one in umma.cuh); running ring counters, hoisted bases
+            const bool leader = elect_one();
             int s = 0; uint32_t ph = 0;
             const size_t plane = (size_t)a.g.P * 8;
             for (int c = blockIdx.x; c < a.n_chunks; c += gridDim.x) {
                 mbar_wait(empty0 + 8 * s, ph ^ 1u);
-                mbar_expect_tx(full0 + 8 * s, stageA + stageG);
+                if (leader) mbar_expect_tx(full0 + 8 * s, stageA + stageG);
                 const size_t p0 = (size_t)a.g.G + (size_t)c * kChunk;
                 uint32_t dA = smem_u32(sA) + (uint32_t)s * stageA;
                 uint32_t dG = smem_u32(sG) + (uint32_t)s * stageG;
@@ -98,23 +100,27 @@ stencil_wgrad_umma_kernel(const WgradArgs a) {
                                               + (p0 - a.halo) * 8;
                     if (a.CP == 3) {
                         // copy cp holds the plane shifted by dw = cp-1 rows
-                        bulk_g2s(dA, pl - 8, PSA, full0 + 8 * s);
-                        bulk_g2s(dA + PSA, pl, PSA, full0 + 8 * s);
-                        bulk_g2s(dA + 2 * PSA, pl + 8, PSA, full0 + 8 * s);
+                        if (leader) {
+                            bulk_g2s(dA, pl - 8, PSA, full0 + 8 * s);
+                            bulk_g2s(dA + PSA, pl, PSA, full0 + 8 * s);
+                            bulk_g2s(dA + 2 * PSA, pl + 8, PSA, full0 + 8 * s);
+                        }
                         dA += 3 * PSA;
                     } else {
-                        bulk_g2s(dA, pl, PSA, full0 + 8 * s);
+                        if (leader) bulk_g2s(dA, pl, PSA, full0 + 8 * s);
                         dA += PSA;
                     }
                 }
                 const __nv_bfloat16* gp = a.Gd + p0 * 8;
-                for (int ng = 0; ng < NG; ++ng, gp += plane, dG += PSG) bulk_g2s(dG, gp, PSG, full0 + 8 * s);
+                for (int ng = 0; ng < NG; ++ng, gp += plane, dG += PSG)
+                    if (leader) bulk_g2s(dG, gp, PSG, full0 + 8 * s);
                 if (++s == a.nstage) { s = 0; ph ^= 1u; }
             }
         }
         __syncwarp();
     } else if (warp == 1) {
-        if (lane == 0) {
+        {
+            const bool leader = elect_one();
             const uint32_t idesc = make_idesc(a.N, 1, 1, a.M);   // both operands MN-major
             // descriptor lo word = (address >> 4) | (LBO = 128 B) << 16; hi = SBO (plane stride) | version
             const uint32_t a_hi = (PSA >> 4) | (1u << 14), g_hi = (PSG >> 4) | (1u << 14);
@@ -135,14 +141,14 @@ stencil_wgrad_umma_kernel(const WgradArgs a) {
                     const uint32_t dcol = tmem_base + (uint32_t)t * a.N;
 #pragma unroll
                     for (int ks = 0; ks < kChunk / 16; ++ks)   // 16 pixels = 256 B per K step
-                        tc_mma(dcol, ((uint64_t)a_hi << 32) | (arow + ks * 16), ((uint64_t)g_hi << 32) | (gB + ks * 16),
-                               idesc, accum | (uint32_t)ks);
+                        if (leader) tc_mma(dcol, ((uint64_t)a_hi << 32) | (arow + ks * 16),
+                                           ((uint64_t)g_hi << 32) | (gB + ks * 16), idesc, accum | (uint32_t)ks);
                 }
                 accum = 1;
-                tc_commit(empty0 + 8 * s);
+                if (leader) tc_commit(empty0 + 8 * s);
                 if (++s == a.nstage) { s = 0; ph ^= 1u; }
             }
-            tc_commit(done);
+            if (leader) tc_commit(done);
         }
         __syncwarp();
     } else {
