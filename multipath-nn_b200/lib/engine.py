@@ -402,19 +402,19 @@ class Engine:
         # ops of pyramid scale k -- layer L at scale k depends on layer L-1 at scale k (same lane)
         # and on layer L at scale k-1 (pooled input; the neighbouring lane), so the scales advance
         # as a wavefront and the small, latency-bound coarse-scale launches hide behind the large
-        # fine-scale ones.  Cross-lane edges are explicit (op.deps -> events); every lane forks
-        # from and joins the main stream inside one op list, so the pattern is valid under capture.
+        # fine-scale ones.  Every lane forks from the main stream at the head of an op list and joins
+        # it at the end (valid under capture); all other cross-lane edges are explicit
+        # (op.deps -> events), including those from lane-0 ops issued earlier in the same list.
         if self._lanes is None:
             self._lanes = {}
-        used = set()
+        used = sorted({getattr(op, 'lane', 0) for op in ops} - {0})
+        for lane in used:                         # fork: every lane starts after what main holds now
+            if lane not in self._lanes:
+                self._lanes[lane] = torch.cuda.Stream(self.dev)
+            self._lanes[lane].wait_stream(main)
         for op in ops:
             lane = getattr(op, 'lane', 0)
-            if lane and lane not in self._lanes:
-                self._lanes[lane] = torch.cuda.Stream(self.dev)
             st = main if lane == 0 else self._lanes[lane]
-            if lane and lane not in used:
-                st.wait_stream(main)              # first use: everything issued on main so far
-                used.add(lane)
             for d in getattr(op, 'deps', ()):
                 if getattr(d, 'lane', 0) != lane and getattr(d, '_ev', None) is not None:
                     st.wait_event(d._ev)
@@ -732,7 +732,10 @@ class _Plan:
                         _vp(r.prob), _vp(self.y), B, n_cls, r.eps, coef(), 1.0 / B, None,
                         dzp, Balloc, eng.gptr(r.fc.params.b), S())
                     ceb.lane = 1
-                    self.bwd_ops.append(self._after(ceb, self.bwd_head_dep))
+                    # a stage without a router only needs p_tr (forward): its head gradients are issued
+                    # ahead of the routing backward so the deepest conv chain starts under it
+                    ceb.early = eng.nodes[nd.parent].router is None
+                    self.bwd_ops.append(ceb if ceb.early else self._after(ceb, self.bwd_head_dep))
                 else:
                     self.bwd_ops.append(lambda r=r, coef=coef: L.softmax_ce_bwd(
                         _vp(r.prob), _vp(self.y), B, n_cls, r.eps, coef(), 1.0 / B, _vp(r.dZ), None, 0, None, S()))
@@ -743,6 +746,8 @@ class _Plan:
                 self._build_router_bwd(nd, Balloc, dyn_k)
             if nd.kind == 'rcm':
                 self._build_rcm_bwd(nd, Balloc)
+        early = [op for op in self.bwd_ops if getattr(op, 'early', False)]
+        self.bwd_ops = early + [op for op in self.bwd_ops if not getattr(op, 'early', False)]
         # ---------------- optimiser ---------------- #
         talr = 1 if (eng.dynamic and bool(net.hypers.talr)) else 0
         stats_ptr = (lambda: ctypes.c_void_p(eng.grad.data_ptr() + 4 * eng.n_theta)) if eng.dynamic else (lambda: None)
@@ -839,7 +844,8 @@ class _Plan:
             L.fc_wgrad(_vp(st.feat), Fext, Balloc, B, _vp(hd.dZ), hd.N, 16, a[0], a[1], a[2], b[0], b[1], b[2], S())
         self._tag(wgrad, 'fc_wgrad', desc='F%d N%d' % (Fext, hd.N), flops=2.0 * B * F * hd.N, nbytes=B * F * 2)
         wgrad.lane = 1
-        self.bwd_ops.append(self._after(wgrad, self.bwd_head_dep))
+        wgrad.early = rt is None
+        self.bwd_ops.append(wgrad if wgrad.early else self._after(wgrad, self.bwd_head_dep))
         # data gradient towards the flattened coarsest scale
         hd.Wfd = torch.zeros((1, hd.N // 8, F, 8), dtype=eng.tdtype, device=eng.dev)
         if leaf is not None:
@@ -853,6 +859,7 @@ class _Plan:
                            B, 0, 0, 0, Balloc, None, 0, None, BF16, BF16, 1, S())
         self._tag(dgrad, 'fc_dgrad', desc='N%d F%d' % (hd.N, F), flops=2.0 * B * F * hd.N, nbytes=B * F * 2)
         dgrad.lane = 1
+        dgrad.early = rt is None
         st.dfeat_op = dgrad                          # the conv chain of this node waits for it
         self.bwd_ops.append(dgrad)
 
