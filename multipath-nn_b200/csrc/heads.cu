@@ -350,20 +350,7 @@ router_tail_fwd_kernel(const float* Z1, int B, const float* g1, const float* b1,
     router_tail_fwd_body(Z1, B, g1, b1, m1, v1, W2, bias2, g2, b2, m2, v2, W3, bias3, ns, d, eps, train, Z2, R, save);
 }
 
-// every router of the net in one launch: one CTA per router
-__global__ void __launch_bounds__(RT_THREADS)
-router_tail_fwd_batched_kernel(const mpnn_router_fwd_desc* __restrict__ descs, int B, float d, float eps, int train) {
-    const mpnn_router_fwd_desc r = descs[blockIdx.x];
-    router_tail_fwd_body(r.Z1, B, r.g1, r.b1, r.m1, r.v1, r.W2, r.bias2, r.g2, r.b2, r.m2, r.v2, r.W3, r.bias3,
-                         r.ns, d, eps, train, r.Z2, r.R, r.save);
-}
-
-extern "C" int mpnn_router_tail_fwd_batched(const mpnn_router_fwd_desc* descs, int n, int B, int C,
-                                            float d, float eps, int train, void* stream) {
-    MPNN_REQUIRE(C == RT_C && n >= 1, "router_tail_fwd_batched: C=%d n=%d", C, n);
-    router_tail_fwd_batched_kernel<<<n, RT_THREADS, 0, (cudaStream_t)stream>>>(descs, B, d, eps, train);
-    return mpnn_check_launch("router_tail_fwd_batched");
-}
+// (the batched variants -- every router in one launch -- live in router_cluster.cu)
 
 extern "C" int mpnn_router_tail_fwd(const float* Z1, int B, int C,
                                     const float* g1, const float* b1, float* m1, float* v1,
@@ -564,7 +551,7 @@ router_tail_bwd_kernel(const float* Z1, const float* Z2, const float* dR, int B,
                          dW3, dbias3, dZ1, scratch, nullptr, 0, nullptr);
 }
 
-// (the batched variant -- every router in one launch -- lives in router_bwd.cu)
+// (the batched variant -- every router in one launch -- lives in router_cluster.cu)
 
 extern "C" int mpnn_router_tail_bwd(const float* Z1, const float* Z2, const float* dR, int B, int C, int ns,
                                     const float* g1, const float* b1, const float* W2,

@@ -1,4 +1,4 @@
-// Backward of every router tail of the net in ONE launch, one 8-CTA thread-block
+// Forward and backward of every router tail of the net in ONE launch each, one 8-CTA thread-block
 // cluster per router (reference: lib/net_types.py router() = FC16-BN-ReLU-FC16-
 // BN-ReLU-FC(n_sinks); TF autodiff through train-mode batch norm).
 //
@@ -220,10 +220,121 @@ router_tail_bwd_cluster_kernel(const mpnn_router_bwd_desc* __restrict__ descs, i
     cluster.sync();          // keep this CTA's shared memory alive until every peer has read it
 }
 
+// ---------------------------------------------------------------------------
+// Forward of every router tail in one launch (same cluster layout): BN1 -> ReLU -> FC16 -> BN2 ->
+// ReLU -> FC(ns).  Train-mode statistics are two-pass (mean, then centred second moment) like
+// tf.nn.moments; each pass is a per-CTA partial + a fixed-order fp64 sum over the cluster.
+__device__ __forceinline__ void cluster_channel_sum(cg::cluster_group& cluster, const float* v, float* part, double* out) {
+    // v[C]: this thread's partial per channel; part[C]: CTA partial (smem, read by the cluster)
+    const int tid = threadIdx.x;
+    if (tid < C) part[tid] = 0.f;
+    __syncthreads();
+    block_add(v, C, part);
+    cluster.sync();
+    if (tid < C) {
+        double t = 0.0;
+        for (int k = 0; k < CL; ++k) t += (double)cluster.map_shared_rank(part, k)[tid];
+        out[tid] = t;
+    }
+    cluster.sync();          // everyone has read `part` before it is reused
+}
+
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(T)
+router_tail_fwd_cluster_kernel(const mpnn_router_fwd_desc* __restrict__ descs, int B, float d, float eps, int train) {
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (int)cluster.block_rank();
+    const mpnn_router_fwd_desc r = descs[blockIdx.x / CL];
+    const int ns = r.ns, tid = threadIdx.x;
+    __shared__ float sW2[C * C], sW3[C * NSMAX], sb2[C], sb3[NSMAX];
+    __shared__ float part[C], a[C], c[C], mean[C];
+    __shared__ double tot[C];
+    sW2[tid] = r.W2[tid];
+    if (tid < C * ns) sW3[tid] = r.W3[tid];
+    if (tid < C) sb2[tid] = r.bias2[tid];
+    if (tid < ns) sb3[tid] = r.bias3[tid];
+    const int Bc = (B + CL - 1) / CL;
+    const int b_lo = rank * Bc, b_hi = min(B, b_lo + Bc);
+    for (int layer = 0; layer < 2; ++layer) {
+        const float* Zin = layer == 0 ? r.Z1 : r.Z2;
+        const float* gg = layer == 0 ? r.g1 : r.g2;
+        const float* bb = layer == 0 ? r.b1 : r.b2;
+        float* ma = layer == 0 ? r.m1 : r.m2;
+        float* va = layer == 0 ? r.v1 : r.v2;
+        __syncthreads();
+        if (train) {
+            float v[C];
+#pragma unroll
+            for (int i = 0; i < C; ++i) v[i] = 0.f;
+            for (int b = b_lo + tid; b < b_hi; b += T) {
+#pragma unroll
+                for (int i = 0; i < C; ++i) v[i] += Zin[(size_t)b * C + i];
+            }
+            cluster_channel_sum(cluster, v, part, tot);
+            if (tid < C) mean[tid] = (float)(tot[tid] / B);
+            __syncthreads();
+#pragma unroll
+            for (int i = 0; i < C; ++i) v[i] = 0.f;
+            for (int b = b_lo + tid; b < b_hi; b += T) {
+#pragma unroll
+                for (int i = 0; i < C; ++i) { const float t = Zin[(size_t)b * C + i] - mean[i]; v[i] = fmaf(t, t, v[i]); }
+            }
+            cluster_channel_sum(cluster, v, part, tot);
+            if (tid < C) {
+                const float var = (float)(tot[tid] / B);
+                const float rs = 1.f / sqrtf(var + eps);
+                a[tid] = gg[tid] * rs;
+                c[tid] = bb[tid] - mean[tid] * a[tid];
+                if (rank == 0) {
+                    ma[tid] = d * ma[tid] + (1.f - d) * mean[tid];
+                    va[tid] = d * va[tid] + (1.f - d) * var;
+                    r.save[layer * 2 * C + tid] = mean[tid];
+                    r.save[layer * 2 * C + C + tid] = rs;
+                }
+            }
+        } else if (tid < C) {
+            const float m = ma[tid], rs = 1.f / sqrtf(va[tid] + eps);
+            a[tid] = gg[tid] * rs;
+            c[tid] = bb[tid] - m * a[tid];
+            if (rank == 0) { r.save[layer * 2 * C + tid] = m; r.save[layer * 2 * C + C + tid] = rs; }
+        }
+        __syncthreads();
+        for (int b = b_lo + tid; b < b_hi; b += T) {
+            float h[C];
+#pragma unroll
+            for (int i = 0; i < C; ++i) h[i] = fmaxf(fmaf(a[i], Zin[(size_t)b * C + i], c[i]), 0.f);
+            if (layer == 0) {
+#pragma unroll
+                for (int j = 0; j < C; ++j) {
+                    float t = sb2[j];
+#pragma unroll
+                    for (int i = 0; i < C; ++i) t = fmaf(h[i], sW2[i * C + j], t);
+                    r.Z2[(size_t)b * C + j] = t;
+                }
+            } else {
+                for (int k = 0; k < ns; ++k) {
+                    float t = sb3[k];
+#pragma unroll
+                    for (int i = 0; i < C; ++i) t = fmaf(h[i], sW3[i * ns + k], t);
+                    r.R[(size_t)b * ns + k] = t;
+                }
+            }
+        }
+        __threadfence_block();      // this CTA re-reads its own Z2 rows in the next layer
+    }
+    cluster.sync();
+}
+
 }  // namespace
 
 extern "C" int mpnn_router_tail_bwd_batched(const mpnn_router_bwd_desc* descs, int n, int B, int Cw, void* stream) {
     MPNN_REQUIRE(Cw == C && n >= 1, "router_tail_bwd_batched: C=%d n=%d", Cw, n);
     router_tail_bwd_cluster_kernel<<<n * CL, T, 0, (cudaStream_t)stream>>>(descs, B);
     return mpnn_check_launch("router_tail_bwd_batched");
+}
+
+extern "C" int mpnn_router_tail_fwd_batched(const mpnn_router_fwd_desc* descs, int n, int B, int Cw,
+                                            float d, float eps, int train, void* stream) {
+    MPNN_REQUIRE(Cw == C && n >= 1, "router_tail_fwd_batched: C=%d n=%d", Cw, n);
+    router_tail_fwd_cluster_kernel<<<n * CL, T, 0, (cudaStream_t)stream>>>(descs, B, d, eps, train);
+    return mpnn_check_launch("router_tail_fwd_batched");
 }

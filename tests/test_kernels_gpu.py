@@ -502,6 +502,45 @@ def test_router_tail(B, ns):
         assert rel_err(G[k].cpu().numpy(), T[k].grad.numpy()) < 2e-4, k
 
 
+@pytest.mark.parametrize('train', [1, 0])
+@pytest.mark.parametrize('B', [24, 1000, 2048 + 77])
+def test_router_tail_fwd_batched_matches_single(B, train):
+    """cluster forward (8 CTAs per router, two-pass moments through DSMEM) against the single-CTA kernel"""
+    from lib.engine import _RT_FWD
+    rng = np.random.default_rng(13)
+    C = 16
+    rows, cases = [], []
+    for ns in (2, 5, 8):
+        Z1 = dev(rng.standard_normal((B, C)).astype(np.float32) * 2 + 0.3)
+        P = {k: dev(rng.standard_normal(sh).astype(np.float32) * sc) for k, sh, sc in [
+            ('g1', C, 1), ('b1', C, .3), ('W2', (C, C), .3), ('c2', C, .1), ('g2', C, 1), ('b2', C, .3),
+            ('W3', (C, ns), .3), ('c3', ns, .1)]}
+        outs = []
+        for which in range(2):
+            st = [dev(rng.standard_normal(C).astype(np.float32) * 0 + 0.1), dev(np.full(C, 1.5, np.float32)),
+                  dev(np.full(C, -0.2, np.float32)), dev(np.full(C, 0.7, np.float32))]
+            outs.append(dict(st=st, Z2=torch.zeros((B, C), device='cuda'), R=torch.zeros((B, ns), device='cuda'),
+                             save=torch.zeros(64, device='cuda')))
+        o = outs[0]
+        L().router_tail_fwd(vp(Z1), B, C, vp(P['g1']), vp(P['b1']), vp(o['st'][0]), vp(o['st'][1]), vp(P['W2']), vp(P['c2']),
+                            vp(P['g2']), vp(P['b2']), vp(o['st'][2]), vp(o['st'][3]), vp(P['W3']), vp(P['c3']), ns,
+                            0.9, 1e-6, train, vp(o['Z2']), vp(o['R']), vp(o['save']), None)
+        o = outs[1]
+        ptr = lambda t: t.data_ptr()
+        rows.append((ptr(Z1), ptr(P['g1']), ptr(P['b1']), ptr(o['st'][0]), ptr(o['st'][1]), ptr(P['W2']), ptr(P['c2']),
+                     ptr(P['g2']), ptr(P['b2']), ptr(o['st'][2]), ptr(o['st'][3]), ptr(P['W3']), ptr(P['c3']),
+                     ptr(o['Z2']), ptr(o['R']), ptr(o['save']), ns, 0))
+        cases.append(outs)
+    table = dev(np.frombuffer(np.array(rows, dtype=_RT_FWD).tobytes(), np.uint8).copy(), torch.uint8)
+    L().router_tail_fwd_batched(vp(table), len(rows), B, C, 0.9, 1e-6, train, None)
+    torch.cuda.synchronize()
+    for ref, got in cases:
+        for k in ('Z2', 'R', 'save'):
+            assert rel_err(got[k].cpu().numpy(), ref[k].cpu().numpy()) < 1e-5, k
+        for a, b in zip(ref['st'], got['st']):
+            np.testing.assert_allclose(b.cpu().numpy(), a.cpu().numpy(), rtol=1e-5, atol=1e-6)
+
+
 @pytest.mark.parametrize('B', [24, 1000, 2048 + 77])
 def test_router_tail_bwd_batched_matches_single(B):
     """The one-launch cluster kernel (8 CTAs per router, DSMEM reductions) against the
