@@ -181,7 +181,7 @@ bn_relu_pool_bwd_kernel(const T* __restrict__ lin, const T* __restrict__ dAct,
                         int C, Geom g, T* __restrict__ dLin, float* __restrict__ dbias) {
     // grid: x strides over pixels (or 2x2 blocks), y = 8-channel plane
     const int kg = blockIdx.y, KG = C / 8;
-    const int HH = POOL ? g.H / 2 : g.H, WW = g.W;
+    const int HH = POOL ? g.H / 2 : g.H, WW = POOL ? g.W / 2 : g.W;
     const int total = g.B * HH * WW;
     float a[8], c[8], pp[8], qq[8], bs[8];
 #pragma unroll
@@ -196,76 +196,56 @@ bn_relu_pool_bwd_kernel(const T* __restrict__ lin, const T* __restrict__ dAct,
             qq[j] = -a[j] * m0 + a[j] * rstd * mean * m1;
         }
     }
-    // POOL: one thread per (image, row pair h, full-resolution column w): coalesced rows; the
-    // 2x2 argmax (first maximum in the order (0,0),(0,1),(1,0),(1,1), like tf.nn.max_pool's
-    // gradient) is resolved between the lane pair (w, w^1) with shuffles.
-    const unsigned lane = threadIdx.x & 31;
-    const unsigned utotal = (unsigned)total;
-    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i - lane < utotal; i += gridDim.x * blockDim.x) {
-        const bool ok = i < utotal;
-        const unsigned ii = ok ? i : 0;
-        const int w = ii % (unsigned)WW;
-        const unsigned r = ii / (unsigned)WW;
-        const int h = r % (unsigned)HH;
-        const int n = r / (unsigned)HH;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int w = i % WW;
+        const int r = i / WW;
+        const int h = r % HH;
+        const int n = r / HH;
         if (POOL) {
-            const int p0 = row_of(g, n, 2 * h, w), p1 = p0 + g.Wp;
-            float v0[8], v1[8];
-            if (ok) {
-                Row8<T>::load(plane_row(lin, kg, g.P, p0), v0);
-                Row8<T>::load(plane_row(lin, kg, g.P, p1), v1);
-            } else {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) { v0[j] = 0.f; v1[j] = 0.f; }
-            }
-            unsigned win = 0;          // bit j: this thread's top pixel wins channel j; bit 8+j: bottom pixel
+            // which of the 2x2 pixels holds the (first) maximum, per channel: 2 bits each
+            unsigned best = 0;
             float dp[8];
             if (dPooled) {
-                const unsigned dx = w & 1;
+                float bv[8];
+                Row8<T>::load(plane_row(lin, kg, g.P, row_of(g, n, 2 * h, 2 * w)), bv);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const float n0 = __shfl_xor_sync(0xffffffffu, v0[j], 1);
-                    const float n1 = __shfl_xor_sync(0xffffffffu, v1[j], 1);
-                    const float e0 = dx ? n0 : v0[j], o0 = dx ? v0[j] : n0;      // (0,0) (0,1)
-                    const float e1 = dx ? n1 : v1[j], o1 = dx ? v1[j] : n1;      // (1,0) (1,1)
-                    unsigned b = 0; float bv = e0;
-                    if (o0 > bv) { b = 1; bv = o0; }
-                    if (e1 > bv) { b = 2; bv = e1; }
-                    if (o1 > bv) { b = 3; }
-                    win |= (b == dx ? 1u : 0u) << j;
-                    win |= (b == 2 + dx ? 1u : 0u) << (8 + j);
+                for (int k = 1; k < 4; ++k) {
+                    float v[8];
+                    Row8<T>::load(plane_row(lin, kg, g.P, row_of(g, n, 2 * h + (k >> 1), 2 * w + (k & 1))), v);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        if (v[j] > bv[j]) { bv[j] = v[j]; best = (best & ~(3u << (2 * j))) | ((unsigned)k << (2 * j)); }
                 }
-                if (ok) Row8<T>::load(plane_row(dPooled, kg, gp.P, row_of(gp, n, h, w >> 1)), dp);
+                Row8<T>::load(plane_row(dPooled, kg, gp.P, row_of(gp, n, h, w)), dp);
             }
-            if (ok) {
 #pragma unroll
-                for (int k = 0; k < 2; ++k) {
-                    const int p = k ? p1 : p0;
-                    const float* lv = k ? v1 : v0;
-                    float out[8];
-                    if (ss) {
-                        float d[8];
-                        load_dy<T>(dAct, dFeat, Balloc, KG, g, kg, n, 2 * h + k, w, p, d);
+            for (int k = 0; k < 4; ++k) {
+                const int hh = 2 * h + (k >> 1), ww = 2 * w + (k & 1);
+                const int p = row_of(g, n, hh, ww);
+                float out[8];
+                if (ss) {
+                    float lv[8], d[8];
+                    Row8<T>::load(plane_row(lin, kg, g.P, p), lv);      // L1 hit: read above for the argmax
+                    load_dy<T>(dAct, dFeat, Balloc, KG, g, kg, n, hh, ww, p, d);
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const float dy = fmaf(a[j], lv[j], c[j]) > 0.f ? d[j] : 0.f;
-                            out[j] = fmaf(a[j], dy, fmaf(pp[j], lv[j], qq[j]));
-                        }
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) out[j] = 0.f;
+                    for (int j = 0; j < 8; ++j) {
+                        const float dy = fmaf(a[j], lv[j], c[j]) > 0.f ? d[j] : 0.f;
+                        out[j] = fmaf(a[j], dy, fmaf(pp[j], lv[j], qq[j]));
                     }
-                    if (dPooled) {
+                } else {
 #pragma unroll
-                        for (int j = 0; j < 8; ++j)
-                            if ((win >> (8 * k + j)) & 1u) out[j] += dp[j];
-                    }
-                    Row8<T>::store(plane_row(dLin, kg, g.P, p), out);
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) bs[j] += out[j];
+                    for (int j = 0; j < 8; ++j) out[j] = 0.f;
                 }
+                if (dPooled) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        if (((best >> (2 * j)) & 3u) == (unsigned)k) out[j] += dp[j];
+                }
+                Row8<T>::store(plane_row(dLin, kg, g.P, p), out);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) bs[j] += out[j];
             }
-        } else if (ok) {
+        } else {
             const int p = row_of(g, n, h, w);
             float lv[8], d[8], out[8];
             Row8<T>::load(plane_row(lin, kg, g.P, p), lv);
@@ -309,8 +289,7 @@ extern "C" int mpnn_bn_relu_pool_bwd(const void* lin, const void* dAct, const vo
     Geom gp = make_geom(B, H / 2, W / 2, G, Pp);
     const bool pool = dPooled != nullptr;
     MPNN_REQUIRE(!pool || (H % 2 == 0 && W % 2 == 0), "bn_relu_pool_bwd: odd size");
-    long long total = (long long)B * (pool ? (H / 2) * W : H * W);
-    MPNN_REQUIRE(total < (1ll << 31), "bn_relu_pool_bwd: too many pixels");
+    long long total = (long long)B * (pool ? (H / 2) * (W / 2) : H * W);
     int gx = (int)((total + 255) / 256);
     int cap = 148 * 16 / (C / 8);
     if (cap < 148) cap = 148;
