@@ -398,7 +398,8 @@ class Engine:
             return
         # Lanes (one CUDA stream each).  0: input packing, routing, optimiser.  1: classifier and
         # router heads, which only feed the losses (forward) or start from them (backward).
-        # 2: weight gradients, which only feed the optimiser.  3+k: the conv / BN / data-gradient
+        # 9 / 10+k: weight gradients of the heads / of the convs at scale k, which only feed the
+        # optimiser and are mutually independent.  3+k: the conv / BN / data-gradient
         # ops of pyramid scale k -- layer L at scale k depends on layer L-1 at scale k (same lane)
         # and on layer L at scale k-1 (pooled input; the neighbouring lane), so the scales advance
         # as a wavefront and the small, latency-bound coarse-scale launches hide behind the large
@@ -735,6 +736,7 @@ class _Plan:
                     # a stage without a router only needs p_tr (forward): its head gradients are issued
                     # ahead of the routing backward so the deepest conv chain starts under it
                     ceb.early = eng.nodes[nd.parent].router is None
+                    hd.ceb_op = ceb
                     self.bwd_ops.append(ceb if ceb.early else self._after(ceb, self.bwd_head_dep))
                 else:
                     self.bwd_ops.append(lambda r=r, coef=coef: L.softmax_ce_bwd(
@@ -843,8 +845,9 @@ class _Plan:
         def wgrad():
             L.fc_wgrad(_vp(st.feat), Fext, Balloc, B, _vp(hd.dZ), hd.N, 16, a[0], a[1], a[2], b[0], b[1], b[2], S())
         self._tag(wgrad, 'fc_wgrad', desc='F%d N%d' % (Fext, hd.N), flops=2.0 * B * F * hd.N, nbytes=B * F * 2)
-        wgrad.lane = 1
+        wgrad.lane = 9                               # off the heads lane: the data gradient below is what the chain waits for
         wgrad.early = rt is None
+        self._after(wgrad, getattr(hd, 'ceb_op', None))
         self.bwd_ops.append(wgrad if wgrad.early else self._after(wgrad, self.bwd_head_dep))
         # data gradient towards the flattened coarsest scale
         hd.Wfd = torch.zeros((1, hd.N // 8, F, 8), dtype=eng.tdtype, device=eng.dev)
@@ -1082,6 +1085,7 @@ class _Plan:
                                 eng.impl_w if (sc.K0 + sc.K1 <= 128 and sc.N <= 256) else 0, S())
             self._tag(wgrad, 'conv_wgrad', desc='H%d K%d+%d N%d' % (sc.geo.H, sc.K0, sc.K1, sc.N), flops=2.0 * B * sc.geo.H * sc.geo.W * 9 * (sc.K0real + sc.K1) * sc.N,
                       nbytes=B * sc.geo.H * sc.geo.W * (sc.K0 + sc.K1 + sc.N) * (2 if dt == BF16 else 4))
+            wgrad.lane = 10 + (sc.lane - 3)          # weight gradients are mutually independent: one lane per scale
             self.bwd_ops.append(self._after(wgrad, elt))
             # data gradient: towards the parent's activation (N0) and the pooled predecessor (N1)
             N0 = sc.K0 if par_grad else 0
