@@ -154,7 +154,7 @@ def main():
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=5)
-    ap.add_argument('--batch', type=int, default=int(os.environ.get('MPNN_BENCH_BATCH', 2048)),
+    ap.add_argument('--batch', type=int, default=int(os.environ.get('MPNN_BENCH_BATCH', 4096)),
                     help='examples per GPU per step (reference trains at 128; see DESIGN.md)')
     ap.add_argument('--precision', default=os.environ.get('MPNN_PRECISION', 'bf16'))
     ap.add_argument('--impl', default='ours')
@@ -303,6 +303,13 @@ def main():
         roof = {'bound': 'hbm', 'achieved': ach_gb, 'peak': pk['hbm_gbs'], 'unit': 'GB/s',
                 'frac': ach_gb / pk['hbm_gbs'], 'traffic': None,
                 'other_ceiling': {'bound': 'tensor', 'achieved': ach_tf, 'frac': ach_tf / pk['bf16_tflops']}}
+    try:
+        tr = json.load(open(os.path.join(ROOT, 'profiles', 'r01_traffic.json'))).get(top)
+        if tr:
+            roof['traffic'] = tr['dram_bytes_per_launch']
+            roof['traffic_of'] = '%s: %d algorithmic bytes (%s)' % (tr['launch'], tr['algorithmic_bytes_per_launch'], tr['source'])
+    except Exception:
+        pass
     roof.update({'kernel': top, 'launches_per_step': d['n'], 'share_of_step': d['ms'] / tot_ms,
                  'peak_source': pk_src + ' (burst; kernels timed one by one with CUDA events)',
                  'per_launch_avg_ms': d['ms'] / d['n']})
@@ -342,6 +349,8 @@ def main():
                 'timing': 'wall clock around net.train.run(feed) with pinned host batches', 'loss': loss},
         'gpu_launches': int(launches),
         'tensor_frac_of_step': value / world * TRAIN_FLOP_PER_IMG / (pk['bf16_tflops_sustained'] * 1e12),
+        # whole step against the HBM ceiling: algorithmic bytes of every launch (op tags) / measured copy bandwidth
+        'hbm_frac_of_step': (sum(getattr(op, 'nbytes', 0.0) for op in ops) / (pk['hbm_gbs'] * 1e9)) / (dev_ms / args.steps * 1e-3),
         'roofline': roof, 'kernel_time_shares': shares,
         'cpu_baseline': {'value': cpu_v, 'unit': 'images/s', 'cores': torch.get_num_threads(), 'kind': 'port',
                          'sample': '%d train steps at batch %d in %.1f s (reference semantics restated on '

@@ -69,6 +69,8 @@ bn_relu_pool_fwd_kernel(const T* __restrict__ lin, int C, Geom g,
                         const float* __restrict__ ss, T* __restrict__ act,
                         T* __restrict__ pooled, Geom gp,
                         T* __restrict__ feat, int Balloc) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int KG = C / 8, kg = blockIdx.y;
     const int HH = POOL ? g.H / 2 : g.H;
     const unsigned total = (unsigned)g.B * HH * g.W;          // host guarantees < 2^31
@@ -142,10 +144,10 @@ extern "C" int mpnn_bn_relu_pool_fwd(const void* lin, int C, int B, int H, int W
     dim3 grid(gx, C / 8);
     cudaStream_t st = (cudaStream_t)stream;
     if (pooled) {
-        MPNN_DISPATCH_DTYPE(dtype, (bn_relu_pool_fwd_kernel<T, true><<<grid, 256, 0, st>>>(
+        MPNN_DISPATCH_DTYPE(dtype, (mpnn_launch_pdl(bn_relu_pool_fwd_kernel<T, true>, grid, dim3(256), 0, st,
             (const T*)lin, C, g, ss, (T*)act, (T*)pooled, gp, (T*)feat, Balloc)));
     } else {
-        MPNN_DISPATCH_DTYPE(dtype, (bn_relu_pool_fwd_kernel<T, false><<<grid, 256, 0, st>>>(
+        MPNN_DISPATCH_DTYPE(dtype, (mpnn_launch_pdl(bn_relu_pool_fwd_kernel<T, false>, grid, dim3(256), 0, st,
             (const T*)lin, C, g, ss, (T*)act, (T*)pooled, gp, (T*)feat, Balloc)));
     }
     return mpnn_check_launch("bn_relu_pool_fwd");

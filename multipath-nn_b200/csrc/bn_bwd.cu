@@ -33,6 +33,8 @@ __global__ void __launch_bounds__(256, 4)
 bn_bwd_reduce_kernel(const T* __restrict__ lin, const T* __restrict__ dAct, const T* __restrict__ dFeat,
                      int Balloc, const float* __restrict__ ss, int C, Geom g, float* __restrict__ partials,
                      const float* __restrict__ mr, const mpnn_bn_bwd_fuse f) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int kg = blockIdx.y, KG = C / 8;
     float a[8], c[8], s0[8], s1[8];
 #pragma unroll
@@ -114,7 +116,7 @@ static int bn_bwd_reduce_impl(const void* lin, const void* dAct, const void* dFe
     mpnn_bn_bwd_fuse f = {};
     if (fp) f = *fp;
     dim3 grid(gx, C / 8);
-    MPNN_DISPATCH_DTYPE(dtype, (bn_bwd_reduce_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(
+    MPNN_DISPATCH_DTYPE(dtype, (mpnn_launch_pdl(bn_bwd_reduce_kernel<T>, grid, dim3(256), 0, (cudaStream_t)stream,
         (const T*)lin, (const T*)dAct, (const T*)dFeat, Balloc, ss, C, g, partials, mr, f)));
     return mpnn_check_launch("bn_bwd_reduce");
 }
@@ -180,6 +182,8 @@ bn_relu_pool_bwd_kernel(const T* __restrict__ lin, const T* __restrict__ dAct,
                         const float* __restrict__ sums, float inv_count,
                         int C, Geom g, T* __restrict__ dLin, float* __restrict__ dbias) {
     // grid: x strides over pixels (or 2x2 blocks), y = 8-channel plane
+    pdl_launch_dependents();
+    pdl_wait();
     const int kg = blockIdx.y, KG = C / 8;
     const int HH = POOL ? g.H / 2 : g.H, WW = POOL ? g.W / 2 : g.W;
     const int total = g.B * HH * WW;
@@ -299,11 +303,11 @@ extern "C" int mpnn_bn_relu_pool_bwd(const void* lin, const void* dAct, const vo
     float inv = (float)(1.0 / count);
     cudaStream_t st = (cudaStream_t)stream;
     if (pool) {
-        MPNN_DISPATCH_DTYPE(dtype, (bn_relu_pool_bwd_kernel<T, true><<<grid, 256, 0, st>>>(
+        MPNN_DISPATCH_DTYPE(dtype, (mpnn_launch_pdl(bn_relu_pool_bwd_kernel<T, true>, grid, dim3(256), 0, st,
             (const T*)lin, (const T*)dAct, (const T*)dFeat, Balloc, (const T*)dPooled, gp, ss, mr, sums,
             inv, C, g, (T*)dLin, dbias)));
     } else {
-        MPNN_DISPATCH_DTYPE(dtype, (bn_relu_pool_bwd_kernel<T, false><<<grid, 256, 0, st>>>(
+        MPNN_DISPATCH_DTYPE(dtype, (mpnn_launch_pdl(bn_relu_pool_bwd_kernel<T, false>, grid, dim3(256), 0, st,
             (const T*)lin, (const T*)dAct, (const T*)dFeat, Balloc, (const T*)dPooled, gp, ss, mr, sums,
             inv, C, g, (T*)dLin, dbias)));
     }

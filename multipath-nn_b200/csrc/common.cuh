@@ -110,6 +110,33 @@ __device__ __forceinline__ const T* plane_row(const T* base, int kg, int P, int 
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
+// ---- programmatic dependent launch (PDL) ---------------------------------- //
+// The conv -> BN -> conv chain of one pyramid scale is a sequence of short dependent launches on
+// one stream.  Kernels of that chain are launched with the programmatic-stream-serialization
+// attribute: the next kernel's CTAs are scheduled (and run their prologue: barrier init, TMEM
+// allocation, shared-memory setup) while the previous kernel drains, and block in
+// griddepcontrol.wait -- which returns only when the previous grid has COMPLETED and its memory is
+// visible -- before touching global memory.  MPNN_PDL=0 disables the attribute.
+#include <cstdlib>
+static inline bool mpnn_pdl_enabled() {
+    static const int v = getenv("MPNN_PDL") ? atoi(getenv("MPNN_PDL")) : 1;
+    return v != 0;
+}
+template <typename... KArgs, typename... Args>
+static inline cudaError_t mpnn_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                          cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = mpnn_pdl_enabled() ? 1 : 0;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+// device side: let the dependent grid start scheduling, then wait for the grid we depend on
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);

@@ -85,6 +85,8 @@ stencil_gemm_umma_kernel(const GemmArgs a) {
             for (int i = threadIdx.x - 64; i < 4 * 2 * NB; i += 128) sstat[i] = 0.f;
         for (int i = threadIdx.x - 64; i < NB; i += 128) sbias[i] = a.bias ? a.bias[n0 + i] : 0.f;
     }
+    pdl_launch_dependents();
+    pdl_wait();                  // everything above is independent of the previous kernel in the stream
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -465,7 +467,8 @@ int mpnn_stencil_gemm_umma(const void* A0, int K0, const void* A1, int K1, const
         }
         attr_set = true;
     }
-    kern<<<dim3(gx, split), kThreads, smem, st>>>(a);
+    cudaError_t le = mpnn_launch_pdl(kern, dim3(gx, split), dim3(kThreads), smem, st, a);
+    if (le != cudaSuccess) { mpnn_set_error("stencil_gemm_umma launch: %s", cudaGetErrorString(le)); return MPNN_ERR_CUDA; }
     return mpnn_check_launch("stencil_gemm_umma");
 }
 
