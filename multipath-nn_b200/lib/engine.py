@@ -262,6 +262,20 @@ class Engine:
     def fetch_param(self, p):
         p.value = self._buf(p).cpu().numpy().reshape(p.value.shape).copy()
 
+    def momentum_numpy(self):
+        """optimiser accumulators, one array per trainable tensor in `self.tparams` order"""
+        a = self.accum.cpu().numpy()
+        return [a[p._bind[2]:p._bind[2] + p.value.size].reshape(p.value.shape).copy() for p in self.tparams]
+
+    def load_momentum(self, arrays):
+        if len(arrays) != len(self.tparams):
+            raise ValueError('load_momentum: %d arrays for %d trainable tensors' % (len(arrays), len(self.tparams)))
+        for p, a in zip(self.tparams, arrays):
+            a = np.asarray(a, dtype=np.float32)
+            if a.shape != p.value.shape:
+                raise ValueError('load_momentum: shape %s != %s' % (a.shape, p.value.shape))
+            self.accum[p._bind[2]:p._bind[2] + a.size].copy_(torch.from_numpy(np.ascontiguousarray(a).reshape(-1)))
+
     def tptr(self, p):
         return ctypes.c_void_p(self.theta.data_ptr() + 4 * p._bind[2]) if p._bind[1] == 'theta' \
             else ctypes.c_void_p(self.state.data_ptr() + 4 * p._bind[2])

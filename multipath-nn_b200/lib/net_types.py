@@ -113,6 +113,10 @@ class Net:
         if self._engine is None:
             from lib.engine import Engine
             self._engine = Engine(self, **self._engine_opts)
+            pending = getattr(self, '_pending_momentum', None)
+            if pending is not None:                  # restored checkpoint (lib/checkpoint.py)
+                self._engine.load_momentum(pending)
+                self._pending_momentum = None
         return self._engine
 
     def eval_stats(self, feed_dict):

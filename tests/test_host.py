@@ -135,3 +135,28 @@ def test_planner_dry_run(kind, prec, impl):
         from lib.layer_types import Chain, Rect
         from lib.net_types import SRNet
         Engine(SRNet(x0_shape=(16, 16, 3), y_shape=(10,), root=Chain(comps=[Rect()])), dry_run=True)
+
+
+def test_checkpoint_format_roundtrip(tmp_path):
+    """lib/checkpoint.py: the 'net' entry is exactly the write_net payload; step / RNG / momentum travel with it"""
+    from lib import checkpoint, serdes
+    from util import tiny_net
+    net = tiny_net('ac', seed=3, k_cpt=4e-9)
+    rng = np.random.default_rng(5)
+    rng.random(7)
+    path = str(tmp_path / 'ck.npy')
+    checkpoint.save_checkpoint(path, net, step=1234, rng=rng)
+    expect_next = rng.random(3)
+    rec = checkpoint.net_record(path)
+    ref = serdes.encode_net(net)
+    assert rec['type'] == ref['type'] and rec['hypers'] == ref['hypers']
+    flat = lambda r: [r['params'][k] for k in sorted(r['params'])] + [x for s in r.get('sinks', []) for x in flat(s)] \
+        + [x for c in r.get('comps', []) for x in flat(c)] + (flat(r['router']) if r.get('router') else [])
+    for a, b in zip(flat(rec['root']), flat(ref['root'])):
+        np.testing.assert_array_equal(a, b)
+    rng2 = np.random.default_rng(0)
+    net2, step = checkpoint.load_checkpoint(path, rng=rng2)
+    assert step == 1234 and type(net2).__name__ == 'ActorNet'
+    np.testing.assert_array_equal(rng2.random(3), expect_next)        # sampling resumes where it stopped
+    serdes.write_net(str(tmp_path / 'plain.npy'), net)
+    assert checkpoint.net_record(str(tmp_path / 'plain.npy'))['type'] == 'ActorNet'

@@ -216,3 +216,36 @@ def test_serdes_roundtrip_through_device(tmp_path):
     s1 = net.eval_stats(_feed(net, x0, y, 1.0)); s2 = net2.eval_stats(_feed(net2, x0, y, 1.0))
     np.testing.assert_allclose(s1[(net, 'moc')], s2[(net2, 'moc')])
     np.testing.assert_allclose(s1[(net, 'acc')], s2[(net2, 'acc')])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('kind', ['sr', 'ac'])
+def test_checkpoint_resume_continues_the_same_trajectory(kind, tmp_path):
+    """3 steps + checkpoint + 2 steps == restore + 2 steps (parameters, momentum and BN running moments)"""
+    from lib import checkpoint
+    hy = dict(k_cpt=4e-9) if kind != 'sr' else {}
+    net = tiny_net(kind, seed=1, **hy).configure(precision='fp32')
+    if kind != 'sr':
+        randomize_routers(net)
+
+    def step(n, t):
+        xb, yb = batch(16, seed=40 + t)
+        f = {n.x0: xb, n.y: yb, n.mode: 'tr', n.λ_lrn: 0.05}
+        if n.dynamic:
+            f[n.τ] = 0.9
+        n.train.run(f)
+    for t in range(3):
+        step(net, t)
+    path = str(tmp_path / 'ck.npy')
+    checkpoint.save_checkpoint(path, net, step=3)
+    for t in range(3, 5):
+        step(net, t)
+    net2, t0 = checkpoint.load_checkpoint(path, precision='fp32')
+    assert t0 == 3
+    for t in range(t0, 5):
+        step(net2, t)
+    e1, e2 = net._get_engine(), net2._get_engine()
+    torch.cuda.synchronize()
+    # the weight-gradient reductions are unordered fp32 atomics: equal up to summation order
+    for a, b in ((e1.theta, e2.theta), (e1.accum, e2.accum), (e1.state, e2.state)):
+        np.testing.assert_allclose(b.cpu().numpy(), a.cpu().numpy(), rtol=2e-5, atol=1e-6)
