@@ -63,6 +63,16 @@ typedef struct {
 int mpnn_pack_weights_batched(const mpnn_pack_desc* descs, int n, int blocks_per_desc,
                               int dtype, void* stream);
 
+/* ---- training-batch augmentation (scripts/lib/data.py:24-34) -------------- */
+/* x [N][H][W][C], y [N][n_cls] fp32: the training set resident on the device.  Per output example i
+ * (all device int arrays of length B, drawn on the host in the reference's order):
+ *   idx[i] sample, flip[i] horizontal mirror, (du[i], dv[i]) row / column shift; pixels shifted in
+ *   from outside the image take the per-channel mean of the image.  Writes x_out [B][H][W][C],
+ *   y_out [B][n_cls]. */
+int mpnn_augment_batch(const float* x, const float* y, int N, int H, int W, int C, int n_cls,
+                       const int* idx, const int* flip, const int* du, const int* dv, int B,
+                       float* x_out, float* y_out, void* stream);
+
 /* ---- stencil GEMM: tf.nn.conv2d SAME (lib/layer_types.py:106-107,181-185) */
 /* out[p][n] = bias[n] + sum_tap sum_k A[p+off(tap)][k] * Wp[tap][k][n]
  * A = concat(A0 (K0 ch), A1 (K1 ch)); columns [0,N0) go to out0, [N0,N0+N1)

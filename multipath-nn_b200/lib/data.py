@@ -64,6 +64,41 @@ class Dataset:
                 x[i, max(a, 0):min(h + a, h), max(b, 0):min(w + b, w)]
         return out, y
 
+    def to_device(self, device='cuda'):
+        """keep the training set resident in HBM for `augmented_training_batch_gpu`"""
+        import torch
+        self._dev = (torch.from_numpy(np.ascontiguousarray(self.x0_tr, dtype=np.float32)).to(device),
+                     torch.from_numpy(np.ascontiguousarray(self.y_tr, dtype=np.float32)).to(device))
+        return self
+
+    def augmented_training_batch_gpu(self, n=128, r_shift=4):
+        """`augmented_training_batch` with the per-example work on the GPU (csrc/augment.cu).  The
+        random numbers are drawn on the host in the same order, so a seeded sampler produces the same
+        batches either way; returns device tensors (x0 fp32 NHWC, y one-hot) that `net.train.run`
+        accepts as feed values."""
+        import ctypes
+        import torch
+        from lib import _cabi
+        if getattr(self, '_dev', None) is None:
+            self.to_device()
+        xd, yd = self._dev
+        rng = self.rng
+        j = rng.integers(0, len(self.x0_tr), n)
+        flip = np.asarray(self.m_sym)[np.argmax(self.y_tr[j], 1)] & (rng.random(n) >= 0.5)
+        du = rng.integers(-r_shift, r_shift + 1, n)
+        dv = rng.integers(-r_shift, r_shift + 1, n)
+        draws = torch.from_numpy(np.stack([j, flip, du, dv]).astype(np.int32)).to(xd.device)
+        h, w, c = self.x0_tr.shape[1:]
+        n_cls = self.y_tr.shape[1]
+        x0 = torch.empty((n, h, w, c), dtype=torch.float32, device=xd.device)
+        y = torch.empty((n, n_cls), dtype=torch.float32, device=xd.device)
+        vp = lambda t: ctypes.c_void_p(t.data_ptr())
+        _cabi.lib().augment_batch(vp(xd), vp(yd), len(self.x0_tr), h, w, c, n_cls, vp(draws[0]), vp(draws[1]),
+                                  vp(draws[2]), vp(draws[3]), n, vp(x0), vp(y),
+                                  ctypes.c_void_p(torch.cuda.current_stream(xd.device).cuda_stream))
+        self._keep = draws          # the launch is asynchronous: keep its operands alive until the next batch
+        return x0, y
+
     def _batch(self, x0, y, n):
         i = self.rng.integers(0, len(x0), n)
         return np.take(x0, i, axis=0), np.take(y, i, axis=0)

@@ -802,3 +802,23 @@ def test_fc_heads_umma(B, F, n_cls, dyn):
     got = np.concatenate([f[i, :B] for i in range(F // 8)], 1)
     ref = dz[:, :n_cls].astype(np.float64) @ bf16_round(Wl).T + dz[:, 16:].astype(np.float64) @ bf16_round(Wr[:F]).T
     assert rel_err(got, ref) < 4e-3
+
+
+def test_gpu_augmentation_reproduces_the_numpy_batches():
+    """csrc/augment.cu against lib/data.py (itself a restatement of scripts/lib/data.py:24-34) with the
+    same seeded sampler: copied pixels bit-exact, mean fill to fp32 rounding, labels exact."""
+    from lib.data import Dataset, synthetic_archive
+    arch = synthetic_archive(300, 10, (32, 32, 3), 10)
+    arch['m_sym'] = np.array([True, False] * 5)
+    arch['x0_tr'] = arch['x0_tr'].astype(np.float32).astype(np.float64)    # fp32-representable pixels, as in the real archives
+    a, b = Dataset(archive=arch, seed=11), Dataset(archive=arch, seed=11)
+    for n in (1, 37, 256):
+        xc, yc = a.augmented_training_batch(n)
+        xg, yg = b.augmented_training_batch_gpu(n)
+        torch.cuda.synchronize()
+        xg, yg = xg.cpu().numpy(), yg.cpu().numpy()
+        np.testing.assert_array_equal(yg, yc.astype(np.float32))
+        xc32 = xc.astype(np.float32)
+        same = xg == xc32
+        assert same.mean() > 0.9999                             # everything but (possibly) a fill value on a rounding tie
+        np.testing.assert_allclose(xg, xc32, rtol=2e-7, atol=0)
