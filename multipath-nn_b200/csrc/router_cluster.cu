@@ -103,7 +103,8 @@ router_tail_bwd_cluster_kernel(const mpnn_router_bwd_desc* __restrict__ descs, i
 #pragma unroll
             for (int k = 0; k < NSMAX; ++k) tR[tid * (NSMAX + 1) + k] = dr[k];
             __syncthreads();
-            for (int row = q; row < T; row += 2) {
+            const int nrow = min(T, b_hi - base);          // rows of this tile that hold examples
+            for (int row = q; row < nrow; row += 2) {
                 const float drv = tR[row * (NSMAX + 1) + gk];
                 acc = fmaf(tH[row * LD + gi], drv, acc);
                 accb += drv;
@@ -166,7 +167,8 @@ router_tail_bwd_cluster_kernel(const mpnn_router_bwd_desc* __restrict__ descs, i
 #pragma unroll
             for (int i = 0; i < C; ++i) { tH[tid * LD + i] = h[i]; tD[tid * LD + i] = dz2[i]; }
             __syncthreads();
-            for (int row = 0; row < T; ++row) {
+            const int nrow = min(T, b_hi - base);
+            for (int row = 0; row < nrow; ++row) {
                 const float dv = tD[row * LD + gj];
                 acc = fmaf(tH[row * LD + gi], dv, acc);
                 accb += dv;

@@ -725,15 +725,18 @@ class _Plan:
                 1 if getattr(hy, 'optimistic', False) else 0, 1 if getattr(hy, 'use_cls_err', False) else 0,
                 _vp(self.dR_tab), _vp(self.route_scratch), _vp(self.c_data), S()))
             n_theta = eng.n_theta
-            self.bwd_ops.append(lambda: L.node_moments(
-                _vp(self.p_tr), len(eng.nodes), B, ctypes.c_void_p(eng.grad.data_ptr() + 4 * n_theta), S()))
+            moments = lambda: L.node_moments(
+                _vp(self.p_tr), len(eng.nodes), B, ctypes.c_void_p(eng.grad.data_ptr() + 4 * n_theta), S())
+            moments.lane = 8                     # only the optimiser reads the TALR moments: off the chain
+            self.bwd_ops.append(moments)
             if eng.switches:
                 # every dR is known right after route_bwd: all router tails backward in one launch
                 rows = [self._router_bwd_desc(nd) for nd in eng.switches]
                 tabb = self._desc_table(_RT_BWD, rows)
                 self.keep.append(tabb)
                 self.bwd_ops.append(lambda: L.router_tail_bwd_batched(_vp(tabb), len(rows), B, 16, S()))
-        self.bwd_head_dep = self.bwd_ops[-1] if self.bwd_ops else None     # routing gradients are complete
+        main_ops = [op for op in self.bwd_ops if getattr(op, 'lane', 0) == 0]
+        self.bwd_head_dep = main_ops[-1] if main_ops else None             # routing gradients are complete
         for nd in reversed(eng.nodes):
             if nd.kind == 'reg':
                 r = self.reg[nd.idx]
