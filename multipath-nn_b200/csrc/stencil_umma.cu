@@ -429,16 +429,25 @@ int mpnn_stencil_gemm_umma(const void* A0, int K0, const void* A1, int K1, const
     }
     MPNN_REQUIRE(split > 0, "stencil_gemm(tcgen05): K=%d N=%d does not fit shared memory", K0 + K1, N);
     size_t w = ((size_t)ntaps * KG * NB * 16 + 127) & ~(size_t)127;
-    size_t smem = w + (size_t)nstage * stage + 256 + (size_t)9 * NB * 4;
-    // CTAs per SM by shared memory and by TMEM columns (alloc blocks when exhausted)
+    // CTAs per SM by shared memory, TMEM columns (alloc blocks when exhausted) and registers.  The kernel
+    // is latency-bound per CTA, so residency beats pipeline depth: take the deepest ring that still gives
+    // the largest number of resident CTAs (e.g. 64-channel layers: 2 stages x 2 CTAs instead of 4 x 1).
     int ncols = 32;
     while (ncols < 2 * NB) ncols <<= 1;
-    int per_sm = (int)((227 * 1024) / (smem + 1024));
-    if (per_sm > 512 / ncols) per_sm = 512 / ncols;
-    if (per_sm > 4) per_sm = 4;
-    if (NB == 32 && per_sm > 3) per_sm = 3;       // register budget of the <32> instantiation
-    if (tune_per_sm && per_sm > tune_per_sm) per_sm = tune_per_sm;
-    if (per_sm < 1) per_sm = 1;
+    int cap = 512 / ncols;
+    if (cap > 4) cap = 4;
+    if (NB == 32 && cap > 3) cap = 3;             // register budget of the <32> instantiation
+    if (tune_per_sm && cap > tune_per_sm) cap = tune_per_sm;
+    if (cap < 1) cap = 1;
+    size_t smem = 0;
+    int per_sm = 0;
+    for (int ns = nstage; ns >= 2; --ns) {
+        const size_t sm_ns = w + (size_t)ns * stage + 256 + (size_t)9 * NB * 4;
+        int fit = (int)((227 * 1024) / (sm_ns + 1024));
+        if (fit > cap) fit = cap;
+        if (fit < 1) fit = 1;
+        if (fit > per_sm) { per_sm = fit; smem = sm_ns; nstage = ns; }
+    }
     GemmArgs a;
     a.dbg = tune_dbg;
     a.bn = mpnn_bn_fuse{};
