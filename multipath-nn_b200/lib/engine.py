@@ -24,7 +24,6 @@ from lib.net_types import n_leaves
 
 F32, BF16 = 0, 1
 HYP_LR, HYP_MU, HYP_TAU, HYP_EPS, HYP_KCPT, HYP_GSCALE, HYP_COUNT = 0, 1, 2, 3, 4, 5, 8
-STATS_CAP = 592          # 4 CTAs per SM worth of partial rows
 MAXS = 8
 
 
@@ -630,12 +629,6 @@ class _Plan:
         self.y = self.f32(B, n_cls)
         self.kcpt = self.f32(B)
         self.kextra = self.f32(B)
-        cmax = 8
-        for nd in eng.nodes:
-            if nd.kind == 'rcm':
-                cmax = max(cmax, max(nd.layer.comps[0].hypers.n_chan))
-        self.partials = self.f32(STATS_CAP * 2 * cmax)
-        self.cnt = ctypes.c_int(0)
         S = lambda: eng.stream
         # fully-connected heads on the tensor cores (bf16/tcgen05 mode): one GEMM per conv stage
         # computes the LogReg logits and the first router layer from the shared feature matrix
