@@ -18,6 +18,10 @@
 //   * "dw stacking" (CP = 3) for K0+K1 <= 40: each plane is staged three times,
 //     shifted by dw = -1, 0, +1 rows, as consecutive 8-row groups of M, so ONE
 //     MMA per kernel row dh covers three taps (rows m = (plane*3 + dw)*8 + c).
+//   * for 16 output channels additionally "row stacking" along N (GS): the G descriptor's group
+//     stride is set to one IMAGE ROW of pixels instead of a plane, so group j of a staged G plane is
+//     that plane displaced by j image rows; with the dw-stacked A this makes ONE MMA per G plane
+//     cover all nine taps (16 instead of 24 MMAs per 128 pixels, no extra staging).
 // Without stacking (CP = 1) a CTA owns TG taps (9, or 3 when 9*N exceeds the
 // 512 TMEM columns) and issues one MMA per tap.
 //
@@ -41,7 +45,11 @@ struct WgradArgs {
     int CP;        // staged copies per plane: 1, or 3 (dw stacking)
     int NM;        // MMAs per 16-pixel step per CTA (taps, or kernel rows when stacked)
     int M;         // 64 or 128
-    int n_chunks, nstage, rowsA, halo;
+    int GS;        // with CP = 3: kernel ROWS stacked along N by giving the G descriptor a group stride of
+                   // (W+1) pixel rows -- group j of one staged G plane is that plane displaced by j image
+                   // rows -- so one MMA per G plane and K step covers all nine taps (GS = groups: 3, or 4
+                   // when M = 128 needs N % 16 == 0; the 4th group is ignored)
+    int n_chunks, nstage, rowsA, rowsG, halo;
     int vec4;      // gradient rows are 16-byte aligned: use vector reductions
 };
 
@@ -56,7 +64,7 @@ stencil_wgrad_umma_kernel(const WgradArgs a) {
     const int kgb = blockIdx.z * 16;                     // first plane of this CTA's M block
     const int KG = min(16, KGall - kgb);                 // planes staged by this CTA
     const uint32_t PSA = (uint32_t)a.rowsA * 16;         // stride between 8-row groups of the A stage
-    const uint32_t PSG = (uint32_t)kChunk * 16;          // plane stride of the G stage
+    const uint32_t PSG = (uint32_t)a.rowsG * 16;         // plane stride of the G stage
     const uint32_t stageA = PSA * KG * a.CP, stageG = PSG * NG;
     uint8_t* sA = smem;
     uint8_t* sG = smem + (size_t)a.nstage * stageA;
@@ -64,7 +72,8 @@ stencil_wgrad_umma_kernel(const WgradArgs a) {
     const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * a.nstage, done = empty0 + 8 * a.nstage;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * a.nstage + 1);
     const int t0 = blockIdx.y * a.NM;                    // first tap (CP=1) / kernel row (CP=3) of this CTA
-    const uint32_t ncols = tmem_cols_pow2(a.NM * a.N);
+    const int NW = a.GS * 8;                             // GS: accumulator columns per G plane
+    const uint32_t ncols = tmem_cols_pow2(a.GS ? NG * NW : a.NM * a.N);
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < a.nstage; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
@@ -111,7 +120,8 @@ stencil_wgrad_umma_kernel(const WgradArgs a) {
                         dA += PSA;
                     }
                 }
-                const __nv_bfloat16* gp = a.Gd + p0 * 8;
+                // GS: the G stage starts one image row early (group j is read j image rows further down)
+                const __nv_bfloat16* gp = a.Gd + (p0 - (a.GS ? (size_t)a.g.Wp : 0)) * 8;
                 for (int ng = 0; ng < NG; ++ng, gp += plane, dG += PSG)
                     if (leader) bulk_g2s(dG, gp, PSG, full0 + 8 * s);
                 if (++s == a.nstage) { s = 0; ph ^= 1u; }
@@ -121,9 +131,10 @@ stencil_wgrad_umma_kernel(const WgradArgs a) {
     } else if (warp == 1) {
         {
             const bool leader = elect_one();
-            const uint32_t idesc = make_idesc(a.N, 1, 1, a.M);   // both operands MN-major
+            const uint32_t idesc = make_idesc(a.GS ? NW : a.N, 1, 1, a.M);   // both operands MN-major
             // descriptor lo word = (address >> 4) | (LBO = 128 B) << 16; hi = SBO (plane stride) | version
-            const uint32_t a_hi = (PSA >> 4) | (1u << 14), g_hi = (PSG >> 4) | (1u << 14);
+            const uint32_t a_hi = (PSA >> 4) | (1u << 14);
+            const uint32_t g_hi = (a.GS ? (uint32_t)a.g.Wp : (PSG >> 4)) | (1u << 14);
             const uint32_t a_lo0 = (((smem_u32(sA) + (uint32_t)a.halo * 16) & 0x3FFFFu) >> 4) | (8u << 16);
             const uint32_t g_lo0 = ((smem_u32(sG) & 0x3FFFFu) >> 4) | (8u << 16);
             const uint32_t a_stage = stageA >> 4, g_stage = stageG >> 4;
@@ -133,6 +144,18 @@ stencil_wgrad_umma_kernel(const WgradArgs a) {
                 tc_fence_after();
                 const uint32_t aB = a_lo0 + (uint32_t)s * a_stage;
                 const uint32_t gB = g_lo0 + (uint32_t)s * g_stage;
+                if (a.GS) {
+                    // D[(plane, dw, c)][(G plane j, dh' , n)]: group dh' of G plane j = rows displaced by dh' image
+                    // rows = kernel row dh = 1 - dh'
+                    for (int j = 0; j < NG; ++j) {
+                        const uint32_t gj = gB + (uint32_t)j * (PSG >> 4);
+                        const uint32_t dcol = tmem_base + (uint32_t)(j * NW);
+#pragma unroll
+                        for (int ks = 0; ks < kChunk / 16; ++ks)
+                            if (leader) tc_mma(dcol, ((uint64_t)a_hi << 32) | (aB + ks * 16),
+                                               ((uint64_t)g_hi << 32) | (gj + ks * 16), idesc, accum | (uint32_t)ks);
+                    }
+                } else
                 for (int t = 0; t < a.NM; ++t) {
                     int off;                                  // row shift (16 B units) of this MMA's A operand
                     if (a.CP == 3) off = (t0 + t - 1) * a.g.Wp;
@@ -165,6 +188,34 @@ stencil_wgrad_umma_kernel(const WgradArgs a) {
         const int rs = k >= a.K0 ? 1 : 0;
         const int kr = rs ? k - a.K0 : k;
         const bool row_live = row_ok && kg < KG;
+        if (a.GS) {
+            for (int j = 0; j < NG; ++j) {
+                const int nn = j * 8;
+                const int cs = nn >= a.Nsplit ? 1 : 0;
+                const WDst d = a.dst[rs][cs];
+                const int n = cs ? nn - a.Nsplit : nn;
+#pragma unroll
+                for (int dh2 = 0; dh2 < 3; ++dh2) {
+                    float v[8];
+                    tc_ld8(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(j * NW + dh2 * 8), v);
+                    const int tap = (2 - dh2) * 3 + dwi;
+                    if (row_live && d.p && kr < d.rows) {
+                        float* dst = d.p + ((size_t)tap * d.rows + kr) * d.ld + n;
+                        if (a.vec4 && (d.ld & 3) == 0) {
+#pragma unroll
+                            for (int i = 0; i < 8; i += 4)
+                                if (n + i < d.cols)
+                                    atomicAdd(reinterpret_cast<float4*>(dst + i),
+                                              make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]));
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i)
+                                if (n + i < d.cols) atomicAdd(dst + i, v[i]);
+                        }
+                    }
+                }
+            }
+        } else
         for (int t = 0; t < a.NM; ++t) {
             const int tap = a.CP == 3 ? (t0 + t) * 3 + dwi : t0 + t;
             for (int c = 0; c < a.N; c += 16) {
@@ -240,9 +291,20 @@ static int launch_wgrad(WgradArgs& a, const float* dbias_src_unused, cudaStream_
     a.NM = n_units;
     if (a.NM * a.N > 512) a.NM = a.ntaps == 9 ? 3 : 1;
     MPNN_REQUIRE(a.NM * a.N <= 512 && n_units % a.NM == 0, "wgrad(tcgen05): N=%d too wide", a.N);
-    a.halo = a.ntaps == 9 ? (a.CP == 3 ? a.g.Wp : a.g.Wp + 1) : 0;
+    a.n_chunks = ceil_div(a.g.rows, kChunk);
+    a.GS = 0;
+    if (a.CP == 3 && NG <= 2) {      // one MMA per G plane instead of one per kernel row: fewer only for N = 16
+        const int gs = a.M == 64 ? 3 : 4;
+        // the G stage of the last chunk ends (gs - 2) image rows past the chunk
+        if (a.g.G >= a.g.Wp && (long long)a.g.G + 128ll * a.n_chunks + (long long)(gs - 2) * a.g.Wp <= a.g.P &&
+            NG * gs * 8 <= 512)
+            a.GS = gs;
+    }
+    a.halo = a.ntaps == 9 ? (a.GS ? 0 : (a.CP == 3 ? a.g.Wp : a.g.Wp + 1)) : 0;
     a.rowsA = kChunk + 2 * a.halo;
-    const size_t stageA = (size_t)a.rowsA * 16 * KG * a.CP, stageG = (size_t)kChunk * 16 * NG;
+    a.rowsG = kChunk + (a.GS ? (a.GS - 1) * a.g.Wp : 0);
+    if (a.GS) a.NM = 1;
+    const size_t stageA = (size_t)a.rowsA * 16 * KG * a.CP, stageG = (size_t)a.rowsG * 16 * NG;
     const size_t kMax = 227 * 1024 - 1024;
     int nstage = (int)((kMax - 256) / (stageA + stageG));
     if (nstage > 4) nstage = 4;
@@ -253,18 +315,17 @@ static int launch_wgrad(WgradArgs& a, const float* dbias_src_unused, cudaStream_
     if (smem < reach) smem = reach;
     MPNN_REQUIRE(smem <= kMax + 1024, "wgrad(tcgen05): shared memory reach %zu", smem);
     int ncols = 32;
-    while (ncols < a.NM * a.N) ncols <<= 1;
+    while (ncols < (a.GS ? NG * a.GS * 8 : a.NM * a.N)) ncols <<= 1;
     int per_sm = (int)((227 * 1024) / (smem + 1024));
     if (per_sm > 512 / ncols) per_sm = 512 / ncols;
     if (per_sm > 4) per_sm = 4;
     if (per_sm < 1) per_sm = 1;
-    a.n_chunks = ceil_div(a.g.rows, kChunk);
     a.nstage = nstage;
     a.vec4 = 1;
     for (int r = 0; r < 2; ++r)
         for (int c = 0; c < 2; ++c)
             if (a.dst[r][c].p && ((uintptr_t)a.dst[r][c].p % 16 != 0)) a.vec4 = 0;
-    const int groups = n_units / a.NM;
+    const int groups = a.GS ? 1 : n_units / a.NM;
     int gx = 148 * per_sm / (groups * mblocks);
     // every CTA ends with a full-size reduction of its accumulators into dW: give each
     // at least 8 chunks of pixels so that the reduction traffic stays small next to the MMAs

@@ -76,6 +76,28 @@ def test_umma_kmajor_descriptors(N, K, row_off):
     assert rel_err(D.cpu().numpy(), ref) < 1e-5
 
 
+@pytest.mark.parametrize('shift', [1, 5, 33])
+def test_umma_mnmajor_group_stride_as_row_shift(shift):
+    """MN-major B operand whose SBO (stride between 8-channel groups) is `shift` 16-byte rows instead of
+    a plane: group j then reads the SAME 8-channel plane displaced by j*shift pixels -- how the weight-
+    gradient kernel stacks the three kernel rows along N without staging copies."""
+    rng = np.random.default_rng(2)
+    K, N = 64, 32
+    a = bf16_round(rng.standard_normal((128, K)))
+    A = np.zeros((16, K, 8), np.float32)
+    for mg in range(16):
+        A[mg] = a[mg * 8:(mg + 1) * 8].T
+    rows = K + 3 * shift
+    plane = bf16_round(rng.standard_normal((rows, 8)))
+    b = np.stack([plane[(n // 8) * shift:(n // 8) * shift + K, n % 8] for n in range(N)])     # B[n][k]
+    A = dev(A, torch.bfloat16); Bm = dev(plane[None], torch.bfloat16)
+    D = torch.zeros((128, N), device='cuda')
+    L().umma_selftest(vp(A), A.numel() * 2, 0, vp(Bm), Bm.numel() * 2, vp(D), N, K, 1, 1,
+                      128, K * 16, 128, shift * 16, None)
+    torch.cuda.synchronize()
+    assert rel_err(D.cpu().numpy(), a.astype(np.float64) @ b.astype(np.float64).T) < 1e-5
+
+
 @pytest.mark.parametrize('N,K,row_off', [(16, 32, 0), (64, 128, 0), (144, 64, 0), (32, 64, 5), (16, 128, 35)])
 def test_umma_mnmajor_descriptors(N, K, row_off):
     """MN-major operands (the wgrad orientation): element (m,k) of A lives at
