@@ -72,7 +72,7 @@ class Clocks:
     def start(self):
         try:
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.gpu), '--query-gpu=' + self.Q,
-                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                          '--format=csv,noheader,nounits', '-lms', '25'],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -208,6 +208,10 @@ def main():
     clocks = Clocks(local)
     if rank == 0:
         clocks.start()
+        t_wait = time.perf_counter()                   # nvidia-smi needs ~0.2 s before its first sample:
+        while not clocks.rows and time.perf_counter() - t_wait < 3.0:   # keep the GPU under load meanwhile
+            net.train.run(feed(0))
+        clocks.rows.clear()                            # samples from here on fall inside the timed regions
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     eng._feed(plan, feed(args.warmup), True)
     barrier()
