@@ -198,20 +198,24 @@ def main():
             print('[bench rank %d] %s' % (rank, msg), file=sys.stderr, flush=True)
 
     # ---------------- warm-up (also captures the CUDA graphs) --------------- #
+    clocks = Clocks(local)
+    if rank == 0:
+        clocks.start()                                 # nvidia-smi needs ~0.2 s before its first sample
     note('warm-up')
     for t in range(args.warmup):
         net.train.run(feed(t))
+    if rank == 0:
+        # wait for the sampler WITHOUT issuing work: a training step contains the all-reduce, so every
+        # rank must run exactly the same number of them
+        torch.cuda.synchronize(dev)
+        t_wait = time.perf_counter()
+        while not clocks.rows and time.perf_counter() - t_wait < 3.0:
+            time.sleep(0.01)
+        clocks.rows.clear()                            # samples from here on fall inside the timed regions
     barrier()
     note('warm-up done')
 
     # ---------------- device-resident timing -> value ---------------------- #
-    clocks = Clocks(local)
-    if rank == 0:
-        clocks.start()
-        t_wait = time.perf_counter()                   # nvidia-smi needs ~0.2 s before its first sample:
-        while not clocks.rows and time.perf_counter() - t_wait < 3.0:   # keep the GPU under load meanwhile
-            net.train.run(feed(0))
-        clocks.rows.clear()                            # samples from here on fall inside the timed regions
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     eng._feed(plan, feed(args.warmup), True)
     barrier()
