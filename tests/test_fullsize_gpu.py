@@ -81,7 +81,7 @@ def test_training_on_a_fixed_batch_reduces_the_objective(maker, kw, C):
         if t in (0, 39):
             torch.cuda.synchronize()
             vals.append(eng.c_tot(eng._plan(B, True, True)))
-    assert np.isfinite(vals).all() and vals[1] < 0.8 * vals[0], vals
+    assert np.isfinite(vals).all() and vals[1] < 0.9 * vals[0], vals
 
 
 def test_bf16_forward_tracks_fp32_on_the_full_net():
