@@ -874,7 +874,9 @@ class _Plan:
         dgrad.lane = 1
         dgrad.early = rt is None
         st.dfeat_op = dgrad                          # the conv chain of this node waits for it
-        self.bwd_ops.append(dgrad)
+        # the router half of dZ comes from the routing backward on lane 0 (normally already ordered through
+        # the leaf's softmax gradient on this lane; explicit for stages that have a router but no leaf)
+        self.bwd_ops.append(dgrad if dgrad.early else self._after(dgrad, self.bwd_head_dep))
 
     def _router_bwd_desc(self, nd):
         eng = self.eng
