@@ -200,3 +200,26 @@ def test_the_check_sees_a_missing_dependency():
         if hasattr(op, 'deps'):
             op.deps = []
     assert any(p[0] == 'fwd_ops' for p in _check(eng, plan))
+
+
+@pytest.mark.parametrize('which', ['sr_chain', 'ac_chain', 'cr_chain', 'ac_tree', 'cr_tree_dyn'])
+def test_reference_architectures_are_race_free(which):
+    """the same check on the nets of arch_and_hypers.py (8 stages, 4 pyramid scales; trees have 2-3 sinks)"""
+    import arch_and_hypers as ah
+    from lib import layer_types
+    layer_types.seed(0)
+    make = {'sr_chain': lambda: ah.sr_chain(8), 'ac_chain': lambda: ah.ac_chain(k_cpt=4e-9),
+            'cr_chain': lambda: ah.cr_chain(k_cpt=4e-9, optimistic=True), 'ac_tree': lambda: ah.ac_tree(k_cpt=4e-9),
+            'cr_tree_dyn': lambda: ah.cr_tree(dyn_k_cpt=True)}[which]
+    net = make()((32, 32, 3), (10,))
+    eng = E.Engine(net, precision='bf16', impl=1, dry_run=True)
+    holder = {}
+    eng.L = Recorder(eng.L, lambda ptr: holder['lookup'](ptr)[2])
+    plan = eng._plan(8, True, True)
+    holder['lookup'] = _tensor_index(eng, plan)
+    problems = _check(eng, plan)
+    assert not problems, problems[:8]
+    ev = eng._plan(8, False, False)                  # inference plan (running BN moments, no backward)
+    holder['lookup'] = _tensor_index(eng, ev)
+    problems = _check(eng, ev)
+    assert not problems, problems[:8]
