@@ -48,3 +48,59 @@ def net_record(path):
     """the `write_net` payload of a checkpoint (or of a plain write_net file)"""
     d = np.load(path, allow_pickle=True)[()]
     return d['net'] if 'format' in d else d
+
+
+def _walk(rec, path=''):
+    """(path, layer record) for every layer record of a net record, preorder"""
+    yield path, rec
+    for i, c in enumerate(rec.get('comps', [])):
+        yield from _walk(c, '%s.comps[%d]' % (path, i))
+    if rec.get('router') is not None:
+        yield from _walk(rec['router'], path + '.router')
+    for i, s in enumerate(rec.get('sinks', [])):
+        yield from _walk(s, '%s/%d' % (path, i))
+
+
+def describe(path):
+    """text summary of a write_net file or checkpoint: net type, hypers, every parameter tensor"""
+    d = np.load(path, allow_pickle=True)[()]
+    rec = d['net'] if 'format' in d else d
+    lines = ['%s: %s' % (path, rec['type'])]
+    if 'format' in d:
+        lines.append('  checkpoint: step %d, momentum %s, sampler rng %s' % (
+            d['step'], 'yes' if d['momentum'] is not None else 'no', 'yes' if d['rng'] is not None else 'no'))
+    lines.append('  hypers: ' + ', '.join('%s=%r' % kv for kv in sorted(rec['hypers'].items())))
+    n = 0
+    for p, layer in _walk(rec['root'], 'root'):
+        for k, v in sorted(layer.get('params', {}).items()):
+            v = np.asarray(v)
+            n += v.size
+            lines.append('  %-44s %-10s %-18s |x| %.4g' % (p + ':' + layer.get('type', '?'), k, tuple(v.shape), float(np.linalg.norm(v))))
+    lines.append('  %d parameters (running BatchNorm moments included)' % n)
+    return '\n'.join(lines)
+
+
+def roundtrip(path):
+    """decode -> encode a net file and compare every array bit for bit (read_net / write_net consistency)"""
+    d = np.load(path, allow_pickle=True)[()]
+    rec = d['net'] if 'format' in d else d
+    again = encode_net(decode_net(rec))
+    assert again['type'] == rec['type'] and again['hypers'] == dict(rec['hypers'])
+    a, b = list(_walk(rec['root'], 'root')), list(_walk(again['root'], 'root'))
+    assert [p for p, _ in a] == [p for p, _ in b], 'topology changed'
+    for (p, la), (_, lb) in zip(a, b):
+        assert sorted(la.get('params', {})) == sorted(lb.get('params', {})), p
+        for k in la.get('params', {}):
+            if not np.array_equal(np.asarray(la['params'][k]), np.asarray(lb['params'][k])):
+                raise AssertionError('%s:%s differs after the round trip' % (p, k))
+    return len(a)
+
+
+if __name__ == '__main__':
+    import sys
+    if len(sys.argv) != 3 or sys.argv[1] not in ('info', 'roundtrip'):
+        raise SystemExit('usage: python -m lib.checkpoint info|roundtrip FILE.npy')
+    if sys.argv[1] == 'info':
+        print(describe(sys.argv[2]))
+    else:
+        print('%s: %d layer records identical after decode -> encode' % (sys.argv[2], roundtrip(sys.argv[2])))

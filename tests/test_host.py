@@ -160,3 +160,16 @@ def test_checkpoint_format_roundtrip(tmp_path):
     np.testing.assert_array_equal(rng2.random(3), expect_next)        # sampling resumes where it stopped
     serdes.write_net(str(tmp_path / 'plain.npy'), net)
     assert checkpoint.net_record(str(tmp_path / 'plain.npy'))['type'] == 'ActorNet'
+
+
+def test_net_file_cli_describe_and_roundtrip(tmp_path):
+    """`python -m lib.checkpoint info|roundtrip`: read_net / write_net consistency on a plain file and a checkpoint"""
+    from lib import checkpoint, serdes
+    from util import tiny_net
+    net = tiny_net('crtree', k_cpt=2e-9)
+    plain, ck = str(tmp_path / 'n.npy'), str(tmp_path / 'c.npy')
+    serdes.write_net(plain, net)
+    checkpoint.save_checkpoint(ck, net, step=9)
+    assert checkpoint.roundtrip(plain) == checkpoint.roundtrip(ck) > 20
+    text = checkpoint.describe(ck)
+    assert 'CriticNet' in text and 'step 9' in text and 'w_horz_0' in text and 'parameters' in text
