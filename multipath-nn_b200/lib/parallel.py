@@ -13,7 +13,7 @@ import os
 import torch
 import torch.distributed as dist
 
-__all__ = ['init_from_env', 'shard', 'allreduce_flat_']
+__all__ = ['init_from_env', 'shard', 'allreduce_flat_', 'experiment_shards', 'run_experiment_parallel']
 
 
 def init_from_env(backend=None, device=None):
@@ -47,3 +47,30 @@ def allreduce_flat_(flat):
     if dist.is_initialized() and dist.get_world_size() > 1:
         dist.all_reduce(flat, op=dist.ReduceOp.SUM)
     return flat
+
+
+# --------------------------------------------------------------------------- #
+# Experiment parallelism: an experiment is a list of independent nets -- eight k_cpt
+# values or eight depths (scripts/train-nets:29-88) -- that the reference trains one after the other
+# (train-nets:159-164).  One net per GPU needs no communication at all.
+# --------------------------------------------------------------------------- #
+def experiment_shards(net_indices, devices):
+    """round-robin assignment {device: [net index, ...]}; devices without work are dropped"""
+    net_indices, devices = list(net_indices), list(devices)
+    if not devices:
+        raise ValueError('no devices')
+    out = {d: net_indices[k::len(devices)] for k, d in enumerate(devices)}
+    return {d: v for d, v in out.items() if v}
+
+
+def run_experiment_parallel(argv, net_indices, devices, python=None):
+    """Re-run the calling driver once per device with `--nets <its share>` and CUDA_VISIBLE_DEVICES set;
+    returns the largest exit code.  `argv` is the driver's own command line without --devices / --nets."""
+    import subprocess
+    import sys
+    procs = []
+    for d, share in experiment_shards(net_indices, devices).items():
+        env = dict(os.environ, CUDA_VISIBLE_DEVICES=str(d))
+        cmd = [python or sys.executable] + list(argv) + ['--nets'] + [str(i) for i in share]
+        procs.append((d, subprocess.Popen(cmd, env=env)))
+    return max((p.wait() for _, p in procs), default=0)

@@ -173,3 +173,18 @@ def test_net_file_cli_describe_and_roundtrip(tmp_path):
     assert checkpoint.roundtrip(plain) == checkpoint.roundtrip(ck) > 20
     text = checkpoint.describe(ck)
     assert 'CriticNet' in text and 'step 9' in text and 'w_horz_0' in text and 'parameters' in text
+
+
+def test_experiment_parallel_sharding(tmp_path):
+    """one worker per GPU, each with its round-robin share of the experiment's nets and its own device"""
+    import sys
+    from lib.parallel import experiment_shards, run_experiment_parallel
+    assert experiment_shards(range(8), [0, 1, 2]) == {0: [0, 3, 6], 1: [1, 4, 7], 2: [2, 5]}
+    assert experiment_shards([4], [0, 1]) == {0: [4]}
+    code = ("import os, sys; open(os.path.join(%r, os.environ['CUDA_VISIBLE_DEVICES']), 'w')"
+            ".write(' '.join(sys.argv[1:]))" % str(tmp_path))
+    rc = run_experiment_parallel(['-c', code, 'cifar10-ac', '--n-iter', '3'], [0, 1, 2], [5, 7], python=sys.executable)
+    assert rc == 0
+    assert (tmp_path / '5').read_text() == 'cifar10-ac --n-iter 3 --nets 0 2'
+    assert (tmp_path / '7').read_text() == 'cifar10-ac --n-iter 3 --nets 1'
+    assert run_experiment_parallel(['-c', 'raise SystemExit(3)'], [0, 1], [0, 1], python=sys.executable) == 3
