@@ -1,83 +1,116 @@
-"""`net_desc` statistics and their text rendering -- same nested-dict schema
-and log format as /root/reference/scripts/lib/desc.py:10-79.
-The per-batch tensors come from `net.eval_stats` (GPU) instead of a TF session;
-the dataset reduction (sum over examples / count, in float64 on the host) is
-the reference's.
+"""Network statistics (`net_desc`) and their log rendering.
+
+Schema and text layout are those of /root/reference/scripts/lib/desc.py:10-79
+(SURVEY App. C), because the plotting scripts and the `NNNN-stats.npy` /
+`NNNN-log.txt` files of `train-nets` consume them:
+
+    net_desc   = {'type', 'stats_tr', 'stats_ts', 'root': layer_desc}
+    layer_desc = {'name', 'stats_tr', 'stats_ts', 'sinks': [layer_desc]}
+
+with every statistic the mean over a whole dataset split of a per-example
+quantity.  Here the per-example quantities come from `net.eval_stats` (one GPU
+forward in 'ev' mode per batch) instead of a TF session; the reduction -- sum over
+examples in float64 on the host, divided by the example count -- is unchanged.
 """
 import numpy as np
 
 __all__ = ['state_tensors', 'mean_net_state', 'net_desc', 'render_net_desc']
 
+_SPLITS = ('stats_tr', 'stats_ts')
+_RULE = '─' * 59
 
+
+# --------------------------------------------------------------------------- #
+# which statistics exist (scripts/train-nets:111-130)
+# --------------------------------------------------------------------------- #
 def state_tensors(net):
-    """Keys of the statistics `eval_stats` produces (train-nets:111-130)."""
+    """{key: key} for every statistic `net.eval_stats` returns; key = (owner, name) where the owner is
+    the net (accuracy, mean op count), a leaf (outcome probabilities, losses) or a switch (|logit|)"""
+    per_leaf = ['p_cor', 'p_inc', 'p_cor_by_cls', 'p_inc_by_cls'] + (['p_tr'] if net.dynamic else []) + ['c_err']
     keys = [(net, 'acc'), (net, 'moc')]
-    for l in net.leaves:
-        keys += [(l, 'p_cor'), (l, 'p_inc'), (l, 'p_cor_by_cls'), (l, 'p_inc_by_cls')]
-        if net.dynamic:
-            keys.append((l, 'p_tr'))
-        keys.append((l, 'c_err'))
-    for l in net.layers:
-        if l.router is not None:
-            keys.append((l, 'x_rte'))
-    return {k: k for k in keys}
+    keys += [(leaf, name) for leaf in net.leaves for name in per_leaf]
+    keys += [(layer, 'x_rte') for layer in net.layers if layer.router is not None]
+    return dict(zip(keys, keys))
+
+
+# --------------------------------------------------------------------------- #
+# dataset means
+# --------------------------------------------------------------------------- #
+class _RunningMean:
+    """float64 sums over the example axis of a stream of batches"""
+
+    def __init__(self, keys):
+        self.total = dict.fromkeys(keys, 0)
+        self.n = 0
+
+    def add(self, batch_stats, n_examples):
+        for key in self.total:
+            self.total[key] = self.total[key] + np.asarray(batch_stats[key], dtype=np.float64).sum(0)
+        self.n += n_examples
+
+    def result(self):
+        return {key: (value / self.n).tolist() for key, value in self.total.items()}
 
 
 def mean_net_state(net, tensors, data, hypers):
-    if len(tensors) == 0:
+    """mean of every requested statistic over the batches `data` yields, as python floats / lists"""
+    if not tensors:
         return {}
-    sums = {k: 0 for k in tensors.keys()}
-    count = 0
+    mean = _RunningMean(tensors.keys())
     for x0, y in data:
-        samples = net.eval_stats({net.x0: x0, net.y: y, **hypers})
-        for k in tensors.keys():
-            sums[k] = sums[k] + np.sum(np.asarray(samples[k], dtype=np.float64), 0)
-        count += len(x0)
-    return {k: (sums[k] / count).tolist() for k in tensors.keys()}
+        feed = {net.x0: x0, net.y: y}
+        feed.update(hypers)
+        mean.add(net.eval_stats(feed), len(x0))
+    return mean.result()
+
+
+def _owned_by(owner, stats):
+    """the statistics of one owner, keyed by name (identity comparison, like the reference's `t == l`)"""
+    return {name: value for (who, name), value in stats.items() if who is owner}
 
 
 def layer_desc(layer, stats_tr, stats_ts):
-    return {'name': layer.name,
-            'stats_tr': {k: v for (t, k), v in stats_tr.items() if t is layer},
-            'stats_ts': {k: v for (t, k), v in stats_ts.items() if t is layer},
-            'sinks': [layer_desc(s, stats_tr, stats_ts) for s in layer.sinks]}
+    node = {'name': layer.name}
+    for split, stats in zip(_SPLITS, (stats_tr, stats_ts)):
+        node[split] = _owned_by(layer, stats)
+    node['sinks'] = [layer_desc(child, stats_tr, stats_ts) for child in layer.sinks]
+    return node
 
 
 def net_desc(net, dataset, hypers={}, state={}):
-    stats_tr = mean_net_state(net, state, dataset.training_set(), hypers)
-    stats_ts = mean_net_state(net, state, dataset.test_set(), hypers)
-    return {'type': type(net).__name__,
-            'stats_tr': {k: v for (t, k), v in stats_tr.items() if t is net},
-            'stats_ts': {k: v for (t, k), v in stats_ts.items() if t is net},
-            'root': layer_desc(net.root, stats_tr, stats_ts)}
+    per_split = [mean_net_state(net, state, batches, hypers)
+                 for batches in (dataset.training_set(), dataset.test_set())]
+    out = {'type': type(net).__name__}
+    for split, stats in zip(_SPLITS, per_split):
+        out[split] = _owned_by(net, stats)
+    out['root'] = layer_desc(net.root, *per_split)
+    return out
 
 
-def render_stats(stats):
-    if len(stats) == 0:
-        return ''
-    scalars = [kv for kv in sorted(stats.items()) if np.ndim(kv[1]) == 0]
-    return '(%s)' % '; '.join('%s=%.3g' % kv for kv in scalars)
+# --------------------------------------------------------------------------- #
+# rendering (the NNNN-log.txt format)
+# --------------------------------------------------------------------------- #
+def _scalars(stats):
+    """'(a=1; b=2)' over the scalar statistics in key order; vectors (per-class entries) are skipped"""
+    shown = ['%s=%.3g' % (name, stats[name]) for name in sorted(stats) if np.ndim(stats[name]) == 0]
+    return '(%s)' % '; '.join(shown) if stats else ''
 
 
-def render_layer_desc(desc, stats_key):
-    lines = '%s %s' % (desc['name'], render_stats(desc[stats_key]))
-    n = len(desc['sinks'])
-    for i, s in enumerate(desc['sinks']):
-        cont = '\n| ' if i < n - 1 else '\n  '
-        lines += '\n↳ ' + render_layer_desc(s, stats_key).replace('\n', cont)
-    return lines
+def _tree(node, split):
+    """one line per layer; sinks hang below their parent on '↳', siblings are joined by '| ' rails"""
+    text = '%s %s' % (node['name'], _scalars(node[split]))
+    last = len(node['sinks']) - 1
+    for i, child in enumerate(node['sinks']):
+        rail = '\n  ' if i == last else '\n| '
+        text += '\n↳ ' + _tree(child, split).replace('\n', rail)
+    return text
 
 
 def render_net_desc(desc, name='Network'):
-    bar = '─' * 59
-    ind = '\n│     '
-    body = [
-        '┌' + bar, '│ ' + name, '├' + bar,
-        '│ Training Set:', '│',
-        '│   [%s] %s' % (desc['type'], render_stats(desc['stats_tr'])),
-        '│     ' + render_layer_desc(desc['root'], 'stats_tr').replace('\n', ind),
-        '│', '│ Test Set:', '│',
-        '│   [%s] %s' % (desc['type'], render_stats(desc['stats_ts'])),
-        '│     ' + render_layer_desc(desc['root'], 'stats_ts').replace('\n', ind),
-        '│']
-    return '\n'.join(body)
+    rows = ['┌' + _RULE, '│ ' + name, '├' + _RULE]
+    for title, split in (('Training Set:', 'stats_tr'), ('Test Set:', 'stats_ts')):
+        rows += ['│ ' + title, '│',
+                 '│   [%s] %s' % (desc['type'], _scalars(desc[split])),
+                 '│     ' + _tree(desc['root'], split).replace('\n', '\n│     '),
+                 '│']
+    return '\n'.join(rows)
