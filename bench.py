@@ -67,7 +67,7 @@ class Clocks:
          'clocks_event_reasons.sw_power_cap')
 
     def __init__(self, gpu):
-        self.rows, self.proc, self.gpu = [], None, gpu
+        self.rows, self.proc, self.gpu, self.mark = [], None, gpu, 0
 
     def start(self):
         try:
@@ -86,12 +86,18 @@ class Clocks:
         if self.proc is None:
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
         self.proc.terminate()
-        sm = [float(r[1]) for r in self.rows if len(r) > 2 and r[1].replace('.', '').isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace('.', '').isdigit()]
+        # samples of the timed regions; a very short run (few steps) may have none, then the samples taken
+        # under the warm-up load stand in and the line says so
+        rows = self.rows[self.mark:]
+        window = 'timed region'
+        if not rows:
+            rows, window = list(self.rows), 'warm-up (timed region shorter than the sampling interval)'
+        sm = [float(r[1]) for r in rows if len(r) > 2 and r[1].replace('.', '').isdigit()]
+        mx = [float(r[2]) for r in rows if len(r) > 2 and r[2].replace('.', '').isdigit()]
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        reasons = sorted({n for r in self.rows if len(r) >= 9 for n, v in zip(names, r[5:9]) if v.lower().startswith('active')})
+        reasons = sorted({n for r in rows if len(r) >= 9 for n, v in zip(names, r[5:9]) if v.lower().startswith('active')})
         return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
-                'reasons': reasons, 'samples': len(sm)}
+                'reasons': reasons, 'samples': len(sm), 'window': window}
 
 
 def cpu_oracle_rate(B, budget_s=20.0, max_steps=50):
@@ -211,7 +217,7 @@ def main():
         t_wait = time.perf_counter()
         while not clocks.rows and time.perf_counter() - t_wait < 3.0:
             time.sleep(0.01)
-        clocks.rows.clear()                            # samples from here on fall inside the timed regions
+        clocks.mark = len(clocks.rows)                 # samples from here on fall inside the timed regions
     barrier()
     note('warm-up done')
 
