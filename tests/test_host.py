@@ -188,3 +188,41 @@ def test_experiment_parallel_sharding(tmp_path):
     assert (tmp_path / '5').read_text() == 'cifar10-ac --n-iter 3 --nets 0 2'
     assert (tmp_path / '7').read_text() == 'cifar10-ac --n-iter 3 --nets 1'
     assert run_experiment_parallel(['-c', 'raise SystemExit(3)'], [0, 1], [0, 1], python=sys.executable) == 3
+
+
+def test_every_pdl_launched_kernel_waits_for_its_predecessor():
+    """A kernel launched with the programmatic-stream-serialization attribute may start while the previous
+    kernel of its stream is still running; it is only correct if it executes griddepcontrol.wait (SASS
+    ACQBULK) before touching global memory.  Every kernel handed to mpnn_launch_pdl must contain it."""
+    import glob
+    import re
+    import shutil
+    import subprocess
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'multipath-nn_b200')
+    so = os.path.join(root, 'lib', 'libmpnn_sm100.so')
+    cuobjdump = shutil.which('cuobjdump') or '/usr/local/cuda/bin/cuobjdump'
+    if not os.path.exists(so) or not os.path.exists(cuobjdump):
+        pytest.skip('library or cuobjdump not available')
+    launched = set()
+    for f in glob.glob(os.path.join(root, 'csrc', '*.cu')):
+        src = open(f).read()
+        launched |= set(re.findall(r'mpnn_launch_pdl\(\s*(\w+)', src))
+        if 'mpnn_launch_pdl(kern' in src:                       # function-pointer launch of the conv kernel
+            launched.add('stencil_gemm_umma_kernel')
+    launched.discard('kern')
+    assert {'bn_relu_pool_fwd_kernel', 'bn_bwd_reduce_kernel', 'bn_relu_pool_bwd_kernel',
+            'stencil_gemm_umma_kernel'} <= launched
+    sass = subprocess.run([cuobjdump, '-sass', so], capture_output=True, text=True).stdout
+    body, seen = {}, None
+    for line in sass.splitlines():
+        m = re.search(r'Function : (\S+)', line)
+        if m:
+            seen = m.group(1)
+            body[seen] = []
+        elif seen is not None:
+            body[seen].append(line)
+    for kernel in launched:
+        variants = [fn for fn in body if kernel in fn]
+        assert variants, kernel
+        for fn in variants:
+            assert any('ACQBULK' in l for l in body[fn]), '%s is launched with PDL but never waits' % fn
