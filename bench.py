@@ -345,7 +345,7 @@ def main():
 
     torch.set_num_threads(os.cpu_count() or 1)
     cpu_B = min(B, 256)
-    cpu_v, cpu_n, cpu_dt = cpu_oracle_rate(cpu_B, budget_s=15.0)
+    cpu_v, cpu_n, cpu_dt = (0.0, 0, 0.0) if os.environ.get('MPNN_BENCH_NO_CPU') else cpu_oracle_rate(cpu_B, budget_s=15.0)
     value = world * B * args.steps / (dev_ms * 1e-3)
     e2e = world * B * args.steps / e2e_s
     h2d = B * (32 * 32 * 3 + 10) * 4 + 8 * 4

@@ -149,6 +149,22 @@ int mpnn_bn_bwd_reduce_fused(const void* lin, const void* dAct, const void* dFea
                              const float* ss, const float* mr, int C,
                              int B, int H, int W, int G, int P,
                              const mpnn_bn_bwd_fuse* f, int dtype, void* stream);
+/* Data gradient of a 3x3 conv with the BatchNorm-backward reduction of the layer BELOW fused into its
+ * epilogue (tcgen05 path only; replaces mpnn_bn_bwd_reduce_fused over (lin, dAct) for that layer):
+ *   out0[p][n] (n < N0) = dAct of the parent activation, out1 (N1 columns) = gradient wrt the pooled
+ *   predecessor, as in mpnn_stencil_gemm(Gd, K, NULL, 0, Wp, 9, NULL, out0, N0, 0, out1, N1, 0, ...);
+ *   with dy' = out0 * [ss0*lin + ss1 > 0] (lin, ss, mr: pre-BN output and constants of the parent's
+ *   BatchNorm, N0 channels) the kernel accumulates sum dy' and sum dy'*lin over the valid pixels and the
+ *   last CTA writes f.sums / adds f.dgamma, f.dbeta exactly like mpnn_bn_bwd_reduce_fused.
+ * TF autodiff of lib/layer_types.py:181-185 and :219-249. */
+typedef struct {
+    const void* lin; const float* ss; const float* mr;
+    mpnn_bn_bwd_fuse f;
+} mpnn_bn_bwd_epi;
+int mpnn_conv_dgrad_bn_reduce(const void* Gd, int K, const void* Wp, void* out0, int N0, void* out1, int N1,
+                              int B, int H, int W, int G, int P, const mpnn_bn_bwd_epi* epi,
+                              int dtype, int impl, void* stream);
+
 /* partials (from bn_bwd_reduce) hold sum dy' and sum dy'*x per channel;
  * sums[0][c] = sum dy', sums[1][c] = sum dy'*xhat; dgamma += sums1, dbeta += sums0 */
 int mpnn_bn_bwd_finalize(const float* partials, int n_parts, int C, const float* mr,

@@ -81,19 +81,7 @@ bn_bwd_reduce_kernel(const T* __restrict__ lin, const T* __restrict__ dAct, cons
 #pragma unroll
             for (int wv = 0; wv < 8; ++wv) t += red[wv][i];
             return t; });
-        if (last) {
-            for (int c = threadIdx.x; c < C; c += blockDim.x) {
-                const double t0 = __ldcg(f.acc + c), t1 = __ldcg(f.acc + C + c);
-                f.acc[c] = 0.0; f.acc[C + c] = 0.0;
-                const double mean = mr[c], rstd = mr[C + c];
-                const double sx = rstd * (t1 - mean * t0);           // sum dy'*xhat
-                f.sums[c] = (float)t0;
-                f.sums[C + c] = (float)sx;
-                if (f.dgamma) f.dgamma[c] += (float)sx;
-                if (f.dbeta) f.dbeta[c] += (float)t0;
-            }
-            if (threadIdx.x == 0) *reinterpret_cast<unsigned*>(f.acc + 2 * C) = 0u;
-        }
+        if (last) mpnn_bn_bwd_finalize_last(f, mr, C);
     }
 }
 
@@ -281,6 +269,129 @@ bn_relu_pool_bwd_kernel(const T* __restrict__ lin, const T* __restrict__ dAct,
     }
 }
 
+// pass 2, v2 (bf16): every row the thread needs (lin, dAct of the 2x2 block, dPooled) is requested
+// before the first use and lin is kept in registers instead of being re-read for the outputs; pixel
+// index split by shifts for power-of-two sizes.  v1 ran at 49 % of DRAM peak, latency-bound.
+struct PixSplitB { int logW, logHH; };
+__device__ __forceinline__ uint4 ldg16b(const void* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+__device__ __forceinline__ void unpack8b(const uint4& r, float v[8]) {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { const float2 f = __bfloat1622float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+}
+
+__global__ void __launch_bounds__(256, 2)
+bn_relu_pool_bwd_v2_kernel(const __nv_bfloat16* __restrict__ lin, const __nv_bfloat16* __restrict__ dAct,
+                           const __nv_bfloat16* __restrict__ dFeat, int Balloc,
+                           const __nv_bfloat16* __restrict__ dPooled, Geom gp,
+                           const float* __restrict__ ss, const float* __restrict__ mr,
+                           const float* __restrict__ sums, float inv_count,
+                           int C, Geom g, PixSplitB ps, __nv_bfloat16* __restrict__ dLin, float* __restrict__ dbias) {
+    typedef __nv_bfloat16 T;
+    pdl_launch_dependents();
+    pdl_wait();
+    const int kg = blockIdx.y;
+    const int HH = g.H / 2, WW = g.W / 2;            // one thread per 2x2 block (this kernel is the pooled case)
+    const int total = g.B * HH * WW;
+    float a[8], c[8], pp[8], qq[8], bs[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { bs[j] = 0.f; a[j] = 0.f; c[j] = 0.f; pp[j] = 0.f; qq[j] = 0.f; }
+    if (ss) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            a[j] = __ldg(ss + kg * 8 + j); c[j] = __ldg(ss + C + kg * 8 + j);
+            const float mean = __ldg(mr + kg * 8 + j), rstd = __ldg(mr + C + kg * 8 + j);
+            const float m0 = __ldg(sums + kg * 8 + j) * inv_count, m1 = __ldg(sums + C + kg * 8 + j) * inv_count;
+            pp[j] = -a[j] * rstd * m1;
+            qq[j] = -a[j] * m0 + a[j] * rstd * mean * m1;
+        }
+    }
+    auto split = [&](int i, int& n, int& h, int& w) {
+        if (ps.logW >= 0) { w = i & (WW - 1); const int r = i >> ps.logW; h = r & (HH - 1); n = r >> ps.logHH; }
+        else { w = i % WW; const int r = i / WW; h = r % HH; n = r / HH; }
+    };
+    const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
+    {
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+            int n, h, w;
+            split(i, n, h, w);
+            const int p00 = row_of(g, n, 2 * h, 2 * w);
+            const int pk[4] = {p00, p00 + 1, p00 + g.Wp, p00 + g.Wp + 1};
+            uint4 Lr[4], Dr[4], Pr = zero4;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                Lr[k] = ldg16b(plane_row(lin, kg, g.P, pk[k]));
+                Dr[k] = (ss && dAct) ? ldg16b(plane_row(dAct, kg, g.P, pk[k])) : zero4;
+            }
+            if (dPooled) Pr = ldg16b(plane_row(dPooled, kg, gp.P, row_of(gp, n, h, w)));
+            // which of the 2x2 pixels holds the (first) maximum, per channel: 2 bits each
+            unsigned best = 0;
+            float dp[8];
+            if (dPooled) {
+                float bv[8];
+                unpack8b(Lr[0], bv);
+#pragma unroll
+                for (int k = 1; k < 4; ++k) {
+                    float v[8];
+                    unpack8b(Lr[k], v);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        if (v[j] > bv[j]) { bv[j] = v[j]; best = (best & ~(3u << (2 * j))) | ((unsigned)k << (2 * j)); }
+                }
+                unpack8b(Pr, dp);
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                float out[8];
+                if (ss) {
+                    float lv[8], d[8];
+                    unpack8b(Lr[k], lv);
+                    unpack8b(Dr[k], d);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float dy = fmaf(a[j], lv[j], c[j]) > 0.f ? d[j] : 0.f;
+                        out[j] = fmaf(a[j], dy, fmaf(pp[j], lv[j], qq[j]));
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) out[j] = 0.f;
+                }
+                if (dPooled) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        if (((best >> (2 * j)) & 3u) == (unsigned)k) out[j] += dp[j];
+                }
+                Row8<T>::store(plane_row(dLin, kg, g.P, pk[k]), out);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) bs[j] += out[j];
+            }
+        }
+    }
+    if (dbias) {
+        // conv bias gradient = column sums of dLin (layer_types.py:181-185: b_k is added before BN)
+        __shared__ float red[8][8];
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float t = warp_sum(bs[j]);
+            if (lane == 0) red[warp][j] = t;
+        }
+        __syncthreads();
+        if (threadIdx.x < 8) {
+            float t = 0.f;
+            for (int wv = 0; wv < 8; ++wv) t += red[wv][threadIdx.x];
+            atomicAdd(dbias + kg * 8 + threadIdx.x, t);
+        }
+    }
+}
+
+static inline int ilog2_exact_b(int v) {
+    if (v <= 0 || (v & (v - 1))) return -1;
+    int l = 0;
+    while ((1 << l) < v) ++l;
+    return l;
+}
+
 extern "C" int mpnn_bn_relu_pool_bwd(const void* lin, const void* dAct, const void* dFeat, int Balloc,
                                      const void* dPooled, int Pp,
                                      const float* ss, const float* mr, const float* sums, double count,
@@ -302,6 +413,16 @@ extern "C" int mpnn_bn_relu_pool_bwd(const void* lin, const void* dAct, const vo
     dim3 grid(gx, C / 8);
     float inv = (float)(1.0 / count);
     cudaStream_t st = (cudaStream_t)stream;
+    static const int v2 = getenv("MPNN_BN_V2") ? atoi(getenv("MPNN_BN_V2")) : 1;
+    if (v2 && dtype == MPNN_BF16 && pool && !dFeat) {
+        PixSplitB ps = {ilog2_exact_b(W / 2), ilog2_exact_b(H / 2)};
+        if (ps.logHH < 0) ps.logW = -1;
+        typedef __nv_bfloat16 T;
+        mpnn_launch_pdl(bn_relu_pool_bwd_v2_kernel, grid, dim3(256), 0, st,
+            (const T*)lin, (const T*)dAct, (const T*)dFeat, Balloc, (const T*)dPooled, gp, ss, mr, sums,
+            inv, C, g, ps, (T*)dLin, dbias);
+        return mpnn_check_launch("bn_relu_pool_bwd");
+    }
     if (pool) {
         MPNN_DISPATCH_DTYPE(dtype, (mpnn_launch_pdl(bn_relu_pool_bwd_kernel<T, true>, grid, dim3(256), 0, st,
             (const T*)lin, (const T*)dAct, (const T*)dFeat, Balloc, (const T*)dPooled, gp, ss, mr, sums,

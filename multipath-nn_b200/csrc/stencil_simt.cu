@@ -9,7 +9,7 @@
 int mpnn_stencil_gemm_umma(const void* A0, int K0, const void* A1, int K1, const void* Wp, int ntaps,
                            const float* bias, void* out0, int N0, int acc0, void* out1, int N1, int acc1,
                            Geom g, float* stats, int stats_cap, int* n_parts, int out_dtype,
-                           const mpnn_bn_fuse* bn, cudaStream_t st);
+                           const mpnn_bn_fuse* bn, const mpnn_bn_bwd_epi* bwd, cudaStream_t st);
 int mpnn_stencil_wgrad_umma(const void* A0, int K0, int K0real, float* dW0, const void* A1, int K1,
                             int K1real, float* dW1, const void* Gd, int N, int Nreal, float* dbias,
                             int ntaps, Geom g, cudaStream_t st);
@@ -136,8 +136,10 @@ static int stencil_gemm_impl(const void* A0, int K0, const void* A1, int K1,
                              void* out0, int N0, int acc0, void* out1, int N1, int acc1,
                              int B, int H, int W, int G, int P,
                              float* stats, int stats_cap, int* n_parts, const mpnn_bn_fuse* bn,
-                             int dtype, int out_dtype, int impl, void* stream) {
+                             int dtype, int out_dtype, int impl, void* stream,
+                             const mpnn_bn_bwd_epi* bwd = nullptr) {
     MPNN_REQUIRE(ntaps == 9 || ntaps == 1, "stencil_gemm: ntaps=%d", ntaps);
+    MPNN_REQUIRE(!bwd || impl == 1, "conv_dgrad_bn_reduce: only the tcgen05 path fuses the BN-backward sums");
     MPNN_REQUIRE(K0 % 8 == 0 && K1 % 8 == 0 && K0 > 0, "stencil_gemm: K0=%d K1=%d", K0, K1);
     MPNN_REQUIRE(N0 % 8 == 0 && N1 % 8 == 0 && N0 + N1 > 0, "stencil_gemm: N0=%d N1=%d", N0, N1);
     MPNN_REQUIRE(K1 == 0 || A1, "stencil_gemm: A1 null");
@@ -152,7 +154,7 @@ static int stencil_gemm_impl(const void* A0, int K0, const void* A1, int K1,
     if (impl == 1) {
         MPNN_REQUIRE(dtype == MPNN_BF16, "stencil_gemm: tcgen05 path needs bf16 operands");
         return mpnn_stencil_gemm_umma(A0, K0, A1, K1, Wp, ntaps, bias, out0, N0, acc0, out1, N1, acc1,
-                                      g, stats, stats_cap, n_parts, out_dtype, bn, st);
+                                      g, stats, stats_cap, n_parts, out_dtype, bn, bwd, st);
     }
 #define GO(T, TO) return launch_gemm_simt<T, TO>(A0, K0, A1, K1, Wp, ntaps, bias, out0, N0, acc0, out1, N1, \
                                                  acc1, g, stats, stats_cap, n_parts, bn, st)
@@ -181,6 +183,14 @@ extern "C" int mpnn_conv_bn_stats(const void* A0, int K0, const void* A1, int K1
     MPNN_REQUIRE(bn, "conv_bn_stats: bn is NULL");
     return stencil_gemm_impl(A0, K0, A1, K1, Wp, 9, bias, out, N, 0, nullptr, 0, 0, B, H, W, G, P,
                              nullptr, 0, nullptr, bn, dtype, dtype, impl, stream);
+}
+
+extern "C" int mpnn_conv_dgrad_bn_reduce(const void* Gd, int K, const void* Wp, void* out0, int N0,
+                                         void* out1, int N1, int B, int H, int W, int G, int P,
+                                         const mpnn_bn_bwd_epi* epi, int dtype, int impl, void* stream) {
+    MPNN_REQUIRE(epi, "conv_dgrad_bn_reduce: epi is NULL");
+    return stencil_gemm_impl(Gd, K, nullptr, 0, Wp, 9, nullptr, out0, N0, 0, out1, N1, 0, B, H, W, G, P,
+                             nullptr, 0, nullptr, nullptr, dtype, dtype, impl, stream, epi);
 }
 
 // --------------------------------------------------------------------------- //

@@ -76,6 +76,21 @@ __device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
         "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
 }
+// the same with the descriptors given as (lo, hi) 32-bit halves: they are packed inside the asm block, so
+// the compiler never sees 64-bit arithmetic on them (it otherwise builds every descriptor with 64-bit
+// add / carry chains in the vector register file and converts lane-by-lane in front of each UTCHMMA)
+__device__ __forceinline__ void tc_mma2(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                        uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        ".reg .b64 da, db;\n"
+        "setp.ne.b32 p, %6, 0;\n"
+        "mov.b64 da, {%1, %2};\n"
+        "mov.b64 db, {%3, %4};\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n"
+        "}" ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(acc) : "memory");
+}
 __device__ __forceinline__ void tc_ld16(uint32_t taddr, float v[16]) {
     uint32_t r[16];
     asm volatile(

@@ -28,6 +28,7 @@
 // A CTA walks pixel chunks of 128 rows accumulating in TMEM across the whole
 // walk; partial sums from different CTAs are combined with fp32
 // red.global.add into the flat gradient buffer the optimiser kernel consumes.
+#include <cstdlib>
 #include "common.cuh"
 #include "umma.cuh"
 #include "../../include/mpnn.h"
@@ -56,6 +57,11 @@ struct WgradArgs {
 constexpr int kWThreads = 192;
 constexpr int kChunk = 128;          // pixels per stage
 
+// NMT = MMAs per 16-pixel step (taps, or kernel rows when stacked: 9, 3 or 1), GST = row stacking along N
+// (then NMT = 1 and N = 16).  Compile-time so that the issue loop is straight-line code with the tap
+// offsets hoisted: with a run-time tap loop the single issuing warp spent ~100 cycles per MMA
+// (ncu: tensor pipe 38 % active, one CTA per SM), which bounded the 32..128-channel layers.
+template <int NMT, bool GST>
 __global__ void __launch_bounds__(kWThreads, 1)
 stencil_wgrad_umma_kernel(const WgradArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -97,33 +103,35 @@ stencil_wgrad_umma_kernel(const WgradArgs a) {
             const bool leader = elect_one();
             int s = 0; uint32_t ph = 0;
             const size_t plane = (size_t)a.g.P * 8;
+            // planes of this CTA's M block: [kgb, kgb + KG) of the concatenation A0 | A1
+            const int nA0 = max(0, min(KG, KG0 - kgb)), nA1 = KG - nA0;
+            const __nv_bfloat16* base0 = a.A0 + (size_t)kgb * plane + ((size_t)a.g.G - a.halo) * 8;
+            const __nv_bfloat16* base1 = a.A1 ? a.A1 + (size_t)max(0, kgb - KG0) * plane + ((size_t)a.g.G - a.halo) * 8 : nullptr;
+            const __nv_bfloat16* baseG = a.Gd + ((size_t)a.g.G - (GST ? (size_t)a.g.Wp : 0)) * 8;
+            const uint32_t cpy = a.CP == 3 ? 3 * PSA : PSA;
             for (int c = blockIdx.x; c < a.n_chunks; c += gridDim.x) {
                 mbar_wait(empty0 + 8 * s, ph ^ 1u);
                 if (leader) mbar_expect_tx(full0 + 8 * s, stageA + stageG);
-                const size_t p0 = (size_t)a.g.G + (size_t)c * kChunk;
+                const size_t coff = (size_t)c * (kChunk * 8);
                 uint32_t dA = smem_u32(sA) + (uint32_t)s * stageA;
                 uint32_t dG = smem_u32(sG) + (uint32_t)s * stageG;
-                for (int kg = 0; kg < KG; ++kg) {
-                    const int kga = kgb + kg;
-                    const __nv_bfloat16* pl = (kga < KG0 ? a.A0 + kga * plane : a.A1 + (kga - KG0) * plane)
-                                              + (p0 - a.halo) * 8;
+                const uint32_t fb = full0 + 8 * s;
+                const __nv_bfloat16* pl = base0 + coff;
+                for (int kg = 0; kg < nA0; ++kg, pl += plane, dA += cpy) {
+                    if (a.CP == 3) {                  // copy cp holds the plane shifted by dw = cp-1 rows
+                        if (leader) { bulk_g2s(dA, pl - 8, PSA, fb); bulk_g2s(dA + PSA, pl, PSA, fb); bulk_g2s(dA + 2 * PSA, pl + 8, PSA, fb); }
+                    } else if (leader) bulk_g2s(dA, pl, PSA, fb);
+                }
+                pl = base1 + coff;
+                for (int kg = 0; kg < nA1; ++kg, pl += plane, dA += cpy) {
                     if (a.CP == 3) {
-                        // copy cp holds the plane shifted by dw = cp-1 rows
-                        if (leader) {
-                            bulk_g2s(dA, pl - 8, PSA, full0 + 8 * s);
-                            bulk_g2s(dA + PSA, pl, PSA, full0 + 8 * s);
-                            bulk_g2s(dA + 2 * PSA, pl + 8, PSA, full0 + 8 * s);
-                        }
-                        dA += 3 * PSA;
-                    } else {
-                        if (leader) bulk_g2s(dA, pl, PSA, full0 + 8 * s);
-                        dA += PSA;
-                    }
+                        if (leader) { bulk_g2s(dA, pl - 8, PSA, fb); bulk_g2s(dA + PSA, pl, PSA, fb); bulk_g2s(dA + 2 * PSA, pl + 8, PSA, fb); }
+                    } else if (leader) bulk_g2s(dA, pl, PSA, fb);
                 }
                 // GS: the G stage starts one image row early (group j is read j image rows further down)
-                const __nv_bfloat16* gp = a.Gd + (p0 - (a.GS ? (size_t)a.g.Wp : 0)) * 8;
+                const __nv_bfloat16* gp = baseG + coff;
                 for (int ng = 0; ng < NG; ++ng, gp += plane, dG += PSG)
-                    if (leader) bulk_g2s(dG, gp, PSG, full0 + 8 * s);
+                    if (leader) bulk_g2s(dG, gp, PSG, fb);
                 if (++s == a.nstage) { s = 0; ph ^= 1u; }
             }
         }
@@ -138,36 +146,47 @@ stencil_wgrad_umma_kernel(const WgradArgs a) {
             const uint32_t a_lo0 = (((smem_u32(sA) + (uint32_t)a.halo * 16) & 0x3FFFFu) >> 4) | (8u << 16);
             const uint32_t g_lo0 = ((smem_u32(sG) & 0x3FFFFu) >> 4) | (8u << 16);
             const uint32_t a_stage = stageA >> 4, g_stage = stageG >> 4;
-            int s = 0; uint32_t ph = 0, accum = 0;
+            int s = 0; uint32_t ph = 0;
+            uint32_t accf = 0;                        // 0 on the CTA's first chunk: the MMAs overwrite the accumulator
+            // row shift (16 B units) of each MMA's A operand, hoisted out of the chunk loop
+            uint32_t offs[NMT];
+#pragma unroll
+            for (int t = 0; t < NMT; ++t) {
+                int off;
+                if (a.CP == 3) off = (t0 + t - 1) * a.g.Wp;
+                else off = a.ntaps == 9 ? ((t0 + t) / 3 - 1) * a.g.Wp + ((t0 + t) % 3 - 1) : 0;
+                offs[t] = (uint32_t)off;
+            }
+            const uint32_t N_ = (uint32_t)a.N, gplane = PSG >> 4;
             for (int c = blockIdx.x; c < a.n_chunks; c += gridDim.x) {
                 mbar_wait(full0 + 8 * s, ph);
                 tc_fence_after();
                 const uint32_t aB = a_lo0 + (uint32_t)s * a_stage;
                 const uint32_t gB = g_lo0 + (uint32_t)s * g_stage;
-                if (a.GS) {
+                if (GST) {
                     // D[(plane, dw, c)][(G plane j, dh' , n)]: group dh' of G plane j = rows displaced by dh' image
-                    // rows = kernel row dh = 1 - dh'
-                    for (int j = 0; j < NG; ++j) {
-                        const uint32_t gj = gB + (uint32_t)j * (PSG >> 4);
+                    // rows = kernel row dh = 1 - dh'   (N = 16: two G planes)
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        const uint32_t gj = gB + (uint32_t)j * gplane;
                         const uint32_t dcol = tmem_base + (uint32_t)(j * NW);
 #pragma unroll
-                        for (int ks = 0; ks < kChunk / 16; ++ks)
-                            if (leader) tc_mma(dcol, ((uint64_t)a_hi << 32) | (aB + ks * 16),
-                                               ((uint64_t)g_hi << 32) | (gj + ks * 16), idesc, accum | (uint32_t)ks);
+                        for (int ks = 0; ks < kChunk / 16; ++ks) {
+                            if (leader) tc_mma2(dcol, aB + ks * 16, a_hi, gj + ks * 16, g_hi, idesc, ks ? 1u : accf);
+                        }
                     }
-                } else
-                for (int t = 0; t < a.NM; ++t) {
-                    int off;                                  // row shift (16 B units) of this MMA's A operand
-                    if (a.CP == 3) off = (t0 + t - 1) * a.g.Wp;
-                    else off = a.ntaps == 9 ? ((t0 + t) / 3 - 1) * a.g.Wp + ((t0 + t) % 3 - 1) : 0;
-                    const uint32_t arow = aB + (uint32_t)off;
-                    const uint32_t dcol = tmem_base + (uint32_t)t * a.N;
+                } else {
 #pragma unroll
-                    for (int ks = 0; ks < kChunk / 16; ++ks)   // 16 pixels = 256 B per K step
-                        if (leader) tc_mma(dcol, ((uint64_t)a_hi << 32) | (arow + ks * 16),
-                                           ((uint64_t)g_hi << 32) | (gB + ks * 16), idesc, accum | (uint32_t)ks);
+                    for (int t = 0; t < NMT; ++t) {
+                        const uint32_t arow = aB + offs[t];
+                        const uint32_t dcol = tmem_base + (uint32_t)t * N_;
+#pragma unroll
+                        for (int ks = 0; ks < kChunk / 16; ++ks) {   // 16 pixels = 256 B per K step
+                            if (leader) tc_mma2(dcol, arow + ks * 16, a_hi, gB + ks * 16, g_hi, idesc, ks ? 1u : accf);
+                        }
+                    }
                 }
-                accum = 1;
+                accf = 1;
                 if (leader) tc_commit(empty0 + 8 * s);
                 if (++s == a.nstage) { s = 0; ph ^= 1u; }
             }
@@ -309,17 +328,29 @@ static int launch_wgrad(WgradArgs& a, const float* dbias_src_unused, cudaStream_
     int nstage = (int)((kMax - 256) / (stageA + stageG));
     if (nstage > 4) nstage = 4;
     MPNN_REQUIRE(nstage >= 2, "wgrad(tcgen05): K=%d N=%d does not fit shared memory", a.K0 + a.K1, a.N);
-    size_t smem = (size_t)nstage * (stageA + stageG) + 256;
-    // the descriptor reads M/8 groups from the start of an A stage: keep that inside the allocation
-    const size_t reach = (size_t)(nstage - 1) * stageA + (size_t)(a.M / 8) * a.rowsA * 16 + 64;
-    if (smem < reach) smem = reach;
-    MPNN_REQUIRE(smem <= kMax + 1024, "wgrad(tcgen05): shared memory reach %zu", smem);
     int ncols = 32;
     while (ncols < (a.GS ? NG * a.GS * 8 : a.NM * a.N)) ncols <<= 1;
-    int per_sm = (int)((227 * 1024) / (smem + 1024));
-    if (per_sm > 512 / ncols) per_sm = 512 / ncols;
-    if (per_sm > 4) per_sm = 4;
-    if (per_sm < 1) per_sm = 1;
+    // residency before ring depth: the single issuing warp of a CTA is latency-bound, a second (third)
+    // resident CTA interleaves its MMAs; take the deepest ring that still gives the most CTAs per SM
+    // (bounded by the TMEM columns: a blocked tcgen05.alloc would stall the extra CTA)
+    static const int tune_wps = getenv("MPNN_TUNE_WGRAD_PER_SM") ? atoi(getenv("MPNN_TUNE_WGRAD_PER_SM")) : 0;
+    int cap = 512 / ncols;
+    if (cap > 3) cap = 3;
+    if (tune_wps && cap > tune_wps) cap = tune_wps;
+    if (cap < 1) cap = 1;
+    size_t smem = 0;
+    int per_sm = 0;
+    for (int ns = nstage; ns >= 2; --ns) {
+        size_t sm = (size_t)ns * (stageA + stageG) + 256;
+        // the descriptor reads M/8 groups from the start of an A stage: keep that inside the allocation
+        const size_t reach = (size_t)(ns - 1) * stageA + (size_t)(a.M / 8) * a.rowsA * 16 + 64;
+        if (sm < reach) sm = reach;
+        int fit = (int)((227 * 1024) / (sm + 1024));
+        if (fit > cap) fit = cap;
+        if (fit < 1) fit = 1;
+        if (fit > per_sm) { per_sm = fit; smem = sm; nstage = ns; }
+    }
+    MPNN_REQUIRE(smem <= kMax + 1024, "wgrad(tcgen05): shared memory reach %zu", smem);
     a.nstage = nstage;
     a.vec4 = 1;
     for (int r = 0; r < 2; ++r)
@@ -331,14 +362,22 @@ static int launch_wgrad(WgradArgs& a, const float* dbias_src_unused, cudaStream_
     // at least 8 chunks of pixels so that the reduction traffic stays small next to the MMAs
     if (gx > ceil_div(a.n_chunks, 8)) gx = ceil_div(a.n_chunks, 8);
     if (gx < 1) gx = 1;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(stencil_wgrad_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)kMax + 1024);
-        if (e != cudaSuccess) { mpnn_set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return MPNN_ERR_CUDA; }
-        attr_set = true;
+    typedef void (*Kern)(const WgradArgs);
+    static const Kern kerns[4] = {stencil_wgrad_umma_kernel<9, false>, stencil_wgrad_umma_kernel<3, false>,
+                                  stencil_wgrad_umma_kernel<1, false>, stencil_wgrad_umma_kernel<1, true>};
+    MPNN_REQUIRE(a.GS ? NG == 2 : (a.NM == 9 || a.NM == 3 || a.NM == 1), "wgrad(tcgen05): NM=%d GS=%d NG=%d", a.NM, a.GS, NG);
+    const Kern kern = a.GS ? kerns[3] : (a.NM == 9 ? kerns[0] : (a.NM == 3 ? kerns[1] : kerns[2]));
+    static bool attr_set[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !attr_set[dev]) {          // per-device function attribute
+        for (int i = 0; i < 4; ++i) {
+            cudaError_t e = cudaFuncSetAttribute(kerns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMax + 1024);
+            if (e != cudaSuccess) { mpnn_set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return MPNN_ERR_CUDA; }
+        }
+        if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
-    stencil_wgrad_umma_kernel<<<dim3(gx, groups, mblocks), kWThreads, smem, st>>>(a);
+    kern<<<dim3(gx, groups, mblocks), kWThreads, smem, st>>>(a);
     return mpnn_check_launch("stencil_wgrad_umma");
 }
 

@@ -9,6 +9,8 @@ A checkpoint is one `.npy` holding a dict:
     'rng'       state of the data-sampling numpy Generator, if given.
 Running statistics of BatchNorm are ordinary (non-trainable) parameters and travel inside 'net'.
 """
+import os
+
 import numpy as np
 
 from lib.serdes import decode_net, encode_net
@@ -18,14 +20,25 @@ __all__ = ['save_checkpoint', 'load_checkpoint', 'net_record']
 FORMAT = 1
 
 
-def save_checkpoint(path, net, step, rng=None):
+def save_checkpoint(path, net, step, rng=None, keep_previous=True):
+    """Atomic: the payload is written to a temporary file in the same directory and moved onto `path`
+    with os.replace, so a crash mid-write never destroys the checkpoint `--resume` reads; the previous
+    checkpoint is kept beside it as `<path>.prev` unless keep_previous is False."""
     eng = getattr(net, '_engine', None)
-    np.save(path, {
+    payload = {
         'format': FORMAT,
         'net': encode_net(net),
         'momentum': eng.momentum_numpy() if eng is not None else None,
         'step': int(step),
-        'rng': rng.bit_generator.state if rng is not None else None})
+        'rng': rng.bit_generator.state if rng is not None else None}
+    tmp = '%s.tmp.%d' % (path, os.getpid())
+    with open(tmp, 'wb') as f:
+        np.save(f, payload)
+        f.flush()
+        os.fsync(f.fileno())
+    if keep_previous and os.path.exists(path):
+        os.replace(path, path + '.prev')
+    os.replace(tmp, path)
 
 
 def load_checkpoint(path, rng=None, **configure):

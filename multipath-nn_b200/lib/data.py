@@ -33,7 +33,9 @@ class Dataset:
         self.x0_ts = archive['x0_ts']
         self.y_tr = archive['y_tr']
         self.y_ts = archive['y_ts']
-        self.m_sym = archive['m_sym']
+        # prep-data writes m_sym as float64 ones/zeros (mnist, cifar-*) or a Python int list (hybrid):
+        # normalise once to a boolean mask (a float & bool raises, an int array would index, not mask)
+        self.m_sym = np.asarray(archive['m_sym']).astype(bool)
         self.x0_vl = self.x0_tr[:0]
         self.y_vl = self.y_tr[:0]
         self.rng = np.random.default_rng(seed)
@@ -51,7 +53,7 @@ class Dataset:
         j = rng.integers(0, len(self.x0_tr), n)
         x = np.asarray(self.x0_tr[j], dtype=np.float64)
         y = np.asarray(self.y_tr[j], dtype=np.float64)
-        flip = np.asarray(self.m_sym)[np.argmax(y, 1)] & (rng.random(n) >= 0.5)
+        flip = self.m_sym[np.argmax(y, 1)] & (rng.random(n) >= 0.5)
         x[flip] = x[flip][:, :, ::-1]
         h, w = x.shape[1:3]
         out = np.empty_like(x)
@@ -84,7 +86,7 @@ class Dataset:
         xd, yd = self._dev
         rng = self.rng
         j = rng.integers(0, len(self.x0_tr), n)
-        flip = np.asarray(self.m_sym)[np.argmax(self.y_tr[j], 1)] & (rng.random(n) >= 0.5)
+        flip = self.m_sym[np.argmax(self.y_tr[j], 1)] & (rng.random(n) >= 0.5)
         du = rng.integers(-r_shift, r_shift + 1, n)
         dv = rng.integers(-r_shift, r_shift + 1, n)
         draws = torch.from_numpy(np.stack([j, flip, du, dv]).astype(np.int32)).to(xd.device)

@@ -41,8 +41,9 @@ _RT_BWD = _struct(['Z1', 'Z2', 'dR', 'g1', 'b1', 'W2', 'g2', 'b2', 'W3', 'save',
 _BN_FUSE = np.dtype([(k, '<u8') for k in ('acc', 'gamma', 'beta', 'm_avg', 'v_avg', 'ss', 'mr')]
                     + [('count', '<f8'), ('d', '<f4'), ('eps', '<f4')], align=True)
 _BN_BWD_FUSE = _struct(['acc', 'sums', 'dgamma', 'dbeta'], [])
+_BN_BWD_EPI = _struct(['lin', 'ss', 'mr', 'acc', 'sums', 'dgamma', 'dbeta'], [])
 assert _PACK.itemsize == 48 and _RT_FWD.itemsize == 136 and _RT_BWD.itemsize == 184
-assert _BN_FUSE.itemsize == 72 and _BN_BWD_FUSE.itemsize == 32
+assert _BN_FUSE.itemsize == 72 and _BN_BWD_FUSE.itemsize == 32 and _BN_BWD_EPI.itemsize == 56
 
 
 def _host_struct(dtype, **fields):
@@ -116,6 +117,7 @@ class Engine:
         self.dynamic = bool(net.dynamic)
         self.critic = type(net).__name__ == 'CriticNet'
         self.stream = None
+        self._snapshot = False
         self._analyse()
         self._alloc_params()
         self._plans = {}
@@ -123,6 +125,8 @@ class Engine:
         self._lanes = None
         self._copy_stream, self._stage, self._stage_i = None, {}, 0
         self.multistream = os.environ.get('MPNN_MULTISTREAM', '1') != '0'
+        self.fuse_bn_red = os.environ.get('MPNN_FUSE_BNRED', '1') != '0'
+        self.fuse_bn_red_min_rows = int(os.environ.get('MPNN_FUSE_BNRED_MIN_ROWS', 65536))
         # per-step scalars travel host->device asynchronously from pinned memory; a ring of slots
         # (each guarded by an event) keeps step t+1's values from overwriting step t's before its
         # copy has executed
@@ -259,10 +263,31 @@ class Engine:
         self._buf(p).copy_(torch.from_numpy(p.value.reshape(-1)))
 
     def fetch_param(self, p):
+        if self._snapshot:
+            return                                    # p.value is current (host_snapshot)
         p.value = self._buf(p).cpu().numpy().reshape(p.value.shape).copy()
 
+    def host_snapshot(self):
+        """Context manager: fetch ALL parameters with one device-to-host copy per flat buffer (trainable |
+        state) and serve `Param.eval()` from the host copies while it is open (serdes / checkpoints read
+        ~150 tensors; one blocking copy each is most of their cost)."""
+        import contextlib
+
+        @contextlib.contextmanager
+        def cm():
+            th, st = self.theta.cpu().numpy(), self.state.cpu().numpy()
+            for p in self.tparams + self.sparams:
+                src = th if p._bind[1] == 'theta' else st
+                p.value = src[p._bind[2]:p._bind[2] + p.value.size].reshape(p.value.shape).copy()
+            self._snapshot = True
+            try:
+                yield self
+            finally:
+                self._snapshot = False
+        return cm()
+
     def momentum_numpy(self):
-        """optimiser accumulators, one array per trainable tensor in `self.tparams` order"""
+        """optimiser accumulators, one array per trainable tensor in `self.tparams` order (one D2H copy)"""
         a = self.accum.cpu().numpy()
         return [a[p._bind[2]:p._bind[2] + p.value.size].reshape(p.value.shape).copy() for p in self.tparams]
 
@@ -654,7 +679,7 @@ class _Plan:
                 for i in range(n_sc):
                     geo = Geo(B, H0 // 2 ** i, W0 // 2 ** i)
                     t = self.planes(cpad, geo)
-                    st.out.append(Ns(t=t, C=cpad, Creal=C0, geo=geo, dact=None, writers=0))
+                    st.out.append(Ns(t=t, C=cpad, Creal=C0, geo=geo, dact=None, writers=0, sc=None, consumers=0, fused_red=False))
                     pk = lambda t=t, i=i, geo=geo: L.pack_input(
                         _vp(self.x0), B, H0, W0, C0, 2 ** i, _vp(t), cpad, geo.G, geo.P, dt, S())
                     pk.lane = 3 + i
@@ -694,6 +719,12 @@ class _Plan:
         # ---------------- routers (all tails in one launch), routing ---------------- #
         if self.rt_fwd:
             bn0 = self.rtr[eng.switches[0].idx].bn1
+            for sw in eng.switches:       # the batched tail launch takes ONE (d, eps) for every router BatchNorm
+                for bn in (self.rtr[sw.idx].bn1, self.rtr[sw.idx].bn2):
+                    if (float(bn.hypers.d), float(bn.hypers.ε)) != (float(bn0.hypers.d), float(bn0.hypers.ε)):
+                        raise NotImplementedError(
+                            'engine: router BatchNorm hypers differ between routers (%r: d=%r, eps=%r vs d=%r, eps=%r)'
+                            % (sw.layer.name, bn.hypers.d, bn.hypers.ε, bn0.hypers.d, bn0.hypers.ε))
             tab = self._desc_table(_RT_FWD, self.rt_fwd)
             self.keep.append(tab)
             tails = lambda: L.router_tail_fwd_batched(
@@ -923,6 +954,7 @@ class _Plan:
         train, bwd = self.bn_train, self.need_bwd
         for k in range(n):
             src = pin[k]
+            src.consumers += 1
             geo = src.geo
             N = n_chan[k]
             K0 = src.C
@@ -1012,7 +1044,19 @@ class _Plan:
                 if sc.feat is not None:
                     st.feat_op = post
             st.sc.append(sc)
-            st.out.append(Ns(t=sc.act, C=N, Creal=N, geo=geo, dact=None, writers=0))
+            st.out.append(Ns(t=sc.act, C=N, Creal=N, geo=geo, dact=None, writers=0, sc=sc, consumers=0, fused_red=False))
+
+    def _bn_bwd_bufs(self, sc):
+        """sums / fp64 accumulator / finalisation struct of a scale's BatchNorm backward (shared by the
+        stand-alone reduction and the one fused into the consumer's data gradient)"""
+        eng = self.eng
+        if getattr(sc, 'sums', None) is None:
+            sc.sums = self.f32(2, sc.N)
+            if getattr(sc, 'acc', None) is None:
+                sc.acc = torch.zeros(2 * sc.N + 1, dtype=torch.float64, device=eng.dev)
+            bn = sc.bn
+            sc.bnb = _host_struct(_BN_BWD_FUSE, acc=_vp(sc.acc), sums=_vp(sc.sums),
+                                  dgamma=eng.gptr(bn.params.γ), dbeta=eng.gptr(bn.params.β))
 
     def _build_rcm_bwd(self, nd, Balloc):
         eng, L, B = self.eng, self.eng.L, self.B
@@ -1055,14 +1099,8 @@ class _Plan:
             dfeat = st.dfeat if (k == n - 1) else None
             dpooled = sc.dpooled      # gradient wrt pooled(lin_k), set by scale k+1's dgrad below
             live = sc.live and (dact is not None or dfeat is not None)
-            sc.sums = self.f32(2, sc.N)
-            if live:
-                bn = sc.bn
-
-                if getattr(sc, 'acc', None) is None:
-                    sc.acc = torch.zeros(2 * sc.N + 1, dtype=torch.float64, device=eng.dev)
-                sc.bnb = _host_struct(_BN_BWD_FUSE, acc=_vp(sc.acc), sums=_vp(sc.sums),
-                                      dgamma=eng.gptr(bn.params.γ), dbeta=eng.gptr(bn.params.β))
+            self._bn_bwd_bufs(sc)
+            if live and not st.out[k].fused_red:   # (fused: the sums arrive with the consumer's data gradient)
 
                 def red(sc=sc, dact=dact, dfeat=dfeat):
                     L.bn_bwd_reduce_fused(_vp(sc.lin), _vp(dact), _vp(dfeat), Balloc, _vp(sc.ss), _vp(sc.mr), sc.N,
@@ -1120,13 +1158,34 @@ class _Plan:
                 out0 = slot.dact
             if N1:
                 prev.dpooled = self.planes(sc.K1, geo)
+            # BatchNorm-backward sums of the layer below ride on this data gradient when it is the only
+            # producer of that layer's dAct (one consumer, no head gradient at that scale): removes the
+            # bn_bwd_reduce pass over (lin, dAct)
+            psc = sc.src.sc if N0 else None
+            # (measured: a win where the 16- / 32-wide fast epilogue applies and the tensor is large; on
+            #  small tensors and in the generic epilogue the stand-alone reduction is as fast or faster)
+            fuse = (psc is not None and eng.fuse_bn_red and impl == 1 and self.bn_train and sc.src.consumers == 1
+                    and psc.live and psc.feat is None and psc.N == N0 and (N0 + N1) in (16, 32)
+                    and B * sc.geo.H * sc.geo.W >= eng.fuse_bn_red_min_rows)
+            if fuse:
+                sc.src.fused_red = True
+                self._bn_bwd_bufs(psc)
+                sc.epi = _host_struct(_BN_BWD_EPI, lin=_vp(psc.lin), ss=_vp(psc.ss), mr=_vp(psc.mr), acc=_vp(psc.acc),
+                                      sums=_vp(psc.sums), dgamma=eng.gptr(psc.bn.params.γ),
+                                      dbeta=eng.gptr(psc.bn.params.β))
 
-            def dgrad(sc=sc, out0=out0, N0=N0, N1=N1, acc0=acc0, prev=prev):
-                L.stencil_gemm(_vp(sc.dlin), sc.N, None, 0, _vp(sc.Wd), 9, None,
-                               _vp(out0), N0, acc0, _vp(prev.dpooled) if N1 else None, N1, 0,
-                               *sc.geo.args(), None, 0, None, dt, dt, impl, S())
-            self._tag(dgrad, 'conv_dgrad', desc='H%d K%d N%d+%d' % (sc.geo.H, sc.N, N0, N1), flops=2.0 * B * sc.geo.H * sc.geo.W * 9 * sc.N * (N0 + N1),
-                      nbytes=B * sc.geo.H * sc.geo.W * (sc.N + N0 + N1) * (2 if dt == BF16 else 4))
+                def dgrad(sc=sc, out0=out0, N0=N0, N1=N1, prev=prev):
+                    L.conv_dgrad_bn_reduce(_vp(sc.dlin), sc.N, _vp(sc.Wd), _vp(out0), N0,
+                                           _vp(prev.dpooled) if N1 else None, N1, *sc.geo.args(),
+                                           ctypes.c_void_p(sc.epi.ctypes.data), dt, impl, S())
+            else:
+                def dgrad(sc=sc, out0=out0, N0=N0, N1=N1, acc0=acc0, prev=prev):
+                    L.stencil_gemm(_vp(sc.dlin), sc.N, None, 0, _vp(sc.Wd), 9, None,
+                                   _vp(out0), N0, acc0, _vp(prev.dpooled) if N1 else None, N1, 0,
+                                   *sc.geo.args(), None, 0, None, dt, dt, impl, S())
+            self._tag(dgrad, 'conv_dgrad', desc='H%d K%d N%d+%d%s' % (sc.geo.H, sc.N, N0, N1, ' +bnred' if fuse else ''),
+                      flops=2.0 * B * sc.geo.H * sc.geo.W * 9 * sc.N * (N0 + N1),
+                      nbytes=B * sc.geo.H * sc.geo.W * (sc.N + N0 + N1 + (N0 if fuse else 0)) * (2 if dt == BF16 else 4))
             dgrad.lane = sc.lane
             if N1:
                 prev.dpooled_op = dgrad

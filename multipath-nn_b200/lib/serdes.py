@@ -84,6 +84,10 @@ def load_params(layer, record):
 
 
 def encode_net(net):
+    eng = getattr(net, '_engine', None)
+    if eng is not None and not getattr(eng, 'dry', False) and not eng._snapshot:
+        with eng.host_snapshot():                  # one device-to-host copy instead of one per tensor
+            return encode_net(net)
     return {'type': type(net).__name__, 'root': encode_layer(net.root),
             'hypers': dict(vars(net.hypers)), 'params': _arrays(net.params)}
 

@@ -1,0 +1,139 @@
+"""Oracle parity at the REAL architecture (arch_and_hypers.py:19-27, 32x32 input, 64..128-channel stages,
+batch 128 = arch_and_hypers.py:35) for every BASELINE.json config: sr_chain(8) on 3- and 1-channel input,
+ac_chain, cr_chain (plain / optimistic / use_cls_err), ac_tree, and the adaptive ac_chain(dyn_k_cpt=True)
+with a per-example k_cpt and with the length-1 `[k]` feed of train-adaptive-nets:102-105.
+
+Compared with the oracle on the same bytes: logits, c_err, router logits, p_tr, routing decisions (bit-exact
+wherever the oracle's margin exceeds the stated tolerance -- the fraction of examples inside that mask is
+printed and must be >= 0.8, so the claim is not vacuous), c_tot and every parameter gradient.
+
+Tolerances.  fp32 mode against the fp64 oracle: forward values 1e-3, the whole gradient vector 2e-3, each
+tensor 1e-2 (ReLU / max-pool near-ties resolve differently in fp32 and fp64; the fp32 and fp64 ORACLES
+differ by up to 2e-4 of the gradient norm for the same reason).  bf16 mode against the
+oracle evaluated in the arithmetic the device stores in (quant='bf16'): forward 5e-2, whole gradient 0.25.
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, 'multipath-nn_b200'), os.path.join(ROOT, 'tests')):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+pytestmark = pytest.mark.gpu
+
+import arch_and_hypers as ah  # noqa: E402
+from lib import layer_types  # noqa: E402
+from oracle.torch_ref import OracleNet  # noqa: E402
+from util import node_paths, record_of, rel_err  # noqa: E402
+
+B = 128
+TOL = {'fp32': dict(fwd=1e-3, grad_all=2e-3, grad_each=1e-2, margin=1e-4),
+       'bf16': dict(fwd=5e-2, grad_all=2.5e-1, grad_each=None, margin=5e-2)}
+
+CASES = {
+    'cifar10-sr': (lambda: ah.sr_chain(8), 3, {}),
+    'mnist-sr': (lambda: ah.sr_chain(8), 1, {}),
+    'cifar10-ac': (lambda: ah.ac_chain(k_cpt=4e-9), 3, {}),
+    'cifar10-cr': (lambda: ah.cr_chain(k_cpt=4e-9), 3, {}),
+    'cr-optimistic': (lambda: ah.cr_chain(k_cpt=1.6e-8, optimistic=True), 3, {}),
+    'cr-use-cls-err': (lambda: ah.cr_chain(k_cpt=1.6e-8, use_cls_err=True), 3, {}),
+    'ac-tree': (lambda: ah.ac_tree(k_cpt=4e-9), 3, {}),
+    'ac-dyn-kcpt-vector': (lambda: ah.ac_chain(dyn_k_cpt=True), 3, {'kc': 'vector'}),
+    'ac-dyn-kcpt-length1': (lambda: ah.ac_chain(dyn_k_cpt=True), 3, {'kc': 'length1'}),
+}
+
+
+def _build(name, prec):
+    maker, C, opt = CASES[name]
+    layer_types.seed(0)
+    net = maker()((32, 32, C), (10,)).configure(precision=prec)
+    rng = np.random.default_rng(1)
+    for l in net.layers:                     # non-trivial routing (the reference zero-initialises the last router layer)
+        if l.router is not None:
+            w = l.router.comps[-1].params.w
+            w.assign((0.5 * rng.standard_normal(w.shape)).astype(np.float32))
+    rng = np.random.default_rng(7)
+    x0 = rng.random((B, 32, 32, C)).astype(np.float32)
+    y = np.eye(10, dtype=np.float32)[rng.integers(0, 10, B)]
+    kc_dev = kc_ref = None
+    if opt.get('kc') == 'vector':
+        kc_dev = kc_ref = rng.choice(ah.k_cpts, B).astype(np.float32)
+    elif opt.get('kc') == 'length1':
+        kc_dev, kc_ref = [ah.k_cpts[4]], np.full(B, ah.k_cpts[4], np.float32)
+    return net, x0, y, kc_dev, kc_ref
+
+
+@pytest.mark.parametrize('prec', ['fp32', 'bf16'])
+@pytest.mark.parametrize('name', list(CASES))
+def test_full_architecture_matches_the_oracle(name, prec):
+    tol = TOL[prec]
+    net, x0, y, kc_dev, kc_ref = _build(name, prec)
+    rec = record_of(net)
+    tau = 0.7 if net.dynamic else None
+    o = OracleNet(rec, torch.float64, quant='bf16' if prec == 'bf16' else None)
+    out, g_ref = o.grads(x0, y, tau=tau, k_cpt=kc_ref)
+    feed = {net.x0: x0, net.y: y}
+    if net.dynamic:
+        feed[net.τ] = tau
+        if kc_dev is not None:
+            feed[net.k_cpt] = kc_dev
+    eng = net._get_engine()
+    eng.train_step(feed, update=False)
+    torch.cuda.synchronize()
+    plan = eng._plan(B, True, True)
+    paths = node_paths(net)
+    worst_fwd = 0.0
+    for nd in eng.regs:
+        ref = out.nodes[paths[nd.idx][0]]
+        e1 = rel_err(plan.reg[nd.idx].Z.cpu().numpy(), ref.comps[1].x.detach().numpy())
+        e2 = rel_err(plan.reg[nd.idx].c_err.cpu().numpy(), ref.c_err.detach().numpy())
+        worst_fwd = max(worst_fwd, e1, e2)
+        assert e1 < tol['fwd'] and e2 < tol['fwd'], ('leaf', paths[nd.idx][0], e1, e2)
+    frac_sure = 1.0
+    if net.dynamic:
+        p_tr = plan.p_tr.cpu().numpy(); dec = plan.dec.cpu().numpy()
+        n_sure = n_all = 0
+        for nd in eng.switches:
+            path = paths[nd.idx][0]
+            r_ref = out.nodes[path].router.x.detach().numpy()
+            assert rel_err(plan.rtr[nd.idx].R.cpu().numpy(), r_ref) < 5 * tol['fwd'], ('router logits', path)
+            srt = np.sort(r_ref, 1)
+            sure = (srt[:, -1] - srt[:, -2]) > tol['margin']
+            n_sure += int(sure.sum()); n_all += sure.size
+            np.testing.assert_array_equal(dec[nd.sw][sure], r_ref.argmax(1)[sure])      # bit-exact decisions
+        frac_sure = n_sure / n_all
+        assert frac_sure >= 0.8, frac_sure
+        for nd in eng.nodes:
+            path = paths[nd.idx][0]
+            assert rel_err(p_tr[nd.idx], out.nodes[path].p_tr.detach().numpy()) < 5 * tol['fwd'], ('p_tr', path)
+        # per-node example counts = sum of p_ev (bit-exact where every decision on the way is outside the margin)
+        p_ev = plan.p_ev.cpu().numpy()
+        leaves = [nd.idx for nd in eng.nodes if not nd.kids]
+        np.testing.assert_array_equal(p_ev[leaves].sum(0), 1.0)
+    c_ref = float(out.c_tot.detach())
+    assert abs(eng.c_tot(plan) - c_ref) < tol['fwd'] * abs(c_ref)
+    g = eng.grads_numpy(with_l2=True)
+    assert len(eng.tparams) == len(o.trainable)
+    num = den = 0.0
+    worst_each, worst_name = 0.0, None
+    gmax = max(float(np.abs(v.numpy()).max()) for v in g_ref.values())
+    for p, (path, role, key, t) in zip(eng.tparams, o.trainable):
+        ref = g_ref[(path, role, key, id(t))].numpy()
+        assert ref.shape == g[p].shape, (path, role, key)
+        num += float(((g[p] - ref) ** 2).sum()); den += float((ref ** 2).sum())
+        n = np.linalg.norm(ref)
+        if n > 1e-3 * gmax * np.sqrt(ref.size):         # tensors with a meaningful gradient
+            e = float(np.linalg.norm(g[p] - ref) / n)
+            if e > worst_each:
+                worst_each, worst_name = e, (path, role, key)
+    err_all = (num / den) ** 0.5
+    print('PARITY %-22s %s  forward %.2e  gradient (all) %.2e  worst tensor %.2e %s  decisions inside the mask %.3f'
+          % (name, prec, worst_fwd, err_all, worst_each, worst_name, frac_sure))
+    assert err_all < tol['grad_all'], err_all
+    if tol['grad_each'] is not None:
+        assert worst_each < tol['grad_each'], (worst_each, worst_name)

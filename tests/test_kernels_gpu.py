@@ -234,6 +234,48 @@ def test_stencil_dgrad_split_outputs(dt, impl):
         assert rel_err(from_planes(o.float().cpu().numpy(), geo, C), ref) < (1e-5 if dt == F32 else 4e-3)
 
 
+@pytest.mark.parametrize('B,H,K,N0,N1', [(5, 8, 16, 16, 0), (40, 16, 16, 16, 16), (9, 8, 32, 32, 0), (130, 32, 16, 16, 0),
+                                         (6, 8, 32, 16, 32), (7, 8, 64, 64, 0), (3, 4, 64, 32, 64), (300, 8, 16, 16, 16)])
+def test_dgrad_with_fused_bn_backward_sums(B, H, K, N0, N1):
+    """mpnn_conv_dgrad_bn_reduce: the data gradient is bit-identical to mpnn_stencil_gemm, and the sums /
+    dgamma / dbeta the last CTA writes match the stand-alone mpnn_bn_bwd_reduce_fused pass over
+    (lin, dAct).  Shapes cover the 16- / 32-wide fast epilogues, the generic one (N = 48, 64, 96) and a
+    grid with more tiles than CTAs; run twice to check that the accumulator cleans itself."""
+    from lib.engine import _BN_BWD_EPI, _BN_BWD_FUSE, _host_struct
+    rng = np.random.default_rng(31)
+    td = torch.bfloat16
+    geo = Geo(B, H, H)
+    mk = lambda C: dev(to_planes(rng.standard_normal((B, H, H, C)).astype(np.float32), geo), td)
+    G, lin = mk(K), mk(N0)
+    Wd = dev(rng.standard_normal((9, K // 8, N0 + N1, 8)).astype(np.float32) * 0.1, td)
+    ss = dev(np.stack([rng.standard_normal(N0), 0.3 * rng.standard_normal(N0)]).astype(np.float32))
+    mr = dev(np.stack([rng.standard_normal(N0), 0.5 + rng.random(N0)]).astype(np.float32))
+    mko = lambda C: torch.zeros((max(C, 8) // 8, geo.P, 8), dtype=td, device='cuda')
+    a0, a1, b0, b1 = mko(N0), mko(N1), mko(N0), mko(N1)
+    L().stencil_gemm(vp(G), K, None, 0, vp(Wd), 9, None, vp(a0), N0, 0, vp(a1) if N1 else None, N1, 0,
+                     B, H, H, geo.G, geo.P, None, 0, None, BF16, BF16, 1, None)
+    acc = torch.zeros(2 * N0 + 1, dtype=torch.float64, device='cuda')
+    sums_a = torch.zeros((2, N0), device='cuda'); dg_a = torch.zeros(N0, device='cuda'); db_a = torch.zeros(N0, device='cuda')
+    fa = _host_struct(_BN_BWD_FUSE, acc=vp(acc), sums=vp(sums_a), dgamma=vp(dg_a), dbeta=vp(db_a))
+    L().bn_bwd_reduce_fused(vp(lin), vp(a0), None, 0, vp(ss), vp(mr), N0, B, H, H, geo.G, geo.P,
+                            ctypes.c_void_p(fa.ctypes.data), BF16, None)
+    sums_b = torch.zeros((2, N0), device='cuda'); dg_b = torch.zeros(N0, device='cuda'); db_b = torch.zeros(N0, device='cuda')
+    epi = _host_struct(_BN_BWD_EPI, lin=vp(lin), ss=vp(ss), mr=vp(mr), acc=vp(acc), sums=vp(sums_b),
+                       dgamma=vp(dg_b), dbeta=vp(db_b))
+    for rep in range(2):
+        dg_b.zero_(); db_b.zero_(); b0.zero_(); b1.zero_()
+        L().conv_dgrad_bn_reduce(vp(G), K, vp(Wd), vp(b0), N0, vp(b1) if N1 else None, N1, B, H, H, geo.G, geo.P,
+                                 ctypes.c_void_p(epi.ctypes.data), BF16, 1, None)
+        torch.cuda.synchronize()
+        assert float(acc.abs().max()) == 0.0
+        for a, b, C in ((a0, b0, N0), (a1, b1, N1)):
+            if C:
+                assert np.array_equal(from_planes(a.float().cpu().numpy(), geo, C), from_planes(b.float().cpu().numpy(), geo, C))
+        scale = float(sums_a.abs().max())
+        for a, b in ((sums_a, sums_b), (dg_a, dg_b), (db_a, db_b)):
+            np.testing.assert_allclose(b.cpu().numpy(), a.cpu().numpy(), rtol=5e-5, atol=5e-6 * scale)
+
+
 @pytest.mark.parametrize('dt,impl,shape', [
     (F32, 0, (6, 8, 3, 16, 32)), (BF16, 0, (6, 8, 3, 16, 32)), (BF16, 1, (6, 8, 3, 16, 32)),
     (BF16, 1, (3, 32, 16, 16, 16)), (BF16, 1, (50, 4, 64, 64, 64)), (BF16, 1, (33, 4, 128, 0, 128)),

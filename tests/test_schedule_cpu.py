@@ -49,6 +49,8 @@ _STRUCTS = {
 _HOST_STRUCTS = {
     'conv_bn_stats': ('bn', E._BN_FUSE, dict(acc='rw', gamma='r', beta='r', m_avg='rw', v_avg='rw', ss='w', mr='w')),
     'bn_bwd_reduce_fused': ('f', E._BN_BWD_FUSE, dict(acc='rw', sums='w', dgamma='w', dbeta='w')),
+    'conv_dgrad_bn_reduce': ('epi', E._BN_BWD_EPI, dict(lin='r', ss='r', mr='r', acc='rw', sums='w', dgamma='w',
+                                                        dbeta='w')),
 }
 
 
@@ -213,12 +215,15 @@ def test_reference_architectures_are_race_free(which):
             'cr_tree_dyn': lambda: ah.cr_tree(dyn_k_cpt=True)}[which]
     net = make()((32, 32, 3), (10,))
     eng = E.Engine(net, precision='bf16', impl=1, dry_run=True)
+    eng.fuse_bn_red_min_rows = 0          # exercise the data gradients that carry the BN-backward sums (large batches)
     holder = {}
     eng.L = Recorder(eng.L, lambda ptr: holder['lookup'](ptr)[2])
     plan = eng._plan(8, True, True)
     holder['lookup'] = _tensor_index(eng, plan)
     problems = _check(eng, plan)
     assert not problems, problems[:8]
+    if which != 'ac_tree' and which != 'cr_tree_dyn':
+        assert any('bnred' in getattr(op, 'desc', '') for op in plan.bwd_ops)
     ev = eng._plan(8, False, False)                  # inference plan (running BN moments, no backward)
     holder['lookup'] = _tensor_index(eng, ev)
     problems = _check(eng, ev)
