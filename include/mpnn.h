@@ -136,8 +136,8 @@ int mpnn_bn_finalize(const float* partials, int n_parts, int C, double count,
 int mpnn_bn_relu_pool_fwd(const void* lin, int C, int B, int H, int W, int G, int P,
                           const float* ss, void* act, void* pooled, int Pp,
                           void* feat, int Balloc, int dtype, void* stream);
-/* backward, pass 1: partial sums of dy' and dy'*xhat (dy' = relu-masked sum
- * of dAct and dFeat); *n_parts rows written. */
+/* backward, pass 1: partial sums of dy' and dy'*(x - mean) (dy' = relu-masked sum
+ * of dAct and dFeat; centred so that nothing cancels against mean * sum dy'); *n_parts rows written. */
 int mpnn_bn_bwd_reduce(const void* lin, const void* dAct, const void* dFeat, int Balloc,
                        const float* ss, const float* mr, int C,
                        int B, int H, int W, int G, int P,
@@ -154,7 +154,7 @@ int mpnn_bn_bwd_reduce_fused(const void* lin, const void* dAct, const void* dFea
  *   out0[p][n] (n < N0) = dAct of the parent activation, out1 (N1 columns) = gradient wrt the pooled
  *   predecessor, as in mpnn_stencil_gemm(Gd, K, NULL, 0, Wp, 9, NULL, out0, N0, 0, out1, N1, 0, ...);
  *   with dy' = out0 * [ss0*lin + ss1 > 0] (lin, ss, mr: pre-BN output and constants of the parent's
- *   BatchNorm, N0 channels) the kernel accumulates sum dy' and sum dy'*lin over the valid pixels and the
+ *   BatchNorm, N0 channels) the kernel accumulates sum dy' and sum dy'*(lin - mean) over the valid pixels and the
  *   last CTA writes f.sums / adds f.dgamma, f.dbeta exactly like mpnn_bn_bwd_reduce_fused.
  * TF autodiff of lib/layer_types.py:181-185 and :219-249. */
 typedef struct {
@@ -165,7 +165,7 @@ int mpnn_conv_dgrad_bn_reduce(const void* Gd, int K, const void* Wp, void* out0,
                               int B, int H, int W, int G, int P, const mpnn_bn_bwd_epi* epi,
                               int dtype, int impl, void* stream);
 
-/* partials (from bn_bwd_reduce) hold sum dy' and sum dy'*x per channel;
+/* partials (from bn_bwd_reduce) hold sum dy' and sum dy'*(x - mean) per channel;
  * sums[0][c] = sum dy', sums[1][c] = sum dy'*xhat; dgamma += sums1, dbeta += sums0 */
 int mpnn_bn_bwd_finalize(const float* partials, int n_parts, int C, const float* mr,
                          float* sums, float* dgamma, float* dbeta, void* stream);

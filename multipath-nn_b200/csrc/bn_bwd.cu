@@ -27,7 +27,7 @@ __device__ __forceinline__ void load_dy(const T* __restrict__ dAct, const T* __r
     }
 }
 
-// pass 1: per-CTA partial sums of dy' and dy'*x (the xhat form is recovered in finalize)
+// pass 1: per-CTA partial sums of dy' and dy'*(x - mean) (scaled by rstd into the xhat form in finalize)
 template <typename T>
 __global__ void __launch_bounds__(256, 4)
 bn_bwd_reduce_kernel(const T* __restrict__ lin, const T* __restrict__ dAct, const T* __restrict__ dFeat,
@@ -36,10 +36,11 @@ bn_bwd_reduce_kernel(const T* __restrict__ lin, const T* __restrict__ dAct, cons
     pdl_launch_dependents();
     pdl_wait();
     const int kg = blockIdx.y, KG = C / 8;
-    float a[8], c[8], s0[8], s1[8];
+    float a[8], c[8], mu[8], s0[8], s1[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         a[j] = ss[kg * 8 + j]; c[j] = ss[C + kg * 8 + j];
+        mu[j] = mr[kg * 8 + j];       // the second sum is taken of dy'*(x - mean): no cancellation against mean * sum dy'
         s0[j] = 0.f; s1[j] = 0.f;
     }
     const int total = g.B * g.H * g.W;
@@ -56,7 +57,7 @@ bn_bwd_reduce_kernel(const T* __restrict__ lin, const T* __restrict__ dAct, cons
         for (int j = 0; j < 8; ++j) {
             const float dy = fmaf(a[j], lv[j], c[j]) > 0.f ? d[j] : 0.f;
             s0[j] += dy;
-            s1[j] = fmaf(dy, lv[j], s1[j]);
+            s1[j] = fmaf(dy, lv[j] - mu[j], s1[j]);
         }
     }
     __shared__ float red[8][16];
@@ -145,8 +146,8 @@ __global__ void bn_bwd_finalize_kernel(const float* __restrict__ partials, int n
         s1 += __shfl_xor_sync(0xffffffffu, s1, o);
     }
     if (lane != 0) return;
-    const double mean = mr[c], rstd = mr[C + c];
-    const double sx = rstd * (s1 - mean * s0);           // sum dy'*xhat
+    const double rstd = mr[C + c];
+    const double sx = rstd * s1;                         // sum dy'*xhat (s1 is already centred)
     sums[c] = (float)s0;
     sums[C + c] = (float)sx;
     if (dgamma) dgamma[c] += (float)sx;

@@ -53,14 +53,14 @@ __device__ __forceinline__ void mpnn_bn_fwd_finalize_last(const mpnn_bn_fuse& f,
     if (threadIdx.x == 0) *reinterpret_cast<unsigned*>(f.acc + 2 * C) = 0u;
 }
 
-// backward finalisation by the last CTA: totals of dy' and dy'*x -> sums in the xhat form
+// backward finalisation by the last CTA: totals of dy' and dy'*(x - mean) -> sums in the xhat form
 // (sums[0] = sum dy', sums[1] = sum dy'*xhat), dgamma / dbeta accumulated; then reset acc + ticket.
 __device__ __forceinline__ void mpnn_bn_bwd_finalize_last(const mpnn_bn_bwd_fuse& f, const float* mr, int C) {
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
         const double t0 = __ldcg(f.acc + c), t1 = __ldcg(f.acc + C + c);
         f.acc[c] = 0.0; f.acc[C + c] = 0.0;
-        const double mean = mr[c], rstd = mr[C + c];
-        const double sx = rstd * (t1 - mean * t0);           // sum dy'*xhat
+        const double rstd = mr[C + c];
+        const double sx = rstd * t1;                         // sum dy'*xhat (t1 = sum dy'*(x - mean))
         f.sums[c] = (float)t0;
         f.sums[C + c] = (float)sx;
         if (f.dgamma) f.dgamma[c] += (float)sx;

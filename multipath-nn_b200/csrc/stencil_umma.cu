@@ -28,7 +28,7 @@ extern "C" int mpnn_has_umma(void) { return 1; }
 namespace {
 
 // fused BN-backward reduction on out0 (data-gradient epilogue): with dy' = dAct * [ss0*lin + ss1 > 0]
-// the CTA accumulates sum dy' and sum dy'*lin per channel of out0; the last CTA converts the totals
+// the CTA accumulates sum dy' and sum dy'*(lin - mean) per channel of out0; the last CTA converts the totals
 // into the xhat form (bn_fuse.cuh).  Replaces the bn_bwd_reduce pass over (lin, dAct).
 struct BwdRed {
     const __nv_bfloat16* lin; const float* ss; const float* mr;
@@ -101,7 +101,7 @@ stencil_gemm_umma_kernel(const GemmArgs a) {
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * a.nstage + 6);   // 16-byte aligned
     float* sstat = reinterpret_cast<float*>(tmem_slot + 4);      // [4 warps][2][NB]
     float* sbias = sstat + 4 * 2 * NB;                           // [NB]
-    float* sred = sbias + NB;                                    // [2][N0]: scale / shift of the BN behind out0 (mode 2)
+    float* sred = sbias + NB;                                    // [3][N0]: scale / shift / mean of the BN behind out0 (mode 2)
     const uint32_t ncols = tmem_cols_pow2(2 * NB);
     constexpr bool FAST = EPI != 0;
     const int stats_mode = EPI == 2 ? 2 : (EPI == 1 ? (a.stats_mode == 1 ? 1 : 0) : a.stats_mode);
@@ -125,7 +125,7 @@ stencil_gemm_umma_kernel(const GemmArgs a) {
     pdl_launch_dependents();
     pdl_wait();                  // everything above is independent of the previous kernel in the stream
     if (stats_mode == 2 && threadIdx.x >= 64)
-        for (int i = threadIdx.x - 64; i < 2 * a.N0; i += 128) sred[i] = a.red.ss[i];
+        for (int i = threadIdx.x - 64; i < 3 * a.N0; i += 128) sred[i] = i < 2 * a.N0 ? a.red.ss[i] : a.red.mr[i - 2 * a.N0];
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -261,14 +261,16 @@ stencil_gemm_umma_kernel(const GemmArgs a) {
         auto red8 = [&](int cc, const float* dv, const float* lv, float* a1, float* a2) {
             const float4* sc4 = reinterpret_cast<const float4*>(sred + cc);
             const float4* sh4 = reinterpret_cast<const float4*>(sred + a.N0 + cc);
-            float sc[8], sh[8];
+            const float4* mu4 = reinterpret_cast<const float4*>(sred + 2 * a.N0 + cc);
+            float sc[8], sh[8], mu[8];
             *reinterpret_cast<float4*>(sc) = sc4[0]; *reinterpret_cast<float4*>(sc + 4) = sc4[1];
             *reinterpret_cast<float4*>(sh) = sh4[0]; *reinterpret_cast<float4*>(sh + 4) = sh4[1];
+            *reinterpret_cast<float4*>(mu) = mu4[0]; *reinterpret_cast<float4*>(mu + 4) = mu4[1];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const float dy = fmaf(sc[j], lv[j], sh[j]) > 0.f ? dv[j] : 0.f;
                 a1[j] += dy;
-                a2[j] = fmaf(dy, lv[j], a2[j]);
+                a2[j] = fmaf(dy, lv[j] - mu[j], a2[j]);      // centred: no cancellation against mean * sum dy'
             }
         };
         // generic epilogue of one 16-column chunk: bias, store (bf16 / fp32 planes or fp32 row-major), sums
@@ -580,7 +582,7 @@ int mpnn_stencil_gemm_umma(const void* A0, int K0, const void* A1, int K1, const
     }
     const size_t stage = (size_t)rowsA * 16 * KC;
     const size_t kMax = 227 * 1024 - 1024;
-    const size_t red_bytes = bwd ? (size_t)8 * N0 : 0;         // staged scale / shift of the BN behind out0
+    const size_t red_bytes = bwd ? (size_t)12 * N0 : 0;        // staged scale / shift / mean of the BN behind out0
     int split = 0, nstage = 0, NB = 0;
     for (int s = 1; s <= 8; s *= 2) {
         if (N % (16 * s)) break;

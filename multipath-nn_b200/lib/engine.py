@@ -636,11 +636,31 @@ class _Plan:
         return op
 
     # -- allocation helpers ------------------------------------------------ #
+    # Every buffer of a plan is a view into a few large zero-filled arenas (bump allocation, 256-byte
+    # aligned): a plan has ~450 buffers, and one torch.zeros each was ~450 fill launches in front of
+    # the first step (they also hid the step's own kernels from a launch-count-limited profiler).
+    _ESZ = {torch.float32: 4, torch.bfloat16: 2, torch.float64: 8, torch.int32: 4, torch.int64: 8, torch.uint8: 1}
+
+    def zeros(self, shape, dtype):
+        shape = tuple(int(v) for v in (shape if isinstance(shape, (tuple, list)) else (shape,)))
+        n = 1
+        for v in shape:
+            n *= v
+        nbytes = _ru(max(n, 1) * self._ESZ[dtype], 256)
+        if getattr(self, '_arena', None) is None or self._arena_off + nbytes > self._arena.numel():
+            chunk = max(nbytes, (256 << 20) if self.B > 512 else (32 << 20))
+            self._arena = torch.zeros(chunk, dtype=torch.uint8, device=self.eng.dev)
+            self._arena_off = 0
+            self.arenas = getattr(self, 'arenas', []) + [self._arena]
+        raw = self._arena[self._arena_off:self._arena_off + n * self._ESZ[dtype]]
+        self._arena_off += nbytes
+        return raw.view(dtype).view(shape)
+
     def planes(self, C, geo):
-        return torch.zeros((C // 8, geo.P, 8), dtype=self.eng.tdtype, device=self.eng.dev)
+        return self.zeros((C // 8, geo.P, 8), self.eng.tdtype)
 
     def f32(self, *shape):
-        return torch.zeros(shape, dtype=torch.float32, device=self.eng.dev)
+        return self.zeros(shape, torch.float32)
 
     def _build(self):
         eng, L, B = self.eng, self.eng.L, self.B
@@ -841,9 +861,9 @@ class _Plan:
         hd.N = 16 * (bool(leaves) + (rt is not None))
         F, Fext = st.F, st.Fext
         hd.Z16 = self.f32(B, 16) if leaves else None
-        hd.Wfc = torch.zeros((1, Fext // 8, hd.N, 8), dtype=eng.tdtype, device=eng.dev)
+        hd.Wfc = self.zeros((1, Fext // 8, hd.N, 8), eng.tdtype)
         hd.bias = self.f32(hd.N)
-        hd.dZ = torch.zeros((hd.N // 8, Balloc, 8), dtype=eng.tdtype, device=eng.dev) if self.need_bwd else None
+        hd.dZ = self.zeros((hd.N // 8, Balloc, 8), eng.tdtype) if self.need_bwd else None
         if leaves:
             fc = eng.nodes[leaves[0]].layer.comps[1]
             hd.fc_leaf = fc
@@ -891,12 +911,12 @@ class _Plan:
         self._after(wgrad, getattr(hd, 'ceb_op', None))
         self.bwd_ops.append(wgrad if wgrad.early else self._after(wgrad, self.bwd_head_dep))
         # data gradient towards the flattened coarsest scale
-        hd.Wfd = torch.zeros((1, hd.N // 8, F, 8), dtype=eng.tdtype, device=eng.dev)
+        hd.Wfd = self.zeros((1, hd.N // 8, F, 8), eng.tdtype)
         if leaf is not None:
             self._pack(leaf.params.w, hd.Wfd, F, n_cls, 1, hd.leaf_off, hd.N, 0, F, ntaps=1)
         if rt is not None:
             self._pack(rt.fc1.params.w, hd.Wfd, F, 16, 1, hd.r_off, hd.N, 0, F, ntaps=1)
-        st.dfeat = torch.zeros((F // 8, Balloc, 8), dtype=eng.tdtype, device=eng.dev)
+        st.dfeat = self.zeros((F // 8, Balloc, 8), eng.tdtype)
 
         def dgrad():
             L.stencil_gemm(_vp(hd.dZ), hd.N, None, 0, _vp(hd.Wfd), 1, None, _vp(st.dfeat), F, 0, None, 0, 0,
@@ -976,11 +996,11 @@ class _Plan:
                 ext = 16 if (self.umma_heads and nd.router is not None and eng.dynamic
                              and bool(eng.net.hypers.dyn_k_cpt)) else 0
                 st.Fext = st.F + ext
-                sc.feat = torch.zeros((st.Fext // 8, Balloc, 8), dtype=eng.tdtype, device=eng.dev)
+                sc.feat = self.zeros((st.Fext // 8, Balloc, 8), eng.tdtype)
                 st.feat = sc.feat
                 if ext:
                     self.kplanes.append(sc.feat[st.F // 8, :, 0])
-            sc.Wf = torch.zeros((9, (K0 + K1) // 8, N, 8), dtype=eng.tdtype, device=eng.dev)
+            sc.Wf = self.zeros((9, (K0 + K1) // 8, N, 8), eng.tdtype)
             sc.ss = self.f32(2, N)
             sc.mr = self.f32(2, N)
             sc.bn = mbn.comps[k]
@@ -999,7 +1019,7 @@ class _Plan:
             if use_stats:
                 # train-mode BN statistics ride on the conv launch (last CTA finalises): no bn_finalize
                 bn = sc.bn
-                sc.acc = torch.zeros(2 * N + 1, dtype=torch.float64, device=eng.dev)
+                sc.acc = self.zeros(2 * N + 1, torch.float64)
                 sc.bnf = _host_struct(_BN_FUSE, acc=_vp(sc.acc), gamma=eng.tptr(bn.params.γ), beta=eng.tptr(bn.params.β),
                                       m_avg=eng.tptr(bn.params.m_avg), v_avg=eng.tptr(bn.params.v_avg),
                                       ss=_vp(sc.ss), mr=_vp(sc.mr), count=float(B * geo.H * geo.W),
@@ -1053,7 +1073,7 @@ class _Plan:
         if getattr(sc, 'sums', None) is None:
             sc.sums = self.f32(2, sc.N)
             if getattr(sc, 'acc', None) is None:
-                sc.acc = torch.zeros(2 * sc.N + 1, dtype=torch.float64, device=eng.dev)
+                sc.acc = self.zeros(2 * sc.N + 1, torch.float64)
             bn = sc.bn
             sc.bnb = _host_struct(_BN_BWD_FUSE, acc=_vp(sc.acc), sums=_vp(sc.sums),
                                   dgamma=eng.gptr(bn.params.γ), dbeta=eng.gptr(bn.params.β))
@@ -1076,7 +1096,7 @@ class _Plan:
         elif heads or nd.router is not None:
             if len(heads) > 1:
                 raise NotImplementedError('engine: more than one LogReg under one node')
-            st.dfeat = torch.zeros_like(st.feat)
+            st.dfeat = self.zeros(tuple(st.feat.shape), st.feat.dtype)
             pairs = []
             if heads:
                 r = self.reg[heads[0]]
@@ -1142,7 +1162,7 @@ class _Plan:
             N1 = sc.K1
             if N0 + N1 == 0:
                 continue
-            sc.Wd = torch.zeros((9, sc.N // 8, N0 + N1, 8), dtype=eng.tdtype, device=eng.dev)
+            sc.Wd = self.zeros((9, sc.N // 8, N0 + N1, 8), eng.tdtype)
             if N0:
                 self._pack(sc.wh, sc.Wd, sc.K0real, sc.N, 1, 0, sc.N, 0, N0 + N1)
             if N1:
@@ -1258,7 +1278,7 @@ class _Plan:
         self.p_tr = self.f32(nn, B)
         self.p_ev = self.f32(nn, B)
         n_sw = max(len(eng.switches), 1)
-        self.dec = torch.zeros((n_sw, B), dtype=torch.int32, device=dev)
+        self.dec = self.zeros((n_sw, B), torch.int32)
         tp = lambda ts: torch.tensor([t.data_ptr() for t in ts] or [0], dtype=torch.int64, device=dev)
         self.R_tab = tp([self.rtr[nd.idx].R for nd in eng.switches])
         self.cerr_tab = tp([self.reg[nd.idx].c_err for nd in eng.regs])

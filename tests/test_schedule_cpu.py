@@ -96,14 +96,19 @@ class Recorder:
 def _tensor_index(*roots):
     """all torch tensors reachable from the given objects -> lookup(pointer) -> containing tensor"""
     seen, found = set(), {}
+    for r in roots:                              # the zero-filled arenas a plan's buffers are carved from are not buffers
+        for a in getattr(r, 'arenas', []):
+            seen.add(id(a))
 
     def walk(o, depth=0):
         if id(o) in seen or depth > 6:
             return
         seen.add(id(o))
         if isinstance(o, torch.Tensor):
-            if o.numel():
-                found[o.data_ptr()] = o
+            if o.numel():                     # (an arena and its first view share a pointer: the view is the buffer)
+                old = found.get(o.data_ptr())
+                if old is None or o.numel() * o.element_size() < old.numel() * old.element_size():
+                    found[o.data_ptr()] = o
         elif isinstance(o, dict):
             for v in o.values():
                 walk(v, depth + 1)
