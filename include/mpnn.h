@@ -292,6 +292,21 @@ int mpnn_gather_images(const void* src, int Bs, int Ps, const int* idx, const in
 int mpnn_scatter_add_images(const void* src, int Bs, int Ps, const int* idx, const int* count,
                             void* dst, int Bd, int Pd, int C, int H, int W, int G, int dtype, void* stream);
 
+/* ---- compacted ev-mode evaluation (statistics of scripts/lib/desc.py:10-36, train-nets:111-130) ----
+ * One switch of the tree on the n examples present at it: dec[b] = first-max argmax of R[b][0..ns)
+ * (R row-major, row stride ldr); for every sink s the ascending list of the rows of this compact batch
+ * that chose it (pos[s][.]), their original example ids (orig[s][.] = parent_orig[pos] or pos itself when
+ * parent_orig is NULL) and count[s].  pos / orig have row stride cap >= n.  dec may be NULL. */
+int mpnn_route_compact(const float* R, int ldr, int ns, int n, const int* parent_orig, int cap,
+                       int* dec, int* pos, int* orig, int* count, void* stream);
+/* Statistics of one classifier over the examples routed to it: Z row-major logits of the parent's compact
+ * batch (row stride ldz), y dense one-hot labels [B][n_cls] indexed by ORIGINAL example id; the examples are
+ * rows pos[j] / ids orig[j], j < *count (count NULL -> j < n; pos / orig NULL -> identity).
+ *   out[0] += #correct, out[1] += #incorrect, out[2 + c] += sum cor*y[c], out[2 + n_cls + c] += sum (1-cor)*y[c]
+ * (p_cor, p_inc, p_cor_by_cls, p_inc_by_cls of train-nets:121-124 summed over the batch; out is double). */
+int mpnn_leaf_stats(const float* Z, int ldz, int n_cls, const float* y, const int* pos, const int* orig,
+                    const int* count, int n, double* out, void* stream);
+
 /* ---- optimiser: minimize_expectation + MomentumOptimizer (lib/net_types.py:24-37) */
 /* For segment s covering theta[seg_start[s] : seg_start[s+1]):
  *   g = grad*hyp[GSCALE] + 2*seg_l2[s]*coef*theta,  coef = node mean p_tr (1 if node_stats==NULL)

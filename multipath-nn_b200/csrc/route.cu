@@ -308,3 +308,104 @@ extern "C" int mpnn_scatter_add_images(const void* src, int Bs, int Ps, const in
                                        void* dst, int Bd, int Pd, int C, int H, int W, int G, int dtype, void* stream) {
     return move_images<true>(src, Bs, Ps, idx, count, dst, Bd, Pd, C, H, W, G, dtype, stream);
 }
+
+// ------------------------------------------------ per-switch compaction (compacted ev-mode evaluator)
+// The reference evaluates every node on the whole batch and weights statistics with the one-hot p_ev
+// (net_types.py:127-131, train-nets:117-130); in 'ev' mode an example only needs the nodes on its own
+// path.  For one switch: dec[b] = first-max argmax of R[b][0..ns) over the n examples present at the
+// switch, and for every sink the ascending list of positions (rows of the parent's compact batch) and
+// of original example ids that chose it -- ballot + prefix scan, order preserving, one CTA.
+__global__ void __launch_bounds__(1024)
+route_compact_kernel(const float* __restrict__ R, int ldr, int ns, int n, const int* __restrict__ parent_orig,
+                     int cap, int* __restrict__ dec, int* __restrict__ pos, int* __restrict__ orig,
+                     int* __restrict__ count) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __shared__ int wcount[8][32];
+    __shared__ int base_s[8];
+    if (threadIdx.x < 8) base_s[threadIdx.x] = 0;
+    __syncthreads();
+    for (int b0 = 0; b0 < n; b0 += 1024) {
+        const int b = b0 + threadIdx.x;
+        int d = -1;
+        if (b < n) {
+            float best = R[(size_t)b * ldr];
+            d = 0;
+            for (int i = 1; i < ns; ++i) {
+                const float v = R[(size_t)b * ldr + i];
+                if (v > best) { best = v; d = i; }           // strict: the first maximum wins (tf.argmax)
+            }
+            if (dec) dec[b] = d;
+        }
+        unsigned m[8];
+        for (int s = 0; s < ns; ++s) {
+            m[s] = __ballot_sync(0xffffffffu, d == s);
+            if (lane == 0) wcount[s][warp] = __popc(m[s]);
+        }
+        __syncthreads();
+        if (d >= 0) {
+            int wbase = 0;
+            for (int w = 0; w < warp; ++w) wbase += wcount[d][w];
+            const int at = base_s[d] + wbase + __popc(m[d] & ((1u << lane) - 1u));
+            pos[(size_t)d * cap + at] = b;
+            orig[(size_t)d * cap + at] = parent_orig ? parent_orig[b] : b;
+        }
+        __syncthreads();
+        if (threadIdx.x < ns) {
+            int tot = 0;
+            for (int w = 0; w < 32; ++w) tot += wcount[threadIdx.x][w];
+            base_s[threadIdx.x] += tot;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x < ns) count[threadIdx.x] = base_s[threadIdx.x];
+}
+
+extern "C" int mpnn_route_compact(const float* R, int ldr, int ns, int n, const int* parent_orig, int cap,
+                                  int* dec, int* pos, int* orig, int* count, void* stream) {
+    MPNN_REQUIRE(R && pos && orig && count && ns >= 1 && ns <= 8 && n >= 0 && cap >= n && ldr >= ns,
+                 "route_compact: ns=%d n=%d cap=%d ldr=%d", ns, n, cap, ldr);
+    route_compact_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(R, ldr, ns, n, parent_orig, cap, dec, pos, orig, count);
+    return mpnn_check_launch("route_compact");
+}
+
+// Leaf statistics of the examples routed to one classifier (train-nets:117-130 with p_ev one-hot):
+//   out[0] += #correct, out[1] += #incorrect, out[2 + c] += sum cor * y[c], out[2 + n_cls + c] += sum (1 - cor) * y[c]
+// cor = [first argmax Z == first argmax y] (layer_types.py:259-260,271-272; softmax + eps-smoothing are monotone).
+__global__ void __launch_bounds__(256)
+leaf_stats_kernel(const float* __restrict__ Z, int ldz, int n_cls, const float* __restrict__ y,
+                  const int* __restrict__ pos, const int* __restrict__ orig, const int* __restrict__ count, int n_fixed,
+                  double* __restrict__ out) {
+    const int n = count ? *count : n_fixed;
+    extern __shared__ float sacc[];                       // [2 + 2 * n_cls]
+    const int na = 2 + 2 * n_cls;
+    for (int i = threadIdx.x; i < na; i += blockDim.x) sacc[i] = 0.f;
+    __syncthreads();
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+        const int row = pos ? pos[j] : j, o = orig ? orig[j] : j;
+        const float* z = Z + (size_t)row * ldz;
+        const float* yy = y + (size_t)o * n_cls;
+        int az = 0, ay = 0;
+        float bz = z[0], by = yy[0];
+        for (int c = 1; c < n_cls; ++c) {
+            if (z[c] > bz) { bz = z[c]; az = c; }
+            if (yy[c] > by) { by = yy[c]; ay = c; }
+        }
+        const bool cor = az == ay;
+        atomicAdd(sacc + (cor ? 0 : 1), 1.f);
+        for (int c = 0; c < n_cls; ++c)
+            if (yy[c] != 0.f) atomicAdd(sacc + 2 + (cor ? 0 : n_cls) + c, yy[c]);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < na; i += blockDim.x)
+        if (sacc[i] != 0.f) atomicAdd(out + i, (double)sacc[i]);
+}
+
+extern "C" int mpnn_leaf_stats(const float* Z, int ldz, int n_cls, const float* y, const int* pos, const int* orig,
+                               const int* count, int n, double* out, void* stream) {
+    MPNN_REQUIRE(Z && y && out && n_cls >= 1 && n_cls <= 1024 && ldz >= n_cls && n >= 0, "leaf_stats: args");
+    int grid = ceil_div(n > 0 ? n : 1, 256);
+    if (grid > 148) grid = 148;
+    leaf_stats_kernel<<<grid, 256, (2 + 2 * n_cls) * sizeof(float), (cudaStream_t)stream>>>(
+        Z, ldz, n_cls, y, pos, orig, count, n, out);
+    return mpnn_check_launch("leaf_stats");
+}
