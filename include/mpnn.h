@@ -318,6 +318,22 @@ int mpnn_talr_momentum_step(float* theta, const float* grad, float* accum, int n
                             const float* seg_l2, int n_seg, const float* node_stats, int talr,
                             const float* hyp /* LR, MU, GSCALE */, void* stream);
 
+/* ---- data-parallel gradient all-reduce (NCCL over NVLink / NVSwitch) ------------------------------
+ * The reference is single-process (scripts/train-nets:159-164).  Data parallelism shards the batch over one
+ * process per GPU; the one collective of a step sums the flat fp32 buffer [gradients | per-node TALR moments]
+ * in place (the 1/world factor is applied by mpnn_talr_momentum_step through hyp[GSCALE]).
+ *   comm      an ncclComm_t (as void*): either one the host application already owns, or one made here:
+ *             rank 0 calls mpnn_comm_unique_id, ships the 128 bytes to the other ranks, then EVERY rank calls
+ *             mpnn_comm_init_rank (collective; binds to the current CUDA device).
+ * NCCL is resolved at run time from the copy already loaded in the process (else libnccl.so.2 /
+ * $MPNN_NCCL_LIB); mpnn_nccl_version() returns 0 when none is available.  The launch is asynchronous on
+ * `stream` and may be captured into a CUDA graph. */
+int mpnn_nccl_version(void);
+int mpnn_comm_unique_id(void* id128 /* host, 128 bytes */);
+int mpnn_comm_init_rank(void** comm /* host, out */, int world, int rank, const void* id128 /* host */);
+int mpnn_comm_destroy(void* comm);
+int mpnn_allreduce_flat(void* comm, float* buf, long long n, void* stream);
+
 /* ---- tcgen05 bring-up probe (tests only) -------------------------------- */
 /* D[128][N] = A[128][K] * B[N][K]^T through one CTA of tcgen05.mma; all
  * operands in the interleaved (no-swizzle) core-matrix layout. */

@@ -9,10 +9,7 @@ CSRC = os.path.join(HERE, 'csrc')
 OUT = os.path.join(HERE, 'lib', 'libmpnn_sm100.so')
 OBJ = os.path.join(HERE, 'build')
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
-FLAGS = ['-O3', '-std=c++17', '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo',
-         '-Xcompiler', '-fPIC', '--use_fast_math=false'] if False else [
-         '-O3', '-std=c++17', '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo',
-         '-Xcompiler', '-fPIC']
+FLAGS = ['-O3', '-std=c++17', '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-Xcompiler', '-fPIC']
 
 
 def _stale(src, obj, deps):
@@ -48,7 +45,7 @@ def build(verbose=False, force=False):
                 raise RuntimeError('nvcc failed on %s' % name)
     objs = [os.path.join(OBJ, s[:-3] + '.o') for s in srcs]
     if jobs or not os.path.exists(OUT):
-        cmd = [NVCC, '-shared', '-o', OUT] + objs + ['-lcudart']
+        cmd = [NVCC, '-shared', '-o', OUT] + objs + ['-lcudart', '-ldl']
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             sys.stderr.write(r.stdout + r.stderr)

@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'libmpnn_sm100.so')
 HEADER = os.path.normpath(os.path.join(HERE, '..', '..', 'include', 'mpnn.h'))
 
-_SCALARS = {'int': ctypes.c_int, 'float': ctypes.c_float, 'double': ctypes.c_double}
+_SCALARS = {'int': ctypes.c_int, 'float': ctypes.c_float, 'double': ctypes.c_double, 'long': ctypes.c_longlong}
 
 
 def parse_header(path=HEADER):
@@ -59,7 +59,7 @@ class _Lib:
             name = 'mpnn_' + name
         fn = getattr(self.dll, name)
         restype = self.protos[name][0]
-        if restype is not ctypes.c_int or name in ('mpnn_version', 'mpnn_has_umma'):
+        if restype is not ctypes.c_int or name in ('mpnn_version', 'mpnn_has_umma', 'mpnn_nccl_version'):
             return fn
 
         def call(*args):

@@ -73,11 +73,11 @@ class Dataset:
                      torch.from_numpy(np.ascontiguousarray(self.y_tr, dtype=np.float32)).to(device))
         return self
 
-    def augmented_training_batch_gpu(self, n=128, r_shift=4):
+    def augmented_training_batch_gpu(self, n=128, r_shift=4, shard=None):
         """`augmented_training_batch` with the per-example work on the GPU (csrc/augment.cu).  The
         random numbers are drawn on the host in the same order, so a seeded sampler produces the same
         batches either way; returns device tensors (x0 fp32 NHWC, y one-hot) that `net.train.run`
-        accepts as feed values."""
+        accepts as feed values.  shard=(rank, world): this rank's part of the global batch."""
         import ctypes
         import torch
         from lib import _cabi
@@ -89,6 +89,15 @@ class Dataset:
         flip = self.m_sym[np.argmax(self.y_tr[j], 1)] & (rng.random(n) >= 0.5)
         du = rng.integers(-r_shift, r_shift + 1, n)
         dv = rng.integers(-r_shift, r_shift + 1, n)
+        if shard is not None:
+            # data parallel: every rank draws the SAME global batch (same seed) and keeps its contiguous shard,
+            # so the union over the ranks is the batch a single process would have drawn
+            rank, world = shard
+            if n % world:
+                raise ValueError('batch %d does not divide over %d ranks' % (n, world))
+            sl = slice(rank * (n // world), (rank + 1) * (n // world))
+            j, flip, du, dv = j[sl], flip[sl], du[sl], dv[sl]
+            n = n // world
         draws = torch.from_numpy(np.stack([j, flip, du, dv]).astype(np.int32)).to(xd.device)
         h, w, c = self.x0_tr.shape[1:]
         n_cls = self.y_tr.shape[1]

@@ -14,7 +14,7 @@ examples in float64 on the host, divided by the example count -- is unchanged.
 """
 import numpy as np
 
-__all__ = ['state_tensors', 'mean_net_state', 'net_desc', 'render_net_desc']
+__all__ = ['state_tensors', 'mean_net_state', 'mean_net_state_compact', 'net_desc', 'render_net_desc']
 
 _SPLITS = ('stats_tr', 'stats_ts')
 _RULE = '─' * 59
@@ -77,9 +77,39 @@ def layer_desc(layer, stats_tr, stats_ts):
     return node
 
 
-def net_desc(net, dataset, hypers={}, state={}):
-    per_split = [mean_net_state(net, state, batches, hypers)
-                 for batches in (dataset.training_set(), dataset.test_set())]
+def mean_net_state_compact(net, data, hypers, batch=4096):
+    """`mean_net_state` for the p_ev-weighted statistics through the compacted evaluator (lib/compact_eval.py):
+    every example only runs the nodes on its own path, the sums stay on the device and are read once.  In 'ev'
+    mode examples are independent (BatchNorm uses its running moments), so the batch size of the pass is free:
+    the 128-example slices the data set yields are regrouped into batches of `batch`."""
+    ev = net.compact_evaluator(batch)
+    ev.reset()
+    k_cpt = hypers.get(getattr(net, 'k_cpt', None)) if net.hypers.__dict__.get('dyn_k_cpt') else None
+    xs, ys, n = [], [], 0
+
+    def flush():
+        nonlocal xs, ys, n
+        if n:
+            ev.run_batch(np.concatenate(xs), np.concatenate(ys), k_cpt=k_cpt)
+        xs, ys, n = [], [], 0
+    for x0, y in data:
+        if n + len(x0) > batch:
+            flush()
+        xs.append(np.asarray(x0, dtype=np.float32)); ys.append(np.asarray(y, dtype=np.float32)); n += len(x0)
+    flush()
+    return ev.result()
+
+
+def net_desc(net, dataset, hypers={}, state={}, compact=False):
+    """compact=True (dynamically-routed nets): statistics from the compacted evaluator -- exact for acc, moc,
+    p_cor, p_inc and the per-class entries; c_err / p_tr / x_rte, which the reference defines on examples
+    that never reach the node, are omitted (no plotting script reads them)"""
+    if compact and net.dynamic:
+        per_split = [mean_net_state_compact(net, batches, hypers)
+                     for batches in (dataset.training_set(), dataset.test_set())]
+    else:
+        per_split = [mean_net_state(net, state, batches, hypers)
+                     for batches in (dataset.training_set(), dataset.test_set())]
     out = {'type': type(net).__name__}
     for split, stats in zip(_SPLITS, per_split):
         out[split] = _owned_by(net, stats)

@@ -117,6 +117,9 @@ class Engine:
         self.dynamic = bool(net.dynamic)
         self.critic = type(net).__name__ == 'CriticNet'
         self.stream = None
+        self.comm = None
+        self.graph_collective = os.environ.get('MPNN_DIST_GRAPH', '1') != '0'
+        self.overlap_allreduce = os.environ.get('MPNN_DIST_OVERLAP', '1') != '0'
         self._snapshot = False
         self._analyse()
         self._alloc_params()
@@ -242,9 +245,12 @@ class Engine:
         n_nodes = len(self.nodes)
         dev = self.dev
         self.theta = torch.zeros(off_t, dtype=torch.float32, device=dev)
-        # gradient buffer carries the per-node p_tr moments in its tail so that
-        # one all-reduce covers both (data-parallel TALR stays replica-consistent)
-        self.grad = torch.zeros(off_t + 2 * n_nodes, dtype=torch.float32, device=dev)
+        # gradient buffer = [per-node p_tr moments (2 per node, padded to 16 bytes) | gradients]: the moments
+        # travel with the gradients through the all-reduce (data-parallel TALR stays replica-consistent) and
+        # sit in FRONT so that the two buckets of the overlapped all-reduce are contiguous: [moments | shallow
+        # stages] and [deep stages] (their gradients are complete first, see _Plan._build)
+        self.g0 = _ru(2 * n_nodes, 4)
+        self.grad = torch.zeros(self.g0 + off_t, dtype=torch.float32, device=dev)
         self.accum = torch.zeros(off_t, dtype=torch.float32, device=dev)
         self.state = torch.zeros(max(off_s, 1), dtype=torch.float32, device=dev)
         self.seg_start = torch.tensor(seg_start, dtype=torch.int32, device=dev)
@@ -252,6 +258,7 @@ class Engine:
         self.seg_mult = torch.tensor(seg_mult, dtype=torch.float32, device=dev)
         self.seg_l2 = torch.tensor(seg_l2, dtype=torch.float32, device=dev)
         self.n_seg = len(seg_node)
+        self.seg_node_list = list(seg_node)
         for p in self.tparams + self.sparams:
             self.push_param(p)
 
@@ -306,18 +313,19 @@ class Engine:
 
     def gptr(self, p):
         assert p._bind[1] == 'theta'
-        return ctypes.c_void_p(self.grad.data_ptr() + 4 * p._bind[2])
+        return ctypes.c_void_p(self.grad.data_ptr() + 4 * (self.g0 + p._bind[2]))
 
     def grads_numpy(self, with_l2=False):
         """{Param: gradient ndarray} of the last backward (before TALR).  The L2
         (c_mod) term is applied inside the optimiser kernel; with_l2 adds it here
         the same way (2 k_l2 mean(p_tr) theta) so the result is d c_tot / d theta."""
-        g = self.grad.cpu().numpy().astype(np.float64)
+        gall = self.grad.cpu().numpy().astype(np.float64)
+        g = gall[self.g0:]
         out = {}
         if with_l2:
             th = self.theta.cpu().numpy().astype(np.float64)
             l2 = self.seg_l2.cpu().numpy(); node = self.seg_node.cpu().numpy()
-            stats = g[self.n_theta:].reshape(-1, 2)
+            stats = gall[:2 * len(self.nodes)].reshape(-1, 2)
         for s, p in enumerate(self.tparams):
             sl = slice(p._bind[2], p._bind[2] + p.value.size)
             v = g[sl].copy()
@@ -432,6 +440,7 @@ class Engine:
         main_p = self.stream = ctypes.c_void_p(main.cuda_stream)
         if not self.multistream:
             for op in ops:
+                self.stream = main_p
                 op()
             return
         # Lanes (one CUDA stream each).  0: input packing, routing, optimiser.  1: classifier and
@@ -457,6 +466,12 @@ class Engine:
             for d in getattr(op, 'deps', ()):
                 if getattr(d, 'lane', 0) != lane and getattr(d, '_ev', None) is not None:
                     st.wait_event(d._ev)
+            if getattr(op, 'wait_all', False):      # ordered after everything issued so far, on every lane
+                for other in [0] + used:
+                    if other != lane:
+                        ev = torch.cuda.Event()
+                        ev.record(main if other == 0 else self._lanes[other])
+                        st.wait_event(ev)
             self.stream = main_p if lane == 0 else ctypes.c_void_p(st.cuda_stream)
             op()
             if getattr(op, 'signal', False):
@@ -480,20 +495,56 @@ class Engine:
             g = self._graphs.get(id(plan))
             if g is None:
                 g = self._capture(plan)
-            g[0].replay()                        # pack + forward + backward
-            if self.dist:
-                self._allreduce()                # the one collective of the step, between the two graphs
-            g[1].replay()                        # TALR + momentum
+            g[0].replay()                        # pack + forward + backward (+ all-reduce + optimiser when captured)
+            if g[1] is not None:
+                if self.dist:
+                    self._allreduce(0, plan.ar_split)   # MPNN_DIST_GRAPH=0: issued eagerly between two graphs
+                g[1].replay()                    # TALR + momentum
             return
         self._compute_ops(plan)
         if update:
             if self.dist:
-                self._allreduce()
+                self._allreduce(0, plan.ar_split)
             self._run(plan.opt_ops)
 
-    def _allreduce(self):
-        from lib.parallel import allreduce_flat_
-        allreduce_flat_(self.grad)               # [gradients | TALR moments]
+    def _init_comm(self):
+        """Our own NCCL communicator (C ABI: mpnn_comm_*): rank 0 makes the unique id, the existing process
+        group ships its 128 bytes, every rank joins.  Owning the communicator keeps the all-reduce on the
+        step's stream and lets it be captured into the step's CUDA graph."""
+        import torch.distributed as dist
+        rank = dist.get_rank()
+        uid = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            self.L.comm_unique_id(ctypes.c_void_p(uid.data_ptr()))
+        t = uid.to(self.dev) if dist.get_backend() == 'nccl' else uid
+        dist.broadcast(t, 0)
+        uid = t.cpu().contiguous()
+        comm = ctypes.c_void_p()
+        with torch.cuda.device(self.dev):
+            self.L.comm_init_rank(ctypes.byref(comm), self.world, rank, ctypes.c_void_p(uid.data_ptr()))
+        self.comm = comm
+
+    def _allreduce(self, lo=0, hi=None, stream=None):
+        """the collective of a step: sum of [TALR moments | gradients] over the replicas, in place.  With the
+        overlapped schedule it is issued as two buckets: grad[split:] (the deep stages, complete first) under
+        the rest of the backward pass, grad[:split] at its end."""
+        if self.comm is None:
+            self._init_comm()
+        hi = self.grad.numel() if hi is None else hi
+        if hi <= lo:
+            return
+        st = stream if stream is not None else ctypes.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)
+        self.L.allreduce_flat(self.comm, ctypes.c_void_p(self.grad.data_ptr() + 4 * lo), hi - lo, st)
+
+    def average_state(self):
+        """BatchNorm running moments are per-replica (each replica normalises with its own shard's moments,
+        SURVEY F3): average them over the replicas before they are serialised or used for statistics"""
+        if self.dist and self.world > 1:
+            if self.comm is None:
+                self._init_comm()
+            st = ctypes.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)
+            self.L.allreduce_flat(self.comm, _vp(self.state), self.state.numel(), st)
+            self.state.mul_(1.0 / self.world)
 
     def _compute_ops(self, plan):
         self._run(plan.pack_ops)
@@ -502,9 +553,10 @@ class Engine:
         self._run(plan.bwd_ops)
 
     def _capture(self, plan):
-        """Two CUDA graphs per plan (compute | optimiser).  The NCCL all-reduce is issued eagerly
-        between them: it is a single launch, and keeping it out of stream capture avoids any
-        interaction between capture and the process group's watchdog."""
+        """One CUDA graph per plan holds the whole step: pack + forward + backward, the gradient all-reduce
+        (data parallel; captured through our own NCCL communicator) and the optimiser.  MPNN_DIST_GRAPH=0
+        keeps the collective out of capture: two graphs (compute | optimiser) with the all-reduce issued
+        eagerly in between."""
         s = torch.cuda.Stream(self.dev)
         s.wait_stream(torch.cuda.current_stream(self.dev))
         keep = (self.theta.clone(), self.accum.clone(), self.state.clone())
@@ -516,10 +568,26 @@ class Engine:
         self.theta.copy_(keep[0]); self.accum.copy_(keep[1]); self.state.copy_(keep[2])
         g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
         before = self.L.launches
-        with torch.cuda.graph(g1):
-            self._compute_ops(plan)
-        with torch.cuda.graph(g2):
-            self._run(plan.opt_ops)
+        one_graph = (not self.dist) or self.graph_collective
+        if self.dist and self.comm is None:
+            self._init_comm()
+        if self.dist:
+            with torch.cuda.stream(s):           # the communicator's first collective (channel setup) stays out of capture
+                self._allreduce()
+            torch.cuda.synchronize(self.dev)
+        if one_graph:
+            # the whole step is ONE graph: with our own communicator the NCCL launch is captured like any kernel
+            with torch.cuda.graph(g1):
+                self._compute_ops(plan)
+                if self.dist:
+                    self._allreduce(0, plan.ar_split)
+                self._run(plan.opt_ops)
+            g2 = None
+        else:
+            with torch.cuda.graph(g1):
+                self._compute_ops(plan)
+            with torch.cuda.graph(g2):
+                self._run(plan.opt_ops)
         plan.graph_launches = self.L.launches - before
         self._graphs[id(plan)] = (g1, g2)
         return self._graphs[id(plan)]
@@ -768,9 +836,8 @@ class _Plan:
                 1 if eng.critic else 0, float(getattr(hy, 'k_dec', 0.0)), float(getattr(hy, 'k_cre', 0.0)),
                 1 if getattr(hy, 'optimistic', False) else 0, 1 if getattr(hy, 'use_cls_err', False) else 0,
                 _vp(self.dR_tab), _vp(self.route_scratch), _vp(self.c_data), S()))
-            n_theta = eng.n_theta
             moments = lambda: L.node_moments(
-                _vp(self.p_tr), len(eng.nodes), B, ctypes.c_void_p(eng.grad.data_ptr() + 4 * n_theta), S())
+                _vp(self.p_tr), len(eng.nodes), B, _vp(eng.grad), S())
             moments.lane = 8                     # only the optimiser reads the TALR moments: off the chain
             self.bwd_ops.append(moments)
             if eng.switches:
@@ -781,6 +848,31 @@ class _Plan:
                 self.bwd_ops.append(lambda: L.router_tail_bwd_batched(_vp(tabb), len(rows), B, 16, S()))
         main_ops = [op for op in self.bwd_ops if getattr(op, 'lane', 0) == 0]
         self.bwd_head_dep = main_ops[-1] if main_ops else None             # routing gradients are complete
+        # data parallel: the gradients of the DEEP stages are complete long before the backward pass ends (it
+        # runs deepest-first) and they are most of the parameters (stages 4-7: 80 % of the conv weights).  Their
+        # all-reduce goes out on its own lane as soon as every launch that writes them has been issued, and
+        # overlaps the backward pass of the shallow stages; the rest [moments | shallow stages] follows the
+        # backward list.  Split = first parameter of the conv stage nearest to half of the parameters.
+        self.ar_split = None                     # None: one all-reduce over the whole buffer
+        split_node = None
+        if eng.dist and eng.overlap_allreduce:
+            offs = {}
+            for sidx, p in enumerate(eng.tparams):
+                offs.setdefault(eng.seg_node_list[sidx], p._bind[2])          # first parameter of each node
+            best = None
+            for cand in eng.nodes:
+                if cand.kind != 'rcm' or cand.idx not in offs:
+                    continue
+                # a classifier's gradients are written by its PARENT's head launches: every node of the deep
+                # bucket must have its parent in the bucket too (except the split node itself)
+                if any(o.idx > cand.idx and o.parent is not None and o.parent < cand.idx for o in eng.nodes):
+                    continue
+                frac = offs[cand.idx] / max(eng.n_theta, 1)                   # share of the parameters in FRONT of it
+                if 0.1 <= frac <= 0.6 and (best is None or abs(frac - 0.3) < abs(best[0] - 0.3)):
+                    best = (frac, cand)
+            if best is not None:
+                split_node = best[1]
+                self.ar_split = eng.g0 + offs[split_node.idx]
         for nd in reversed(eng.nodes):
             if nd.kind == 'reg':
                 r = self.reg[nd.idx]
@@ -809,13 +901,19 @@ class _Plan:
                 self._build_router_bwd(nd, Balloc, dyn_k)
             if nd.kind == 'rcm':
                 self._build_rcm_bwd(nd, Balloc)
+            if split_node is not None and nd.idx == split_node.idx:
+                def ar_deep():
+                    eng._allreduce(self.ar_split, None, stream=S())
+                ar_deep.kind, ar_deep.lane, ar_deep.wait_all = 'allreduce', 20, True
+                self.bwd_ops.append(ar_deep)
         early = [op for op in self.bwd_ops if getattr(op, 'early', False)]
         self.bwd_ops = early + [op for op in self.bwd_ops if not getattr(op, 'early', False)]
         # ---------------- optimiser ---------------- #
         talr = 1 if (eng.dynamic and bool(net.hypers.talr)) else 0
-        stats_ptr = (lambda: ctypes.c_void_p(eng.grad.data_ptr() + 4 * eng.n_theta)) if eng.dynamic else (lambda: None)
+        stats_ptr = (lambda: _vp(eng.grad)) if eng.dynamic else (lambda: None)
         self.opt_ops.append(lambda: L.talr_momentum_step(
-            _vp(eng.theta), _vp(eng.grad), _vp(eng.accum), eng.n_theta, _vp(eng.seg_start), _vp(eng.seg_node),
+            _vp(eng.theta), ctypes.c_void_p(eng.grad.data_ptr() + 4 * eng.g0), _vp(eng.accum), eng.n_theta,
+            _vp(eng.seg_start), _vp(eng.seg_node),
             _vp(eng.seg_mult), _vp(eng.seg_l2), eng.n_seg, stats_ptr(), talr, _vp(eng.hyp), S()))
         self._finish_pack()
 

@@ -119,6 +119,14 @@ class Net:
                 self._pending_momentum = None
         return self._engine
 
+    def compact_evaluator(self, batch=4096):
+        """compacted 'ev'-mode evaluator of this net (lib/compact_eval.py), cached per batch capacity"""
+        cache = self.__dict__.setdefault('_compact_eval', {})
+        if batch not in cache:
+            from lib.compact_eval import CompactEvaluator
+            cache[batch] = CompactEvaluator(self._get_engine(), batch)
+        return cache[batch]
+
     def eval_stats(self, feed_dict):
         """Per-example `state_tensors` (train-nets:111-130) for one batch, as a
         dict {(net|layer, name): ndarray}; `mode` defaults to 'ev'."""

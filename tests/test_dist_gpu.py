@@ -27,7 +27,7 @@ from util import batch, randomize_routers, record_of, tiny_net  # noqa: E402
 pytestmark = pytest.mark.gpu
 
 
-def _worker(rank, world, port, rec, x0, y, q):
+def _worker(rank, world, port, rec, x0, y, q, graphs):
     os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR='127.0.0.1',
                       MASTER_PORT=str(port))
     for p in (ROOT, os.path.join(ROOT, 'multipath-nn_b200'), os.path.join(ROOT, 'tests')):
@@ -36,7 +36,7 @@ def _worker(rank, world, port, rec, x0, y, q):
     from lib import parallel, serdes
     torch.cuda.set_device(rank)
     r, w = parallel.init_from_env('nccl', device=torch.device('cuda', rank))
-    net = serdes.decode_net(rec).configure(precision='fp32', dist=True)
+    net = serdes.decode_net(rec).configure(precision='fp32', dist=True, graphs=graphs)
     xs, ys = parallel.shard(x0, rank, world), parallel.shard(y, rank, world)
     eng = net._get_engine()
     snaps = []
@@ -50,14 +50,15 @@ def _worker(rank, world, port, rec, x0, y, q):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs two GPUs')
-def test_two_rank_nccl_replicas_are_bit_identical_and_match_the_oracle():
+@pytest.mark.parametrize('graphs', [False, True])        # eager launches | the whole step (all-reduce included) as one CUDA graph
+def test_two_rank_nccl_replicas_are_bit_identical_and_match_the_oracle(graphs):
     net = randomize_routers(tiny_net('ac', k_cpt=4e-9))
     rec = record_of(net)
     x0, y = batch(32, seed=4)
     ctx = mp.get_context('spawn')
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, rec, x0, y, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, rec, x0, y, q, graphs)) for r in range(2)]
     for p in procs:
         p.start()
     res = sorted([q.get(timeout=600) for _ in procs], key=lambda t: t[0])

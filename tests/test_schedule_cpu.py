@@ -162,6 +162,8 @@ def _check(eng, plan):
             lane = getattr(op, 'lane', 0)
             if lane in last_in_lane:
                 preds.append(last_in_lane[lane])
+            if getattr(op, 'wait_all', False):         # Engine._run orders it after everything issued so far
+                preds.extend(range(j))
             for i in preds:
                 assert i < j, 'dependency on a later op'
                 before[j] |= before[i] | {i}
