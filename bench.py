@@ -305,7 +305,7 @@ class Run:
         value = self.world * self.B * steps / (ms * 1e-3)
         return {
             'config': self.config, 'workload': self.cfg['what'], 'batch_per_gpu': self.B,
-            'dtype': 'bf16' if self.eng.dtype == 1 else 'f32',
+            'dtype': 'bf16' if self.eng.dtype == 1 else ('f32 (bf16x3 on tcgen05)' if self.eng.split else 'f32'),
             'conv_impl': 'tcgen05' if self.eng.impl == 1 else 'simt', 'value': value, 'unit': 'images/s',
             'ms_per_step': ms / steps, 'e2e': self.world * self.B * steps / e2e_s, 'steps': steps,
             'launches_per_step': launches // max(steps, 1), 'train_mflop_per_img': self.flop / 1e6,
@@ -318,7 +318,8 @@ def per_launch_profile(run):
     """eager replay of the step's launch list on ONE stream, a CUDA event pair around every launch (3 passes, the
     last one kept).  Returns [(op, ms)] with op.kind / op.desc / op.flops / op.nbytes (lib/engine.py::_tag)."""
     eng, plan, L = run.eng, run.plan, run.eng.L
-    ops = plan.pack_ops + plan.fwd_ops + plan.bwd_ops + plan.opt_ops
+    # (collectives are left out: this replay runs on rank 0 alone)
+    ops = [op for op in plan.pack_ops + plan.fwd_ops + plan.bwd_ops + plan.opt_ops if getattr(op, 'kind', '') != 'allreduce']
     called, saved = [], {}
     for name in L.protos:                                   # untagged launches are labelled by their C-ABI entry
         short = name[5:]
@@ -411,6 +412,8 @@ def main():
     args.warmup = max(args.warmup, 3)
 
     import torch.distributed as dist
+    if os.environ.get('NCCL_DEBUG', 'VERSION').upper() == 'VERSION':
+        os.environ['NCCL_DEBUG'] = 'WARN'          # NCCL's version banner goes to stdout, which carries the ONE JSON line
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     if world > 1:
@@ -448,7 +451,7 @@ def main():
                 for b in (128, 4096):
                     if (c, b) != (args.config, B) and (c, b, args.precision) not in todo:
                         todo.append((c, b, args.precision))
-            todo += [(args.config, 128, 'fp32'), (args.config, 4096, 'fp32')]
+            todo += [(args.config, 128, 'bf16x3'), (args.config, 4096, 'bf16x3'), (args.config, 128, 'fp32'), (args.config, 4096, 'fp32')]
         for c, b, prec in todo:
             r = Run(c, b, prec, dev, rank, world)
             sweep.append(r.summary(30 if b > 128 else 100, 3, flush, pk))

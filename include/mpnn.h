@@ -54,6 +54,8 @@ int mpnn_pack_weights(const float* w, int ntaps, int I, int O, int mode,
                       int k_off, int Ktot, int n_off, int Ntot,
                       void* packed, int dtype, void* stream);
 
+/* mode | 4: the RESIDUAL of the bf16 rounding, w - bf16(w), is packed instead of w ("lo" part of the bf16x3
+ * precision mode, see mpnn_split_planes). */
 /* the same for a whole table of tensors in one launch (device array of descriptors);
  * additionally mode 2: ((float*)packed)[n_off + o] = w[o], o < O (fp32 vector copy) */
 typedef struct {
@@ -62,6 +64,14 @@ typedef struct {
 } mpnn_pack_desc;
 int mpnn_pack_weights_batched(const mpnn_pack_desc* descs, int n, int blocks_per_desc,
                               int dtype, void* stream);
+
+/* fp32 planes -> (hi | lo) bf16 planes with x = hi + lo: src [C/8][P][8] fp32, dst [2*C/8][P][8] bf16, planes
+ * [0, C/8) = bf16(x), planes [C/8, 2*C/8) = bf16(x - bf16(x)).  Operand format of the "bf16x3" precision mode:
+ * a fp32 product is evaluated on the tensor cores as a_hi*b_hi + a_lo*b_hi + a_hi*b_lo (2^-16 relative) with
+ * fp32 accumulation, i.e. mpnn_stencil_gemm with A0 = dst (2C channels), A1 = dst (its first C channels) and
+ * weights packed as [hi; hi; lo] along K.  Carries the reference's fp32 arithmetic (lib/layer_types.py:106-107)
+ * onto tcgen05 within the 1e-3 tolerance. */
+int mpnn_split_planes(const float* src, int C, int P, void* dst, void* stream);
 
 /* ---- training-batch augmentation (scripts/lib/data.py:24-34) -------------- */
 /* x [N][H][W][C], y [N][n_cls] fp32: the training set resident on the device.  Per output example i
@@ -111,6 +121,14 @@ int mpnn_conv_bn_stats(const void* A0, int K0, const void* A1, int K1,
                        const void* Wp, const float* bias, void* out, int N,
                        int B, int H, int W, int G, int P, const mpnn_bn_fuse* bn,
                        int dtype, int impl, void* stream);
+
+/* the same with accumulation into `out` (acc != 0: out += conv, the statistics are those of the stored
+ * values) and an output dtype chosen separately from the operand dtype (0 fp32 planes, 1 bf16 planes); bn may
+ * be NULL (no statistics). */
+int mpnn_conv_acc_bn_stats(const void* A0, int K0, const void* A1, int K1,
+                           const void* Wp, const float* bias, void* out, int N, int acc,
+                           int B, int H, int W, int G, int P, const mpnn_bn_fuse* bn,
+                           int dtype, int out_dtype, int impl, void* stream);
 
 /* weight gradient of the above:
  *   dW0[tap][k][n] += sum_p A0[p+off][k] * Gd[p][n]   (k < K0real, n < Nreal)

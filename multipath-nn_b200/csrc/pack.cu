@@ -85,10 +85,12 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, int ntaps, int 
         int i = (e / O) % I;
         int t = e / (O * I);
         int k, n, tap;
-        if (mode == 0) { k = k_off + i; n = n_off + o; tap = t; }
-        else           { k = k_off + o; n = n_off + i; tap = ntaps - 1 - t; }
+        if ((mode & 3) == 0) { k = k_off + i; n = n_off + o; tap = t; }
+        else                 { k = k_off + o; n = n_off + i; tap = ntaps - 1 - t; }
         size_t dst = (((size_t)tap * (Ktot / 8) + (k >> 3)) * Ntot + n) * 8 + (k & 7);
-        packed[dst] = cvt_from_float<T>(w[e]);
+        float v = w[e];
+        if (mode & 4) v -= __bfloat162float(__float2bfloat16_rn(v));     // residual of the bf16 rounding ("lo" part)
+        packed[dst] = cvt_from_float<T>(v);
     }
 }
 
@@ -109,10 +111,12 @@ __global__ void pack_weights_batched_kernel(const mpnn_pack_desc* __restrict__ d
         int i = (e / d.O) % d.I;
         int t = e / (d.O * d.I);
         int k, n, tap;
-        if (d.mode == 0) { k = d.k_off + i; n = d.n_off + o; tap = t; }
-        else             { k = d.k_off + o; n = d.n_off + i; tap = d.ntaps - 1 - t; }
+        if ((d.mode & 3) == 0) { k = d.k_off + i; n = d.n_off + o; tap = t; }
+        else                   { k = d.k_off + o; n = d.n_off + i; tap = d.ntaps - 1 - t; }
         size_t dst = (((size_t)tap * (d.Ktot / 8) + (k >> 3)) * d.Ntot + n) * 8 + (k & 7);
-        packed[dst] = cvt_from_float<T>(__ldg(d.w + e));
+        float v = __ldg(d.w + e);
+        if (d.mode & 4) v -= __bfloat162float(__float2bfloat16_rn(v));   // residual of the bf16 rounding ("lo" part)
+        packed[dst] = cvt_from_float<T>(v);
     }
 }
 
@@ -128,7 +132,7 @@ extern "C" int mpnn_pack_weights(const float* w, int ntaps, int I, int O, int mo
                                  int k_off, int Ktot, int n_off, int Ntot,
                                  void* packed, int dtype, void* stream) {
     MPNN_REQUIRE(Ktot % 8 == 0, "pack_weights: Ktot %% 8");
-    if (mode == 0) MPNN_REQUIRE(k_off + I <= Ktot && n_off + O <= Ntot, "pack_weights: range");
+    if ((mode & 3) == 0) MPNN_REQUIRE(k_off + I <= Ktot && n_off + O <= Ntot, "pack_weights: range");
     else           MPNN_REQUIRE(k_off + O <= Ktot && n_off + I <= Ntot, "pack_weights: range (dgrad)");
     int total = ntaps * I * O;
     int grid = (total + 255) / 256;
@@ -136,4 +140,34 @@ extern "C" int mpnn_pack_weights(const float* w, int ntaps, int I, int O, int mo
     MPNN_DISPATCH_DTYPE(dtype, (pack_weights_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(
         w, ntaps, I, O, mode, k_off, Ktot, n_off, Ntot, (T*)packed)));
     return mpnn_check_launch("pack_weights");
+}
+
+// --------------------------------------------------------------------------- //
+// fp32 planes -> two bf16 planes sets (hi | lo) with x = hi + lo up to 2^-17 |x|: the operand format of the
+// "bf16x3" precision mode, where a fp32 product a*b is evaluated on the tensor cores as
+// a_hi*b_hi + a_lo*b_hi + a_hi*b_lo (relative error ~2^-16) with fp32 accumulation.
+// src [C/8][P][8] fp32, dst [2*C/8][P][8] bf16: planes [0, C/8) = hi, [C/8, 2*C/8) = lo.
+// --------------------------------------------------------------------------- //
+__global__ void __launch_bounds__(256)
+split_planes_kernel(const float* __restrict__ src, long long rows, __nv_bfloat16* __restrict__ dst) {
+    for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < rows; r += (long long)gridDim.x * blockDim.x) {
+        float v[8], hi[8], lo[8];
+        Row8<float>::load(src + r * 8, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            hi[j] = __bfloat162float(__float2bfloat16_rn(v[j]));
+            lo[j] = v[j] - hi[j];
+        }
+        Row8<__nv_bfloat16>::store(dst + r * 8, hi);
+        Row8<__nv_bfloat16>::store(dst + (rows + r) * 8, lo);
+    }
+}
+
+extern "C" int mpnn_split_planes(const float* src, int C, int P, void* dst, void* stream) {
+    MPNN_REQUIRE(src && dst && C % 8 == 0 && C > 0 && P > 0, "split_planes: C=%d P=%d", C, P);
+    const long long rows = (long long)(C / 8) * P;
+    long long g = (rows + 255) / 256;
+    if (g > 148 * 16) g = 148 * 16;
+    split_planes_kernel<<<(int)g, 256, 0, (cudaStream_t)stream>>>(src, rows, (__nv_bfloat16*)dst);
+    return mpnn_check_launch("split_planes");
 }

@@ -185,6 +185,17 @@ extern "C" int mpnn_conv_bn_stats(const void* A0, int K0, const void* A1, int K1
                              nullptr, 0, nullptr, bn, dtype, dtype, impl, stream);
 }
 
+// the general form: accumulate into `out` (acc != 0), output dtype chosen separately from the operand dtype; the
+// fused BN statistics are those of the values finally stored.  Used by the bf16x3 mode, where a conv is two
+// launches (horizontal operand, then the pooled predecessor accumulated on top) with fp32 planes out.
+extern "C" int mpnn_conv_acc_bn_stats(const void* A0, int K0, const void* A1, int K1,
+                                      const void* Wp, const float* bias, void* out, int N, int acc,
+                                      int B, int H, int W, int G, int P, const mpnn_bn_fuse* bn,
+                                      int dtype, int out_dtype, int impl, void* stream) {
+    return stencil_gemm_impl(A0, K0, A1, K1, Wp, 9, bias, out, N, acc, nullptr, 0, 0, B, H, W, G, P,
+                             nullptr, 0, nullptr, bn, dtype, out_dtype, impl, stream);
+}
+
 extern "C" int mpnn_conv_dgrad_bn_reduce(const void* Gd, int K, const void* Wp, void* out0, int N0,
                                          void* out1, int N1, int B, int H, int W, int G, int P,
                                          const mpnn_bn_bwd_epi* epi, int dtype, int impl, void* stream) {

@@ -298,7 +298,7 @@ stencil_gemm_umma_kernel(const GemmArgs a) {
                     __nv_bfloat16* d = plane_row((__nv_bfloat16*)base, kgp, a.g.P, p);
                     if (accf && inrange) { float t[8]; Row8<__nv_bfloat16>::load(d, t);
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) o[i] += t[i]; }
+                        for (int i = 0; i < 8; ++i) { o[i] += t[i]; v[hh * 8 + i] = o[i]; } }   // sums see the accumulated value
                     const uint4 u = pack_bf16x8(o);
                     if (inrange) *reinterpret_cast<uint4*>(d) = u;
                     if (stats_mode == 2 && valid && cc < a.N0) {
@@ -312,7 +312,7 @@ stencil_gemm_umma_kernel(const GemmArgs a) {
                         float* d = plane_row((float*)base, kgp, a.g.P, p);
                         if (accf) { float t[8]; Row8<float>::load(d, t);
 #pragma unroll
-                            for (int i = 0; i < 8; ++i) o[i] += t[i]; }
+                            for (int i = 0; i < 8; ++i) { o[i] += t[i]; v[hh * 8 + i] = o[i]; } }
                         Row8<float>::store(d, o);
                     } else {
                         // fp32 row-major [row][ld]: logits of the fully-connected heads

@@ -30,6 +30,8 @@ class CompactEvaluator:
     def __init__(self, eng, batch=4096):
         if not eng.dynamic:
             raise ValueError('compacted evaluation is for dynamically-routed nets (an SRNet has one path)')
+        if eng.split:
+            raise NotImplementedError('compacted evaluation runs in fp32 or bf16 precision (not bf16x3)')
         self.eng, self.L, self.B = eng, eng.L, int(batch)
         self.plan = plan = eng._plan(self.B, False, False)      # buffers, packed operands, BN constants
         self.n_cls = eng.net.hypers.y_shape[0]

@@ -103,11 +103,18 @@ class Engine:
             self.dev = torch.device('cpu')
         else:
             self.dev = torch.device('cuda', torch.cuda.current_device() if device is None else device)
-        assert precision in ('fp32', 'bf16')
-        self.dtype = F32 if precision == 'fp32' else BF16
-        self.tdtype = torch.float32 if precision == 'fp32' else torch.bfloat16
+        assert precision in ('fp32', 'bf16', 'bf16x3')
+        # 'bf16x3': fp32 storage and elementwise arithmetic like 'fp32', but the convolutions run on the tensor
+        # cores: every fp32 operand is split into two bf16 planes sets (x = hi + lo, mpnn_split_planes) and a
+        # product is evaluated as a_hi*b_hi + a_lo*b_hi + a_hi*b_lo with fp32 accumulation (2^-16 relative) --
+        # the reference's fp32 arithmetic (layer_types.py:106-107) on tcgen05 within the 1e-3 tolerance
+        self.split = precision == 'bf16x3'
+        self.dtype = BF16 if precision == 'bf16' else F32
+        self.tdtype = torch.bfloat16 if precision == 'bf16' else torch.float32
         # stencil implementation: 0 = SIMT fp32-accumulate, 1 = tcgen05
-        self.impl = (1 if (precision == 'bf16' and self.L.mpnn_has_umma()) else 0) if impl is None else impl
+        self.impl = (1 if (precision != 'fp32' and self.L.mpnn_has_umma()) else 0) if impl is None else impl
+        if self.split and self.impl != 1:
+            raise RuntimeError('precision bf16x3 needs the tcgen05 kernels')
         # weight gradient follows the conv implementation (per launch it drops back to the
         # SIMT kernel when the shape exceeds what the tcgen05 wgrad tiles: K0+K1 > 128)
         self.impl_w = self.impl
@@ -727,6 +734,18 @@ class _Plan:
     def planes(self, C, geo):
         return self.zeros((C // 8, geo.P, 8), self.eng.tdtype)
 
+    def _split(self, t, C, geo, lane, ops=None):
+        """bf16x3 mode: (hi | lo) bf16 copy of an fp32 planes tensor and the launch that fills it"""
+        eng, L = self.eng, self.eng.L
+        dst = self.zeros((2 * C // 8, geo.P, 8), torch.bfloat16)
+
+        def sp():
+            L.split_planes(_vp(t), C, geo.P, _vp(dst), eng.stream)
+        self._tag(sp, 'split', nbytes=C * geo.P * 8)
+        sp.lane = lane
+        (self.fwd_ops if ops is None else ops).append(sp)
+        return dst, sp
+
     def f32(self, *shape):
         return self.zeros(shape, torch.float32)
 
@@ -745,14 +764,14 @@ class _Plan:
         S = lambda: eng.stream
         # fully-connected heads on the tensor cores (bf16/tcgen05 mode): one GEMM per conv stage
         # computes the LogReg logits and the first router layer from the shared feature matrix
-        self.umma_heads = eng.impl == 1 and n_cls <= 16
+        self.umma_heads = eng.impl == 1 and n_cls <= 16 and not eng.split
         Balloc = _ru(B, 128) if self.umma_heads else _ru(B, 8)
         self.Balloc = Balloc
         self.node = {}
         self.reg, self.rtr, self.heads = {}, {}, {}
         self.pack_list, self.rt_fwd, self.keep, self.kplanes = [], [], [], []
         self.last_head_op = None
-        cpad_q = 16 if dt == BF16 else 8
+        cpad_q = 16 if (dt == BF16 or eng.split) else 8
         dyn_k = eng.dynamic and bool(net.hypers.dyn_k_cpt)
 
         # ---------------- forward ---------------- #
@@ -767,11 +786,14 @@ class _Plan:
                 for i in range(n_sc):
                     geo = Geo(B, H0 // 2 ** i, W0 // 2 ** i)
                     t = self.planes(cpad, geo)
-                    st.out.append(Ns(t=t, C=cpad, Creal=C0, geo=geo, dact=None, writers=0, sc=None, consumers=0, fused_red=False))
+                    st.out.append(Ns(t=t, C=cpad, Creal=C0, geo=geo, dact=None, writers=0, sc=None, consumers=0, fused_red=False,
+                                     split=None, split_op=None))
                     pk = lambda t=t, i=i, geo=geo: L.pack_input(
                         _vp(self.x0), B, H0, W0, C0, 2 ** i, _vp(t), cpad, geo.G, geo.P, dt, S())
                     pk.lane = 3 + i
                     self.fwd_ops.append(pk)
+                    if eng.split:
+                        st.out[-1].split, st.out[-1].split_op = self._split(t, cpad, geo, 3 + i)
                 st.needs_grad = False
             elif nd.kind == 'rcm':
                 self._build_rcm_fwd(nd, st, Balloc)
@@ -937,7 +959,7 @@ class _Plan:
         tab = self._desc_table(_PACK, self.pack_list)
         self.keep.append(tab)
         n = len(self.pack_list)
-        self.pack_ops.append(lambda: L.pack_weights_batched(_vp(tab), n, 32, eng.dtype, eng.stream))
+        self.pack_ops.append(lambda: L.pack_weights_batched(_vp(tab), n, 32, BF16 if eng.split else eng.dtype, eng.stream))
 
     def _pack(self, param, packed, I, O, mode, k_off, Ktot, n_off, Ntot, ntaps=9):
         """mode 0: forward operand, 1: dgrad operand (transposed, taps flipped), 2: fp32 vector copy"""
@@ -1098,7 +1120,7 @@ class _Plan:
                 st.feat = sc.feat
                 if ext:
                     self.kplanes.append(sc.feat[st.F // 8, :, 0])
-            sc.Wf = self.zeros((9, (K0 + K1) // 8, N, 8), eng.tdtype)
+            sc.Wf = None if eng.split else self.zeros((9, (K0 + K1) // 8, N, 8), eng.tdtype)
             sc.ss = self.f32(2, N)
             sc.mr = self.f32(2, N)
             sc.bn = mbn.comps[k]
@@ -1108,11 +1130,18 @@ class _Plan:
             sc.wh, sc.wv, sc.bk = wh, wv, bk
             if tuple(wh.shape[:2]) != (3, 3):
                 raise NotImplementedError('engine: conv window %s' % (wh.shape[:2],))
-            self._pack(wh, sc.Wf, sc.K0real, sc.N, 0, 0, sc.K0 + sc.K1, 0, sc.N)
-            if wv is not None:
-                self._pack(wv, sc.Wf, sc.K1, sc.N, 0, sc.K0, sc.K0 + sc.K1, 0, sc.N)
+            if not eng.split:
+                self._pack(wh, sc.Wf, sc.K0real, sc.N, 0, 0, sc.K0 + sc.K1, 0, sc.N)
+                if wv is not None:
+                    self._pack(wv, sc.Wf, sc.K1, sc.N, 0, sc.K0, sc.K0 + sc.K1, 0, sc.N)
             prev = st.sc[k - 1] if k > 0 else None
             use_stats = sc.live and train
+            if eng.split:
+                self._build_conv_fwd_split(sc, prev, use_stats, B, Balloc, st)
+                st.sc.append(sc)
+                st.out.append(Ns(t=sc.act, C=N, Creal=N, geo=geo, dact=None, writers=0, sc=sc, consumers=0, fused_red=False,
+                                 split=getattr(sc, 'act_split', None), split_op=getattr(sc, 'post_op', None)))
+                continue
 
             if use_stats:
                 # train-mode BN statistics ride on the conv launch (last CTA finalises): no bn_finalize
@@ -1162,7 +1191,79 @@ class _Plan:
                 if sc.feat is not None:
                     st.feat_op = post
             st.sc.append(sc)
-            st.out.append(Ns(t=sc.act, C=N, Creal=N, geo=geo, dact=None, writers=0, sc=sc, consumers=0, fused_red=False))
+            st.out.append(Ns(t=sc.act, C=N, Creal=N, geo=geo, dact=None, writers=0, sc=sc, consumers=0, fused_red=False,
+                             split=getattr(sc, 'act_split', None), split_op=getattr(sc, 'post_op', None)))
+
+    def _build_conv_fwd_split(self, sc, prev, use_stats, B, Balloc, st):
+        """bf16x3 mode: the conv of one scale as up to two tcgen05 launches over (hi | lo) operands --
+        horizontal input, then the pooled predecessor accumulated on top -- with fp32 planes out; the BN moments
+        ride on the last launch.  Followed by the fp32 BN / ReLU / pool kernel and the splits of what it wrote."""
+        eng, L = self.eng, self.eng.L
+        S = lambda: eng.stream
+        geo, N, K0, K1 = sc.geo, sc.N, sc.K0, sc.K1
+        sc.lane = 3 + int(round(np.log2(eng.net.hypers.x0_shape[0] / geo.H)))
+
+        def pack3(w, K, Kreal):
+            W3 = self.zeros((9, 3 * K // 8, N, 8), torch.bfloat16)
+            for k_off, mode in ((0, 0), (K, 0), (2 * K, 4)):            # [hi; hi; lo] along K
+                self._pack(w, W3, Kreal, N, mode, k_off, 3 * K, 0, N)
+            return W3
+        sc.W3h = pack3(sc.wh, K0, sc.K0real)
+        sc.W3v = pack3(sc.wv, K1, K1) if sc.wv is not None else None
+        bnp = None
+        if use_stats:
+            bn = sc.bn
+            sc.acc = self.zeros(2 * N + 1, torch.float64)
+            sc.bnf = _host_struct(_BN_FUSE, acc=_vp(sc.acc), gamma=eng.tptr(bn.params.γ), beta=eng.tptr(bn.params.β),
+                                  m_avg=eng.tptr(bn.params.m_avg), v_avg=eng.tptr(bn.params.v_avg),
+                                  ss=_vp(sc.ss), mr=_vp(sc.mr), count=float(B * geo.H * geo.W),
+                                  d=float(bn.hypers.d), eps=float(bn.hypers.ε))
+            bnp = ctypes.c_void_p(sc.bnf.ctypes.data)
+        two = prev is not None
+
+        def conv_h(sc=sc):
+            L.conv_acc_bn_stats(_vp(sc.src.split), 2 * K0, _vp(sc.src.split), K0, _vp(sc.W3h), eng.tptr(sc.bk),
+                                _vp(sc.lin), N, 0, *geo.args(), None if two else bnp, BF16, F32, 1, S())
+        self._tag(conv_h, 'conv_fwd', desc='H%d K3x%d N%d' % (geo.H, K0, N), flops=3 * 2.0 * B * geo.H * geo.W * 9 * sc.K0real * N,
+                  nbytes=B * geo.H * geo.W * (3 * K0 * 2 + N * 4))
+        conv_h.lane = sc.lane
+        self._after(conv_h, sc.src.split_op)
+        self.fwd_ops.append(conv_h)
+        if two:
+            def conv_v(sc=sc, prev=prev):
+                L.conv_acc_bn_stats(_vp(prev.pooled_split), 2 * K1, _vp(prev.pooled_split), K1, _vp(sc.W3v), None,
+                                    _vp(sc.lin), N, 1, *geo.args(), bnp, BF16, F32, 1, S())
+            self._tag(conv_v, 'conv_fwd', desc='H%d K3x%d N%d +acc' % (geo.H, K1, N), flops=3 * 2.0 * B * geo.H * geo.W * 9 * K1 * N,
+                      nbytes=B * geo.H * geo.W * (3 * K1 * 2 + 2 * N * 4))
+            conv_v.lane = sc.lane
+            self._after(conv_v, prev.post_op)
+            self.fwd_ops.append(conv_v)
+        if sc.live and not use_stats:
+            bn = sc.bn
+
+            def fin(sc=sc, bn=bn):             # inference: scale/shift from the running moments
+                L.bn_finalize(None, 0, N, float(B * geo.H * geo.W), eng.tptr(bn.params.γ), eng.tptr(bn.params.β),
+                              eng.tptr(bn.params.m_avg), eng.tptr(bn.params.v_avg),
+                              float(bn.hypers.d), float(bn.hypers.ε), 0, _vp(sc.ss), _vp(sc.mr), S())
+            self._tag(fin, 'bn_finalize')
+            fin.lane = sc.lane
+            self.fwd_ops.append(fin)
+        sc.act_split = sc.pooled_split = None
+        if sc.live or sc.pooled is not None:
+            def post(sc=sc):
+                L.bn_relu_pool_fwd(_vp(sc.lin), N, *geo.args(), _vp(sc.ss) if sc.live else None,
+                                   _vp(sc.act), _vp(sc.pooled), sc.geo_p.P if sc.pooled is not None else 0,
+                                   _vp(sc.feat), Balloc, F32, S())
+            self._tag(post, 'bn_fwd', nbytes=B * geo.H * geo.W * N * 4 * (1 + (sc.act is not None) + 0.25 * (sc.pooled is not None) + (sc.feat is not None)))
+            post.lane = sc.lane
+            self.fwd_ops.append(post)
+            sc.post_op = post
+            if sc.feat is not None:
+                st.feat_op = post
+            if sc.act is not None:
+                sc.act_split, sc.post_op = self._split(sc.act, N, geo, sc.lane)
+            if sc.pooled is not None:
+                sc.pooled_split, sc.post_op = self._split(sc.pooled, N, sc.geo_p, sc.lane)
 
     def _bn_bwd_bufs(self, sc):
         """sums / fp64 accumulator / finalisation struct of a scale's BatchNorm backward (shared by the
@@ -1244,6 +1345,9 @@ class _Plan:
             self._after(elt, getattr(sc, 'dpooled_op', None))      # written by scale k+1's data gradient
             self.bwd_ops.append(elt)
             prev = st.sc[k - 1] if k > 0 else None
+            if eng.split:
+                self._build_conv_bwd_split(sc, prev, elt, par_grad, B)
+                continue
 
             def wgrad(sc=sc, prev=prev):
                 L.stencil_wgrad(_vp(sc.src.t), sc.K0, sc.K0real, eng.gptr(sc.wh),
@@ -1308,6 +1412,61 @@ class _Plan:
             if N1:
                 prev.dpooled_op = dgrad
             self.bwd_ops.append(dgrad)
+
+    def _build_conv_bwd_split(self, sc, prev, elt, par_grad, B):
+        """bf16x3 mode: dLin (fp32) is split into (hi | lo); the weight gradient is three tcgen05 launches
+        (A_hi x G_hi, A_lo x G_hi, A_hi x G_lo, all reduced into the same fp32 gradient tensors), the data
+        gradient one launch over [G_hi | G_lo | G_hi] x [W_hi; W_hi; W_lo] with fp32 planes out."""
+        eng, L = self.eng, self.eng.L
+        S = lambda: eng.stream
+        geo, N, K0, K1 = sc.geo, sc.N, sc.K0, sc.K1
+        sc.dlin_split, sp = self._split(sc.dlin, N, geo, sc.lane, ops=self.bwd_ops)
+        self._after(sp, elt)
+        lo = lambda t, C: ctypes.c_void_p(t.data_ptr() + (C // 8) * geo.P * 16)      # the lo planes of a split tensor
+        a_hi, a_lo = _vp(sc.src.split), lo(sc.src.split, K0)
+        p_hi = _vp(prev.pooled_split) if prev is not None else None
+        p_lo = lo(prev.pooled_split, K1) if prev is not None else None
+        g_hi, g_lo = _vp(sc.dlin_split), lo(sc.dlin_split, N)
+        dWv = eng.gptr(sc.wv) if sc.wv is not None else None
+        for i, (a0, a1, g) in enumerate(((a_hi, p_hi, g_hi), (a_lo, p_lo, g_hi), (a_hi, p_hi, g_lo))):
+            def wgrad(a0=a0, a1=a1, g=g):
+                L.stencil_wgrad(a0, K0, sc.K0real, eng.gptr(sc.wh), a1, K1, K1, dWv, g, N, N, None, 9,
+                                *geo.args(), BF16, 1 if (K0 + K1 <= 128 and N <= 256) else 0, S())
+            self._tag(wgrad, 'conv_wgrad', desc='H%d K%d+%d N%d x3[%d]' % (geo.H, K0, K1, N, i),
+                      flops=2.0 * B * geo.H * geo.W * 9 * (sc.K0real + K1) * N, nbytes=B * geo.H * geo.W * (K0 + K1 + N) * 2)
+            wgrad.lane = 10 + (sc.lane - 3)
+            self.bwd_ops.append(self._after(wgrad, sp))
+        N0 = K0 if par_grad else 0
+        N1 = K1
+        if N0 + N1 == 0:
+            return
+        sc.Wd3 = self.zeros((9, 3 * N // 8, N0 + N1, 8), torch.bfloat16)
+        for k_off, mode in ((0, 1), (N, 1), (2 * N, 5)):                       # [hi; hi; lo] along K (= output channels)
+            if N0:
+                self._pack(sc.wh, sc.Wd3, sc.K0real, N, mode, k_off, 3 * N, 0, N0 + N1)
+            if N1:
+                self._pack(sc.wv, sc.Wd3, K1, N, mode, k_off, 3 * N, N0, N0 + N1)
+        acc0, out0 = 0, None
+        if N0:
+            slot = sc.src
+            if slot.dact is None:
+                slot.dact = self.planes(slot.C, geo)
+            acc0 = 1 if slot.writers > 0 else 0
+            slot.writers += 1
+            out0 = slot.dact
+        if N1:
+            prev.dpooled = self.planes(K1, geo)
+
+        def dgrad(out0=out0, acc0=acc0):
+            L.stencil_gemm(_vp(sc.dlin_split), 2 * N, _vp(sc.dlin_split), N, _vp(sc.Wd3), 9, None,
+                           _vp(out0), N0, acc0, _vp(prev.dpooled) if N1 else None, N1, 0,
+                           *geo.args(), None, 0, None, BF16, F32, 1, S())
+        self._tag(dgrad, 'conv_dgrad', desc='H%d K3x%d N%d+%d' % (geo.H, N, N0, N1), flops=3 * 2.0 * B * geo.H * geo.W * 9 * N * (N0 + N1),
+                  nbytes=B * geo.H * geo.W * (3 * N * 2 + (N0 + N1) * 4))
+        dgrad.lane = sc.lane
+        if N1:
+            prev.dpooled_op = dgrad
+        self.bwd_ops.append(dgrad)
 
     # -- router ------------------------------------------------------------ #
     def _build_router_fwd(self, nd, Balloc, dyn_k, emit_fc=True):

@@ -276,6 +276,58 @@ def test_dgrad_with_fused_bn_backward_sums(B, H, K, N0, N1):
             np.testing.assert_allclose(b.cpu().numpy(), a.cpu().numpy(), rtol=5e-5, atol=5e-6 * scale)
 
 
+@pytest.mark.parametrize('B,H,Cin,Cp,Cout', [(3, 8, 16, 0, 16), (4, 16, 16, 16, 32), (5, 4, 64, 32, 64), (130, 32, 16, 16, 16),
+                                              (6, 4, 128, 0, 128)])
+def test_bf16x3_conv_reaches_fp32_accuracy_on_the_tensor_cores(B, H, Cin, Cp, Cout):
+    """mpnn_split_planes + residual weight packing + mpnn_conv_acc_bn_stats: the conv of FP32 operands evaluated as
+    a_hi*w_hi + a_lo*w_hi + a_hi*w_lo on tcgen05 (fp32 planes out, pooled predecessor accumulated by a second
+    launch, BN moments of the final values) against the exact conv: 1e-4, where plain bf16 gives 4e-3."""
+    from lib.engine import _BN_FUSE, _host_struct
+    rng = np.random.default_rng(11)
+    x = rng.standard_normal((B, H, H, Cin)).astype(np.float32)
+    xp = rng.standard_normal((B, H, H, Cp)).astype(np.float32) if Cp else None
+    wh = (rng.standard_normal((3, 3, Cin, Cout)) / np.sqrt(9 * Cin)).astype(np.float32)
+    wv = (rng.standard_normal((3, 3, Cp, Cout)) / np.sqrt(9 * Cp)).astype(np.float32) if Cp else None
+    bias = rng.standard_normal(Cout).astype(np.float32)
+    geo = Geo(B, H, H)
+
+    def split(a, C):
+        src = dev(to_planes(a, geo, C))
+        dst = torch.zeros((2 * C // 8, geo.P, 8), dtype=torch.bfloat16, device='cuda')
+        L().split_planes(vp(src), C, geo.P, vp(dst), None)
+        return src, dst
+
+    def pack3(w, C):
+        W3 = torch.zeros((9, 3 * C // 8, Cout, 8), dtype=torch.bfloat16, device='cuda')
+        for k_off, mode in ((0, 0), (C, 0), (2 * C, 4)):
+            pack_w(w, 3 * C, k_off, Cout, 0, W3, mode, BF16)
+        return W3
+    xs, xsp = split(x, Cin)
+    hi = xsp[:Cin // 8].float().cpu().numpy(); lo = xsp[Cin // 8:].float().cpu().numpy()
+    assert rel_err(hi + lo, xs.cpu().numpy()) < 2e-5                       # x = hi + lo up to 2^-17
+    out = torch.zeros((Cout // 8, geo.P, 8), device='cuda')
+    acc = torch.zeros(2 * Cout + 1, dtype=torch.float64, device='cuda')
+    gm, bt = torch.ones(Cout, device='cuda'), torch.zeros(Cout, device='cuda')
+    ss, mr = torch.zeros((2, Cout), device='cuda'), torch.zeros((2, Cout), device='cuda')
+    f = _host_struct(_BN_FUSE, acc=vp(acc), gamma=vp(gm), beta=vp(bt), m_avg=None, v_avg=None, ss=vp(ss), mr=vp(mr),
+                     count=float(B * H * H), d=0.9, eps=1e-6)
+    fp = ctypes.c_void_p(f.ctypes.data)
+    W3h = pack3(wh, Cin)
+    L().conv_acc_bn_stats(vp(xsp), 2 * Cin, vp(xsp), Cin, vp(W3h), vp(dev(bias)), vp(out), Cout, 0,
+                          B, H, H, geo.G, geo.P, None if Cp else fp, BF16, F32, 1, None)
+    if Cp:
+        _, psp = split(xp, Cp)
+        W3v = pack3(wv, Cp)
+        L().conv_acc_bn_stats(vp(psp), 2 * Cp, vp(psp), Cp, vp(W3v), None, vp(out), Cout, 1,
+                              B, H, H, geo.G, geo.P, fp, BF16, F32, 1, None)
+    torch.cuda.synchronize()
+    ref = _ref_conv(x, xp, wh, wv, bias, lambda a: a)
+    y = from_planes(out.cpu().numpy(), geo, Cout)
+    assert rel_err(y, ref) < 1e-4, rel_err(y, ref)
+    np.testing.assert_allclose(mr[0].cpu().numpy(), ref.mean((0, 1, 2)), rtol=1e-3, atol=1e-4)
+    np.testing.assert_allclose(mr[1].cpu().numpy(), 1 / np.sqrt(ref.var((0, 1, 2)) + 1e-6), rtol=1e-3)
+
+
 @pytest.mark.parametrize('dt,impl,shape', [
     (F32, 0, (6, 8, 3, 16, 32)), (BF16, 0, (6, 8, 3, 16, 32)), (BF16, 1, (6, 8, 3, 16, 32)),
     (BF16, 1, (3, 32, 16, 16, 16)), (BF16, 1, (50, 4, 64, 64, 64)), (BF16, 1, (33, 4, 128, 0, 128)),

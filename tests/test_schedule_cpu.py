@@ -48,6 +48,7 @@ _STRUCTS = {
 }
 _HOST_STRUCTS = {
     'conv_bn_stats': ('bn', E._BN_FUSE, dict(acc='rw', gamma='r', beta='r', m_avg='rw', v_avg='rw', ss='w', mr='w')),
+    'conv_acc_bn_stats': ('bn', E._BN_FUSE, dict(acc='rw', gamma='r', beta='r', m_avg='rw', v_avg='rw', ss='w', mr='w')),
     'bn_bwd_reduce_fused': ('f', E._BN_BWD_FUSE, dict(acc='rw', sums='w', dgamma='w', dbeta='w')),
     'conv_dgrad_bn_reduce': ('epi', E._BN_BWD_EPI, dict(lin='r', ss='r', mr='r', acc='rw', sums='w', dgamma='w',
                                                         dbeta='w')),
@@ -178,7 +179,7 @@ def _check(eng, plan):
     return problems
 
 
-@pytest.mark.parametrize('prec,impl', [('bf16', 1), ('fp32', 0)])
+@pytest.mark.parametrize('prec,impl', [('bf16', 1), ('fp32', 0), ('bf16x3', 1)])
 @pytest.mark.parametrize('kind,hy', [('sr', {}), ('ac', dict(k_cpt=4e-9)), ('cr', dict(k_cpt=4e-9)),
                                      ('actree', dict(k_cpt=2e-9)), ('ac', dict(dyn_k_cpt=True))])
 def test_every_conflicting_pair_of_launches_is_ordered(kind, hy, prec, impl):
