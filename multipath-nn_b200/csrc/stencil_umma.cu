@@ -609,6 +609,9 @@ int mpnn_stencil_gemm_umma(const void* A0, int K0, const void* A1, int K1, const
     if (cap > 4) cap = 4;
     if (NB == 32 && cap > (bwd ? 2 : 3)) cap = bwd ? 2 : 3;      // register budgets of the instantiations
     if (NB == 16 && bwd && cap > 3) cap = 3;
+    // the generic-width instantiations need ~108 registers: two CTAs per SM are resident (ncu: occupancy limit 2 by
+    // registers); a grid sized for three ran as 1.5 waves
+    if (NB != 16 && NB != 32 && cap > 2) cap = 2;
     if (tune_per_sm && cap > tune_per_sm) cap = tune_per_sm;
     if (cap < 1) cap = 1;
     size_t smem = 0;
@@ -678,8 +681,22 @@ int mpnn_stencil_gemm_umma(const void* A0, int K0, const void* A1, int K1, const
         for (int i = 0; i < 20; ++i) {
             cudaError_t e2 = cudaFuncSetAttribute(all[i], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMax);   // + static smem stays under 227 KB
             if (e2 != cudaSuccess) { mpnn_set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e2)); return MPNN_ERR_CUDA; }
+            // without this the driver picks the L1 / shared-memory split heuristically and may leave room for fewer
+            // CTAs per SM than the grid was sized for (ncu: occupancy limit 2 by shared memory where 3 x 68 KB fit;
+            // the persistent grid then ran as 1.5 waves)
+            cudaFuncSetAttribute(all[i], cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         }
         if (dev >= 0 && dev < 64) attr_set[dev] = true;
+    }
+    static const int tune_occ = getenv("MPNN_TUNE_OCC") ? atoi(getenv("MPNN_TUNE_OCC")) : 0;
+    if (tune_occ) {      // tuning aid: clamp the persistent grid to what the occupancy calculator reports
+        int occ = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kThreads, smem) == cudaSuccess && occ >= 1 && occ < per_sm) {
+            int g2 = 148 * occ / split;
+            if (g2 < 1) g2 = 1;
+            if (gx > g2) gx = g2;
+            if (n_parts && stats) *n_parts = gx;
+        }
     }
     cudaError_t le = mpnn_launch_pdl(kern, dim3(gx, split), dim3(kThreads), smem, st, a);
     if (le != cudaSuccess) { mpnn_set_error("stencil_gemm_umma launch: %s", cudaGetErrorString(le)); return MPNN_ERR_CUDA; }
