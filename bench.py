@@ -412,8 +412,8 @@ def main():
     args.warmup = max(args.warmup, 3)
 
     import torch.distributed as dist
-    if os.environ.get('NCCL_DEBUG', 'VERSION').upper() == 'VERSION':
-        os.environ['NCCL_DEBUG'] = 'WARN'          # NCCL's version banner goes to stdout, which carries the ONE JSON line
+    if os.environ.get('NCCL_DEBUG', '').upper() in ('VERSION', 'WARN'):
+        del os.environ['NCCL_DEBUG']               # NCCL's version banner goes to stdout, which carries the ONE JSON line
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     if world > 1:

@@ -18,7 +18,7 @@ import numpy as np
 import torch
 
 from lib import _cabi
-from lib.layer_types import (BatchNorm, Chain, CrossEntropyError, LinTrans, MultiscaleBatchNorm,
+from lib.layer_types import (BatchNorm, Chain, Conv, CrossEntropyError, LinTrans, MultiscaleBatchNorm,
                              MultiscaleConvMax, MultiscaleRect, Param, Rect, Select, Softmax, ToPyramid)
 from lib.net_types import n_leaves
 
@@ -71,6 +71,13 @@ def _is_chain(layer, types):
 _PYR = [ToPyramid]
 _RCM = [MultiscaleConvMax, MultiscaleBatchNorm, MultiscaleRect]
 _REG = [Select, LinTrans, Softmax, CrossEntropyError]
+# standalone Conv (lib/layer_types.py:55-74) as a tree node: 3x3 SAME conv + bias -> BatchNorm -> ReLU on ONE
+# tensor -- the input image, a pyramid scale picked by a leading Select, or the tensor of the node above --
+# and a classifier that flattens a tensor without a Select.  Arithmetically a one-scale MultiscaleConvMax
+# stage: the same kernels serve it (mpnn_conv_bn_stats / mpnn_stencil_gemm with A1 = NULL).
+_CNV = [Conv, BatchNorm, Rect]
+_CNVS = [Select, Conv, BatchNorm, Rect]
+_REGF = [LinTrans, Softmax, CrossEntropyError]
 _RTR = [Select, LinTrans, BatchNorm, Rect, LinTrans, BatchNorm, Rect, LinTrans]
 
 
@@ -163,12 +170,32 @@ class Engine:
                 nd.kind = 'pyr'
             elif _is_chain(layer, _RCM):
                 nd.kind = 'rcm'
+                nd.cm, nd.mbn, nd.sel = layer.comps[0], layer.comps[1], None
                 if layer.comps[0].hypers.supp != 3:
                     raise NotImplementedError('engine: MultiscaleConvMax supp=%r' % layer.comps[0].hypers.supp)
+            elif _is_chain(layer, _CNV) or _is_chain(layer, _CNVS):
+                nd.kind = 'rcm'
+                off = 1 if isinstance(layer.comps[0], Select) else 0
+                conv, bn = layer.comps[off], layer.comps[off + 1]
+                if conv.hypers.supp != 3 or conv.hypers.res:
+                    raise NotImplementedError('engine: standalone Conv with supp=%r res=%r (3x3 without the residual '
+                                              'initialisation is what the stencil kernels serve)' % (conv.hypers.supp, conv.hypers.res))
+                if conv.hypers.n_chan % 16:
+                    raise NotImplementedError('engine: Conv n_chan=%d (multiples of 16)' % conv.hypers.n_chan)
+                # the stage code reads a MultiscaleConvMax / MultiscaleBatchNorm pair: present the Conv as one scale
+                nd.cm = Ns(hypers=Ns(n_chan=[conv.hypers.n_chan], supp=3, k_l2=conv.hypers.k_l2),
+                           params=Ns(w_horz_0=conv.params.w, b_0=conv.params.b))
+                nd.mbn = Ns(comps=[bn])
+                nd.sel = layer.comps[0].hypers.i if off else None
+                nd.tensor_in = not off
             elif _is_chain(layer, _REG):
                 nd.kind = 'reg'
+                nd.fc, nd.ce = layer.comps[1], layer.comps[3]
                 if layer.comps[0].hypers.i != -1:
                     raise NotImplementedError('engine: LogReg must select the coarsest scale')
+            elif _is_chain(layer, _REGF):
+                nd.kind = 'reg'
+                nd.fc, nd.ce = layer.comps[0], layer.comps[2]
             else:
                 raise NotImplementedError(
                     'engine: tree node %r (%s) is not one of the hot-path compositions '
@@ -187,12 +214,18 @@ class Engine:
             for i, s in enumerate(layer.sinks):
                 visit(s, nd.idx, i)
         visit(net.root, None, 0)
-        if self.nodes[0].kind != 'pyr':
-            raise NotImplementedError('engine: the root must be the ToPyramid chain')
+        if self.nodes[0].kind != 'pyr' and not getattr(self.nodes[0], 'tensor_in', False):
+            raise NotImplementedError('engine: the root must be the ToPyramid chain or a Conv-BatchNorm-Rect chain')
+        for nd in self.nodes:
+            par = self.nodes[nd.parent] if nd.parent is not None else None
+            if getattr(nd, 'tensor_in', False) and par is not None and par.kind == 'pyr':
+                raise NotImplementedError('engine: %r takes a tensor but sits under the pyramid (lead with Select)' % nd.layer.name)
+            if nd.kind == 'rcm' and nd.sel is not None and (par is None or par.kind != 'pyr'):
+                raise NotImplementedError('engine: Select + Conv must sit directly under the ToPyramid node')
         for nd in self.nodes:
             if nd.kind == 'reg' and nd.kids:
                 raise NotImplementedError('engine: LogReg with sinks')
-            if nd.kind in ('rcm', 'reg') and self.nodes[nd.parent].kind == 'reg':
+            if nd.kind in ('rcm', 'reg') and nd.parent is not None and self.nodes[nd.parent].kind == 'reg':
                 raise NotImplementedError('engine: node under a LogReg')
             if nd.kind == 'pyr' and nd.idx != 0:
                 raise NotImplementedError('engine: nested ToPyramid')
@@ -232,6 +265,8 @@ class Engine:
                             raise NotImplementedError('engine: LinTrans(res=True)')
                         l2 = float(layer.hypers.k_l2)
                     elif isinstance(layer, MultiscaleConvMax) and key.startswith('w_'):
+                        l2 = float(layer.hypers.k_l2)
+                    elif isinstance(layer, Conv) and key == 'w':
                         l2 = float(layer.hypers.k_l2)
                     off_t = _ru(off_t, 4)          # 16-byte aligned: vector reductions into the gradient
                     p._bind = (self, 'theta', off_t)
@@ -740,6 +775,24 @@ class _Plan:
     def planes(self, C, geo):
         return self.zeros((C // 8, geo.P, 8), self.eng.tdtype)
 
+    def _image_slot(self):
+        """pseudo parent of a Conv chain at the root: the input image as one padded-planes tensor"""
+        if getattr(self, '_img', None) is None:
+            eng, L, B = self.eng, self.eng.L, self.B
+            H0, W0, C0 = eng.net.hypers.x0_shape
+            cpad = _ru(C0, 16 if (eng.dtype == BF16 or eng.split) else 8)
+            geo = Geo(B, H0, W0)
+            t = self.planes(cpad, geo)
+            slot = Ns(t=t, C=cpad, Creal=C0, geo=geo, dact=None, writers=0, sc=None, consumers=0, fused_red=False,
+                      split=None, split_op=None)
+            pk = lambda: L.pack_input(_vp(self.x0), B, H0, W0, C0, 1, _vp(t), cpad, geo.G, geo.P, eng.dtype, eng.stream)
+            pk.lane = 3
+            self.fwd_ops.append(pk)
+            if eng.split:
+                slot.split, slot.split_op = self._split(t, cpad, geo, 3)
+            self._img = Ns(out=[slot], needs_grad=False)
+        return self._img
+
     def _split(self, t, C, geo, lane, ops=None):
         """bf16x3 mode: (hi | lo) bf16 copy of an fp32 planes tensor and the launch that fills it"""
         eng, L = self.eng, self.eng.L
@@ -805,8 +858,8 @@ class _Plan:
                 self._build_rcm_fwd(nd, st, Balloc)
             elif nd.kind == 'reg':
                 par = self.node[nd.parent]
-                fc = lay.comps[1]
-                eps = float(lay.comps[3].hypers.ε)
+                fc = nd.fc
+                eps = float(nd.ce.hypers.ε)
                 if self.umma_heads:
                     hd = self.heads[nd.parent]          # logits come from the parent's head GEMM
                     r = Ns(Zbuf=hd.Z16, Z=hd.Z16[:, :n_cls], ldz=16, prob=self.f32(B, n_cls),
@@ -991,7 +1044,7 @@ class _Plan:
         hd.bias = self.f32(hd.N)
         hd.dZ = self.zeros((hd.N // 8, Balloc, 8), eng.tdtype) if self.need_bwd else None
         if leaves:
-            fc = eng.nodes[leaves[0]].layer.comps[1]
+            fc = eng.nodes[leaves[0]].fc
             hd.fc_leaf = fc
             self._pack(fc.params.w, hd.Wfc, F, n_cls, 0, 0, Fext, hd.leaf_off, hd.N, ntaps=1)
             self._pack(fc.params.b, hd.bias, 1, n_cls, 2, 0, 8, hd.leaf_off, hd.N, ntaps=1)
@@ -1080,11 +1133,17 @@ class _Plan:
         dt, impl = eng.dtype, eng.impl
         S = lambda: eng.stream
         lay = nd.layer
-        cm, mbn = lay.comps[0], lay.comps[1]
-        par = self.node[nd.parent]
+        cm, mbn = nd.cm, nd.mbn
+        if nd.parent is None:                     # a Conv chain at the root: its input tensor is the image itself
+            par = self._image_slot()
+        else:
+            par = self.node[nd.parent]
         n_chan = list(cm.hypers.n_chan)
         n = len(n_chan)
-        pin = par.out[len(par.out) - n:]
+        if nd.sel is not None:                    # Select(i) + Conv: one scale of the pyramid
+            pin = [par.out[nd.sel]]
+        else:
+            pin = par.out[len(par.out) - n:]
         st.pin = pin
         st.needs_grad = True
         st.out, st.sc = [], []
@@ -1093,7 +1152,7 @@ class _Plan:
 
         def live(k):
             for c in kid_rcm:
-                m = len(eng.nodes[c].layer.comps[0].hypers.n_chan)
+                m = len(eng.nodes[c].cm.hypers.n_chan)
                 if k >= n - m:
                     return True
             return k == n - 1 and has_heads
@@ -1109,7 +1168,7 @@ class _Plan:
                     dpooled=None, geo_p=None)
             sc.lin = self.planes(N, geo)
             sc.act = self.planes(N, geo) if any(
-                k >= n - len(eng.nodes[c].layer.comps[0].hypers.n_chan) for c in kid_rcm) else None
+                k >= n - len(eng.nodes[c].cm.hypers.n_chan) for c in kid_rcm) else None
             sc.pooled = None
             if k < n - 1:
                 sc.geo_p = pin[k + 1].geo
@@ -1289,9 +1348,8 @@ class _Plan:
         S = lambda: eng.stream
         st = self.node[nd.idx]
         lay = nd.layer
-        cm = lay.comps[0]
         n = len(st.sc)
-        par = self.node[nd.parent]
+        par = self.node[nd.parent] if nd.parent is not None else self._image_slot()
         par_grad = par.needs_grad
         # gradient of the heads wrt the flattened coarsest scale
         heads = [k for k in nd.kids if eng.nodes[k].kind == 'reg']

@@ -34,7 +34,7 @@ TOL = {'fp32': dict(fwd=1e-3, grad=1e-3, margin=1e-4, step=2e-3),
 
 def _nets(kind, hy, seed=0):
     net = tiny_net(kind, seed=seed, **{k: v for k, v in hy.items() if not k.startswith('_')})
-    if kind != 'sr':
+    if kind not in ('sr', 'cnv', 'cnvpyr'):
         randomize_routers(net)
     return net
 
@@ -60,7 +60,9 @@ CASES = [('sr', {}), ('ac', dict(k_cpt=4e-9)), ('cr', dict(k_cpt=4e-9)),
          #  3e-2 bf16 error of the losses is amplified -- here to 0.25-0.31 on two routers, 0.1-0.2 upstream of them --
          #  while fp32 stays at 1e-3 and the other bf16 cases at 0.01-0.14: scratch/diag_bf16_case.py)
          ('sr', dict(x0_shape=(16, 16, 1))), ('ac', dict(k_cpt=4e-9, x0_shape=(16, 16, 1), n_cls=5, _bf16_grad=0.4)),
-         ('crtree', dict(k_cpt=2e-9, n_cls=2)), ('cr', dict(dyn_k_cpt=True, optimistic=True))]
+         ('crtree', dict(k_cpt=2e-9, n_cls=2)), ('cr', dict(dyn_k_cpt=True, optimistic=True)),
+         # standalone Conv chains: on the image, and on a pyramid scale picked by Select
+         ('cnv', {}), ('cnvpyr', dict(x0_shape=(16, 16, 1)))]
 
 
 @pytest.mark.parametrize('prec', ['fp32', 'bf16'])
@@ -131,7 +133,7 @@ def test_forward_and_gradients(kind, hy, prec):
 
 
 @pytest.mark.parametrize('prec', ['fp32', 'bf16'])
-@pytest.mark.parametrize('kind,hy', [('sr', {}), ('ac', dict(k_cpt=4e-9)), ('cr', dict(k_cpt=4e-9))])
+@pytest.mark.parametrize('kind,hy', [('sr', {}), ('ac', dict(k_cpt=4e-9)), ('cr', dict(k_cpt=4e-9)), ('cnv', {})])
 def test_training_steps_track_the_oracle(kind, hy, prec):
     """3 x net.train.run(...) with the reference's schedules: parameters and
     BatchNorm EMAs follow the oracle."""

@@ -6,7 +6,7 @@ import numpy as np
 
 from lib import layer_types as lt
 from lib import serdes
-from lib.layer_types import (BatchNorm, Chain, CrossEntropyError, LinTrans, MultiscaleBatchNorm,
+from lib.layer_types import (BatchNorm, Chain, Conv, CrossEntropyError, LinTrans, MultiscaleBatchNorm,
                              MultiscaleConvMax, MultiscaleRect, Rect, Select, Softmax, ToPyramid)
 from lib.net_types import ActorNet, CriticNet, SRNet
 
@@ -41,6 +41,16 @@ def tiny_net(kind='ac', n_cls=10, x0_shape=(16, 16, 3), seed=0, **hypers):
     """16x16 input, 3-scale pyramid, stages [16,16,16] -> [16,16] -> [32];
     'sr' is a chain, 'ac'/'cr' route at both inner stages, 'tree' has a 3-way switch."""
     lt.seed(seed)
+    if kind in ('cnv', 'cnvpyr'):
+        # standalone Conv (layer_types.py:55-74) chains: on the image itself, or on one pyramid scale via Select
+        cnv = lambda n, *sinks, pre=(): Chain(name='ConvBlock', sinks=sinks, comps=list(pre) + [
+            Conv(n_chan=n, supp=3, k_l2=K_L2, σ_w=1), BatchNorm(), Rect()])
+        flat = Chain(name='LogReg', comps=[_fc(n_cls), Softmax(), CrossEntropyError()])
+        if kind == 'cnv':
+            root = cnv(16, cnv(32, flat))
+        else:
+            root = pyr(2, cnv(16, cnv(16, flat), pre=[Select(i=1)]))
+        return SRNet(x0_shape=x0_shape, y_shape=(n_cls,), root=root)
     if kind == 'sr':
         root = pyr(3, rcm([16, 16, 16], rcm([16, 16], rcm([32], reg(n_cls)))))
         return SRNet(x0_shape=x0_shape, y_shape=(n_cls,), root=root)
