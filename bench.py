@@ -176,7 +176,7 @@ def cpu_oracle_rate(config, B, budget_s=15.0, max_steps=50):
     return n * B / dt, n, dt
 
 
-def run_reference(args, rank, world):
+def run_reference(args, rank, world, emit):
     """--impl reference: the reference's CPU implementation of the path (its oracle port; the TF graph itself
     cannot be installed here) on the box's host cores, same config / batch / steps / warm-up as our arm.  Only if
     the whole run would exceed a few minutes the per-step sample is cut to a smaller batch (stated in `sample`)."""
@@ -218,7 +218,7 @@ def run_reference(args, rank, world):
                    'batch_per_gpu': B, 'sample_batch': sample_B},
         'cpu_baseline': {'value': v, 'unit': 'images/s', 'cores': torch.get_num_threads(), 'kind': 'port', 'sample': sample},
         'e2e': {'value': v, 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # --------------------------------------------------------------------------- #
@@ -404,11 +404,21 @@ def main():
     ap.add_argument('--no-sweep', action='store_true', help='skip the `configs` array (other configs / batches)')
     ap.add_argument('--profile', action='store_true', help='print per-kernel-kind time shares')
     args = ap.parse_args()
+    # stdout carries exactly ONE JSON line: anything a library prints to fd 1 meanwhile (NCCL's version banner on
+    # the first communicator) is sent to stderr, and the real stdout comes back for the final print
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        print(json.dumps(line), flush=True)
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
     local = int(os.environ.get('LOCAL_RANK', '0'))
     if args.impl == 'reference':
-        return run_reference(args, rank, world)
+        return run_reference(args, rank, world, emit)
     args.warmup = max(args.warmup, 3)
 
     import torch.distributed as dist
@@ -508,7 +518,7 @@ def main():
         'hbm_frac_of_step': (run.hbm_bytes_per_step() / (pk['hbm_gbs'] * 1e9)) / (dev_ms / args.steps * 1e-3),
         'roofline': roof, 'families': families, 'serialised_kernel_ms': tot_ms,
         'configs': sweep, 'cpu_baseline': cpu, 'clocks': clk}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 

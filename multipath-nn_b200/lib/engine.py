@@ -823,7 +823,16 @@ class _Plan:
         S = lambda: eng.stream
         # fully-connected heads on the tensor cores (bf16/tcgen05 mode): one GEMM per conv stage
         # computes the LogReg logits and the first router layer from the shared feature matrix
-        self.umma_heads = eng.impl == 1 and n_cls <= 16 and not eng.split
+        def head_features(nd):              # inputs of the heads of a stage: its coarsest (or only) output, flattened
+            x = nd.layer.x
+            x = x[-1] if isinstance(x, (list, tuple)) else x
+            return int(np.prod(x.shape))
+        with_heads = [nd for nd in eng.nodes if nd.kind == 'rcm' and (
+            nd.router is not None or any(eng.nodes[k].kind == 'reg' for k in nd.kids))]
+        # the head GEMM keeps [W_leaf | W_r1] resident in shared memory: F/8 x 32 x 16 bytes must fit (F = 2048 at the
+        # reference architecture; a Conv chain at full resolution has F = H*W*C and takes the CUDA-core heads)
+        fits = all((head_features(nd) + 16) // 8 * 32 * 16 <= 150 * 1024 for nd in with_heads)
+        self.umma_heads = eng.impl == 1 and n_cls <= 16 and not eng.split and fits
         Balloc = _ru(B, 128) if self.umma_heads else _ru(B, 8)
         self.Balloc = Balloc
         self.node = {}

@@ -35,4 +35,7 @@ def case(H, C, pool=True, dt=1):
 
 
 if __name__ == '__main__':
-    case(32, 16); case(16, 32); case(16, 16); case(8, 64); case(4, 128, pool=False)
+    if len(sys.argv) > 1 and sys.argv[1] == 'h32':
+        case(32, 16)
+    else:
+        case(32, 16); case(16, 32); case(16, 16); case(8, 64); case(4, 128, pool=False)

@@ -106,6 +106,14 @@ if __name__ == '__main__':
         conv_case(4, 64, 64, 64)
         conv_case(4, 128, 0, 128)
         conv_case(4, 16, 16, 16)
+    if what == 'h32fwd':
+        conv_case(32, 16, 0, 16)
+    if what == 'h32dgrad':
+        conv_case(32, 16, 0, 16, stats=2, bias=False)
+    if what == 'h32wgrad':
+        wgrad_case(32, 16, 0, 16)
+    if what == 'h8wgrad':
+        wgrad_case(8, 64, 0, 64)
     if what == 'gemm1':
         conv_case(32, 16, 0, 16)
         conv_case(16, 32, 0, 32)
