@@ -115,6 +115,11 @@ typedef struct {
     float* ss; float* mr;            /* outputs, [2][C] each */
     double count;                    /* B*H*W */
     float d; float eps;
+    int defer;                       /* 1: the producer only ADDS its partial sums into acc (no ticket, no finalisation, acc is
+                                      * not reset: the caller zeroes it once per step); the constants are derived by the
+                                      * consumer, mpnn_bn_relu_pool_fwd_acc -- takes the fence / ticket / last-CTA round trips
+                                      * (3.4 us) off the dependent-launch chain */
+    int reserved;
 } mpnn_bn_fuse;
 /* mpnn_stencil_gemm (9 taps, single output, no accumulate) + fused BN statistics of `out` */
 int mpnn_conv_bn_stats(const void* A0, int K0, const void* A1, int K1,
@@ -154,6 +159,12 @@ int mpnn_bn_finalize(const float* partials, int n_parts, int C, double count,
 int mpnn_bn_relu_pool_fwd(const void* lin, int C, int B, int H, int W, int G, int P,
                           const float* ss, void* act, void* pooled, int Pp,
                           void* feat, int Balloc, int dtype, void* stream);
+/* mpnn_bn_relu_pool_fwd with the train-mode constants derived IN the kernel from the totals a producer launched with
+ * bn->defer = 1 has accumulated in bn->acc: every thread recomputes scale / shift of its 8 channels (2 doubles each),
+ * one CTA per plane writes bn->ss, bn->mr and updates the running moments (lib/layer_types.py:231-238). */
+int mpnn_bn_relu_pool_fwd_acc(const void* lin, int C, int B, int H, int W, int G, int P,
+                              const mpnn_bn_fuse* bn, void* act, void* pooled, int Pp,
+                              void* feat, int Balloc, int dtype, void* stream);
 /* backward, pass 1: partial sums of dy' and dy'*(x - mean) (dy' = relu-masked sum
  * of dAct and dFeat; centred so that nothing cancels against mean * sum dy'); *n_parts rows written. */
 int mpnn_bn_bwd_reduce(const void* lin, const void* dAct, const void* dFeat, int Balloc,

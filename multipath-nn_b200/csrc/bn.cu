@@ -4,6 +4,7 @@
 // Reference: lib/layer_types.py:109-110 (pool), :196-199 (ReLU), :219-249 (BN).
 #include "common.cuh"
 #include "../../include/mpnn.h"
+#include "bn_fuse.cuh"
 
 // ------------------------------------------------------------------ finalize
 __global__ void bn_finalize_kernel(const float* __restrict__ partials, int n_parts, int C, double count,
@@ -68,15 +69,33 @@ __global__ void __launch_bounds__(256)
 bn_relu_pool_fwd_kernel(const T* __restrict__ lin, int C, Geom g,
                         const float* __restrict__ ss, T* __restrict__ act,
                         T* __restrict__ pooled, Geom gp,
-                        T* __restrict__ feat, int Balloc) {
+                        T* __restrict__ feat, int Balloc, const mpnn_bn_fuse bn) {
     pdl_launch_dependents();
     pdl_wait();
     const int KG = C / 8, kg = blockIdx.y;
     const int HH = POOL ? g.H / 2 : g.H;
     const unsigned total = (unsigned)g.B * HH * g.W;          // host guarantees < 2^31
     float a[8], c[8];
-    const bool affine = ss && (act || feat);
-    if (affine) {
+    const bool affine = (ss || bn.acc) && (act || feat);
+    if (bn.acc) {
+        // deferred train-mode statistics: the producer left the totals in bn.acc; every thread derives the constants
+        // of its 8 channels, the first CTA of the plane publishes them and updates the running moments
+        const bool pub = blockIdx.x == 0 && threadIdx.x == 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int ch = kg * 8 + j;
+            float mean, var, rstd;
+            mpnn_bn_consts_from_acc(bn, C, ch, a[j], c[j], mean, var, rstd);
+            if (pub) {
+                bn.ss[ch] = a[j]; bn.ss[C + ch] = c[j];
+                bn.mr[ch] = mean; bn.mr[C + ch] = rstd;
+                if (bn.m_avg) {
+                    bn.m_avg[ch] = bn.d * bn.m_avg[ch] + (1.f - bn.d) * mean;
+                    bn.v_avg[ch] = bn.d * bn.v_avg[ch] + (1.f - bn.d) * var;
+                }
+            }
+        }
+    } else if (affine) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) { a[j] = __ldg(ss + kg * 8 + j); c[j] = __ldg(ss + C + kg * 8 + j); }
     }
@@ -98,7 +117,7 @@ bn_relu_pool_fwd_kernel(const T* __restrict__ lin, int C, Geom g,
 #pragma unroll
                 for (int j = 0; j < 8; ++j) { v0[j] = 0.f; v1[j] = 0.f; }
             }
-            if (ok && act && ss) {
+            if (ok && act && affine) {
                 float o[8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) o[j] = fmaxf(fmaf(a[j], v0[j], c[j]), 0.f);
@@ -125,13 +144,15 @@ bn_relu_pool_fwd_kernel(const T* __restrict__ lin, int C, Geom g,
     }
 }
 
-extern "C" int mpnn_bn_relu_pool_fwd(const void* lin, int C, int B, int H, int W, int G, int P,
-                                     const float* ss, void* act, void* pooled, int Pp,
-                                     void* feat, int Balloc, int dtype, void* stream) {
+static int bn_relu_pool_fwd_impl(const void* lin, int C, int B, int H, int W, int G, int P,
+                                 const float* ss, const mpnn_bn_fuse* bnp, void* act, void* pooled, int Pp,
+                                 void* feat, int Balloc, int dtype, void* stream) {
     MPNN_REQUIRE(C % 8 == 0, "bn_relu_pool_fwd: C=%d", C);
     MPNN_REQUIRE(!(pooled && feat), "bn_relu_pool_fwd: pooled and feat are exclusive");
-    MPNN_REQUIRE(pooled || ss, "bn_relu_pool_fwd: nothing to do");
+    MPNN_REQUIRE(pooled || ss || bnp, "bn_relu_pool_fwd: nothing to do");
     MPNN_REQUIRE(!pooled || (H % 2 == 0 && W % 2 == 0), "bn_relu_pool_fwd: odd size");
+    MPNN_REQUIRE(!bnp || (bnp->acc && bnp->gamma && bnp->beta && bnp->ss && bnp->mr && bnp->count > 0),
+                 "bn_relu_pool_fwd_acc: incomplete mpnn_bn_fuse");
     Geom g = make_geom(B, H, W, G, P);
     Geom gp = make_geom(B, H / 2, W / 2, G, Pp);
     long long total = (long long)B * (pooled ? (H / 2) * W : H * W);
@@ -143,13 +164,27 @@ extern "C" int mpnn_bn_relu_pool_fwd(const void* lin, int C, int B, int H, int W
     if (gx < 1) gx = 1;
     dim3 grid(gx, C / 8);
     cudaStream_t st = (cudaStream_t)stream;
+    mpnn_bn_fuse bn = {};
+    if (bnp) bn = *bnp;
     if (pooled) {
         MPNN_DISPATCH_DTYPE(dtype, (mpnn_launch_pdl(bn_relu_pool_fwd_kernel<T, true>, grid, dim3(256), 0, st,
-            (const T*)lin, C, g, ss, (T*)act, (T*)pooled, gp, (T*)feat, Balloc)));
+            (const T*)lin, C, g, ss, (T*)act, (T*)pooled, gp, (T*)feat, Balloc, bn)));
     } else {
         MPNN_DISPATCH_DTYPE(dtype, (mpnn_launch_pdl(bn_relu_pool_fwd_kernel<T, false>, grid, dim3(256), 0, st,
-            (const T*)lin, C, g, ss, (T*)act, (T*)pooled, gp, (T*)feat, Balloc)));
+            (const T*)lin, C, g, ss, (T*)act, (T*)pooled, gp, (T*)feat, Balloc, bn)));
     }
     return mpnn_check_launch("bn_relu_pool_fwd");
 }
 
+extern "C" int mpnn_bn_relu_pool_fwd(const void* lin, int C, int B, int H, int W, int G, int P,
+                                     const float* ss, void* act, void* pooled, int Pp,
+                                     void* feat, int Balloc, int dtype, void* stream) {
+    return bn_relu_pool_fwd_impl(lin, C, B, H, W, G, P, ss, nullptr, act, pooled, Pp, feat, Balloc, dtype, stream);
+}
+
+extern "C" int mpnn_bn_relu_pool_fwd_acc(const void* lin, int C, int B, int H, int W, int G, int P,
+                                         const mpnn_bn_fuse* bn, void* act, void* pooled, int Pp,
+                                         void* feat, int Balloc, int dtype, void* stream) {
+    MPNN_REQUIRE(bn, "bn_relu_pool_fwd_acc: bn is NULL");
+    return bn_relu_pool_fwd_impl(lin, C, B, H, W, G, P, nullptr, bn, act, pooled, Pp, feat, Balloc, dtype, stream);
+}

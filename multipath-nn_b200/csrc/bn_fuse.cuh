@@ -29,6 +29,26 @@ __device__ __forceinline__ bool mpnn_acc_and_ticket(double* acc, int C, int n0, 
     return s_last != 0;
 }
 
+// deferred variant: only the fp64 adds; the consumer kernel derives the constants from the totals
+template <typename F>
+__device__ __forceinline__ void mpnn_acc_only(double* acc, int C, int n0, int nb, F val) {
+    for (int i = threadIdx.x; i < 2 * nb; i += blockDim.x)
+        atomicAdd(acc + (size_t)(i / nb) * C + n0 + i % nb, (double)val(i));
+}
+
+// scale / shift of channel c from the accumulated totals (the arithmetic of mpnn_bn_fwd_finalize_last)
+__device__ __forceinline__ void mpnn_bn_consts_from_acc(const mpnn_bn_fuse& f, int C, int c, float& a, float& sh,
+                                                        float& mean, float& var, float& rstd) {
+    const double s = f.acc[c], s2 = f.acc[C + c];
+    const double m = s / f.count;
+    double v = s2 / f.count - m * m;
+    if (v < 0.0) v = 0.0;
+    mean = (float)m; var = (float)v;
+    rstd = 1.0f / sqrtf(var + f.eps);
+    a = f.gamma[c] * rstd;
+    sh = f.beta[c] - mean * a;
+}
+
 // forward finalisation by the last CTA (lib/layer_types.py:219-249): batch moments ->
 // scale/shift (ss), mean/rstd (mr), running averages; then reset acc + ticket.
 __device__ __forceinline__ void mpnn_bn_fwd_finalize_last(const mpnn_bn_fuse& f, int C) {

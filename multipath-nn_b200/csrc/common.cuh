@@ -122,6 +122,10 @@ static inline bool mpnn_pdl_enabled() {
     static const int v = getenv("MPNN_PDL") ? atoi(getenv("MPNN_PDL")) : 1;
     return v != 0;
 }
+static inline unsigned mpnn_pdl_min_ctas() {       // MPNN_PDL_MIN_CTAS=n: only grids of at least n CTAs take the attribute
+    static const int v = getenv("MPNN_PDL_MIN_CTAS") ? atoi(getenv("MPNN_PDL_MIN_CTAS")) : 0;
+    return (unsigned)v;
+}
 template <typename... KArgs, typename... Args>
 static inline cudaError_t mpnn_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
                                           cudaStream_t st, Args... args) {
@@ -129,7 +133,7 @@ static inline cudaError_t mpnn_launch_pdl(void (*kernel)(KArgs...), dim3 grid, d
     cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at[0].val.programmaticStreamSerializationAllowed = mpnn_pdl_enabled() ? 1 : 0;
+    at[0].val.programmaticStreamSerializationAllowed = (mpnn_pdl_enabled() && grid.x * grid.y * grid.z >= mpnn_pdl_min_ctas()) ? 1 : 0;
     cfg.attrs = at; cfg.numAttrs = 1;
     return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }

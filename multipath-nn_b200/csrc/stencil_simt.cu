@@ -93,7 +93,9 @@ stencil_gemm_simt(const T* __restrict__ A0, int K0, const T* __restrict__ A1, in
             int which = threadIdx.x / NB, j = threadIdx.x % NB;
             stats[((size_t)blockIdx.x * 2 + which) * N + n0 + j] = t;
         }
-        if (bn.acc) {
+        if (bn.acc && bn.defer) {
+            mpnn_acc_only(bn.acc, N, n0, NB, [&](int i) { return red[0][i] + red[1][i] + red[2][i] + red[3][i]; });
+        } else if (bn.acc) {
             const bool last = mpnn_acc_and_ticket(bn.acc, N, n0, NB, gridDim.x * gridDim.y,
                                                   [&](int i) { return red[0][i] + red[1][i] + red[2][i] + red[3][i]; });
             if (last) mpnn_bn_fwd_finalize_last(bn, N);

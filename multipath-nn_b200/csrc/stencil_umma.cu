@@ -472,7 +472,10 @@ stencil_gemm_umma_kernel(const GemmArgs a) {
             a.stats[((size_t)blockIdx.x * 2 + which) * a.N + n0 + j] = t;
         }
     }
-    if (stats_mode == 1 && a.bn.acc) {
+    if (stats_mode == 1 && a.bn.acc && a.bn.defer) {
+        mpnn_acc_only(a.bn.acc, a.N, n0, NB, [&](int i) {
+            return sstat[i] + sstat[2 * NB + i] + sstat[4 * NB + i] + sstat[6 * NB + i]; });
+    } else if (stats_mode == 1 && a.bn.acc) {
         const bool last = mpnn_acc_and_ticket(a.bn.acc, a.N, n0, NB, gridDim.x * gridDim.y, [&](int i) {
             return sstat[i] + sstat[2 * NB + i] + sstat[4 * NB + i] + sstat[6 * NB + i]; });
         if (last) mpnn_bn_fwd_finalize_last(a.bn, a.N);

@@ -39,11 +39,11 @@ _RT_BWD = _struct(['Z1', 'Z2', 'dR', 'g1', 'b1', 'W2', 'g2', 'b2', 'W3', 'save',
                    'dbias2', 'dg2', 'dbt2', 'dW3', 'dbias3', 'dZ1', 'scratch', 'dZ1p', 'dbias1'],
                   ['ns', 'Balloc'])
 _BN_FUSE = np.dtype([(k, '<u8') for k in ('acc', 'gamma', 'beta', 'm_avg', 'v_avg', 'ss', 'mr')]
-                    + [('count', '<f8'), ('d', '<f4'), ('eps', '<f4')], align=True)
+                    + [('count', '<f8'), ('d', '<f4'), ('eps', '<f4'), ('defer', '<i4'), ('reserved', '<i4')], align=True)
 _BN_BWD_FUSE = _struct(['acc', 'sums', 'dgamma', 'dbeta'], [])
 _BN_BWD_EPI = _struct(['lin', 'ss', 'mr', 'acc', 'sums', 'dgamma', 'dbeta'], [])
 assert _PACK.itemsize == 48 and _RT_FWD.itemsize == 136 and _RT_BWD.itemsize == 184
-assert _BN_FUSE.itemsize == 72 and _BN_BWD_FUSE.itemsize == 32 and _BN_BWD_EPI.itemsize == 56
+assert _BN_FUSE.itemsize == 80 and _BN_BWD_FUSE.itemsize == 32 and _BN_BWD_EPI.itemsize == 56
 
 
 def _host_struct(dtype, **fields):
@@ -135,6 +135,9 @@ class Engine:
         self.graph_collective = os.environ.get('MPNN_DIST_GRAPH', '1') != '0'
         self.overlap_allreduce = os.environ.get('MPNN_DIST_OVERLAP', '1') != '0'
         self.lane_priority = os.environ.get('MPNN_LANE_PRIORITY', '0') != '0'
+        # train-mode BN statistics: the conv only accumulates the totals, the BN / ReLU / pool kernel behind it derives
+        # the constants (MPNN_DEFER_BN=0: the conv's last CTA finalises them, as in round 1)
+        self.defer_bn = os.environ.get('MPNN_DEFER_BN', '0') != '0'
         self._snapshot = False
         self._analyse()
         self._alloc_params()
@@ -775,6 +778,21 @@ class _Plan:
     def planes(self, C, geo):
         return self.zeros((C // 8, geo.P, 8), self.eng.tdtype)
 
+    def _acc_f(self, n):
+        """fp64 accumulator of deferred forward BN statistics: a slice of one pool that a single memset at the head
+        of the step clears (the deferred protocol does not clean up after itself)"""
+        if getattr(self, '_accpool', None) is None:
+            self._accpool = self.zeros(1 << 14, torch.float64)
+            self._accpool_off = 0
+            pool = self._accpool
+            self.pack_ops.append(lambda: pool.zero_())
+        off = self._accpool_off
+        n = _ru(n, 2)
+        if off + n > self._accpool.numel():
+            raise RuntimeError('engine: BN accumulator pool exhausted')
+        self._accpool_off = off + n
+        return self._accpool[off:off + n]
+
     def _image_slot(self):
         """pseudo parent of a Conv chain at the root: the input image as one padded-planes tensor"""
         if getattr(self, '_img', None) is None:
@@ -1220,11 +1238,11 @@ class _Plan:
             if use_stats:
                 # train-mode BN statistics ride on the conv launch (last CTA finalises): no bn_finalize
                 bn = sc.bn
-                sc.acc = self.zeros(2 * N + 1, torch.float64)
-                sc.bnf = _host_struct(_BN_FUSE, acc=_vp(sc.acc), gamma=eng.tptr(bn.params.γ), beta=eng.tptr(bn.params.β),
+                sc.acc_f = self._acc_f(2 * N + 1) if eng.defer_bn else self.zeros(2 * N + 1, torch.float64)
+                sc.bnf = _host_struct(_BN_FUSE, acc=_vp(sc.acc_f), gamma=eng.tptr(bn.params.γ), beta=eng.tptr(bn.params.β),
                                       m_avg=eng.tptr(bn.params.m_avg), v_avg=eng.tptr(bn.params.v_avg),
                                       ss=_vp(sc.ss), mr=_vp(sc.mr), count=float(B * geo.H * geo.W),
-                                      d=float(bn.hypers.d), eps=float(bn.hypers.ε))
+                                      d=float(bn.hypers.d), eps=float(bn.hypers.ε), defer=1 if eng.defer_bn else 0)
 
                 def conv(sc=sc, prev=prev):
                     L.conv_bn_stats(_vp(sc.src.t), sc.K0, _vp(prev.pooled) if prev is not None else None, sc.K1,
@@ -1254,10 +1272,16 @@ class _Plan:
                 fin.lane = sc.lane
                 self.fwd_ops.append(fin)
             if sc.live or sc.pooled is not None:
-                def post(sc=sc):
-                    L.bn_relu_pool_fwd(_vp(sc.lin), sc.N, *sc.geo.args(), _vp(sc.ss) if sc.live else None,
-                                       _vp(sc.act), _vp(sc.pooled), sc.geo_p.P if sc.pooled is not None else 0,
-                                       _vp(sc.feat), Balloc, dt, S())
+                if use_stats and eng.defer_bn:
+                    def post(sc=sc):
+                        L.bn_relu_pool_fwd_acc(_vp(sc.lin), sc.N, *sc.geo.args(), ctypes.c_void_p(sc.bnf.ctypes.data),
+                                               _vp(sc.act), _vp(sc.pooled), sc.geo_p.P if sc.pooled is not None else 0,
+                                               _vp(sc.feat), Balloc, dt, S())
+                else:
+                    def post(sc=sc):
+                        L.bn_relu_pool_fwd(_vp(sc.lin), sc.N, *sc.geo.args(), _vp(sc.ss) if sc.live else None,
+                                           _vp(sc.act), _vp(sc.pooled), sc.geo_p.P if sc.pooled is not None else 0,
+                                           _vp(sc.feat), Balloc, dt, S())
                 self._tag(post, 'bn_fwd', nbytes=B * sc.geo.H * sc.geo.W * sc.N * (2 if dt == BF16 else 4) * (1 + (sc.act is not None) + 0.25 * (sc.pooled is not None) + (sc.feat is not None)))
                 post.lane = sc.lane
                 sc.post_op = post
@@ -1287,11 +1311,11 @@ class _Plan:
         bnp = None
         if use_stats:
             bn = sc.bn
-            sc.acc = self.zeros(2 * N + 1, torch.float64)
-            sc.bnf = _host_struct(_BN_FUSE, acc=_vp(sc.acc), gamma=eng.tptr(bn.params.γ), beta=eng.tptr(bn.params.β),
+            sc.acc_f = self._acc_f(2 * N + 1) if eng.defer_bn else self.zeros(2 * N + 1, torch.float64)
+            sc.bnf = _host_struct(_BN_FUSE, acc=_vp(sc.acc_f), gamma=eng.tptr(bn.params.γ), beta=eng.tptr(bn.params.β),
                                   m_avg=eng.tptr(bn.params.m_avg), v_avg=eng.tptr(bn.params.v_avg),
                                   ss=_vp(sc.ss), mr=_vp(sc.mr), count=float(B * geo.H * geo.W),
-                                  d=float(bn.hypers.d), eps=float(bn.hypers.ε))
+                                  d=float(bn.hypers.d), eps=float(bn.hypers.ε), defer=1 if eng.defer_bn else 0)
             bnp = ctypes.c_void_p(sc.bnf.ctypes.data)
         two = prev is not None
 
@@ -1324,10 +1348,15 @@ class _Plan:
             self.fwd_ops.append(fin)
         sc.act_split = sc.pooled_split = None
         if sc.live or sc.pooled is not None:
-            def post(sc=sc):
-                L.bn_relu_pool_fwd(_vp(sc.lin), N, *geo.args(), _vp(sc.ss) if sc.live else None,
-                                   _vp(sc.act), _vp(sc.pooled), sc.geo_p.P if sc.pooled is not None else 0,
-                                   _vp(sc.feat), Balloc, F32, S())
+            if use_stats and eng.defer_bn:
+                def post(sc=sc):
+                    L.bn_relu_pool_fwd_acc(_vp(sc.lin), N, *geo.args(), bnp, _vp(sc.act), _vp(sc.pooled),
+                                           sc.geo_p.P if sc.pooled is not None else 0, _vp(sc.feat), Balloc, F32, S())
+            else:
+                def post(sc=sc):
+                    L.bn_relu_pool_fwd(_vp(sc.lin), N, *geo.args(), _vp(sc.ss) if sc.live else None,
+                                       _vp(sc.act), _vp(sc.pooled), sc.geo_p.P if sc.pooled is not None else 0,
+                                       _vp(sc.feat), Balloc, F32, S())
             self._tag(post, 'bn_fwd', nbytes=B * geo.H * geo.W * N * 4 * (1 + (sc.act is not None) + 0.25 * (sc.pooled is not None) + (sc.feat is not None)))
             post.lane = sc.lane
             self.fwd_ops.append(post)

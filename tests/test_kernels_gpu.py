@@ -234,6 +234,45 @@ def test_stencil_dgrad_split_outputs(dt, impl):
         assert rel_err(from_planes(o.float().cpu().numpy(), geo, C), ref) < (1e-5 if dt == F32 else 4e-3)
 
 
+@pytest.mark.parametrize('dt,impl', [(F32, 0), (BF16, 1)])
+@pytest.mark.parametrize('B,H,K0,K1,N', [(3, 8, 16, 0, 16), (40, 16, 16, 16, 32), (7, 4, 64, 32, 64), (300, 8, 16, 0, 16)])
+def test_deferred_bn_statistics_equal_the_last_cta_protocol(dt, impl, B, H, K0, K1, N):
+    """bn.defer = 1: the conv only adds its partial sums into acc and mpnn_bn_relu_pool_fwd_acc derives scale / shift,
+    mean / rstd and the running moments -- same numbers as the conv's last-CTA finalisation + mpnn_bn_relu_pool_fwd"""
+    from lib.engine import _BN_FUSE, _host_struct
+    rng = np.random.default_rng(23)
+    td = torch.float32 if dt == F32 else torch.bfloat16
+    geo, gp = Geo(B, H, H), Geo(B, H // 2, H // 2)
+    mk = lambda C: dev(to_planes(rng.standard_normal((B, H, H, C)).astype(np.float32), geo), td)
+    A0, A1 = mk(K0), (mk(K1) if K1 else None)
+    Wp = dev(rng.standard_normal((9, (K0 + K1) // 8, N, 8)).astype(np.float32) * 0.1, td)
+    bias = dev(rng.standard_normal(N).astype(np.float32))
+    gamma, beta = dev(rng.standard_normal(N).astype(np.float32)), dev(rng.standard_normal(N).astype(np.float32))
+    res = []
+    for defer in (0, 1):
+        acc = torch.zeros(2 * N + 2, dtype=torch.float64, device='cuda')
+        ss, mr = torch.zeros((2, N), device='cuda'), torch.zeros((2, N), device='cuda')
+        ma, va = torch.zeros(N, device='cuda'), torch.ones(N, device='cuda')
+        lin = torch.zeros((N // 8, geo.P, 8), dtype=td, device='cuda')
+        act = torch.zeros_like(lin)
+        pooled = torch.zeros((N // 8, gp.P, 8), dtype=td, device='cuda')
+        f = _host_struct(_BN_FUSE, acc=vp(acc), gamma=vp(gamma), beta=vp(beta), m_avg=vp(ma), v_avg=vp(va),
+                         ss=vp(ss), mr=vp(mr), count=float(B * H * H), d=0.9, eps=1e-6, defer=defer)
+        fp = ctypes.c_void_p(f.ctypes.data)
+        L().conv_bn_stats(vp(A0), K0, vp(A1), K1, vp(Wp), vp(bias), vp(lin), N, B, H, H, geo.G, geo.P, fp, dt, impl, None)
+        if defer:
+            L().bn_relu_pool_fwd_acc(vp(lin), N, B, H, H, geo.G, geo.P, fp, vp(act), vp(pooled), gp.P, None, 0, dt, None)
+        else:
+            L().bn_relu_pool_fwd(vp(lin), N, B, H, H, geo.G, geo.P, vp(ss), vp(act), vp(pooled), gp.P, None, 0, dt, None)
+        torch.cuda.synchronize()
+        res.append([t.float().cpu().numpy() for t in (lin, act, pooled, ss, mr, ma, va)])
+    for a, b, name in zip(res[0], res[1], ('lin', 'act', 'pooled', 'ss', 'mr', 'm_avg', 'v_avg')):
+        if name in ('lin', 'pooled'):
+            assert np.array_equal(a, b), name
+        else:
+            np.testing.assert_allclose(b, a, rtol=2e-5, atol=2e-6, err_msg=name)
+
+
 @pytest.mark.parametrize('B,H,K,N0,N1', [(5, 8, 16, 16, 0), (40, 16, 16, 16, 16), (9, 8, 32, 32, 0), (130, 32, 16, 16, 0),
                                          (6, 8, 32, 16, 32), (7, 8, 64, 64, 0), (3, 4, 64, 32, 64), (300, 8, 16, 16, 16)])
 def test_dgrad_with_fused_bn_backward_sums(B, H, K, N0, N1):

@@ -49,6 +49,7 @@ _STRUCTS = {
 _HOST_STRUCTS = {
     'conv_bn_stats': ('bn', E._BN_FUSE, dict(acc='rw', gamma='r', beta='r', m_avg='rw', v_avg='rw', ss='w', mr='w')),
     'conv_acc_bn_stats': ('bn', E._BN_FUSE, dict(acc='rw', gamma='r', beta='r', m_avg='rw', v_avg='rw', ss='w', mr='w')),
+    'bn_relu_pool_fwd_acc': ('bn', E._BN_FUSE, dict(acc='r', gamma='r', beta='r', m_avg='rw', v_avg='rw', ss='w', mr='w')),
     'bn_bwd_reduce_fused': ('f', E._BN_BWD_FUSE, dict(acc='rw', sums='w', dgamma='w', dbeta='w')),
     'conv_dgrad_bn_reduce': ('epi', E._BN_BWD_EPI, dict(lin='r', ss='r', mr='r', acc='rw', sums='w', dgamma='w',
                                                         dbeta='w')),
@@ -98,8 +99,8 @@ def _tensor_index(*roots):
     """all torch tensors reachable from the given objects -> lookup(pointer) -> containing tensor"""
     seen, found = set(), {}
     for r in roots:                              # the zero-filled arenas a plan's buffers are carved from are not buffers
-        for a in getattr(r, 'arenas', []):
-            seen.add(id(a))
+        for a in list(getattr(r, 'arenas', [])) + [getattr(r, '_accpool', None)]:   # (nor is the pool the deferred
+            seen.add(id(a))                                                          #  BN accumulators are slices of)
 
     def walk(o, depth=0):
         if id(o) in seen or depth > 6:
