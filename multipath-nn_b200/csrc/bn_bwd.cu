@@ -95,7 +95,9 @@ static int bn_bwd_reduce_impl(const void* lin, const void* dAct, const void* dFe
     MPNN_REQUIRE(!fp || (fp->acc && fp->sums), "bn_bwd_reduce_fused: incomplete mpnn_bn_bwd_fuse");
     Geom g = make_geom(B, H, W, G, P);
     int total = B * H * W;
-    int gx = ceil_div(total, 256 * 4);
+    // latency-bound when small: one pixel per thread as long as that is at most ~4 CTAs per SM, else four
+    int gx = ceil_div(total, 256);
+    if ((long long)gx * (C / 8) > 148 * 4) gx = ceil_div(total, 256 * 4);
     int lim = 148 * 8 / (C / 8);
     if (lim < 74) lim = 74;
     if (gx > lim) gx = lim;

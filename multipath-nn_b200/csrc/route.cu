@@ -68,13 +68,104 @@ __global__ void route_fwd_kernel(const int* __restrict__ parent, const int* __re
     }
 }
 
+
+// ---- staged variants ---------------------------------------------------------------------------------
+// The walk is a chain of small dependent steps per example; in the kernels above every step goes through
+// global memory (tree tables, pointer tables, the per-node running values), i.e. ~n_nodes x several L2
+// round trips back to back.  For trees of up to RT_STAGED_MAX nodes the tables are staged in shared memory
+// once per CTA, the per-example running values live in a shared-memory column per thread, and the
+// per-example inputs are fetched up front with independent loads.  Same arithmetic, same order.
+#define RT_STAGED_MAX 32
+#define RT_T 64
+struct RtTables {
+    int *parent, *sink_idx, *n_sinks, *sw, *err, *child;
+    float *floor_, *ops;
+    const float** Rn;          // per node: logits of its router (switches only)
+    float** dRn;
+    const float** cen;         // per node: c_err / d_cor vectors of its classifier (leaves only)
+    const float** dcn;
+    float* col;                // [ncol][n][RT_T]
+};
+static size_t rt_smem_bytes(int n, int ncol) {
+    return (size_t)n * (5 * 4 + RT_MAXS * 4 + 2 * 4 + 4 * 8) + (size_t)ncol * n * RT_T * 4 + 64;
+}
+__device__ __forceinline__ RtTables rt_carve(unsigned char* sm, int n, int ncol) {
+    RtTables t;
+    t.Rn = reinterpret_cast<const float**>(sm);  sm += (size_t)n * 8;
+    t.dRn = reinterpret_cast<float**>(sm);       sm += (size_t)n * 8;
+    t.cen = reinterpret_cast<const float**>(sm); sm += (size_t)n * 8;
+    t.dcn = reinterpret_cast<const float**>(sm); sm += (size_t)n * 8;
+    t.parent = reinterpret_cast<int*>(sm);   sm += (size_t)n * 4;
+    t.sink_idx = reinterpret_cast<int*>(sm); sm += (size_t)n * 4;
+    t.n_sinks = reinterpret_cast<int*>(sm);  sm += (size_t)n * 4;
+    t.sw = reinterpret_cast<int*>(sm);       sm += (size_t)n * 4;
+    t.err = reinterpret_cast<int*>(sm);      sm += (size_t)n * 4;
+    t.child = reinterpret_cast<int*>(sm);    sm += (size_t)n * RT_MAXS * 4;
+    t.floor_ = reinterpret_cast<float*>(sm); sm += (size_t)n * 4;
+    t.ops = reinterpret_cast<float*>(sm);    sm += (size_t)n * 4;
+    t.col = reinterpret_cast<float*>(sm);
+    return t;
+}
+
+__device__ __forceinline__ void rt_prefetch(const void* p) { asm volatile("prefetch.global.L1 [%0];" :: "l"(p)); }
+
+__global__ void __launch_bounds__(RT_T)
+route_fwd_staged_kernel(const int* __restrict__ parent, const int* __restrict__ sink_idx,
+                        const int* __restrict__ n_sinks, const float* __restrict__ floor_,
+                        const int* __restrict__ sw, int n_nodes,
+                        const float* const* __restrict__ R, const float* __restrict__ hyp, int B,
+                        float* __restrict__ p_tr, float* __restrict__ p_ev, int* __restrict__ dec) {
+    extern __shared__ __align__(16) unsigned char rt_sm[];
+    const RtTables t = rt_carve(rt_sm, n_nodes, 2);
+    const int tid = threadIdx.x;
+    for (int i = tid; i < n_nodes; i += RT_T) {
+        t.parent[i] = i ? parent[i] : 0; t.sink_idx[i] = sink_idx[i]; t.n_sinks[i] = n_sinks[i];
+        t.sw[i] = sw[i]; t.floor_[i] = floor_[i];
+        t.Rn[i] = n_sinks[i] >= 2 ? R[sw[i]] : nullptr;
+    }
+    __syncthreads();
+    const int b = blockIdx.x * RT_T + tid;
+    if (b >= B) return;
+    const float tau = hyp[MPNN_HYP_TAU], eps = hyp[MPNN_HYP_EPS];
+    for (int i = 0; i < n_nodes; ++i)                        // every router's logits of this example: in flight together
+        if (t.Rn[i]) rt_prefetch(t.Rn[i] + (size_t)b * t.n_sinks[i]);
+    float* pt_c = t.col + tid;                               // [n][RT_T] columns of this thread
+    float* pe_c = t.col + (size_t)n_nodes * RT_T + tid;
+    pt_c[0] = 1.f; pe_c[0] = 1.f;
+    p_tr[b] = 1.f; p_ev[b] = 1.f;
+    // siblings share their parent's softmax: evaluate it once, when the first sink (sink_idx 0) comes up
+    float sm[RT_MAXS];
+    int d = 0, sm_of = -1;
+    for (int i = 1; i < n_nodes; ++i) {
+        const int par = t.parent[i], ns = t.n_sinks[par];
+        float pt = pt_c[par * RT_T], pe = pe_c[par * RT_T];
+        if (ns >= 2) {
+            const int si = t.sink_idx[i];
+            if (sm_of != par) {
+                d = route_softmax(t.Rn[par] + (size_t)b * ns, ns, tau, sm);
+                sm_of = par;
+                if (dec) dec[(size_t)t.sw[par] * B + b] = d;
+            }
+            pt = (pt - eps * t.floor_[par]) * pick(sm, si) + eps * t.floor_[i];
+            pe = pe * (d == si ? 1.f : 0.f);
+        }
+        pt_c[i * RT_T] = pt; pe_c[i * RT_T] = pe;
+        p_tr[(size_t)i * B + b] = pt;
+        p_ev[(size_t)i * B + b] = pe;
+    }
+}
+
 extern "C" int mpnn_route_fwd(const int* parent, const int* sink_idx, const int* n_sinks,
                               const float* floor_, const int* sw, int n_nodes,
                               const float* const* R, const float* hyp, int B,
                               float* p_tr, float* p_ev, int* dec, void* stream) {
     MPNN_REQUIRE(n_nodes >= 1 && B >= 1 && hyp, "route_fwd: args");
-    route_fwd_kernel<<<ceil_div(B, 128), 128, 0, (cudaStream_t)stream>>>(
-        parent, sink_idx, n_sinks, floor_, sw, n_nodes, R, hyp, B, p_tr, p_ev, dec);
+    if (n_nodes <= RT_STAGED_MAX)
+        route_fwd_staged_kernel<<<ceil_div(B, RT_T), RT_T, rt_smem_bytes(n_nodes, 2), (cudaStream_t)stream>>>(
+            parent, sink_idx, n_sinks, floor_, sw, n_nodes, R, hyp, B, p_tr, p_ev, dec);
+    else
+        route_fwd_kernel<<<ceil_div(B, 128), 128, 0, (cudaStream_t)stream>>>(
+            parent, sink_idx, n_sinks, floor_, sw, n_nodes, R, hyp, B, p_tr, p_ev, dec);
     return mpnn_check_launch("route_fwd");
 }
 
@@ -181,6 +272,134 @@ __global__ void route_bwd_kernel(const int* parent, const int* sink_idx,
     if (c_data) c_data[b] = total;
 }
 
+
+__global__ void __launch_bounds__(RT_T)
+route_bwd_staged_kernel(const int* __restrict__ parent, const int* __restrict__ sink_idx,
+                        const int* __restrict__ n_sinks, const int* __restrict__ child,
+                        const float* __restrict__ floor_, const int* __restrict__ sw,
+                        const float* __restrict__ ops, const int* __restrict__ err, int n_nodes,
+                        const float* const* __restrict__ R, const float* __restrict__ hyp, int B,
+                        const float* __restrict__ p_tr,
+                        const float* const* __restrict__ c_err, const float* const* __restrict__ d_cor,
+                        const float* __restrict__ k_cpt,
+                        int critic, float k_dec, float k_cre, int optimistic, int use_cls_err,
+                        float* const* __restrict__ dR, float* __restrict__ c_data) {
+    extern __shared__ __align__(16) unsigned char rt_sm[];
+    const RtTables t = rt_carve(rt_sm, n_nodes, 5);
+    const int tid = threadIdx.x, n = n_nodes;
+    for (int i = tid; i < n; i += RT_T) {
+        t.parent[i] = i ? parent[i] : 0; t.sink_idx[i] = sink_idx[i]; t.n_sinks[i] = n_sinks[i];
+        t.sw[i] = sw[i]; t.floor_[i] = floor_[i]; t.ops[i] = ops[i]; t.err[i] = err[i];
+        const bool is_sw = n_sinks[i] >= 2;
+        t.Rn[i] = is_sw ? R[sw[i]] : nullptr;
+        t.dRn[i] = is_sw ? dR[sw[i]] : nullptr;
+        t.cen[i] = err[i] >= 0 ? c_err[err[i]] : nullptr;
+        t.dcn[i] = (err[i] >= 0 && use_cls_err) ? d_cor[err[i]] : nullptr;
+        for (int j = 0; j < RT_MAXS; ++j) t.child[i * RT_MAXS + j] = child[i * RT_MAXS + j];
+    }
+    __syncthreads();
+    const int b = blockIdx.x * RT_T + tid;
+    if (b >= B) return;
+    const float invB = 1.f / (float)B;
+    const float tau = hyp[MPNN_HYP_TAU], eps = hyp[MPNN_HYP_EPS];
+    const float kc = k_cpt ? k_cpt[b] : hyp[MPNN_HYP_KCPT];
+    const size_t cs = (size_t)n * RT_T;
+    float* pt_c = t.col + tid;                 // p_tr of every node
+    float* ce_c = t.col + cs + tid;            // c_err of every node (0 off the leaves)
+    float* g_c = t.col + 2 * cs + tid;         // actor: dL/dp_tr; critic: c_ev
+    float* o_c = t.col + 3 * cs + tid;         // critic: c_opt
+    float* dc_c = t.col + 4 * cs + tid;        // critic with use_cls_err: 1 - d_cor
+    // per-example inputs: independent loads, issued together
+    for (int i = 0; i < n; ++i)
+        if (t.Rn[i]) rt_prefetch(t.Rn[i] + (size_t)b * t.n_sinks[i]);
+#pragma unroll 4
+    for (int i = 0; i < n; ++i) {
+        pt_c[i * RT_T] = p_tr[(size_t)i * B + b];
+        ce_c[i * RT_T] = t.cen[i] ? t.cen[i][b] : 0.f;
+        if (use_cls_err) dc_c[i * RT_T] = t.dcn[i] ? 1.f - t.dcn[i][b] : 0.f;
+    }
+    float total = 0.f;
+    float sm[RT_MAXS];
+    int sm_of = -1, d = 0;
+    if (!critic) {
+        for (int i = 0; i < n; ++i) {
+            const float local = ce_c[i * RT_T] + kc * t.ops[i];
+            g_c[i * RT_T] = local * invB;
+            total += pt_c[i * RT_T] * local;
+        }
+        for (int i = n - 1; i >= 1; --i) {
+            const int par = t.parent[i], ns = t.n_sinks[par];
+            float g = g_c[i * RT_T];
+            if (ns >= 2) {
+                if (sm_of != par) { route_softmax(t.Rn[par] + (size_t)b * ns, ns, tau, sm); sm_of = par; }
+                g *= pick(sm, t.sink_idx[i]);
+            }
+            g_c[par * RT_T] += g;
+        }
+        for (int i = 0; i < n; ++i) {
+            const int ns = t.n_sinks[i];
+            if (ns < 2) continue;
+            const float* r = t.Rn[i] + (size_t)b * ns;
+            float gs[RT_MAXS], rv[RT_MAXS];
+            route_softmax(r, ns, tau, sm);
+            sm_of = i;
+            const float pt = pt_c[i * RT_T];
+            float dot = 0.f, r2 = 0.f;
+#pragma unroll
+            for (int j = 0; j < RT_MAXS; ++j) {
+                gs[j] = 0.f; rv[j] = 0.f;
+                if (j < ns) {
+                    rv[j] = r[j];
+                    gs[j] = g_c[t.child[i * RT_MAXS + j] * RT_T] * (pt - eps * t.floor_[i]);
+                    dot = fmaf(sm[j], gs[j], dot);
+                    r2 = fmaf(rv[j], rv[j], r2);
+                }
+            }
+            float* out = t.dRn[i] + (size_t)b * ns;
+#pragma unroll
+            for (int j = 0; j < RT_MAXS; ++j)
+                if (j < ns) out[j] = sm[j] * (gs[j] - dot) / tau + pt * k_dec * 2.f * rv[j] * invB;
+            total += pt * k_dec * r2;
+        }
+    } else {
+        for (int i = n - 1; i >= 0; --i) {
+            const int ns = t.n_sinks[i];
+            const float ce_true = ce_c[i * RT_T];
+            const float ce = use_cls_err ? dc_c[i * RT_T] : ce_true;
+            const float base = ce + kc * t.ops[i];
+            const float pt = pt_c[i * RT_T];
+            float cre = 0.f;
+            if (ns < 2) {
+                float e = base, o = base;
+                for (int j = 0; j < ns; ++j) {
+                    const int ch = t.child[i * RT_MAXS + j];
+                    e += g_c[ch * RT_T]; o += o_c[ch * RT_T];
+                }
+                g_c[i * RT_T] = e; o_c[i * RT_T] = o;
+            } else {
+                const float* r = t.Rn[i] + (size_t)b * ns;
+                d = route_softmax(r, ns, tau, sm);
+                float mn = INFINITY;
+                float* out = t.dRn[i] + (size_t)b * ns;
+                for (int j = 0; j < ns; ++j) {
+                    const int ch = t.child[i * RT_MAXS + j];
+                    const float ev = g_c[ch * RT_T], op = o_c[ch * RT_T];
+                    mn = fminf(mn, op);
+                    const float tgt = optimistic ? op : ev;
+                    const float dlt = r[j] + tgt;
+                    cre = fmaf(dlt, dlt, cre);
+                    out[j] = pt * invB * k_cre * 2.f * dlt;
+                }
+                cre *= k_cre;
+                g_c[i * RT_T] = base + g_c[t.child[i * RT_MAXS + d] * RT_T];
+                o_c[i * RT_T] = base + mn;
+            }
+            total += pt * (ce_true + cre);
+        }
+    }
+    if (c_data) c_data[b] = total;
+}
+
 extern "C" int mpnn_route_bwd(const int* parent, const int* sink_idx, const int* n_sinks, const int* child,
                               const float* floor_, const int* sw, const float* ops, const int* err,
                               int n_nodes, const float* const* R, const float* hyp, int B,
@@ -190,9 +409,14 @@ extern "C" int mpnn_route_bwd(const int* parent, const int* sink_idx, const int*
                               int critic, float k_dec, float k_cre, int optimistic, int use_cls_err,
                               float* const* dR, float* scratch, float* c_data, void* stream) {
     MPNN_REQUIRE(n_nodes >= 1 && B >= 1 && hyp, "route_bwd: args");
-    route_bwd_kernel<<<ceil_div(B, 128), 128, 0, (cudaStream_t)stream>>>(
-        parent, sink_idx, n_sinks, child, floor_, sw, ops, err, n_nodes, R, hyp, B, p_tr, p_ev, c_err, d_cor,
-        k_cpt, critic, k_dec, k_cre, optimistic, use_cls_err, dR, scratch, c_data);
+    if (n_nodes <= RT_STAGED_MAX)
+        route_bwd_staged_kernel<<<ceil_div(B, RT_T), RT_T, rt_smem_bytes(n_nodes, 5), (cudaStream_t)stream>>>(
+            parent, sink_idx, n_sinks, child, floor_, sw, ops, err, n_nodes, R, hyp, B, p_tr, c_err, d_cor,
+            k_cpt, critic, k_dec, k_cre, optimistic, use_cls_err, dR, c_data);
+    else
+        route_bwd_kernel<<<ceil_div(B, 128), 128, 0, (cudaStream_t)stream>>>(
+            parent, sink_idx, n_sinks, child, floor_, sw, ops, err, n_nodes, R, hyp, B, p_tr, p_ev, c_err, d_cor,
+            k_cpt, critic, k_dec, k_cre, optimistic, use_cls_err, dR, scratch, c_data);
     return mpnn_check_launch("route_bwd");
 }
 

@@ -614,6 +614,9 @@ int mpnn_stencil_gemm_umma(const void* A0, int K0, const void* A1, int K1, const
     if (NB == 16 && bwd && cap > 3) cap = 3;
     // the generic-width instantiations need ~108 registers: two CTAs per SM are resident (ncu: occupancy limit 2 by
     // registers); a grid sized for three ran as 1.5 waves
+    const int n_kc_ = ceil_div(KG, KC);
+    const int ks = (ntaps == 9 && n_kc_ == 1) ? KG / 2 : 0;
+    const bool fast_ok = !tune_generic && out_dtype == MPNN_BF16 && !acc0 && !acc1 && !stats;
     if (NB != 16 && NB != 32 && cap > 2) cap = 2;
     if (tune_per_sm && cap > tune_per_sm) cap = tune_per_sm;
     if (cap < 1) cap = 1;
@@ -660,8 +663,6 @@ int mpnn_stencil_gemm_umma(const void* A0, int K0, const void* A1, int K1, const
     static const Kern wide[5] = {stencil_gemm_umma_kernel<0, 2, 0>, stencil_gemm_umma_kernel<0, 3, 0>,
                                  stencil_gemm_umma_kernel<0, 4, 0>, stencil_gemm_umma_kernel<0, 6, 0>,
                                  stencil_gemm_umma_kernel<0, 8, 0>};
-    const int ks = (ntaps == 9 && a.n_kc == 1) ? KG / 2 : 0;
-    const bool fast_ok = !tune_generic && a.out_mode == 0 && !acc0 && !acc1 && !stats;
     const int e = bwd ? 1 : 0;
     Kern kern = generic[NB == 16 ? 0 : (NB == 32 ? 1 : 2)];
     if (fast_ok && NB == 16 && ks >= 1 && ks <= 2) kern = fast16[e][ks - 1];

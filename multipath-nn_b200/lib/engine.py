@@ -135,6 +135,9 @@ class Engine:
         self.graph_collective = os.environ.get('MPNN_DIST_GRAPH', '1') != '0'
         self.overlap_allreduce = os.environ.get('MPNN_DIST_OVERLAP', '1') != '0'
         self.lane_priority = os.environ.get('MPNN_LANE_PRIORITY', '0') != '0'
+        # classifier / router-input heads rotate over this many lanes (1: all on the one heads lane, in stage order)
+        self.head_lanes = max(1, int(os.environ.get('MPNN_HEAD_LANES', '4')))
+        self.pack_blocks = max(1, int(os.environ.get('MPNN_PACK_BLOCKS', '32')))      # CTAs per weight tensor in the packing launch
         # train-mode BN statistics: the conv only accumulates the totals, the BN / ReLU / pool kernel behind it derives
         # the constants (MPNN_DEFER_BN=0: the conv's last CTA finalises them, as in round 1)
         self.defer_bn = os.environ.get('MPNN_DEFER_BN', '0') != '0'
@@ -508,7 +511,7 @@ class Engine:
                 # step; weight gradients (9, 10+k), TALR moments (8) and the gradient all-reduce (20) only feed the
                 # optimiser: they run at lower stream priority, so their CTAs fill SMs the chain leaves idle
                 # instead of delaying it.  Measured: +2 % at B = 128, -3 % at B = 4096 -> off unless MPNN_LANE_PRIORITY=1
-                hi = self.lane_priority and lane in (1, 3, 4, 5, 6, 7)
+                hi = self.lane_priority and (lane in (1, 3, 4, 5, 6, 7) or 21 <= lane < 40)
                 self._lanes[lane] = torch.cuda.Stream(self.dev, priority=-1 if hi else 0)
             self._lanes[lane].wait_stream(main)
         for op in ops:
@@ -857,6 +860,7 @@ class _Plan:
         self.reg, self.rtr, self.heads = {}, {}, {}
         self.pack_list, self.rt_fwd, self.keep, self.kplanes = [], [], [], []
         self.last_head_op = None
+        self.head_ops = []
         cpad_q = 16 if (dt == BF16 or eng.split) else 8
         dyn_k = eng.dynamic and bool(net.hypers.dyn_k_cpt)
 
@@ -904,8 +908,9 @@ class _Plan:
                 ce = lambda r=r: L.softmax_ce_fwd(
                     _vp(r.Zbuf), r.ldz, _vp(self.y), B, n_cls, r.eps, _vp(r.prob), _vp(r.c_err), _vp(r.d_cor), S())
                 if self.umma_heads:
-                    ce.lane = 1                       # follows its head GEMM on the heads lane
+                    ce.lane = hd.lane                 # follows its head GEMM on that head's lane
                     self.last_head_op = ce
+                    self.head_ops.append(ce)
                 self.fwd_ops.append(ce)
             if nd.router is not None:
                 self._build_router_fwd(nd, Balloc, dyn_k, emit_fc=not self.umma_heads)
@@ -926,7 +931,7 @@ class _Plan:
             tails = lambda: L.router_tail_fwd_batched(
                 _vp(tab), len(self.rt_fwd), B, 16, float(bn0.hypers.d), float(bn0.hypers.ε),
                 1 if self.bn_train else 0, S())
-            self.fwd_ops.append(self._after(tails, self.last_head_op))   # needs every head GEMM / loss
+            self.fwd_ops.append(self._after(tails, *(self.head_ops or [self.last_head_op])))   # needs every head GEMM / loss
         if eng.dynamic:
             self._build_routing()
 
@@ -993,7 +998,7 @@ class _Plan:
                     ceb = lambda r=r, coef=coef, dzp=dzp: L.softmax_ce_bwd(
                         _vp(r.prob), _vp(self.y), B, n_cls, r.eps, coef(), 1.0 / B, None,
                         dzp, Balloc, eng.gptr(r.fc.params.b), S())
-                    ceb.lane = 1
+                    ceb.lane = hd.lane
                     # a stage without a router only needs p_tr (forward): its head gradients are issued
                     # ahead of the routing backward so the deepest conv chain starts under it
                     ceb.early = eng.nodes[nd.parent].router is None
@@ -1045,7 +1050,7 @@ class _Plan:
         tab = self._desc_table(_PACK, self.pack_list)
         self.keep.append(tab)
         n = len(self.pack_list)
-        self.pack_ops.append(lambda: L.pack_weights_batched(_vp(tab), n, 32, BF16 if eng.split else eng.dtype, eng.stream))
+        self.pack_ops.append(lambda: L.pack_weights_batched(_vp(tab), n, eng.pack_blocks, BF16 if eng.split else eng.dtype, eng.stream))
 
     def _pack(self, param, packed, I, O, mode, k_off, Ktot, n_off, Ntot, ntaps=9):
         """mode 0: forward operand, 1: dgrad operand (transposed, taps flipped), 2: fp32 vector copy"""
@@ -1065,6 +1070,9 @@ class _Plan:
         rt = self.rtr.get(nd.idx)
         hd = Ns(leaf_off=0 if leaves else None, r_off=(16 if leaves else 0) if rt is not None else None)
         hd.N = 16 * (bool(leaves) + (rt is not None))
+        # heads only feed the losses / the routers: off the conv lanes, and spread over a few lanes of their own so
+        # that a head never queues behind the head of another stage
+        hd.lane = 1 if eng.head_lanes == 1 else 21 + len(self.heads) % eng.head_lanes
         F, Fext = st.F, st.Fext
         hd.Z16 = self.f32(B, 16) if leaves else None
         hd.Wfc = self.zeros((1, Fext // 8, hd.N, 8), eng.tdtype)
@@ -1090,9 +1098,10 @@ class _Plan:
             L.stencil_gemm(_vp(st.feat), Fext, None, 0, _vp(hd.Wfc), 1, _vp(hd.bias), _vp(o0), n0, 0, _vp(o1), n1, 0,
                            B, 0, 0, 0, Balloc, None, 0, None, BF16, 2, 1, S())
         self._tag(gemm, 'fc_fwd', desc='F%d N%d' % (Fext, hd.N), flops=2.0 * B * F * hd.N, nbytes=B * F * 2)
-        gemm.lane = 1
+        gemm.lane = hd.lane
         self._after(gemm, getattr(st, 'feat_op', None))
         self.last_head_op = gemm
+        self.head_ops.append(gemm)
         self.fwd_ops.append(gemm)
 
     def _build_heads_bwd(self, nd, st, dyn_k):
@@ -1128,7 +1137,7 @@ class _Plan:
             L.stencil_gemm(_vp(hd.dZ), hd.N, None, 0, _vp(hd.Wfd), 1, None, _vp(st.dfeat), F, 0, None, 0, 0,
                            B, 0, 0, 0, Balloc, None, 0, None, BF16, BF16, 1, S())
         self._tag(dgrad, 'fc_dgrad', desc='N%d F%d' % (hd.N, F), flops=2.0 * B * F * hd.N, nbytes=B * F * 2)
-        dgrad.lane = 1
+        dgrad.lane = hd.lane
         dgrad.early = rt is None
         st.dfeat_op = dgrad                          # the conv chain of this node waits for it
         # the router half of dZ comes from the routing backward on lane 0 (normally already ordered through

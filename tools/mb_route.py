@@ -11,7 +11,7 @@ B = int(os.environ.get('B', 4096))
 L = _cabi.lib()
 vp = lambda t: None if t is None else ctypes.c_void_p(t.data_ptr())
 layer_types.seed(0)
-net = ah.ac_chain(k_cpt=4e-9)((32, 32, 3), (10,)).configure(precision='bf16')
+net = ah.ac_chain(k_cpt=4e-9)((32, 32, 3), (10,)).configure(precision='bf16', graphs=os.environ.get('GRAPHS', '1') != '0')
 rng = np.random.default_rng(1)
 for l in net.layers:
     if l.router is not None:
