@@ -229,6 +229,18 @@ int mpnn_softmax_ce_fwd(const float* Z, int ldz /* row stride of Z */, const flo
 int mpnn_softmax_ce_bwd(const float* prob, const float* y, int B, int n, float eps,
                         const float* coef, float coef_scale, float* dZ,
                         void* dZp, int Balloc, float* dbias, void* stream);
+/* SquaredError (lib/layer_types.py:255-260) on the LinTrans output x = Z: c_err = sum_j (x - y)^2,
+ * d_cor = [argmax x == argmax y]; out [B][n] = dense copy of x (read by the backward).
+ * Backward: dZ = coef*coef_scale * 2 (x - y), outputs as in mpnn_softmax_ce_bwd. */
+int mpnn_squared_err_fwd(const float* Z, int ldz, const float* y, int B, int n,
+                         float* out, float* c_err, float* d_cor, void* stream);
+int mpnn_squared_err_bwd(const float* out, const float* y, int B, int n,
+                         const float* coef, float coef_scale, float* dZ,
+                         void* dZp, int Balloc, float* dbias, void* stream);
+/* SuperclassCrossEntropyError (lib/layer_types.py:274-285): y_sup [B][n_sup] = y [B][n_cls] @ w_cls [n_cls][n_sup];
+ * the loss is mpnn_softmax_ce_fwd / _bwd with y_sup in place of y and n = n_sup. */
+int mpnn_superclass_targets(const float* y, const float* w_cls, int B, int n_cls, int n_sup,
+                            float* y_sup, void* stream);
 
 /* Router tail (arch_and_hypers.py:45-49): BN -> ReLU -> FC(16) -> BN -> ReLU -> FC(ns)
  * applied to Z1 = output of the first router FC.  One CTA.

@@ -41,6 +41,40 @@ __device__ __forceinline__ float pick(const float (&v)[RT_MAXS], int idx) {
     return out;
 }
 
+// the same with the arrays sized for the widest switch of the net (block-uniform, 2 / 4 / 8): a 2-sink chain
+// does not pay for 8 predicated slots per step of the walk
+template <int NS>
+__device__ __forceinline__ int route_softmax_t(const float* r, int ns, float tau, float (&sm)[NS]) {
+    float mx = -INFINITY, mr = -INFINITY;
+    int dec = 0;
+#pragma unroll
+    for (int j = 0; j < NS; ++j) {
+        sm[j] = 0.f;
+        if (j < ns) {
+            float v = r[j];
+            if (v > mr) { mr = v; dec = j; }          // first maximal index (tf.argmax)
+            sm[j] = v / tau;
+            mx = fmaxf(mx, sm[j]);
+        }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < NS; ++j)
+        if (j < ns) { sm[j] = expf(sm[j] - mx); s += sm[j]; }
+    const float inv = 1.f / s;
+#pragma unroll
+    for (int j = 0; j < NS; ++j) sm[j] *= inv;
+    return dec;
+}
+
+template <int NS>
+__device__ __forceinline__ float pick_t(const float (&v)[NS], int idx) {
+    float out = 0.f;
+#pragma unroll
+    for (int j = 0; j < NS; ++j) out = (j == idx) ? v[j] : out;
+    return out;
+}
+
 __global__ void route_fwd_kernel(const int* __restrict__ parent, const int* __restrict__ sink_idx,
                                  const int* __restrict__ n_sinks, const float* __restrict__ floor_,
                                  const int* __restrict__ sw, int n_nodes,
@@ -109,21 +143,11 @@ __device__ __forceinline__ RtTables rt_carve(unsigned char* sm, int n, int ncol)
 
 __device__ __forceinline__ void rt_prefetch(const void* p) { asm volatile("prefetch.global.L1 [%0];" :: "l"(p)); }
 
-__global__ void __launch_bounds__(RT_T)
-route_fwd_staged_kernel(const int* __restrict__ parent, const int* __restrict__ sink_idx,
-                        const int* __restrict__ n_sinks, const float* __restrict__ floor_,
-                        const int* __restrict__ sw, int n_nodes,
-                        const float* const* __restrict__ R, const float* __restrict__ hyp, int B,
-                        float* __restrict__ p_tr, float* __restrict__ p_ev, int* __restrict__ dec) {
-    extern __shared__ __align__(16) unsigned char rt_sm[];
-    const RtTables t = rt_carve(rt_sm, n_nodes, 2);
+template <int NS>
+__device__ __forceinline__ void route_fwd_walk(const RtTables& t, int n_nodes, const float* __restrict__ hyp, int B,
+                                               float* __restrict__ p_tr, float* __restrict__ p_ev,
+                                               int* __restrict__ dec) {
     const int tid = threadIdx.x;
-    for (int i = tid; i < n_nodes; i += RT_T) {
-        t.parent[i] = i ? parent[i] : 0; t.sink_idx[i] = sink_idx[i]; t.n_sinks[i] = n_sinks[i];
-        t.sw[i] = sw[i]; t.floor_[i] = floor_[i];
-        t.Rn[i] = n_sinks[i] >= 2 ? R[sw[i]] : nullptr;
-    }
-    __syncthreads();
     const int b = blockIdx.x * RT_T + tid;
     if (b >= B) return;
     const float tau = hyp[MPNN_HYP_TAU], eps = hyp[MPNN_HYP_EPS];
@@ -134,7 +158,7 @@ route_fwd_staged_kernel(const int* __restrict__ parent, const int* __restrict__ 
     pt_c[0] = 1.f; pe_c[0] = 1.f;
     p_tr[b] = 1.f; p_ev[b] = 1.f;
     // siblings share their parent's softmax: evaluate it once, when the first sink (sink_idx 0) comes up
-    float sm[RT_MAXS];
+    float sm[NS];
     int d = 0, sm_of = -1;
     for (int i = 1; i < n_nodes; ++i) {
         const int par = t.parent[i], ns = t.n_sinks[par];
@@ -142,17 +166,41 @@ route_fwd_staged_kernel(const int* __restrict__ parent, const int* __restrict__ 
         if (ns >= 2) {
             const int si = t.sink_idx[i];
             if (sm_of != par) {
-                d = route_softmax(t.Rn[par] + (size_t)b * ns, ns, tau, sm);
+                d = route_softmax_t<NS>(t.Rn[par] + (size_t)b * ns, ns, tau, sm);
                 sm_of = par;
                 if (dec) dec[(size_t)t.sw[par] * B + b] = d;
             }
-            pt = (pt - eps * t.floor_[par]) * pick(sm, si) + eps * t.floor_[i];
+            pt = (pt - eps * t.floor_[par]) * pick_t<NS>(sm, si) + eps * t.floor_[i];
             pe = pe * (d == si ? 1.f : 0.f);
         }
         pt_c[i * RT_T] = pt; pe_c[i * RT_T] = pe;
         p_tr[(size_t)i * B + b] = pt;
         p_ev[(size_t)i * B + b] = pe;
     }
+}
+
+__global__ void __launch_bounds__(RT_T)
+route_fwd_staged_kernel(const int* __restrict__ parent, const int* __restrict__ sink_idx,
+                        const int* __restrict__ n_sinks, const float* __restrict__ floor_,
+                        const int* __restrict__ sw, int n_nodes,
+                        const float* const* __restrict__ R, const float* __restrict__ hyp, int B,
+                        float* __restrict__ p_tr, float* __restrict__ p_ev, int* __restrict__ dec) {
+    extern __shared__ __align__(16) unsigned char rt_sm[];
+    const RtTables t = rt_carve(rt_sm, n_nodes, 2);
+    const int tid = threadIdx.x;
+    __shared__ int s_nsmax;
+    if (tid == 0) s_nsmax = 0;
+    __syncthreads();
+    for (int i = tid; i < n_nodes; i += RT_T) {
+        t.parent[i] = i ? parent[i] : 0; t.sink_idx[i] = sink_idx[i]; t.n_sinks[i] = n_sinks[i];
+        t.sw[i] = sw[i]; t.floor_[i] = floor_[i];
+        t.Rn[i] = n_sinks[i] >= 2 ? R[sw[i]] : nullptr;
+        atomicMax(&s_nsmax, n_sinks[i]);
+    }
+    __syncthreads();
+    if (s_nsmax <= 2)      route_fwd_walk<2>(t, n_nodes, hyp, B, p_tr, p_ev, dec);
+    else if (s_nsmax <= 4) route_fwd_walk<4>(t, n_nodes, hyp, B, p_tr, p_ev, dec);
+    else                   route_fwd_walk<RT_MAXS>(t, n_nodes, hyp, B, p_tr, p_ev, dec);
 }
 
 extern "C" int mpnn_route_fwd(const int* parent, const int* sink_idx, const int* n_sinks,
@@ -273,31 +321,12 @@ __global__ void route_bwd_kernel(const int* parent, const int* sink_idx,
 }
 
 
-__global__ void __launch_bounds__(RT_T)
-route_bwd_staged_kernel(const int* __restrict__ parent, const int* __restrict__ sink_idx,
-                        const int* __restrict__ n_sinks, const int* __restrict__ child,
-                        const float* __restrict__ floor_, const int* __restrict__ sw,
-                        const float* __restrict__ ops, const int* __restrict__ err, int n_nodes,
-                        const float* const* __restrict__ R, const float* __restrict__ hyp, int B,
-                        const float* __restrict__ p_tr,
-                        const float* const* __restrict__ c_err, const float* const* __restrict__ d_cor,
-                        const float* __restrict__ k_cpt,
-                        int critic, float k_dec, float k_cre, int optimistic, int use_cls_err,
-                        float* const* __restrict__ dR, float* __restrict__ c_data) {
-    extern __shared__ __align__(16) unsigned char rt_sm[];
-    const RtTables t = rt_carve(rt_sm, n_nodes, 5);
+template <int NS>
+__device__ __forceinline__ void route_bwd_walk(const RtTables& t, int n_nodes, const float* __restrict__ hyp, int B,
+                                               const float* __restrict__ p_tr, const float* __restrict__ k_cpt,
+                                               int critic, float k_dec, float k_cre, int optimistic, int use_cls_err,
+                                               float* __restrict__ c_data) {
     const int tid = threadIdx.x, n = n_nodes;
-    for (int i = tid; i < n; i += RT_T) {
-        t.parent[i] = i ? parent[i] : 0; t.sink_idx[i] = sink_idx[i]; t.n_sinks[i] = n_sinks[i];
-        t.sw[i] = sw[i]; t.floor_[i] = floor_[i]; t.ops[i] = ops[i]; t.err[i] = err[i];
-        const bool is_sw = n_sinks[i] >= 2;
-        t.Rn[i] = is_sw ? R[sw[i]] : nullptr;
-        t.dRn[i] = is_sw ? dR[sw[i]] : nullptr;
-        t.cen[i] = err[i] >= 0 ? c_err[err[i]] : nullptr;
-        t.dcn[i] = (err[i] >= 0 && use_cls_err) ? d_cor[err[i]] : nullptr;
-        for (int j = 0; j < RT_MAXS; ++j) t.child[i * RT_MAXS + j] = child[i * RT_MAXS + j];
-    }
-    __syncthreads();
     const int b = blockIdx.x * RT_T + tid;
     if (b >= B) return;
     const float invB = 1.f / (float)B;
@@ -319,7 +348,7 @@ route_bwd_staged_kernel(const int* __restrict__ parent, const int* __restrict__ 
         if (use_cls_err) dc_c[i * RT_T] = t.dcn[i] ? 1.f - t.dcn[i][b] : 0.f;
     }
     float total = 0.f;
-    float sm[RT_MAXS];
+    float sm[NS];
     int sm_of = -1, d = 0;
     if (!critic) {
         for (int i = 0; i < n; ++i) {
@@ -331,8 +360,8 @@ route_bwd_staged_kernel(const int* __restrict__ parent, const int* __restrict__ 
             const int par = t.parent[i], ns = t.n_sinks[par];
             float g = g_c[i * RT_T];
             if (ns >= 2) {
-                if (sm_of != par) { route_softmax(t.Rn[par] + (size_t)b * ns, ns, tau, sm); sm_of = par; }
-                g *= pick(sm, t.sink_idx[i]);
+                if (sm_of != par) { route_softmax_t<NS>(t.Rn[par] + (size_t)b * ns, ns, tau, sm); sm_of = par; }
+                g *= pick_t<NS>(sm, t.sink_idx[i]);
             }
             g_c[par * RT_T] += g;
         }
@@ -340,13 +369,13 @@ route_bwd_staged_kernel(const int* __restrict__ parent, const int* __restrict__ 
             const int ns = t.n_sinks[i];
             if (ns < 2) continue;
             const float* r = t.Rn[i] + (size_t)b * ns;
-            float gs[RT_MAXS], rv[RT_MAXS];
-            route_softmax(r, ns, tau, sm);
+            float gs[NS], rv[NS];
+            route_softmax_t<NS>(r, ns, tau, sm);
             sm_of = i;
             const float pt = pt_c[i * RT_T];
             float dot = 0.f, r2 = 0.f;
 #pragma unroll
-            for (int j = 0; j < RT_MAXS; ++j) {
+            for (int j = 0; j < NS; ++j) {
                 gs[j] = 0.f; rv[j] = 0.f;
                 if (j < ns) {
                     rv[j] = r[j];
@@ -357,7 +386,7 @@ route_bwd_staged_kernel(const int* __restrict__ parent, const int* __restrict__ 
             }
             float* out = t.dRn[i] + (size_t)b * ns;
 #pragma unroll
-            for (int j = 0; j < RT_MAXS; ++j)
+            for (int j = 0; j < NS; ++j)
                 if (j < ns) out[j] = sm[j] * (gs[j] - dot) / tau + pt * k_dec * 2.f * rv[j] * invB;
             total += pt * k_dec * r2;
         }
@@ -378,7 +407,7 @@ route_bwd_staged_kernel(const int* __restrict__ parent, const int* __restrict__ 
                 g_c[i * RT_T] = e; o_c[i * RT_T] = o;
             } else {
                 const float* r = t.Rn[i] + (size_t)b * ns;
-                d = route_softmax(r, ns, tau, sm);
+                d = route_softmax_t<NS>(r, ns, tau, sm);
                 float mn = INFINITY;
                 float* out = t.dRn[i] + (size_t)b * ns;
                 for (int j = 0; j < ns; ++j) {
@@ -398,6 +427,43 @@ route_bwd_staged_kernel(const int* __restrict__ parent, const int* __restrict__ 
         }
     }
     if (c_data) c_data[b] = total;
+}
+
+__global__ void __launch_bounds__(RT_T)
+route_bwd_staged_kernel(const int* __restrict__ parent, const int* __restrict__ sink_idx,
+                        const int* __restrict__ n_sinks, const int* __restrict__ child,
+                        const float* __restrict__ floor_, const int* __restrict__ sw,
+                        const float* __restrict__ ops, const int* __restrict__ err, int n_nodes,
+                        const float* const* __restrict__ R, const float* __restrict__ hyp, int B,
+                        const float* __restrict__ p_tr,
+                        const float* const* __restrict__ c_err, const float* const* __restrict__ d_cor,
+                        const float* __restrict__ k_cpt,
+                        int critic, float k_dec, float k_cre, int optimistic, int use_cls_err,
+                        float* const* __restrict__ dR, float* __restrict__ c_data) {
+    extern __shared__ __align__(16) unsigned char rt_sm[];
+    const RtTables t = rt_carve(rt_sm, n_nodes, 5);
+    const int tid = threadIdx.x, n = n_nodes;
+    __shared__ int s_nsmax;
+    if (tid == 0) s_nsmax = 0;
+    __syncthreads();
+    for (int i = tid; i < n; i += RT_T) {
+        t.parent[i] = i ? parent[i] : 0; t.sink_idx[i] = sink_idx[i]; t.n_sinks[i] = n_sinks[i];
+        t.sw[i] = sw[i]; t.floor_[i] = floor_[i]; t.ops[i] = ops[i]; t.err[i] = err[i];
+        const bool is_sw = n_sinks[i] >= 2;
+        atomicMax(&s_nsmax, n_sinks[i]);
+        t.Rn[i] = is_sw ? R[sw[i]] : nullptr;
+        t.dRn[i] = is_sw ? dR[sw[i]] : nullptr;
+        t.cen[i] = err[i] >= 0 ? c_err[err[i]] : nullptr;
+        t.dcn[i] = (err[i] >= 0 && use_cls_err) ? d_cor[err[i]] : nullptr;
+        for (int j = 0; j < RT_MAXS; ++j) t.child[i * RT_MAXS + j] = child[i * RT_MAXS + j];
+    }
+    __syncthreads();
+    if (s_nsmax <= 2)
+        route_bwd_walk<2>(t, n, hyp, B, p_tr, k_cpt, critic, k_dec, k_cre, optimistic, use_cls_err, c_data);
+    else if (s_nsmax <= 4)
+        route_bwd_walk<4>(t, n, hyp, B, p_tr, k_cpt, critic, k_dec, k_cre, optimistic, use_cls_err, c_data);
+    else
+        route_bwd_walk<RT_MAXS>(t, n, hyp, B, p_tr, k_cpt, critic, k_dec, k_cre, optimistic, use_cls_err, c_data);
 }
 
 extern "C" int mpnn_route_bwd(const int* parent, const int* sink_idx, const int* n_sinks, const int* child,

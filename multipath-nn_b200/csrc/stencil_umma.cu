@@ -688,7 +688,7 @@ int mpnn_stencil_gemm_umma(const void* A0, int K0, const void* A1, int K1, const
             // without this the driver picks the L1 / shared-memory split heuristically and may leave room for fewer
             // CTAs per SM than the grid was sized for (ncu: occupancy limit 2 by shared memory where 3 x 68 KB fit;
             // the persistent grid then ran as 1.5 waves)
-            cudaFuncSetAttribute(all[i], cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            if (!getenv("MPNN_TUNE_NO_CARVEOUT")) cudaFuncSetAttribute(all[i], cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         }
         if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }

@@ -374,7 +374,7 @@ static int launch_wgrad(WgradArgs& a, const float* dbias_src_unused, cudaStream_
         for (int i = 0; i < 4; ++i) {
             cudaError_t e = cudaFuncSetAttribute(kerns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMax + 1024);
             if (e != cudaSuccess) { mpnn_set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return MPNN_ERR_CUDA; }
-            cudaFuncSetAttribute(kerns[i], cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            if (!getenv("MPNN_TUNE_NO_CARVEOUT")) cudaFuncSetAttribute(kerns[i], cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         }
         if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }

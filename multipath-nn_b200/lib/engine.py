@@ -19,7 +19,8 @@ import torch
 
 from lib import _cabi
 from lib.layer_types import (BatchNorm, Chain, Conv, CrossEntropyError, LinTrans, MultiscaleBatchNorm,
-                             MultiscaleConvMax, MultiscaleRect, Param, Rect, Select, Softmax, ToPyramid)
+                             MultiscaleConvMax, MultiscaleRect, Param, Rect, Select, Softmax, SquaredError,
+                             SuperclassCrossEntropyError, ToPyramid)
 from lib.net_types import n_leaves
 
 F32, BF16 = 0, 1
@@ -70,15 +71,33 @@ def _is_chain(layer, types):
 
 _PYR = [ToPyramid]
 _RCM = [MultiscaleConvMax, MultiscaleBatchNorm, MultiscaleRect]
-_REG = [Select, LinTrans, Softmax, CrossEntropyError]
 # standalone Conv (lib/layer_types.py:55-74) as a tree node: 3x3 SAME conv + bias -> BatchNorm -> ReLU on ONE
 # tensor -- the input image, a pyramid scale picked by a leading Select, or the tensor of the node above --
 # and a classifier that flattens a tensor without a Select.  Arithmetically a one-scale MultiscaleConvMax
 # stage: the same kernels serve it (mpnn_conv_bn_stats / mpnn_stencil_gemm with A1 = NULL).
 _CNV = [Conv, BatchNorm, Rect]
 _CNVS = [Select, Conv, BatchNorm, Rect]
-_REGF = [LinTrans, Softmax, CrossEntropyError]
 _RTR = [Select, LinTrans, BatchNorm, Rect, LinTrans, BatchNorm, Rect, LinTrans]
+
+
+def _leaf_spec(layer):
+    """[Select,] LinTrans + one of the error layers of lib/layer_types.py:255-285 -> (select, fc, error layer, kind):
+    'ce' Softmax + CrossEntropyError, 'sce' Softmax + SuperclassCrossEntropyError, 'sq' SquaredError (on the
+    LinTrans output itself); None for anything else"""
+    if not isinstance(layer, Chain):
+        return None
+    comps = list(layer.comps)
+    sel = comps.pop(0) if comps and isinstance(comps[0], Select) else None
+    if not comps or not isinstance(comps[0], LinTrans):
+        return None
+    fc, tail = comps[0], comps[1:]
+    if len(tail) == 2 and isinstance(tail[0], Softmax) and type(tail[1]) is CrossEntropyError:
+        return sel, fc, tail[1], 'ce'
+    if len(tail) == 2 and isinstance(tail[0], Softmax) and type(tail[1]) is SuperclassCrossEntropyError:
+        return sel, fc, tail[1], 'sce'
+    if len(tail) == 1 and type(tail[0]) is SquaredError:
+        return sel, fc, tail[0], 'sq'
+    return None
 
 
 class Geo:
@@ -194,14 +213,19 @@ class Engine:
                 nd.mbn = Ns(comps=[bn])
                 nd.sel = layer.comps[0].hypers.i if off else None
                 nd.tensor_in = not off
-            elif _is_chain(layer, _REG):
+            elif _leaf_spec(layer) is not None:
                 nd.kind = 'reg'
-                nd.fc, nd.ce = layer.comps[1], layer.comps[3]
-                if layer.comps[0].hypers.i != -1:
+                sel, nd.fc, nd.ce, nd.loss = _leaf_spec(layer)
+                if sel is not None and sel.hypers.i != -1:
                     raise NotImplementedError('engine: LogReg must select the coarsest scale')
-            elif _is_chain(layer, _REGF):
-                nd.kind = 'reg'
-                nd.fc, nd.ce = layer.comps[0], layer.comps[2]
+                n_cls, n_out = net.hypers.y_shape[0], nd.fc.hypers.n_chan
+                if nd.loss == 'sce':
+                    w_cls = None if nd.ce.hypers.w_cls is None else np.asarray(nd.ce.hypers.w_cls, np.float32)
+                    if w_cls is None or w_cls.shape != (n_cls, n_out):
+                        raise ValueError('SuperclassCrossEntropyError of %r: w_cls must be (%d, %d)' % (layer.name, n_cls, n_out))
+                    nd.w_cls = w_cls
+                elif n_out != n_cls:
+                    raise ValueError('classifier %r has %d outputs for %d classes' % (layer.name, n_out, n_cls))
             else:
                 raise NotImplementedError(
                     'engine: tree node %r (%s) is not one of the hot-path compositions '
@@ -853,7 +877,7 @@ class _Plan:
         # the head GEMM keeps [W_leaf | W_r1] resident in shared memory: F/8 x 32 x 16 bytes must fit (F = 2048 at the
         # reference architecture; a Conv chain at full resolution has F = H*W*C and takes the CUDA-core heads)
         fits = all((head_features(nd) + 16) // 8 * 32 * 16 <= 150 * 1024 for nd in with_heads)
-        self.umma_heads = eng.impl == 1 and n_cls <= 16 and not eng.split and fits
+        self.umma_heads = eng.impl == 1 and all(nd.fc.hypers.n_chan <= 16 for nd in eng.regs) and not eng.split and fits
         Balloc = _ru(B, 128) if self.umma_heads else _ru(B, 8)
         self.Balloc = Balloc
         self.node = {}
@@ -890,23 +914,37 @@ class _Plan:
             elif nd.kind == 'reg':
                 par = self.node[nd.parent]
                 fc = nd.fc
-                eps = float(nd.ce.hypers.ε)
+                n_out = fc.hypers.n_chan           # = n_cls, or the number of superclasses
+                eps = float(nd.ce.hypers.ε) if nd.loss != 'sq' else 0.0
                 if self.umma_heads:
                     hd = self.heads[nd.parent]          # logits come from the parent's head GEMM
-                    r = Ns(Zbuf=hd.Z16, Z=hd.Z16[:, :n_cls], ldz=16, prob=self.f32(B, n_cls),
+                    r = Ns(Zbuf=hd.Z16, Z=hd.Z16[:, :n_out], ldz=16, prob=self.f32(B, n_out),
                            c_err=self.f32(B), d_cor=self.f32(B), dZ=None, fc=fc, eps=eps)
                 else:
-                    zb = self.f32(B, n_cls)
-                    r = Ns(Zbuf=zb, Z=zb, ldz=n_cls, prob=self.f32(B, n_cls), c_err=self.f32(B),
-                           d_cor=self.f32(B), dZ=self.f32(B, n_cls) if bwd else None, fc=fc, eps=eps)
+                    zb = self.f32(B, n_out)
+                    r = Ns(Zbuf=zb, Z=zb, ldz=n_out, prob=self.f32(B, n_out), c_err=self.f32(B),
+                           d_cor=self.f32(B), dZ=self.f32(B, n_out) if bwd else None, fc=fc, eps=eps)
                     F = par.F
-                    fcf = lambda par=par, r=r, fc=fc, F=F: L.fc_fwd(
+                    fcf = lambda par=par, r=r, fc=fc, F=F, n_out=n_out: L.fc_fwd(
                         _vp(par.feat), F, Balloc, B, eng.tptr(fc.params.w), eng.tptr(fc.params.b), None,
-                        n_cls, _vp(r.Zbuf), dt, S())
+                        n_out, _vp(r.Zbuf), dt, S())
                     self.fwd_ops.append(self._after(fcf, getattr(par, 'feat_op', None)))
+                r.n, r.loss, r.y = n_out, nd.loss, self.y
+                if nd.loss == 'sce':
+                    # SuperclassCrossEntropyError (lib/layer_types.py:274-285): the targets are y @ w_cls, refreshed
+                    # with the labels at the head of every step
+                    w_cls = torch.tensor(nd.w_cls, dtype=torch.float32, device=eng.dev)
+                    r.y = self.f32(B, n_out)
+                    self.keep.append(w_cls)
+                    self.pack_ops.append(lambda r=r, w_cls=w_cls, n_out=n_out: L.superclass_targets(
+                        _vp(self.y), _vp(w_cls), B, n_cls, n_out, _vp(r.y), S()))
                 self.reg[nd.idx] = r
-                ce = lambda r=r: L.softmax_ce_fwd(
-                    _vp(r.Zbuf), r.ldz, _vp(self.y), B, n_cls, r.eps, _vp(r.prob), _vp(r.c_err), _vp(r.d_cor), S())
+                if nd.loss == 'sq':                    # SquaredError on the LinTrans output; r.prob keeps that output
+                    ce = lambda r=r: L.squared_err_fwd(
+                        _vp(r.Zbuf), r.ldz, _vp(r.y), B, r.n, _vp(r.prob), _vp(r.c_err), _vp(r.d_cor), S())
+                else:
+                    ce = lambda r=r: L.softmax_ce_fwd(
+                        _vp(r.Zbuf), r.ldz, _vp(r.y), B, r.n, r.eps, _vp(r.prob), _vp(r.c_err), _vp(r.d_cor), S())
                 if self.umma_heads:
                     ce.lane = hd.lane                 # follows its head GEMM on that head's lane
                     self.last_head_op = ce
@@ -995,9 +1033,7 @@ class _Plan:
                 if self.umma_heads:
                     hd = self.heads[nd.parent]
                     dzp = ctypes.c_void_p(hd.dZ.data_ptr() + (hd.leaf_off // 8) * Balloc * 16)
-                    ceb = lambda r=r, coef=coef, dzp=dzp: L.softmax_ce_bwd(
-                        _vp(r.prob), _vp(self.y), B, n_cls, r.eps, coef(), 1.0 / B, None,
-                        dzp, Balloc, eng.gptr(r.fc.params.b), S())
+                    ceb = lambda r=r, coef=coef, dzp=dzp: self._loss_bwd(r, coef(), None, dzp, eng.gptr(r.fc.params.b))
                     ceb.lane = hd.lane
                     # a stage without a router only needs p_tr (forward): its head gradients are issued
                     # ahead of the routing backward so the deepest conv chain starts under it
@@ -1005,10 +1041,9 @@ class _Plan:
                     hd.ceb_op = ceb
                     self.bwd_ops.append(ceb if ceb.early else self._after(ceb, self.bwd_head_dep))
                 else:
-                    self.bwd_ops.append(lambda r=r, coef=coef: L.softmax_ce_bwd(
-                        _vp(r.prob), _vp(self.y), B, n_cls, r.eps, coef(), 1.0 / B, _vp(r.dZ), None, 0, None, S()))
+                    self.bwd_ops.append(lambda r=r, coef=coef: self._loss_bwd(r, coef(), _vp(r.dZ), None, None))
                     self.bwd_ops.append(lambda r=r, par=par: L.fc_bwd_weight(
-                        _vp(par.feat), par.F, Balloc, B, None, _vp(r.dZ), n_cls,
+                        _vp(par.feat), par.F, Balloc, B, None, _vp(r.dZ), r.n,
                         eng.gptr(r.fc.params.w), eng.gptr(r.fc.params.b), dt, S()))
             if nd.router is not None and not self.umma_heads:
                 self._build_router_bwd(nd, Balloc, dyn_k)
@@ -1081,8 +1116,8 @@ class _Plan:
         if leaves:
             fc = eng.nodes[leaves[0]].fc
             hd.fc_leaf = fc
-            self._pack(fc.params.w, hd.Wfc, F, n_cls, 0, 0, Fext, hd.leaf_off, hd.N, ntaps=1)
-            self._pack(fc.params.b, hd.bias, 1, n_cls, 2, 0, 8, hd.leaf_off, hd.N, ntaps=1)
+            self._pack(fc.params.w, hd.Wfc, F, fc.hypers.n_chan, 0, 0, Fext, hd.leaf_off, hd.N, ntaps=1)
+            self._pack(fc.params.b, hd.bias, 1, fc.hypers.n_chan, 2, 0, 8, hd.leaf_off, hd.N, ntaps=1)
         if rt is not None:
             rows = F + (1 if dyn_k else 0)
             self._pack(rt.fc1.params.w, hd.Wfc, rows, 16, 0, 0, Fext, hd.r_off, hd.N, ntaps=1)
@@ -1104,6 +1139,16 @@ class _Plan:
         self.head_ops.append(gemm)
         self.fwd_ops.append(gemm)
 
+    def _loss_bwd(self, r, coef, dZ, dZp, dbias):
+        """gradient of a leaf's error layer wrt the LinTrans output (fp32 rows and / or the bf16 planes operand)"""
+        L, B = self.eng.L, self.B
+        if r.loss == 'sq':
+            L.squared_err_bwd(_vp(r.prob), _vp(r.y), B, r.n, coef, 1.0 / B, dZ, dZp, self.Balloc if dZp else 0,
+                              dbias, self.eng.stream)
+        else:
+            L.softmax_ce_bwd(_vp(r.prob), _vp(r.y), B, r.n, r.eps, coef, 1.0 / B, dZ, dZp,
+                             self.Balloc if dZp else 0, dbias, self.eng.stream)
+
     def _build_heads_bwd(self, nd, st, dyn_k):
         eng, L, B, Balloc = self.eng, self.eng.L, self.B, self.Balloc
         S = lambda: eng.stream
@@ -1113,7 +1158,7 @@ class _Plan:
         F, Fext = st.F, st.Fext
         leaf = getattr(hd, 'fc_leaf', None)
         # weight gradients of both heads in one launch
-        a = (eng.gptr(leaf.params.w), F, n_cls) if leaf is not None else (None, 0, 0)
+        a = (eng.gptr(leaf.params.w), F, leaf.hypers.n_chan) if leaf is not None else (None, 0, 0)
         b = (eng.gptr(rt.fc1.params.w), F + (1 if dyn_k else 0), 16) if rt is not None else (None, 0, 0)
         if leaf is None:
             a, b = b, (None, 0, 0)
@@ -1128,7 +1173,7 @@ class _Plan:
         # data gradient towards the flattened coarsest scale
         hd.Wfd = self.zeros((1, hd.N // 8, F, 8), eng.tdtype)
         if leaf is not None:
-            self._pack(leaf.params.w, hd.Wfd, F, n_cls, 1, hd.leaf_off, hd.N, 0, F, ntaps=1)
+            self._pack(leaf.params.w, hd.Wfd, F, leaf.hypers.n_chan, 1, hd.leaf_off, hd.N, 0, F, ntaps=1)
         if rt is not None:
             self._pack(rt.fc1.params.w, hd.Wfd, F, 16, 1, hd.r_off, hd.N, 0, F, ntaps=1)
         st.dfeat = self.zeros((F // 8, Balloc, 8), eng.tdtype)

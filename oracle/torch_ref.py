@@ -293,6 +293,19 @@ class OracleNet:
         elif kind == 'SquaredError':                # layer_types.py:255-260
             nd.c_err = ((x - y) ** 2).sum(1)
             nd.delta_cor = (first_argmax(x, 1) == first_argmax(y, 1)).to(self.dtype)
+        elif kind == 'SuperclassCrossEntropyError':  # layer_types.py:274-285
+            eps = _eps(hy)
+            y_sup = y @ torch.as_tensor(np.asarray(hy['w_cls']), dtype=self.dtype)
+            n_sup = y_sup.shape[1]
+            p_cls = eps / n_sup + (1 - eps) * x
+            nd.c_err = -(y_sup * torch.log(p_cls)).sum(1)
+            nd.delta_cor = (first_argmax(x, 1) == first_argmax(y_sup, 1)).to(self.dtype)
+        elif kind == 'ActivityError':               # layer_types.py:287-293 (c_mod is PER EXAMPLE here)
+            nd.c_mod = hy.get('α', 0.0) * (x ** 2).sum(tuple(range(1, x.dim())))
+        elif kind == 'Dropout':                     # layer_types.py:212-217: tf.nn.dropout(x, keep_prob=λ), every mode
+            lam = hy.get('λ', 1)
+            if lam != 1:
+                raise NotImplementedError('oracle: Dropout(λ=%r) draws from TF\'s random stream' % lam)
         else:
             raise NotImplementedError('oracle: layer type %r' % kind)
         return nd

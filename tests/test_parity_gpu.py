@@ -34,7 +34,7 @@ TOL = {'fp32': dict(fwd=1e-3, grad=1e-3, margin=1e-4, step=2e-3),
 
 def _nets(kind, hy, seed=0):
     net = tiny_net(kind, seed=seed, **{k: v for k, v in hy.items() if not k.startswith('_')})
-    if kind not in ('sr', 'cnv', 'cnvpyr'):
+    if not kind.startswith(('sr', 'cnv')):
         randomize_routers(net)
     return net
 
@@ -62,7 +62,9 @@ CASES = [('sr', {}), ('ac', dict(k_cpt=4e-9)), ('cr', dict(k_cpt=4e-9)),
          ('sr', dict(x0_shape=(16, 16, 1))), ('ac', dict(k_cpt=4e-9, x0_shape=(16, 16, 1), n_cls=5, _bf16_grad=0.4)),
          ('crtree', dict(k_cpt=2e-9, n_cls=2)), ('cr', dict(dyn_k_cpt=True, optimistic=True)),
          # standalone Conv chains: on the image, and on a pyramid scale picked by Select
-         ('cnv', {}), ('cnvpyr', dict(x0_shape=(16, 16, 1)))]
+         ('cnv', {}), ('cnvpyr', dict(x0_shape=(16, 16, 1))),
+         # the other error layers (layer_types.py:255-285): SquaredError on the LinTrans output, superclass cross-entropy
+         ('srsq', {}), ('acsq', dict(k_cpt=4e-9)), ('srsce', {}), ('crsce', dict(k_cpt=4e-9))]
 
 
 @pytest.mark.parametrize('prec', ['fp32', 'bf16'])
@@ -86,7 +88,8 @@ def test_forward_and_gradients(kind, hy, prec):
     for nd in eng.regs:
         path = paths[nd.idx][0]
         ref = out.nodes[path]
-        z_ref = ref.comps[-3].x.detach().numpy()          # the LinTrans of [Select,] LinTrans, Softmax, CrossEntropyError
+        k_fc = next(i for i, c in enumerate(paths[nd.idx][1].comps) if type(c).__name__ == 'LinTrans')
+        z_ref = ref.comps[k_fc].x.detach().numpy()        # the LinTrans of [Select,] LinTrans, [Softmax,] <error layer>
         assert rel_err(plan.reg[nd.idx].Z.cpu().numpy(), z_ref) < tol['fwd'], ('logits', path)
         assert rel_err(plan.reg[nd.idx].c_err.cpu().numpy(), ref.c_err.detach().numpy()) < tol['fwd'], ('c_err', path)
     if net.dynamic:

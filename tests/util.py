@@ -7,7 +7,8 @@ import numpy as np
 from lib import layer_types as lt
 from lib import serdes
 from lib.layer_types import (BatchNorm, Chain, Conv, CrossEntropyError, LinTrans, MultiscaleBatchNorm,
-                             MultiscaleConvMax, MultiscaleRect, Rect, Select, Softmax, ToPyramid)
+                             MultiscaleConvMax, MultiscaleRect, Rect, Select, Softmax, SquaredError,
+                             SuperclassCrossEntropyError, ToPyramid)
 from lib.net_types import ActorNet, CriticNet, SRNet
 
 K_L2 = 1e-4
@@ -33,7 +34,23 @@ def rcm(n_chan, *sinks):
         MultiscaleConvMax(n_chan=list(n_chan), supp=3, k_l2=K_L2, σ_w=1), MultiscaleBatchNorm(), MultiscaleRect()])
 
 
+N_SUP = 4
+
+
+def superclasses(n_cls, n_sup=N_SUP):
+    """class j belongs to superclass j mod n_sup"""
+    return np.eye(n_sup, dtype=np.float32)[np.arange(n_cls) % n_sup]
+
+
+_LEAF = ['ce']          # error layer of the classifiers built by reg(): 'ce' | 'sq' | 'sce' (set by tiny_net)
+
+
 def reg(n_cls):
+    if _LEAF[0] == 'sq':      # SquaredError on the LinTrans output (layer_types.py:255-260)
+        return Chain(name='LinReg', comps=[Select(i=-1), _fc(n_cls), SquaredError()])
+    if _LEAF[0] == 'sce':     # SuperclassCrossEntropyError (layer_types.py:274-285)
+        return Chain(name='LogReg', comps=[Select(i=-1), _fc(N_SUP), Softmax(),
+                                           SuperclassCrossEntropyError(w_cls=superclasses(n_cls))])
     return Chain(name='LogReg', comps=[Select(i=-1), _fc(n_cls), Softmax(), CrossEntropyError()])
 
 
@@ -41,6 +58,17 @@ def tiny_net(kind='ac', n_cls=10, x0_shape=(16, 16, 3), seed=0, **hypers):
     """16x16 input, 3-scale pyramid, stages [16,16,16] -> [16,16] -> [32];
     'sr' is a chain, 'ac'/'cr' route at both inner stages, 'tree' has a 3-way switch."""
     lt.seed(seed)
+    _LEAF[0] = 'ce'
+    for suffix in ('sq', 'sce'):          # 'srsq', 'acsce', ...: the same nets with another error layer on the leaves
+        if kind.endswith(suffix) and kind not in ('sq', 'sce'):
+            kind, _LEAF[0] = kind[:-len(suffix)], suffix
+    try:
+        return _tiny_net(kind, n_cls, x0_shape, **hypers)
+    finally:
+        _LEAF[0] = 'ce'
+
+
+def _tiny_net(kind, n_cls, x0_shape, **hypers):
     if kind in ('cnv', 'cnvpyr'):
         # standalone Conv (layer_types.py:55-74) chains: on the image itself, or on one pyramid scale via Select
         cnv = lambda n, *sinks, pre=(): Chain(name='ConvBlock', sinks=sinks, comps=list(pre) + [
