@@ -30,7 +30,8 @@ extern "C" {
 /* Per-step scalars live in a small DEVICE float array `hyp` so that a captured
  * CUDA graph can be replayed with new values (net_types.py:139-145 feeds). */
 enum { MPNN_HYP_LR = 0, MPNN_HYP_MU = 1, MPNN_HYP_TAU = 2, MPNN_HYP_EPS = 3,
-       MPNN_HYP_KCPT = 4, MPNN_HYP_GSCALE = 5, MPNN_HYP_COUNT = 8 };
+       MPNN_HYP_KCPT = 4, MPNN_HYP_GSCALE = 5, MPNN_HYP_DRAW = 6 /* bits of a uint32: Dropout draw counter */,
+       MPNN_HYP_COUNT = 8 };
 
 const char* mpnn_last_error(void);
 int mpnn_version(void);
@@ -241,6 +242,37 @@ int mpnn_squared_err_bwd(const float* out, const float* y, int B, int n,
  * the loss is mpnn_softmax_ce_fwd / _bwd with y_sup in place of y and n = n_sup. */
 int mpnn_superclass_targets(const float* y, const float* w_cls, int B, int n_cls, int n_sup,
                             float* y_sup, void* stream);
+
+/* MaxPool (lib/layer_types.py:86-94), 2x2 window and step 2 -- with the reference's swapped (ksize, strides)
+ * arguments the one configuration where window = `stride` and step = `supp` coincide -- on a padded-planes
+ * tensor: out (planes at H/2 x W/2, Pp rows per plane) and / or feat, the flattened (h, w, c) feature layout
+ * [F/8][Balloc][8] of the pooled tensor.  Backward: dx = (dout + dfeat) at the first maximum of each 2x2 block,
+ * zero elsewhere (all of dx is written).  TF autodiff of tf.nn.max_pool. */
+int mpnn_maxpool2_fwd(const void* x, int C, int B, int H, int W, int G, int P,
+                      void* out, int Pp, void* feat, int Balloc, int dtype, void* stream);
+int mpnn_maxpool2_bwd(const void* x, const void* dout, const void* dfeat, int Balloc,
+                      int C, int B, int H, int W, int G, int P, int Pp, void* dx, int dtype, void* stream);
+/* GlobalMaxPool (lib/layer_types.py:96-100): feat [C/8][Balloc][8] = max over the image, arg (int32, same shape)
+ * = h * W + w of the first maximum; backward scatters dfeat to the recorded positions (all of dx is written). */
+int mpnn_global_maxpool_fwd(const void* x, int C, int B, int H, int W, int G, int P,
+                            void* feat, int* arg, int Balloc, int dtype, void* stream);
+int mpnn_global_maxpool_bwd(const void* dfeat, const int* arg, int Balloc, int C, int B, int H, int W,
+                            int G, int P, void* dx, int dtype, void* stream);
+
+/* ActivityError (lib/layer_types.py:287-293): cost[b] = alpha * sum_{h,w,c} x^2 (a per-example c_mod);
+ * backward: dx (+)= scale * coef[b] * x (scale = 2 alpha / B; coef = the node's p_tr row, NULL: 1;
+ * acc = 0 writes dx on the image pixels, acc != 0 adds to it). */
+int mpnn_activity_fwd(const void* x, int C, int B, int H, int W, int G, int P, float alpha,
+                      float* cost, int dtype, void* stream);
+int mpnn_activity_bwd(const void* x, int C, int B, int H, int W, int G, int P, const float* coef,
+                      float scale, void* dx, int acc, int dtype, void* stream);
+
+/* Dropout (lib/layer_types.py:212-217; tf.nn.dropout(x, keep), every mode): x *= m / keep in place, m from a
+ * counter-based hash of (seed, hyp[MPNN_HYP_DRAW], NHWC element index) -- see csrc/activity.cu.  x is a planes
+ * tensor (feat = 0) or its flattened feature copy [H*W*C/8][Balloc][8] (feat = 1): both see the same mask.
+ * The backward pass is the same call on the gradient. */
+int mpnn_dropout(void* x, int C, int B, int H, int W, int G, int P, int feat, int Balloc,
+                 float keep, unsigned seed, const float* hyp, int dtype, void* stream);
 
 /* Router tail (arch_and_hypers.py:45-49): BN -> ReLU -> FC(16) -> BN -> ReLU -> FC(ns)
  * applied to Z1 = output of the first router FC.  One CTA.

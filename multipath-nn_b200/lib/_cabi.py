@@ -10,7 +10,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'libmpnn_sm100.so')
 HEADER = os.path.normpath(os.path.join(HERE, '..', '..', 'include', 'mpnn.h'))
 
-_SCALARS = {'int': ctypes.c_int, 'float': ctypes.c_float, 'double': ctypes.c_double, 'long': ctypes.c_longlong}
+_SCALARS = {'int': ctypes.c_int, 'float': ctypes.c_float, 'double': ctypes.c_double, 'long': ctypes.c_longlong,
+            'unsigned': ctypes.c_uint}
 
 
 def parse_header(path=HEADER):

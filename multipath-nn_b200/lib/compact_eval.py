@@ -32,6 +32,8 @@ class CompactEvaluator:
             raise ValueError('compacted evaluation is for dynamically-routed nets (an SRNet has one path)')
         if eng.split:
             raise NotImplementedError('compacted evaluation runs in fp32 or bf16 precision (not bf16x3)')
+        if any(getattr(nd, 'maxpool', False) or getattr(nd, 'gmp', False) for nd in eng.nodes):
+            raise NotImplementedError('compacted evaluation does not cover MaxPool / GlobalMaxPool blocks')
         if any(nd.loss != 'ce' for nd in eng.regs):
             raise NotImplementedError('compacted evaluation scores Softmax + CrossEntropyError classifiers only')
         self.eng, self.L, self.B = eng, eng.L, int(batch)

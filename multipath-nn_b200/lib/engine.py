@@ -18,13 +18,13 @@ import numpy as np
 import torch
 
 from lib import _cabi
-from lib.layer_types import (BatchNorm, Chain, Conv, CrossEntropyError, LinTrans, MultiscaleBatchNorm,
-                             MultiscaleConvMax, MultiscaleRect, Param, Rect, Select, Softmax, SquaredError,
-                             SuperclassCrossEntropyError, ToPyramid)
+from lib.layer_types import (ActivityError, BatchNorm, Chain, Conv, CrossEntropyError, Dropout, GlobalMaxPool,
+                             LinTrans, MaxPool, MultiscaleBatchNorm, MultiscaleConvMax, MultiscaleRect, Param,
+                             Rect, Select, Softmax, SquaredError, SuperclassCrossEntropyError, ToPyramid)
 from lib.net_types import n_leaves
 
 F32, BF16 = 0, 1
-HYP_LR, HYP_MU, HYP_TAU, HYP_EPS, HYP_KCPT, HYP_GSCALE, HYP_COUNT = 0, 1, 2, 3, 4, 5, 8
+HYP_LR, HYP_MU, HYP_TAU, HYP_EPS, HYP_KCPT, HYP_GSCALE, HYP_DRAW, HYP_COUNT = 0, 1, 2, 3, 4, 5, 6, 8
 MAXS = 8
 
 
@@ -64,9 +64,46 @@ def _vp(t):
     return None if t is None else ctypes.c_void_p(t.data_ptr())
 
 
+def _comps(layer):
+    """comps of a chain without the ones that are the identity as configured: Dropout(λ=1) (tf.nn.dropout with
+    keep_prob 1, the default of lib/layer_types.py:212-217) and ActivityError (:287-293; α = 0 is no cost at all, α != 0
+    behind the Rect of a Conv block is picked up by _activity)"""
+    out = []
+    for c in layer.comps:
+        if type(c) is Dropout:
+            prev = out[-1] if out else None
+            if float(c.hypers.λ) != 1.0 and not (isinstance(prev, Rect) and len(out) >= 3 and isinstance(out[-3], Conv)):
+                raise NotImplementedError('engine: Dropout(λ=%r) is served directly behind the Rect of a '
+                                          'Conv-BatchNorm-Rect block (elsewhere only keep_prob 1)' % c.hypers.λ)
+            continue
+        if type(c) is ActivityError:
+            prev = out[-1] if out else None
+            if float(c.hypers.α) != 0.0 and not (isinstance(prev, Rect) and len(out) >= 3 and isinstance(out[-3], Conv)):
+                raise NotImplementedError('engine: ActivityError(α=%r) is served directly behind the Rect of a '
+                                          'Conv-BatchNorm-Rect block (elsewhere only α = 0)' % c.hypers.α)
+            continue
+        out.append(c)
+    return out
+
+
+def _dropout(layer):
+    """keep probability of the Dropout behind the Rect of a Conv block (1: none)"""
+    keep = [float(c.hypers.λ) for c in layer.comps if type(c) is Dropout and float(c.hypers.λ) != 1.0]
+    if len(keep) > 1:
+        raise NotImplementedError('engine: more than one Dropout in a block')
+    return keep[0] if keep else 1.0
+
+
+def _activity(layer):
+    """α of the ActivityError behind the Rect of a Conv block (0: none)"""
+    return sum(float(c.hypers.α) for c in layer.comps if type(c) is ActivityError)
+
+
 def _is_chain(layer, types):
-    return (isinstance(layer, Chain) and len(layer.comps) == len(types)
-            and all(isinstance(c, t) for c, t in zip(layer.comps, types)))
+    if not isinstance(layer, Chain):
+        return False
+    comps = _comps(layer)
+    return len(comps) == len(types) and all(isinstance(c, t) for c, t in zip(comps, types))
 
 
 _PYR = [ToPyramid]
@@ -81,13 +118,13 @@ _RTR = [Select, LinTrans, BatchNorm, Rect, LinTrans, BatchNorm, Rect, LinTrans]
 
 
 def _leaf_spec(layer):
-    """[Select,] LinTrans + one of the error layers of lib/layer_types.py:255-285 -> (select, fc, error layer, kind):
+    """[Select | GlobalMaxPool,] LinTrans + one of the error layers of lib/layer_types.py:255-285 -> (select, fc, error layer, kind):
     'ce' Softmax + CrossEntropyError, 'sce' Softmax + SuperclassCrossEntropyError, 'sq' SquaredError (on the
     LinTrans output itself); None for anything else"""
     if not isinstance(layer, Chain):
         return None
-    comps = list(layer.comps)
-    sel = comps.pop(0) if comps and isinstance(comps[0], Select) else None
+    comps = _comps(layer)
+    sel = comps.pop(0) if comps and isinstance(comps[0], (Select, GlobalMaxPool)) else None
     if not comps or not isinstance(comps[0], LinTrans):
         return None
     fc, tail = comps[0], comps[1:]
@@ -178,6 +215,7 @@ class Engine:
             self._hyp_ring = [t.pin_memory() for t in self._hyp_ring]
         self._hyp_ev = [None] * len(self._hyp_ring)
         self._hyp_i = 0
+        self.draw = 0
         self.hyp_host = self._hyp_ring[0]
         self.hyp = torch.zeros(HYP_COUNT, dtype=torch.float32, device=self.dev)
 
@@ -195,13 +233,27 @@ class Engine:
                 nd.kind = 'pyr'
             elif _is_chain(layer, _RCM):
                 nd.kind = 'rcm'
-                nd.cm, nd.mbn, nd.sel = layer.comps[0], layer.comps[1], None
-                if layer.comps[0].hypers.supp != 3:
-                    raise NotImplementedError('engine: MultiscaleConvMax supp=%r' % layer.comps[0].hypers.supp)
-            elif _is_chain(layer, _CNV) or _is_chain(layer, _CNVS):
+                nd.cm, nd.mbn, nd.sel = _comps(layer)[0], _comps(layer)[1], None
+                if nd.cm.hypers.supp != 3:
+                    raise NotImplementedError('engine: MultiscaleConvMax supp=%r' % nd.cm.hypers.supp)
+            elif any(_is_chain(layer, pat) for pat in (_CNV, _CNVS, _CNV + [MaxPool], _CNVS + [MaxPool])):
                 nd.kind = 'rcm'
-                off = 1 if isinstance(layer.comps[0], Select) else 0
-                conv, bn = layer.comps[off], layer.comps[off + 1]
+                comps = _comps(layer)
+                off = 1 if isinstance(comps[0], Select) else 0
+                conv, bn = comps[off], comps[off + 1]
+                nd.maxpool = isinstance(comps[-1], MaxPool)
+                nd.act_alpha = _activity(layer)
+                nd.keep = _dropout(layer)
+                if (nd.act_alpha or nd.keep != 1.0) and self.split:
+                    raise NotImplementedError('engine: ActivityError / Dropout in bf16x3 precision')
+                if nd.act_alpha and nd.keep != 1.0:
+                    raise NotImplementedError('engine: ActivityError and Dropout in one block')
+                if nd.maxpool and (comps[-1].hypers.stride, comps[-1].hypers.supp) != (2, 2):
+                    # tf.nn.max_pool(x, strides, k_shape): window = stride, step = supp
+                    raise NotImplementedError('engine: MaxPool(stride=%r, supp=%r): the 2 / 2 window is served'
+                                              % (comps[-1].hypers.stride, comps[-1].hypers.supp))
+                if nd.maxpool and self.split:
+                    raise NotImplementedError('engine: MaxPool in bf16x3 precision')
                 if conv.hypers.supp != 3 or conv.hypers.res:
                     raise NotImplementedError('engine: standalone Conv with supp=%r res=%r (3x3 without the residual '
                                               'initialisation is what the stencil kernels serve)' % (conv.hypers.supp, conv.hypers.res))
@@ -211,12 +263,13 @@ class Engine:
                 nd.cm = Ns(hypers=Ns(n_chan=[conv.hypers.n_chan], supp=3, k_l2=conv.hypers.k_l2),
                            params=Ns(w_horz_0=conv.params.w, b_0=conv.params.b))
                 nd.mbn = Ns(comps=[bn])
-                nd.sel = layer.comps[0].hypers.i if off else None
+                nd.sel = comps[0].hypers.i if off else None
                 nd.tensor_in = not off
             elif _leaf_spec(layer) is not None:
                 nd.kind = 'reg'
                 sel, nd.fc, nd.ce, nd.loss = _leaf_spec(layer)
-                if sel is not None and sel.hypers.i != -1:
+                nd.gmp = isinstance(sel, GlobalMaxPool)
+                if sel is not None and not nd.gmp and sel.hypers.i != -1:
                     raise NotImplementedError('engine: LogReg must select the coarsest scale')
                 n_cls, n_out = net.hypers.y_shape[0], nd.fc.hypers.n_chan
                 if nd.loss == 'sce':
@@ -253,6 +306,13 @@ class Engine:
             if nd.kind == 'rcm' and nd.sel is not None and (par is None or par.kind != 'pyr'):
                 raise NotImplementedError('engine: Select + Conv must sit directly under the ToPyramid node')
         for nd in self.nodes:
+            if nd.kind == 'reg' and getattr(nd, 'gmp', False):
+                par = self.nodes[nd.parent]
+                if len(par.kids) != 1 or par.router is not None or not hasattr(par, 'tensor_in') \
+                        or getattr(par, 'maxpool', False) or self.split:
+                    raise NotImplementedError('engine: a GlobalMaxPool classifier must be the only sink of a '
+                                              'Conv-BatchNorm-Rect block (no router, no MaxPool, not bf16x3)')
+                par.gmp = True
             if nd.kind == 'reg' and nd.kids:
                 raise NotImplementedError('engine: LogReg with sinks')
             if nd.kind in ('rcm', 'reg') and nd.parent is not None and self.nodes[nd.parent].kind == 'reg':
@@ -446,6 +506,8 @@ class Engine:
         h[HYP_LR] = float(feed.get(net.λ_lrn, hy.λ_lrn))
         h[HYP_MU] = float(feed.get(net.μ_lrn, hy.μ_lrn))
         h[HYP_GSCALE] = 1.0 / self.world
+        self.draw = (self.draw + 1) & 0xFFFFFFFF       # Dropout masks: one draw per evaluation (bits of a uint32)
+        h.view(torch.int32)[HYP_DRAW] = self.draw - (1 << 32) if self.draw >= (1 << 31) else self.draw
         if self.dynamic:
             h[HYP_TAU] = float(feed.get(net.τ, hy.τ))
             h[HYP_EPS] = float(feed.get(net.ϵ, hy.ε))
@@ -748,6 +810,8 @@ class Engine:
         else:
             data = float(sum(plan.reg[nd.idx].c_err.double().mean() for nd in self.regs))
             w = torch.ones(len(self.nodes), dtype=torch.float64, device=self.dev)
+        for idx, sc in plan.activity:               # per-example ActivityError costs, weighted like the node's c_mod
+            data += float((sc.c_act.double() * (plan.p_tr[idx].double() if self.dynamic else 1.0)).mean())
         mod = 0.0
         seg_l2 = self.seg_l2.cpu().numpy(); seg_node = self.seg_node.cpu().numpy()
         for s, p in enumerate(self.tparams):
@@ -885,6 +949,7 @@ class _Plan:
         self.pack_list, self.rt_fwd, self.keep, self.kplanes = [], [], [], []
         self.last_head_op = None
         self.head_ops = []
+        self.activity = []                       # (node, scale) pairs that carry an ActivityError cost
         cpad_q = 16 if (dt == BF16 or eng.split) else 8
         dyn_k = eng.dynamic and bool(net.hypers.dyn_k_cpt)
 
@@ -1248,7 +1313,10 @@ class _Plan:
             sc = Ns(k=k, geo=geo, N=N, K0=K0, K0real=src.Creal, K1=K1, src=src, live=live(k),
                     dpooled=None, geo_p=None)
             sc.lin = self.planes(N, geo)
-            sc.act = self.planes(N, geo) if any(
+            pooled_out = getattr(nd, 'maxpool', False)          # [Conv, BN, Rect, MaxPool]: the sinks see the pooled tensor
+            gmp = getattr(nd, 'gmp', False)                     # the classifier below takes GlobalMaxPool features
+            act_alpha = getattr(nd, 'act_alpha', 0.0)           # ActivityError behind the ReLU: a per-example cost
+            sc.act = self.planes(N, geo) if pooled_out or gmp or act_alpha or any(
                 k >= n - len(eng.nodes[c].cm.hypers.n_chan) for c in kid_rcm) else None
             sc.pooled = None
             if k < n - 1:
@@ -1256,7 +1324,7 @@ class _Plan:
                 sc.pooled = self.planes(N, sc.geo_p)
             sc.feat = None
             if k == n - 1 and has_heads:
-                st.F = geo.H * geo.W * N
+                st.F = N if gmp else (geo.H // 2) * (geo.W // 2) * N if pooled_out else geo.H * geo.W * N
                 # tcgen05 heads with a per-example k_cpt feature (net_types.py:149-160): the feature
                 # alpha_cpt*k_cpt lives in channel 0 of one extra (16-aligned) pair of planes
                 ext = 16 if (self.umma_heads and nd.router is not None and eng.dynamic
@@ -1266,6 +1334,8 @@ class _Plan:
                 st.feat = sc.feat
                 if ext:
                     self.kplanes.append(sc.feat[st.F // 8, :, 0])
+                if pooled_out or gmp:
+                    sc.feat = None                  # written by the pooling kernel (st.feat), not by BN / ReLU
             sc.Wf = None if eng.split else self.zeros((9, (K0 + K1) // 8, N, 8), eng.tdtype)
             sc.ss = self.f32(2, N)
             sc.mr = self.f32(2, N)
@@ -1312,6 +1382,7 @@ class _Plan:
             sc.lane = 3 + int(round(np.log2(eng.net.hypers.x0_shape[0] / geo.H)))
             conv.lane = sc.lane
             self._after(conv, getattr(prev, 'post_op', None) if prev is not None else None)   # pooled input
+            self._after(conv, getattr(src, 'op', None))        # a MaxPool-ed parent tensor comes from another lane
             self.fwd_ops.append(conv)
             if sc.live and not use_stats:
                 bn = sc.bn
@@ -1343,6 +1414,54 @@ class _Plan:
                 if sc.feat is not None:
                     st.feat_op = post
             st.sc.append(sc)
+            sc.keep = getattr(nd, 'keep', 1.0)
+            if sc.keep != 1.0:
+                # Dropout behind the ReLU: the activations (and the flattened copy the heads read) are scaled in
+                # place by m / keep; every sink sees the dropped tensor
+                sc.drop_seed = (0x9E3779B9 * (nd.idx + 1)) & 0xFFFFFFFF
+
+                def drop(sc=sc):
+                    if sc.act is not None:
+                        L.dropout(_vp(sc.act), sc.N, *sc.geo.args(), 0, 0, sc.keep, sc.drop_seed, _vp(eng.hyp), dt, S())
+                    if sc.feat is not None:
+                        L.dropout(_vp(sc.feat), sc.N, *sc.geo.args(), 1, Balloc, sc.keep, sc.drop_seed, _vp(eng.hyp), dt, S())
+                drop.lane = sc.lane
+                self.fwd_ops.append(drop)
+                sc.post_op = drop
+                if sc.feat is not None:
+                    st.feat_op = drop
+            sc.act_alpha = act_alpha
+            if act_alpha:
+                sc.c_act = self.f32(B)
+
+                def acost(sc=sc):
+                    L.activity_fwd(_vp(sc.act), sc.N, *sc.geo.args(), sc.act_alpha, _vp(sc.c_act), dt, S())
+                acost.lane = sc.lane
+                self.fwd_ops.append(acost)
+                self.activity.append((nd.idx, sc))
+            if pooled_out or gmp:
+                # the features of the heads come from the pooling kernel, not from the BN / ReLU kernel
+                # (sc.feat was cleared before `post` was built, see below)
+                geo_q = Geo(B, geo.H // 2, geo.W // 2) if pooled_out else None
+                sc.mp = Ns(feat=st.feat if has_heads else None, geo=geo_q,
+                           out=self.planes(N, geo_q) if pooled_out and kid_rcm else None,
+                           arg=self.zeros((N // 8, Balloc, 8), torch.int32) if gmp else None)
+                if pooled_out:
+                    def pool(sc=sc):
+                        L.maxpool2_fwd(_vp(sc.act), sc.N, *sc.geo.args(), _vp(sc.mp.out), sc.mp.geo.P,
+                                       _vp(sc.mp.feat), Balloc, dt, S())
+                else:
+                    def pool(sc=sc):
+                        L.global_maxpool_fwd(_vp(sc.act), sc.N, *sc.geo.args(), _vp(sc.mp.feat), _vp(sc.mp.arg), Balloc, dt, S())
+                self._tag(pool, 'pool_fwd', nbytes=B * geo.H * geo.W * N * (2 if dt == BF16 else 4) * 1.25)
+                pool.lane = sc.lane
+                self.fwd_ops.append(pool)
+                if sc.mp.feat is not None:
+                    st.feat_op = pool
+                if pooled_out:
+                    st.out.append(Ns(t=sc.mp.out, C=N, Creal=N, geo=geo_q, dact=None, writers=0, sc=None, consumers=0,
+                                     fused_red=False, split=None, split_op=None, op=pool, dact_ops=[]))
+                    continue
             st.out.append(Ns(t=sc.act, C=N, Creal=N, geo=geo, dact=None, writers=0, sc=sc, consumers=0, fused_red=False,
                              split=getattr(sc, 'act_split', None), split_op=getattr(sc, 'post_op', None)))
 
@@ -1473,6 +1592,47 @@ class _Plan:
             dact = st.out[k].dact                    # written by child conv stages (already built)
             dfeat = st.dfeat if (k == n - 1) else None
             dpooled = sc.dpooled      # gradient wrt pooled(lin_k), set by scale k+1's dgrad below
+            mp = getattr(sc, 'mp', None)
+            if mp is not None and (dact is not None or dfeat is not None):
+                # MaxPool / GlobalMaxPool behind the ReLU: route the sinks' gradients back to the maxima first
+                full = self.planes(sc.N, geo)
+                if mp.arg is None:
+                    def unpool(sc=sc, dact=dact, dfeat=dfeat, full=full):
+                        L.maxpool2_bwd(_vp(sc.act), _vp(dact), _vp(dfeat), Balloc, sc.N, *sc.geo.args(),
+                                       sc.mp.geo.P, _vp(full), dt, S())
+                else:
+                    def unpool(sc=sc, dfeat=dfeat, full=full):
+                        L.global_maxpool_bwd(_vp(dfeat), _vp(sc.mp.arg), Balloc, sc.N, *sc.geo.args(), _vp(full), dt, S())
+                self._tag(unpool, 'pool_bwd', nbytes=B * geo.H * geo.W * sc.N * (2 if dt == BF16 else 4) * 2.25)
+                unpool.lane = sc.lane
+                self._after(unpool, getattr(st, 'dfeat_op', None) if dfeat is not None else None,
+                            *getattr(st.out[k], 'dact_ops', []))
+                self.bwd_ops.append(unpool)
+                dact, dfeat = full, None
+            if getattr(sc, 'keep', 1.0) != 1.0 and (dact is not None or dfeat is not None):
+                def dropb(sc=sc, dact=dact, dfeat=dfeat):
+                    if dact is not None:
+                        L.dropout(_vp(dact), sc.N, *sc.geo.args(), 0, 0, sc.keep, sc.drop_seed, _vp(eng.hyp), dt, S())
+                    if dfeat is not None:
+                        L.dropout(_vp(dfeat), sc.N, *sc.geo.args(), 1, Balloc, sc.keep, sc.drop_seed, _vp(eng.hyp), dt, S())
+                dropb.lane = sc.lane
+                self._after(dropb, getattr(st, 'dfeat_op', None) if dfeat is not None else None,
+                            *getattr(st.out[k], 'dact_ops', []))
+                self.bwd_ops.append(dropb)
+            if getattr(sc, 'act_alpha', 0.0):
+                # gradient of alpha * sum x^2, weighted like the node's other costs: 1/B, times p_tr when routed
+                acc = 1 if dact is not None else 0
+                if dact is None:
+                    dact = self.planes(sc.N, geo)
+                coef = (lambda nd=nd: ctypes.c_void_p(self.p_tr.data_ptr() + 4 * nd.idx * B)) if eng.dynamic \
+                    else (lambda: None)
+
+                def agrad(sc=sc, dact=dact, acc=acc, coef=coef):
+                    L.activity_bwd(_vp(sc.act), sc.N, *sc.geo.args(), coef(), 2.0 * sc.act_alpha / B, _vp(dact), acc, dt, S())
+                agrad.lane = sc.lane
+                if getattr(sc, 'mp', None) is None:
+                    self._after(agrad, *getattr(st.out[k], 'dact_ops', []))
+                self.bwd_ops.append(agrad)
             live = sc.live and (dact is not None or dfeat is not None)
             self._bn_bwd_bufs(sc)
             if live and not st.out[k].fused_red:   # (fused: the sums arrive with the consumer's data gradient)
@@ -1544,6 +1704,7 @@ class _Plan:
             #  small tensors and in the generic epilogue the stand-alone reduction is as fast or faster)
             fuse = (psc is not None and eng.fuse_bn_red and impl == 1 and self.bn_train and sc.src.consumers == 1
                     and psc.live and psc.feat is None and psc.N == N0 and (N0 + N1) in (16, 32)
+                    and not getattr(psc, 'act_alpha', 0.0) and getattr(psc, 'keep', 1.0) == 1.0
                     and B * sc.geo.H * sc.geo.W >= eng.fuse_bn_red_min_rows)
             if fuse:
                 sc.src.fused_red = True
@@ -1567,6 +1728,8 @@ class _Plan:
             dgrad.lane = sc.lane
             if N1:
                 prev.dpooled_op = dgrad
+            if N0 and hasattr(sc.src, 'dact_ops'):
+                sc.src.dact_ops.append(dgrad)
             self.bwd_ops.append(dgrad)
 
     def _build_conv_bwd_split(self, sc, prev, elt, par_grad, B):

@@ -158,6 +158,10 @@ class OracleNet:
         self.trainable = []  # (owner_path, role, key, tensor); role 'layer'|'router'
         self._collect(record['root'], '')
         self.momentum = {id(t): torch.zeros_like(t) for _, _, _, t in self.trainable}
+        # TF's dropout stream cannot be restated: a test that exercises Dropout(λ < 1) supplies the keep masks of
+        # one evaluation here, in the order the Dropout layers are linked (preorder)
+        self.dropout_masks = None
+        self._drop_i = 0
 
     # -- parameters ------------------------------------------------------- #
     def _collect(self, rec, path):
@@ -305,7 +309,12 @@ class OracleNet:
         elif kind == 'Dropout':                     # layer_types.py:212-217: tf.nn.dropout(x, keep_prob=λ), every mode
             lam = hy.get('λ', 1)
             if lam != 1:
-                raise NotImplementedError('oracle: Dropout(λ=%r) draws from TF\'s random stream' % lam)
+                if self.dropout_masks is None:
+                    raise NotImplementedError('oracle: Dropout(λ=%r) draws from TF\'s random stream '
+                                              '(set dropout_masks)' % lam)
+                m = torch.as_tensor(np.asarray(self.dropout_masks[self._drop_i]), dtype=self.dtype)
+                self._drop_i += 1
+                nd.x = self._q(x * m / lam)
         else:
             raise NotImplementedError('oracle: layer type %r' % kind)
         return nd
@@ -331,6 +340,7 @@ class OracleNet:
         router (Ns(x, c_mod, n_ops)) or None, and for critics c_ev/c_opt/c_cre.
         """
         dt = self.dtype
+        self._drop_i = 0
         x0 = torch.as_tensor(np.asarray(x0), dtype=dt)
         y = torch.as_tensor(np.asarray(y), dtype=dt)
         B = x0.shape[0]

@@ -542,6 +542,66 @@ def test_fused_bn_statistics_match_the_two_launch_path(dt, impl, B, H, K0, K1, N
 
 
 @pytest.mark.parametrize('dt', [F32, BF16])
+@pytest.mark.parametrize('B,H,C', [(3, 8, 16), (37, 4, 32), (20, 16, 8)])
+def test_maxpool_and_global_maxpool(dt, B, H, C):
+    """mpnn_maxpool2_fwd/bwd and mpnn_global_maxpool_fwd/bwd against numpy (layer_types.py:86-100; gradients to the
+    first maximum)"""
+    rng = np.random.default_rng(41)
+    td = torch.float32 if dt == F32 else torch.bfloat16
+    rd = (lambda a: a) if dt == F32 else bf16_round
+    geo, gp = Geo(B, H, H), Geo(B, H // 2, H // 2)
+    x = rd(rng.standard_normal((B, H, H, C)).astype(np.float32))
+    X = dev(to_planes(x, geo), td)
+    Balloc = (B + 7) // 8 * 8
+    F = (H // 2) ** 2 * C
+    out = torch.zeros((C // 8, gp.P, 8), dtype=td, device='cuda')
+    feat = torch.zeros((F // 8, Balloc, 8), dtype=td, device='cuda')
+    L().maxpool2_fwd(vp(X), C, B, H, H, geo.G, geo.P, vp(out), gp.P, vp(feat), Balloc, dt, None)
+    torch.cuda.synchronize()
+    blocks = x.reshape(B, H // 2, 2, H // 2, 2, C).transpose(0, 1, 3, 2, 4, 5).reshape(B, H // 2, H // 2, 4, C)
+    ref = blocks.max(3)
+    assert np.array_equal(from_planes(out.float().cpu().numpy(), gp, C), ref)
+    f = feat.float().cpu().numpy()
+    assert np.array_equal(np.concatenate([f[i, :B] for i in range(F // 8)], 1), ref.reshape(B, -1))
+    # backward: pooled-tensor gradient + head gradient, routed to the first maximum of each block
+    dout = rd(rng.standard_normal(ref.shape).astype(np.float32))
+    dfe = rd(rng.standard_normal((B, F)).astype(np.float32))
+    DF = np.zeros((F // 8, Balloc, 8), np.float32)
+    for i in range(F // 8):
+        DF[i, :B] = dfe[:, i * 8:(i + 1) * 8]
+    dx = torch.zeros_like(X)
+    L().maxpool2_bwd(vp(X), vp(dev(to_planes(dout, gp), td)), vp(dev(DF, td)), Balloc, C, B, H, H, geo.G, geo.P, gp.P,
+                     vp(dx), dt, None)
+    torch.cuda.synchronize()
+    d = rd(dout + dfe.reshape(ref.shape)) if dt == F32 else dout + dfe.reshape(ref.shape)
+    am = blocks.argmax(3)                                                  # first maximum
+    refdx = np.zeros_like(blocks)
+    np.put_along_axis(refdx, am[:, :, :, None, :], d[:, :, :, None, :], 3)
+    refdx = refdx.reshape(B, H // 2, H // 2, 2, 2, C).transpose(0, 1, 3, 2, 4, 5).reshape(B, H, H, C)
+    got = from_planes(dx.float().cpu().numpy(), geo, C)
+    np.testing.assert_allclose(got, rd(refdx), rtol=0, atol=0 if dt == F32 else 2e-2)
+    # global max pool
+    gf = torch.zeros((C // 8, Balloc, 8), dtype=td, device='cuda')
+    arg = torch.zeros((C // 8, Balloc, 8), dtype=torch.int32, device='cuda')
+    L().global_maxpool_fwd(vp(X), C, B, H, H, geo.G, geo.P, vp(gf), vp(arg), Balloc, dt, None)
+    torch.cuda.synchronize()
+    g = gf.float().cpu().numpy()
+    assert np.array_equal(np.concatenate([g[i, :B] for i in range(C // 8)], 1), x.reshape(B, -1, C).max(1))
+    a = arg.cpu().numpy()
+    assert np.array_equal(np.concatenate([a[i, :B] for i in range(C // 8)], 1), x.reshape(B, -1, C).argmax(1))
+    dg = rd(rng.standard_normal((B, C)).astype(np.float32))
+    DG = np.zeros((C // 8, Balloc, 8), np.float32)
+    for i in range(C // 8):
+        DG[i, :B] = dg[:, i * 8:(i + 1) * 8]
+    dx2 = torch.zeros_like(X)
+    L().global_maxpool_bwd(vp(dev(DG, td)), vp(arg), Balloc, C, B, H, H, geo.G, geo.P, vp(dx2), dt, None)
+    torch.cuda.synchronize()
+    ref2 = np.zeros((B, H * H, C), np.float32)
+    np.put_along_axis(ref2, x.reshape(B, -1, C).argmax(1)[:, None, :], dg[:, None, :], 1)
+    assert np.array_equal(from_planes(dx2.float().cpu().numpy(), geo, C), ref2.reshape(B, H, H, C))
+
+
+@pytest.mark.parametrize('dt', [F32, BF16])
 @pytest.mark.parametrize('B,F,n,extra', [(5, 256, 10, False), (37, 512, 16, True), (128, 2048, 2, False)])
 def test_fc_fwd_bwd(dt, B, F, n, extra):
     rng = np.random.default_rng(8)

@@ -52,6 +52,20 @@ def _feed(net, x0, y, tau=0.7, kc=None, lr=None, mode=None):
     return f
 
 
+def _dropout_masks(eng, B, draw):
+    from util import dropout_mask
+    masks, shape = [], tuple(eng.net.hypers.x0_shape)
+    for nd in eng.nodes:                                   # preorder, like the oracle links them
+        if nd.kind != 'rcm':
+            continue
+        n = nd.cm.hypers.n_chan[-1]
+        if getattr(nd, 'keep', 1.0) != 1.0:
+            masks.append(dropout_mask((0x9E3779B9 * (nd.idx + 1)) & 0xFFFFFFFF, draw, (B, shape[0], shape[1], n), nd.keep))
+        if getattr(nd, 'maxpool', False):
+            shape = (shape[0] // 2, shape[1] // 2)
+    return masks
+
+
 CASES = [('sr', {}), ('ac', dict(k_cpt=4e-9)), ('cr', dict(k_cpt=4e-9)),
          ('cr', dict(k_cpt=1e-8, optimistic=True)), ('cr', dict(k_cpt=1e-8, use_cls_err=True)),
          ('actree', dict(k_cpt=2e-9)), ('ac', dict(dyn_k_cpt=True)), ('ac', dict(k_cpt=1e-8, talr=False)),
@@ -64,7 +78,9 @@ CASES = [('sr', {}), ('ac', dict(k_cpt=4e-9)), ('cr', dict(k_cpt=4e-9)),
          # standalone Conv chains: on the image, and on a pyramid scale picked by Select
          ('cnv', {}), ('cnvpyr', dict(x0_shape=(16, 16, 1))),
          # the other error layers (layer_types.py:255-285): SquaredError on the LinTrans output, superclass cross-entropy
-         ('srsq', {}), ('acsq', dict(k_cpt=4e-9)), ('srsce', {}), ('crsce', dict(k_cpt=4e-9))]
+         ('srsq', {}), ('acsq', dict(k_cpt=4e-9)), ('srsce', {}), ('crsce', dict(k_cpt=4e-9)),
+         # MaxPool blocks, GlobalMaxPool classifier, identity-configured Dropout / ActivityError (layer_types.py:86-100)
+         ('cnvmp', {}), ('cnvgmp', {}), ('cnvact', {}), ('cnvdrop', {})]
 
 
 @pytest.mark.parametrize('prec', ['fp32', 'bf16'])
@@ -77,8 +93,11 @@ def test_forward_and_gradients(kind, hy, prec):
     x0, y = batch(B, x0_shape=hy.get('x0_shape', (16, 16, 3)), n_cls=hy.get('n_cls', 10), seed=3)
     kc = np.random.default_rng(3).choice([0.0, 1e-9, 6.4e-8], B).astype(np.float32) if hy.get('dyn_k_cpt') else None
     o = OracleNet(rec, torch.float64, quant='bf16' if prec == 'bf16' else None)
-    out, g_ref = o.grads(x0, y, tau=0.7, k_cpt=kc)
     eng = net._get_engine()
+    if kind == 'cnvdrop':
+        # the device's masks for its next evaluation (draw counter + 1), restated in numpy for the oracle
+        o.dropout_masks = _dropout_masks(eng, B, eng.draw + 1)
+    out, g_ref = o.grads(x0, y, tau=0.7, k_cpt=kc)
     feed = _feed(net, x0, y, 0.7, kc)
     eng.train_step(feed, update=False)
     torch.cuda.synchronize()
@@ -136,7 +155,8 @@ def test_forward_and_gradients(kind, hy, prec):
 
 
 @pytest.mark.parametrize('prec', ['fp32', 'bf16'])
-@pytest.mark.parametrize('kind,hy', [('sr', {}), ('ac', dict(k_cpt=4e-9)), ('cr', dict(k_cpt=4e-9)), ('cnv', {})])
+@pytest.mark.parametrize('kind,hy', [('sr', {}), ('ac', dict(k_cpt=4e-9)), ('cr', dict(k_cpt=4e-9)), ('cnv', {}),
+                                     ('cnvmp', {}), ('crsce', dict(k_cpt=4e-9))])
 def test_training_steps_track_the_oracle(kind, hy, prec):
     """3 x net.train.run(...) with the reference's schedules: parameters and
     BatchNorm EMAs follow the oracle."""

@@ -6,9 +6,9 @@ import numpy as np
 
 from lib import layer_types as lt
 from lib import serdes
-from lib.layer_types import (BatchNorm, Chain, Conv, CrossEntropyError, LinTrans, MultiscaleBatchNorm,
-                             MultiscaleConvMax, MultiscaleRect, Rect, Select, Softmax, SquaredError,
-                             SuperclassCrossEntropyError, ToPyramid)
+from lib.layer_types import (ActivityError, BatchNorm, Chain, Conv, CrossEntropyError, Dropout, GlobalMaxPool, LinTrans,
+                             MaxPool, MultiscaleBatchNorm, MultiscaleConvMax, MultiscaleRect, Rect, Select, Softmax,
+                             SquaredError, SuperclassCrossEntropyError, ToPyramid)
 from lib.net_types import ActorNet, CriticNet, SRNet
 
 K_L2 = 1e-4
@@ -69,6 +69,24 @@ def tiny_net(kind='ac', n_cls=10, x0_shape=(16, 16, 3), seed=0, **hypers):
 
 
 def _tiny_net(kind, n_cls, x0_shape, **hypers):
+    if kind in ('cnvmp', 'cnvgmp', 'cnvact', 'cnvdrop'):
+        # the plain-CNN layers of layer_types.py:86-100, 212-217, 287-293: Conv-BN-ReLU-MaxPool blocks (with the
+        # identity-configured Dropout / ActivityError in the chain) and a GlobalMaxPool classifier
+        blk = lambda n, *sinks, tail=(): Chain(name='ConvBlock', sinks=sinks, comps=[
+            Conv(n_chan=n, supp=3, k_l2=K_L2, σ_w=1), BatchNorm(), Rect()] + list(tail))
+        if kind == 'cnvmp':
+            flat = Chain(name='LogReg', comps=[Dropout(), _fc(n_cls), Softmax(), CrossEntropyError()])
+            root = blk(16, blk(32, flat, tail=[MaxPool(stride=2, supp=2)]), tail=[ActivityError(), MaxPool(stride=2, supp=2)])
+        elif kind == 'cnvdrop':     # Dropout(keep < 1) behind the ReLU, in front of a MaxPool and in front of the classifier
+            flat = Chain(name='LogReg', comps=[_fc(n_cls), Softmax(), CrossEntropyError()])
+            root = blk(16, blk(32, flat, tail=[Dropout(λ=0.75)]), tail=[Dropout(λ=0.5), MaxPool(stride=2, supp=2)])
+        elif kind == 'cnvact':      # an activity cost on both blocks, with and without a MaxPool behind it
+            flat = Chain(name='LogReg', comps=[_fc(n_cls), Softmax(), CrossEntropyError()])
+            root = blk(16, blk(32, flat, tail=[ActivityError(α=2e-3)]), tail=[ActivityError(α=1e-3), MaxPool(stride=2, supp=2)])
+        else:
+            gap = Chain(name='LogReg', comps=[GlobalMaxPool(), _fc(n_cls), Softmax(), CrossEntropyError()])
+            root = blk(16, blk(32, gap), tail=[MaxPool(stride=2, supp=2)])
+        return SRNet(x0_shape=x0_shape, y_shape=(n_cls,), root=root)
     if kind in ('cnv', 'cnvpyr'):
         # standalone Conv (layer_types.py:55-74) chains: on the image itself, or on one pyramid scale via Select
         cnv = lambda n, *sinks, pre=(): Chain(name='ConvBlock', sinks=sinks, comps=list(pre) + [
@@ -90,6 +108,20 @@ def _tiny_net(kind, n_cls, x0_shape, **hypers):
     else:
         root = pyr(3, rcm([16, 16, 16], reg(n_cls), rcm([16, 16], reg(n_cls), rcm([32], reg(n_cls)))))
     return cls(x0_shape=x0_shape, y_shape=(n_cls,), root=root, **hypers)
+
+
+def dropout_mask(seed, draw, shape, keep):
+    """numpy restatement of the device's Dropout mask (csrc/activity.cu): keep <=> mix(mix(i * 0x9E3779B9 + seed)
+    ^ (draw * 0x85EBCA6B)) < keep * 2^32 over the NHWC element index i"""
+    def mix(x):
+        x = x.copy()
+        x ^= x >> np.uint32(16); x *= np.uint32(0x7feb352d); x ^= x >> np.uint32(15)
+        x *= np.uint32(0x846ca68b); x ^= x >> np.uint32(16)
+        return x
+    with np.errstate(over='ignore'):
+        i = np.arange(int(np.prod(shape)), dtype=np.uint32)
+        u = mix(mix(i * np.uint32(0x9E3779B9) + np.uint32(seed)) ^ np.uint32((draw * 0x85EBCA6B) & 0xFFFFFFFF))
+    return (u.astype(np.uint64) < np.uint64(int(keep * 4294967296.0))).reshape(shape).astype(np.float32)
 
 
 def randomize_routers(net, seed=1, scale=0.5):

@@ -114,6 +114,12 @@ if __name__ == '__main__':
         wgrad_case(32, 16, 0, 16)
     if what == 'h8wgrad':
         wgrad_case(8, 64, 0, 64)
+    if what == 'h4':                                              # coarse-scale layers at the reference's batch (B=128)
+        conv_case(4, 64, 64, 64)
+        conv_case(4, 64, 64, 64, stats=False)
+        conv_case(4, 128, 0, 128)
+        conv_case(4, 128, 0, 64, stats=False, bias=False, n1=0)
+        wgrad_case(4, 64, 64, 64)
     if what == 'gemm1':
         conv_case(32, 16, 0, 16)
         conv_case(16, 32, 0, 32)
