@@ -45,6 +45,11 @@ int mpnn_has_umma(void);
  * (H = H0/step, W = W0/step, Cpad channels, extra channels zero). */
 int mpnn_pack_input(const float* x0, int B, int H0, int W0, int C0, int step,
                     void* planes, int Cpad, int G, int P, int dtype, void* stream);
+/* MultiscaleLLN (lib/layer_types.py:126-147) on the `step`-strided subsample of an RGB image (one pyramid
+ * scale): out [B][H0/step][W0/step][3] fp32 = x / (local luminance / local density + eps), Gaussian window of
+ * standard deviation sigma and half-width ceil(2 sigma).  Followed by mpnn_pack_input(out, ..., step = 1). */
+int mpnn_lln(const float* x0, int B, int H0, int W0, int C0, int step, float sigma, float eps,
+             float* out, void* stream);
 
 /* HWIO fp32 conv weights (lib/layer_types.py:158-173) or (n_in,n_chan) FC
  * weights -> packed operand  Wp[tap][Ktot/8][Ntot][8].

@@ -68,6 +68,54 @@ extern "C" int mpnn_pack_input(const float* x0, int B, int H0, int W0, int C0, i
 }
 
 // --------------------------------------------------------------------------- //
+// MultiscaleLLN (lib/layer_types.py:126-147) on one pyramid scale of an RGB image: local luminance
+//   lum(h, w) = sum_{|u|,|v| <= s} g(u, v) * (0.2126 R + 0.7152 G + 0.0722 B)(h + u, w + v)    (zero outside the image)
+// with g(u, v) = exp(-(u^2 + v^2) / (2 sigma^2)) / (2 pi sigma^2), s = ceil(2 sigma); density = the same sum over
+// an image of ones (so borders are normalised by the weight that falls inside); out = x / (lum / density + eps).
+// x0 is the full-resolution NHWC image, the scale is its `step`-strided subsample (ToPyramid, :118-125);
+// out is NHWC fp32 at the scale's size.  One thread per output pixel.
+// --------------------------------------------------------------------------- //
+__global__ void __launch_bounds__(256)
+lln_kernel(const float* __restrict__ x0, int B, int H0, int W0, int step, float sigma, float eps, int s,
+           float* __restrict__ out) {
+    const int H = H0 / step, W = W0 / step;
+    const int total = B * H * W;
+    const float inv2s2 = 1.f / (2.f * sigma * sigma), norm = 1.f / (2.f * 3.14159265358979323846f * sigma * sigma);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int w = i % W, h = (i / W) % H, n = i / (W * H);
+        float lum = 0.f, den = 0.f;
+        for (int u = -s; u <= s; ++u) {
+            const int hh = h + u;
+            if (hh < 0 || hh >= H) continue;
+            for (int v = -s; v <= s; ++v) {
+                const int ww = w + v;
+                if (ww < 0 || ww >= W) continue;
+                const float gk = expf(-(float)(u * u + v * v) * inv2s2) * norm;
+                const float* p = x0 + (((size_t)n * H0 + (size_t)hh * step) * W0 + (size_t)ww * step) * 3;
+                lum = fmaf(gk, 0.2126f * __ldg(p) + 0.7152f * __ldg(p + 1) + 0.0722f * __ldg(p + 2), lum);
+                den = fmaf(gk, 0.2126f + 0.7152f + 0.0722f, den);
+            }
+        }
+        const float k = 1.f / (lum / den + eps);
+        const float* p = x0 + (((size_t)n * H0 + (size_t)h * step) * W0 + (size_t)w * step) * 3;
+        float* o = out + (size_t)i * 3;
+        o[0] = __ldg(p) * k; o[1] = __ldg(p + 1) * k; o[2] = __ldg(p + 2) * k;
+    }
+}
+
+extern "C" int mpnn_lln(const float* x0, int B, int H0, int W0, int C0, int step, float sigma, float eps,
+                        float* out, void* stream) {
+    MPNN_REQUIRE(x0 && out && C0 == 3, "lln: the luminance weights are defined for 3 channels (C0=%d)", C0);
+    MPNN_REQUIRE(step >= 1 && H0 % step == 0 && W0 % step == 0 && sigma > 0.f, "lln: step=%d sigma=%g", step, (double)sigma);
+    const int s = (int)ceilf(2.f * sigma);
+    const long long total = (long long)B * (H0 / step) * (W0 / step);
+    int grid = (int)((total + 255) / 256);
+    if (grid > 148 * 16) grid = 148 * 16;
+    lln_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x0, B, H0, W0, step, sigma, eps, s, out);
+    return mpnn_check_launch("lln");
+}
+
+// --------------------------------------------------------------------------- //
 // Weight packing:  w[t][i][o] (HWIO / (n_in,n_chan)) -> Wp[tap][Ktot/8][Ntot][8]
 // --------------------------------------------------------------------------- //
 template <typename T> __device__ __forceinline__ T cvt_from_float(float v);

@@ -19,8 +19,9 @@ import torch
 
 from lib import _cabi
 from lib.layer_types import (ActivityError, BatchNorm, Chain, Conv, CrossEntropyError, Dropout, GlobalMaxPool,
-                             LinTrans, MaxPool, MultiscaleBatchNorm, MultiscaleConvMax, MultiscaleRect, Param,
-                             Rect, Select, Softmax, SquaredError, SuperclassCrossEntropyError, ToPyramid)
+                             LinTrans, MaxPool, MultiscaleBatchNorm, MultiscaleConvMax, MultiscaleLLN,
+                             MultiscaleRect, Param, Rect, Select, Softmax, SquaredError,
+                             SuperclassCrossEntropyError, ToPyramid)
 from lib.net_types import n_leaves
 
 F32, BF16 = 0, 1
@@ -229,8 +230,11 @@ class Engine:
         def visit(layer, parent, sink_idx):
             nd = Ns(layer=layer, idx=len(self.nodes), parent=parent, sink_idx=sink_idx, kids=[],
                     router=layer.router)
-            if _is_chain(layer, _PYR):
+            if _is_chain(layer, _PYR) or _is_chain(layer, _PYR + [MultiscaleLLN]):
                 nd.kind = 'pyr'
+                nd.lln = _comps(layer)[1] if len(_comps(layer)) > 1 else None     # local luminance normalisation of every scale
+                if nd.lln is not None and net.hypers.x0_shape[2] != 3:
+                    raise ValueError('MultiscaleLLN weighs R, G, B: the input has %d channels' % net.hypers.x0_shape[2])
             elif _is_chain(layer, _RCM):
                 nd.kind = 'rcm'
                 nd.cm, nd.mbn, nd.sel = _comps(layer)[0], _comps(layer)[1], None
@@ -959,7 +963,7 @@ class _Plan:
             st = Ns()
             self.node[nd.idx] = st
             if nd.kind == 'pyr':
-                n_sc = lay.comps[0].hypers.n_scales
+                n_sc = _comps(lay)[0].hypers.n_scales
                 cpad = _ru(C0, cpad_q)
                 st.out = []
                 for i in range(n_sc):
@@ -967,8 +971,19 @@ class _Plan:
                     t = self.planes(cpad, geo)
                     st.out.append(Ns(t=t, C=cpad, Creal=C0, geo=geo, dact=None, writers=0, sc=None, consumers=0, fused_red=False,
                                      split=None, split_op=None))
-                    pk = lambda t=t, i=i, geo=geo: L.pack_input(
-                        _vp(self.x0), B, H0, W0, C0, 2 ** i, _vp(t), cpad, geo.G, geo.P, dt, S())
+                    if getattr(nd, 'lln', None) is not None:
+                        # MultiscaleLLN behind ToPyramid: normalise the scale in fp32 NHWC, then pack that
+                        tmp = self.f32(B, geo.H, geo.W, C0)
+
+                        def lln(i=i, tmp=tmp, hy=nd.lln.hypers):
+                            L.lln(_vp(self.x0), B, H0, W0, C0, 2 ** i, float(hy.σ), float(hy.ϵ), _vp(tmp), S())
+                        lln.lane = 3 + i
+                        self.fwd_ops.append(lln)
+                        pk = lambda t=t, geo=geo, tmp=tmp: L.pack_input(
+                            _vp(tmp), B, geo.H, geo.W, C0, 1, _vp(t), cpad, geo.G, geo.P, dt, S())
+                    else:
+                        pk = lambda t=t, i=i, geo=geo: L.pack_input(
+                            _vp(self.x0), B, H0, W0, C0, 2 ** i, _vp(t), cpad, geo.G, geo.P, dt, S())
                     pk.lane = 3 + i
                     self.fwd_ops.append(pk)
                     if eng.split:

@@ -213,7 +213,10 @@ class OracleNet:
         if kind == 'NoOp':
             pass
         elif kind == 'Chain':                       # layer_types.py:299-310
-            for c in rec['comps']:
+            for i, c in enumerate(rec['comps']):
+                # (bf16 restatement: the device rounds the pyramid where it is packed, i.e. behind a MultiscaleLLN)
+                nxt = rec['comps'][i + 1]['type'] if i + 1 < len(rec['comps']) else None
+                self._raw_pyramid = c['type'] == 'ToPyramid' and nxt == 'MultiscaleLLN'
                 cn = self._link(c, x, y, mode)
                 nd.comps.append(cn)
                 x = cn.x
@@ -255,8 +258,24 @@ class OracleNet:
             nd.x = x.amax(tuple(range(1, x.dim() - 1)))
         elif kind == 'ToPyramid':                   # layer_types.py:118-125
             h, w = x.shape[1:3]
-            nd.x = [self._qf(tf_resize_legacy(x, h // 2 ** i, w // 2 ** i))
+            qf = (lambda t: t) if getattr(self, '_raw_pyramid', False) else self._qf
+            nd.x = [qf(tf_resize_legacy(x, h // 2 ** i, w // 2 ** i))
                     for i in range(hy.get('n_scales', 1))]
+        elif kind == 'MultiscaleLLN':               # layer_types.py:126-147
+            sig, e = hy.get('σ', 3), hy.get('ϵ', 1e-3)
+            s = int(np.ceil(2 * sig))
+            u = np.linspace(-s, s, 2 * s + 1)[:, None, None, None]
+            v = np.linspace(-s, s, 2 * s + 1)[:, None, None]
+            k = (np.exp(-(u ** 2 + v ** 2) / (2 * sig ** 2)) / (2 * np.pi * sig ** 2)
+                 * np.array([[0.2126], [0.7152], [0.0722]]))                      # HWIO, (2s+1, 2s+1, 3, 1)
+            kt = torch.tensor(k, dtype=self.dtype)
+            out = []
+            for x_i in x:
+                # pad by s, SAME conv, crop the middle = the zero-padded correlation at every pixel
+                lum = tf_conv2d_same(x_i, kt)
+                den = tf_conv2d_same(torch.ones_like(x_i), kt)
+                out.append(self._qf(x_i / (lum / den + e)))
+            nd.x = out
         elif kind == 'MultiscaleConvMax':           # layer_types.py:149-194
             n = len(hy['n_chan'])
             xin = x[len(x) - n:]

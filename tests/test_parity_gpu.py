@@ -80,7 +80,9 @@ CASES = [('sr', {}), ('ac', dict(k_cpt=4e-9)), ('cr', dict(k_cpt=4e-9)),
          # the other error layers (layer_types.py:255-285): SquaredError on the LinTrans output, superclass cross-entropy
          ('srsq', {}), ('acsq', dict(k_cpt=4e-9)), ('srsce', {}), ('crsce', dict(k_cpt=4e-9)),
          # MaxPool blocks, GlobalMaxPool classifier, identity-configured Dropout / ActivityError (layer_types.py:86-100)
-         ('cnvmp', {}), ('cnvgmp', {}), ('cnvact', {}), ('cnvdrop', {})]
+         ('cnvmp', {}), ('cnvgmp', {}), ('cnvact', {}), ('cnvdrop', {}),
+         # MultiscaleLLN (layer_types.py:126-147) behind ToPyramid
+         ('srlln', {}), ('aclln', dict(k_cpt=4e-9))]
 
 
 @pytest.mark.parametrize('prec', ['fp32', 'bf16'])

@@ -7,7 +7,7 @@ import numpy as np
 from lib import layer_types as lt
 from lib import serdes
 from lib.layer_types import (ActivityError, BatchNorm, Chain, Conv, CrossEntropyError, Dropout, GlobalMaxPool, LinTrans,
-                             MaxPool, MultiscaleBatchNorm, MultiscaleConvMax, MultiscaleRect, Rect, Select, Softmax,
+                             MaxPool, MultiscaleBatchNorm, MultiscaleConvMax, MultiscaleLLN, MultiscaleRect, Rect, Select, Softmax,
                              SquaredError, SuperclassCrossEntropyError, ToPyramid)
 from lib.net_types import ActorNet, CriticNet, SRNet
 
@@ -25,8 +25,12 @@ def router(n_sinks):
                                        Rect(), _fc(n_sinks, 0)])
 
 
+_LLN = [False]          # local luminance normalisation behind ToPyramid (set by tiny_net for the '...lln' kinds)
+
+
 def pyr(n_scales, *sinks):
-    return Chain(name='ToPyramid', sinks=sinks, comps=[ToPyramid(n_scales=n_scales)])
+    comps = [ToPyramid(n_scales=n_scales)] + ([MultiscaleLLN(σ=2)] if _LLN[0] else [])
+    return Chain(name='ToPyramid', sinks=sinks, comps=comps)
 
 
 def rcm(n_chan, *sinks):
@@ -62,10 +66,12 @@ def tiny_net(kind='ac', n_cls=10, x0_shape=(16, 16, 3), seed=0, **hypers):
     for suffix in ('sq', 'sce'):          # 'srsq', 'acsce', ...: the same nets with another error layer on the leaves
         if kind.endswith(suffix) and kind not in ('sq', 'sce'):
             kind, _LEAF[0] = kind[:-len(suffix)], suffix
+    if kind.endswith('lln'):              # 'srlln', 'aclln': MultiscaleLLN (layer_types.py:126-147) on every pyramid scale
+        kind, _LLN[0] = kind[:-3], True
     try:
         return _tiny_net(kind, n_cls, x0_shape, **hypers)
     finally:
-        _LEAF[0] = 'ce'
+        _LEAF[0], _LLN[0] = 'ce', False
 
 
 def _tiny_net(kind, n_cls, x0_shape, **hypers):
