@@ -18,6 +18,7 @@ net.train.run(feed) with pinned HOST batches (H2D inside the timed region, loss 
 `configs` = the same two numbers for every config at B = 128 and B = 4096 (fp32 mode included).
 """
 import argparse
+import gc
 import json
 import os
 import subprocess
@@ -159,7 +160,7 @@ def _oracle_step(o, cfg, x, y, t, rng):
     o.train_step(x.numpy(), y.numpy(), lr=lam(t), tau=cfg['tau'](t) if cfg['tau'] else None, k_cpt=kc)
 
 
-def cpu_oracle_rate(config, B, budget_s=15.0, max_steps=50):
+def cpu_oracle_rate(config, B, budget_s=15.0, max_steps=400):
     """Reference semantics restated on PyTorch-CPU (oracle/torch_ref.py): full train steps (forward 'tr',
     autograd backward, TALR + momentum) on a bounded sample of the workload."""
     cfg = _configs()[config]
@@ -466,6 +467,7 @@ def main():
             r = Run(c, b, prec, dev, rank, world)
             sweep.append(r.summary(30 if b > 128 else 100, 3, flush, pk))
             del r
+            gc.collect()                              # plans are reference cycles: free the run's buffers now
             torch.cuda.empty_cache()
 
     # ---------------- per-launch profile (rank 0) ---------------- #

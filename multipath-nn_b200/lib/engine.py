@@ -719,19 +719,30 @@ class Engine:
             with torch.cuda.stream(s):           # the communicator's first collective (channel setup) stays out of capture
                 self._allreduce()
             torch.cuda.synchronize(self.dev)
-        if one_graph:
-            # the whole step is ONE graph: with our own communicator the NCCL launch is captured like any kernel
-            with torch.cuda.graph(g1):
-                self._compute_ops(plan)
-                if self.dist:
-                    self._allreduce(0, plan.ar_split)
-                self._run(plan.opt_ops)
-            g2 = None
-        else:
-            with torch.cuda.graph(g1):
-                self._compute_ops(plan)
-            with torch.cuda.graph(g2):
-                self._run(plan.opt_ops)
+        # The cyclic garbage collector must not run inside capture: freeing a tensor of an engine that was dropped
+        # earlier (plans and their launch closures are reference cycles) makes the allocator record an event on a
+        # capturing stream, which invalidates the capture.  Collect now, keep the collector off until capture ends.
+        import gc
+        gc.collect()
+        gc_was_on = gc.isenabled()
+        gc.disable()
+        try:
+            if one_graph:
+                # the whole step is ONE graph: with our own communicator the NCCL launch is captured like any kernel
+                with torch.cuda.graph(g1):
+                    self._compute_ops(plan)
+                    if self.dist:
+                        self._allreduce(0, plan.ar_split)
+                    self._run(plan.opt_ops)
+                g2 = None
+            else:
+                with torch.cuda.graph(g1):
+                    self._compute_ops(plan)
+                with torch.cuda.graph(g2):
+                    self._run(plan.opt_ops)
+        finally:
+            if gc_was_on:
+                gc.enable()
         plan.graph_launches = self.L.launches - before
         self._graphs[id(plan)] = (g1, g2)
         return self._graphs[id(plan)]
