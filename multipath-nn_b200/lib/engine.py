@@ -1433,7 +1433,7 @@ class _Plan:
                         L.bn_relu_pool_fwd(_vp(sc.lin), sc.N, *sc.geo.args(), _vp(sc.ss) if sc.live else None,
                                            _vp(sc.act), _vp(sc.pooled), sc.geo_p.P if sc.pooled is not None else 0,
                                            _vp(sc.feat), Balloc, dt, S())
-                self._tag(post, 'bn_fwd', nbytes=B * sc.geo.H * sc.geo.W * sc.N * (2 if dt == BF16 else 4) * (1 + (sc.act is not None) + 0.25 * (sc.pooled is not None) + (sc.feat is not None)))
+                self._tag(post, 'bn_fwd', desc='H%d C%d' % (sc.geo.H, sc.N), nbytes=B * sc.geo.H * sc.geo.W * sc.N * (2 if dt == BF16 else 4) * (1 + (sc.act is not None) + 0.25 * (sc.pooled is not None) + (sc.feat is not None)))
                 post.lane = sc.lane
                 sc.post_op = post
                 self.fwd_ops.append(post)
@@ -1556,7 +1556,7 @@ class _Plan:
                     L.bn_relu_pool_fwd(_vp(sc.lin), N, *geo.args(), _vp(sc.ss) if sc.live else None,
                                        _vp(sc.act), _vp(sc.pooled), sc.geo_p.P if sc.pooled is not None else 0,
                                        _vp(sc.feat), Balloc, F32, S())
-            self._tag(post, 'bn_fwd', nbytes=B * geo.H * geo.W * N * 4 * (1 + (sc.act is not None) + 0.25 * (sc.pooled is not None) + (sc.feat is not None)))
+            self._tag(post, 'bn_fwd', desc='H%d C%d' % (geo.H, N), nbytes=B * geo.H * geo.W * N * 4 * (1 + (sc.act is not None) + 0.25 * (sc.pooled is not None) + (sc.feat is not None)))
             post.lane = sc.lane
             self.fwd_ops.append(post)
             sc.post_op = post
@@ -1666,7 +1666,7 @@ class _Plan:
                 def red(sc=sc, dact=dact, dfeat=dfeat):
                     L.bn_bwd_reduce_fused(_vp(sc.lin), _vp(dact), _vp(dfeat), Balloc, _vp(sc.ss), _vp(sc.mr), sc.N,
                                           *sc.geo.args(), ctypes.c_void_p(sc.bnb.ctypes.data), dt, S())
-                self._tag(red, 'bn_bwd_reduce', nbytes=B * sc.geo.H * sc.geo.W * sc.N * (2 if dt == BF16 else 4) * 2)
+                self._tag(red, 'bn_bwd_reduce', desc='H%d C%d' % (sc.geo.H, sc.N), nbytes=B * sc.geo.H * sc.geo.W * sc.N * (2 if dt == BF16 else 4) * 2)
                 red.lane = sc.lane
                 if dfeat is not None:
                     self._after(red, getattr(st, 'dfeat_op', None))
@@ -1680,7 +1680,7 @@ class _Plan:
                                    _vp(sc.ss) if live else None, _vp(sc.mr), _vp(sc.sums),
                                    float(B * sc.geo.H * sc.geo.W), sc.N, *sc.geo.args(), _vp(sc.dlin),
                                    eng.gptr(sc.bk), dt, S())
-            self._tag(elt, 'bn_bwd', nbytes=B * sc.geo.H * sc.geo.W * sc.N * (2 if dt == BF16 else 4) * 3)
+            self._tag(elt, 'bn_bwd', desc='H%d C%d' % (sc.geo.H, sc.N), nbytes=B * sc.geo.H * sc.geo.W * sc.N * (2 if dt == BF16 else 4) * (3 + 0.25 * (dpooled is not None)))
             elt.lane = sc.lane
             if dfeat is not None:
                 self._after(elt, getattr(st, 'dfeat_op', None))

@@ -108,12 +108,17 @@ def main():
             b = to_bytes(m['dram__bytes_read.sum'], u['dram__bytes_read.sum']) + to_bytes(m['dram__bytes_write.sum'], u['dram__bytes_write.sum'])
             key = lname
             if rep == 'r02_prof_bn':
-                key = 'bn_bwd' if 'bwd_v2' in name or 'pool_bwd' in name else 'bn_fwd' if 'pool_fwd' in name else None
+                key = 'bn_bwd H32 C16' if 'bwd_v2' in name or 'pool_bwd' in name else 'bn_fwd H32 C16' if 'pool_fwd' in name else None
             if bkey and key:
                 traffic.setdefault(bkey, {})[key] = {
                     'dram_bytes': b, 'source': 'profiles/%s (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of this launch)' % dst}
     if traffic:
-        json.dump(traffic, open(os.path.join(PROF, 'r02_traffic.json'), 'w'), indent=1)
+        tpath = os.path.join(PROF, 'r02_traffic.json')
+        merged = json.load(open(tpath)) if os.path.exists(tpath) else {}       # captures of earlier calls stay
+        for bkey, d in traffic.items():
+            merged.setdefault(bkey, {}).update(d)
+        merged.get('B4096', {}).pop('bn_fwd', None)
+        json.dump(merged, open(tpath, 'w'), indent=1)
     raw = os.path.join(OUT, 'r02_ncu_routing_kernels_raw.csv')
     if os.path.exists(raw):
         rows = list(csv.reader(open(raw)))

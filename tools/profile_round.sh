@@ -18,7 +18,7 @@ B=4096 timeout 900 ncu --set full --clock-control none --import-source on -k reg
 B=4096 timeout 900 ncu --set full --clock-control none --import-source on -k regex:"stencil_gemm_umma" --launch-skip 1 --launch-count 1 -o gpurun_out/r02_prof_conv_dgrad python tools/mb_conv.py h32dgrad > /dev/null 2>&1
 B=4096 timeout 900 ncu --set full --clock-control none --import-source on -k regex:"stencil_wgrad_umma" --launch-skip 1 --launch-count 1 -o gpurun_out/r02_prof_wgrad_h32 python tools/mb_conv.py h32wgrad > /dev/null 2>&1
 B=4096 timeout 900 ncu --set full --clock-control none --import-source on -k regex:"stencil_wgrad_umma" --launch-skip 1 --launch-count 1 -o gpurun_out/r02_prof_wgrad_h8 python tools/mb_conv.py h8wgrad > /dev/null 2>&1
-B=4096 timeout 900 ncu --set full --clock-control none -k regex:"bn_" -c 4 -o gpurun_out/r02_prof_bn python tools/mb_bn.py h32 > /dev/null 2>&1
+B=4096 timeout 900 ncu --set full --clock-control none -k regex:"bn_relu_pool_fwd|bn_relu_pool_bwd" --launch-skip 10 --launch-count 2 -o gpurun_out/r02_prof_bn python tools/mb_bn.py h32 > /dev/null 2>&1
 # (what comes back is capped at 64 MiB: the 40-launch capture of the small kernels is exported to CSV here and dropped)
 GRAPHS=0 B=4096 timeout 900 ncu --set full --clock-control none -k regex:"route_|router_tail|gather|scatter|compact|leaf_stats|softmax_ce|talr|node_moments" --launch-skip 40 --launch-count 40 -o /tmp/r02_prof_route python tools/mb_route.py > /dev/null 2>&1
 ncu -i /tmp/r02_prof_route.ncu-rep --page raw --csv > gpurun_out/r02_ncu_routing_kernels_raw.csv 2> /dev/null
