@@ -587,7 +587,16 @@ int mpnn_stencil_gemm_umma(const void* A0, int K0, const void* A1, int K1, const
     const size_t kMax = 227 * 1024 - 1024;
     const size_t red_bytes = bwd ? (size_t)12 * N0 : 0;        // staged scale / shift / mean of the BN behind out0
     int split = 0, nstage = 0, NB = 0;
-    for (int s = 1; s <= 8; s *= 2) {
+    // 64-column slices take the register-accumulator epilogue (fast64 below) on grids that fill the GPU, and a
+    // 128-wide output is cut into two of them (measured on the whole step at B = 4096: 2.758 -> 2.741 ms with the
+    // cut, 2.756 without; no effect at B = 128, where the grids stay below the threshold).  Note what bounds these
+    // layers either way: the tensor core fetches its shared-memory operands at ~64 B/clk -- 111-129 clk per
+    // M128 x N64 x K16 MMA (6 KB) against 32 clk of math (profiles/r02_ncu_conv_h4_b4096.csv).
+    static const int tune_fast64 = getenv("MPNN_TUNE_FAST64") ? atoi(getenv("MPNN_TUNE_FAST64")) : 1;
+    const bool want64 = tune_fast64 && !tune_generic && ntaps == 9 && !bwd && !stats && !acc0 && !acc1 &&
+                        out_dtype == MPNN_BF16 && KC == KG && (KG == 4 || KG == 8 || KG == 12 || KG == 16) &&
+                        ceil_div(g.rows, 128) >= 148;
+    for (int s = (want64 && N % 64 == 0 && N0 % 64 == 0) ? N / 64 : 1; s <= 8; s *= 2) {
         if (N % (16 * s)) break;
         NB = N / s;
         if (NB > 256) continue;
@@ -617,7 +626,9 @@ int mpnn_stencil_gemm_umma(const void* A0, int K0, const void* A1, int K1, const
     const int n_kc_ = ceil_div(KG, KC);
     const int ks = (ntaps == 9 && n_kc_ == 1) ? KG / 2 : 0;
     const bool fast_ok = !tune_generic && out_dtype == MPNN_BF16 && !acc0 && !acc1 && !stats;
+    const bool use64 = want64 && NB == 64;
     if (NB != 16 && NB != 32 && cap > 2) cap = 2;
+    if (use64) cap = 1;                                        // registers: 128 accumulators per thread
     if (tune_per_sm && cap > tune_per_sm) cap = tune_per_sm;
     if (cap < 1) cap = 1;
     size_t smem = 0;
@@ -659,6 +670,11 @@ int mpnn_stencil_gemm_umma(const void* A0, int K0, const void* A1, int K1, const
                                        stencil_gemm_umma_kernel<32, 3, 1>, stencil_gemm_umma_kernel<32, 4, 1>},
                                       {stencil_gemm_umma_kernel<32, 1, 2>, stencil_gemm_umma_kernel<32, 2, 2>,
                                        stencil_gemm_umma_kernel<32, 3, 2>, stencil_gemm_umma_kernel<32, 4, 2>}};
+    // 64-column slices with the register-accumulator epilogue (K = 32 / 64 / 96 / 128): the generic epilogue costs
+    // ~400 instructions per 16-column chunk per warp (bias, warp-level column sums, output-mode dispatch) and bounded
+    // the 64- / 128-channel layers at ~3x their MMA time; one CTA per SM, ~190 registers per thread
+    static const Kern fast64[4] = {stencil_gemm_umma_kernel<64, 2, 1>, stencil_gemm_umma_kernel<64, 4, 1>,
+                                   stencil_gemm_umma_kernel<64, 6, 1>, stencil_gemm_umma_kernel<64, 8, 1>};
     // generic slice width (N >= 48), generic epilogue, unrolled issue loop for the K of the 32..128-channel layers
     static const Kern wide[5] = {stencil_gemm_umma_kernel<0, 2, 0>, stencil_gemm_umma_kernel<0, 3, 0>,
                                  stencil_gemm_umma_kernel<0, 4, 0>, stencil_gemm_umma_kernel<0, 6, 0>,
@@ -667,7 +683,8 @@ int mpnn_stencil_gemm_umma(const void* A0, int K0, const void* A1, int K1, const
     Kern kern = generic[NB == 16 ? 0 : (NB == 32 ? 1 : 2)];
     if (fast_ok && NB == 16 && ks >= 1 && ks <= 2) kern = fast16[e][ks - 1];
     if (fast_ok && NB == 32 && ks >= 1 && ks <= 4) kern = fast32[e][ks - 1];
-    if (!tune_generic && NB != 16 && NB != 32) {
+    if (use64) kern = fast64[ks / 2 - 1];
+    if (!tune_generic && NB != 16 && NB != 32 && !use64) {
         const int wi = ks == 2 ? 0 : ks == 3 ? 1 : ks == 4 ? 2 : ks == 6 ? 3 : ks == 8 ? 4 : -1;
         if (wi >= 0) kern = wide[wi];
     }
@@ -676,13 +693,14 @@ int mpnn_stencil_gemm_umma(const void* A0, int K0, const void* A1, int K1, const
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-        Kern all[20] = {generic[0], generic[1], generic[2]};
+        Kern all[24] = {generic[0], generic[1], generic[2]};
         for (int i = 0; i < 2; ++i) {
             for (int j = 0; j < 2; ++j) all[3 + 2 * i + j] = fast16[i][j];
             for (int j = 0; j < 4; ++j) all[7 + 4 * i + j] = fast32[i][j];
         }
         for (int j = 0; j < 5; ++j) all[15 + j] = wide[j];
-        for (int i = 0; i < 20; ++i) {
+        for (int j = 0; j < 4; ++j) all[20 + j] = fast64[j];
+        for (int i = 0; i < 24; ++i) {
             cudaError_t e2 = cudaFuncSetAttribute(all[i], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMax);   // + static smem stays under 227 KB
             if (e2 != cudaSuccess) { mpnn_set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e2)); return MPNN_ERR_CUDA; }
             // without this the driver picks the L1 / shared-memory split heuristically and may leave room for fewer

@@ -33,6 +33,8 @@ METRICS = ['gpu__time_duration.sum', 'launch__grid_size', 'launch__block_size', 
            'sm__inst_executed_pipe_tensor.sum', 'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active',
            'smsp__inst_executed.sum', 'smsp__issue_active.avg.pct_of_peak_sustained_active',
            'sm__warps_active.avg.pct_of_peak_sustained_active', 'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum',
+           'l1tex__data_pipe_tc_wavefronts_mem_shared.sum', 'l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed',
+           'sm__cycles_elapsed.max',
            'smsp__average_warp_latency_issue_stalled_long_scoreboard.pct', 'smsp__average_warp_latency_issue_stalled_barrier.pct']
 
 
@@ -93,6 +95,7 @@ def main():
             'r02_prof_wgrad_h8': ('r02_ncu_full_wgrad_h8.csv', 'B4096', 'conv_wgrad H8 K64+0 N64'),
             'r02_prof_bn': ('r02_ncu_full_bn_h32.csv', 'B4096', None),
             'r02_prof_h4_b128': ('r02_ncu_conv_h4_b128.csv', None, None),
+            'r02_prof_h4_b4096': ('r02_ncu_conv_h4_b4096.csv', None, None),
             'r02_prof_router_b128': ('r02_ncu_small_kernels_b128.csv', None, None),
             'r02_prof_k32n64': ('r02_ncu_full_conv_k32n64.csv', None, None)}
     for rep, (dst, bkey, lname) in reps.items():
