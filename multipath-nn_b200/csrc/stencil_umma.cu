@@ -83,7 +83,9 @@ __device__ __forceinline__ void unpack_bf16x8(const uint4& u, float* v) {
 // output-mode dispatch); 2: the same with the fused BN-backward sums (separate instantiation: the two kinds
 // of sums have different register footprints and the accumulators must not spill).
 template <int NBT, int KS, int EPI>
-__global__ void __launch_bounds__(kThreads, NBT == 16 ? (EPI == 2 ? 3 : 4) : (NBT == 32 ? (EPI == 2 ? 2 : 3) : 1))
+// (32-wide slices at two CTAs per SM: at three the 64 register accumulators of the BN sums spilled -- 96 registers,
+//  16-48 bytes of stack -- and H16 32->32 ran at 53 us instead of 49)
+__global__ void __launch_bounds__(kThreads, NBT == 16 ? (EPI == 2 ? 3 : 4) : (NBT == 32 ? 2 : 1))
 stencil_gemm_umma_kernel(const GemmArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -587,16 +589,7 @@ int mpnn_stencil_gemm_umma(const void* A0, int K0, const void* A1, int K1, const
     const size_t kMax = 227 * 1024 - 1024;
     const size_t red_bytes = bwd ? (size_t)12 * N0 : 0;        // staged scale / shift / mean of the BN behind out0
     int split = 0, nstage = 0, NB = 0;
-    // 64-column slices take the register-accumulator epilogue (fast64 below) on grids that fill the GPU, and a
-    // 128-wide output is cut into two of them (measured on the whole step at B = 4096: 2.758 -> 2.741 ms with the
-    // cut, 2.756 without; no effect at B = 128, where the grids stay below the threshold).  Note what bounds these
-    // layers either way: the tensor core fetches its shared-memory operands at ~64 B/clk -- 111-129 clk per
-    // M128 x N64 x K16 MMA (6 KB) against 32 clk of math (profiles/r02_ncu_conv_h4_b4096.csv).
-    static const int tune_fast64 = getenv("MPNN_TUNE_FAST64") ? atoi(getenv("MPNN_TUNE_FAST64")) : 1;
-    const bool want64 = tune_fast64 && !tune_generic && ntaps == 9 && !bwd && !stats && !acc0 && !acc1 &&
-                        out_dtype == MPNN_BF16 && KC == KG && (KG == 4 || KG == 8 || KG == 12 || KG == 16) &&
-                        ceil_div(g.rows, 128) >= 148;
-    for (int s = (want64 && N % 64 == 0 && N0 % 64 == 0) ? N / 64 : 1; s <= 8; s *= 2) {
+    for (int s = 1; s <= 8; s *= 2) {
         if (N % (16 * s)) break;
         NB = N / s;
         if (NB > 256) continue;
@@ -619,16 +612,14 @@ int mpnn_stencil_gemm_umma(const void* A0, int K0, const void* A1, int K1, const
     while (ncols < 2 * NB) ncols <<= 1;
     int cap = 512 / ncols;
     if (cap > 4) cap = 4;
-    if (NB == 32 && cap > (bwd ? 2 : 3)) cap = bwd ? 2 : 3;      // register budgets of the instantiations
+    if (NB == 32 && cap > 2) cap = 2;                            // register budgets of the instantiations
     if (NB == 16 && bwd && cap > 3) cap = 3;
     // the generic-width instantiations need ~108 registers: two CTAs per SM are resident (ncu: occupancy limit 2 by
     // registers); a grid sized for three ran as 1.5 waves
     const int n_kc_ = ceil_div(KG, KC);
     const int ks = (ntaps == 9 && n_kc_ == 1) ? KG / 2 : 0;
     const bool fast_ok = !tune_generic && out_dtype == MPNN_BF16 && !acc0 && !acc1 && !stats;
-    const bool use64 = want64 && NB == 64;
     if (NB != 16 && NB != 32 && cap > 2) cap = 2;
-    if (use64) cap = 1;                                        // registers: 128 accumulators per thread
     if (tune_per_sm && cap > tune_per_sm) cap = tune_per_sm;
     if (cap < 1) cap = 1;
     size_t smem = 0;
@@ -670,11 +661,6 @@ int mpnn_stencil_gemm_umma(const void* A0, int K0, const void* A1, int K1, const
                                        stencil_gemm_umma_kernel<32, 3, 1>, stencil_gemm_umma_kernel<32, 4, 1>},
                                       {stencil_gemm_umma_kernel<32, 1, 2>, stencil_gemm_umma_kernel<32, 2, 2>,
                                        stencil_gemm_umma_kernel<32, 3, 2>, stencil_gemm_umma_kernel<32, 4, 2>}};
-    // 64-column slices with the register-accumulator epilogue (K = 32 / 64 / 96 / 128): the generic epilogue costs
-    // ~400 instructions per 16-column chunk per warp (bias, warp-level column sums, output-mode dispatch) and bounded
-    // the 64- / 128-channel layers at ~3x their MMA time; one CTA per SM, ~190 registers per thread
-    static const Kern fast64[4] = {stencil_gemm_umma_kernel<64, 2, 1>, stencil_gemm_umma_kernel<64, 4, 1>,
-                                   stencil_gemm_umma_kernel<64, 6, 1>, stencil_gemm_umma_kernel<64, 8, 1>};
     // generic slice width (N >= 48), generic epilogue, unrolled issue loop for the K of the 32..128-channel layers
     static const Kern wide[5] = {stencil_gemm_umma_kernel<0, 2, 0>, stencil_gemm_umma_kernel<0, 3, 0>,
                                  stencil_gemm_umma_kernel<0, 4, 0>, stencil_gemm_umma_kernel<0, 6, 0>,
@@ -683,8 +669,7 @@ int mpnn_stencil_gemm_umma(const void* A0, int K0, const void* A1, int K1, const
     Kern kern = generic[NB == 16 ? 0 : (NB == 32 ? 1 : 2)];
     if (fast_ok && NB == 16 && ks >= 1 && ks <= 2) kern = fast16[e][ks - 1];
     if (fast_ok && NB == 32 && ks >= 1 && ks <= 4) kern = fast32[e][ks - 1];
-    if (use64) kern = fast64[ks / 2 - 1];
-    if (!tune_generic && NB != 16 && NB != 32 && !use64) {
+    if (!tune_generic && NB != 16 && NB != 32) {
         const int wi = ks == 2 ? 0 : ks == 3 ? 1 : ks == 4 ? 2 : ks == 6 ? 3 : ks == 8 ? 4 : -1;
         if (wi >= 0) kern = wide[wi];
     }
@@ -693,14 +678,13 @@ int mpnn_stencil_gemm_umma(const void* A0, int K0, const void* A1, int K1, const
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-        Kern all[24] = {generic[0], generic[1], generic[2]};
+        Kern all[20] = {generic[0], generic[1], generic[2]};
         for (int i = 0; i < 2; ++i) {
             for (int j = 0; j < 2; ++j) all[3 + 2 * i + j] = fast16[i][j];
             for (int j = 0; j < 4; ++j) all[7 + 4 * i + j] = fast32[i][j];
         }
         for (int j = 0; j < 5; ++j) all[15 + j] = wide[j];
-        for (int j = 0; j < 4; ++j) all[20 + j] = fast64[j];
-        for (int i = 0; i < 24; ++i) {
+        for (int i = 0; i < 20; ++i) {
             cudaError_t e2 = cudaFuncSetAttribute(all[i], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMax);   // + static smem stays under 227 KB
             if (e2 != cudaSuccess) { mpnn_set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e2)); return MPNN_ERR_CUDA; }
             // without this the driver picks the L1 / shared-memory split heuristically and may leave room for fewer
