@@ -306,7 +306,7 @@ class Run:
         value = self.world * self.B * steps / (ms * 1e-3)
         return {
             'config': self.config, 'workload': self.cfg['what'], 'batch_per_gpu': self.B,
-            'dtype': 'bf16' if self.eng.dtype == 1 else ('f32 (bf16x3 on tcgen05)' if self.eng.split else 'f32'),
+            'dtype': 'bf16' if self.eng.dtype == 1 else ('f32 (%s on tcgen05)' % {2: 'bf16x3', 3: 'bf16x6'}[self.eng.split] if self.eng.split else 'f32'),
             'conv_impl': 'tcgen05' if self.eng.impl == 1 else 'simt', 'value': value, 'unit': 'images/s',
             'ms_per_step': ms / steps, 'e2e': self.world * self.B * steps / e2e_s, 'steps': steps,
             'launches_per_step': launches // max(steps, 1), 'train_mflop_per_img': self.flop / 1e6,
@@ -462,7 +462,7 @@ def main():
                 for b in (128, 4096):
                     if (c, b) != (args.config, B) and (c, b, args.precision) not in todo:
                         todo.append((c, b, args.precision))
-            todo += [(args.config, 128, 'bf16x3'), (args.config, 4096, 'bf16x3'), (args.config, 128, 'fp32'), (args.config, 4096, 'fp32')]
+            todo += [(args.config, b, p) for p in ('bf16x3', 'bf16x6', 'fp32') for b in (128, 4096)]
         for c, b, prec in todo:
             r = Run(c, b, prec, dev, rank, world)
             sweep.append(r.summary(30 if b > 128 else 100, 3, flush, pk))

@@ -61,7 +61,9 @@ int mpnn_pack_weights(const float* w, int ntaps, int I, int O, int mode,
                       void* packed, int dtype, void* stream);
 
 /* mode | 4: the RESIDUAL of the bf16 rounding, w - bf16(w), is packed instead of w ("lo" part of the bf16x3
- * precision mode, see mpnn_split_planes). */
+ * precision mode, see mpnn_split_planes; "mid" part of the bf16x6 mode).
+ * mode | 8: the residual of two roundings, w - bf16(w) - bf16(w - bf16(w)) ("lo" part of the bf16x6 mode, see
+ * mpnn_split_planes3). */
 /* the same for a whole table of tensors in one launch (device array of descriptors);
  * additionally mode 2: ((float*)packed)[n_off + o] = w[o], o < O (fp32 vector copy) */
 typedef struct {
@@ -78,6 +80,14 @@ int mpnn_pack_weights_batched(const mpnn_pack_desc* descs, int n, int blocks_per
  * weights packed as [hi; hi; lo] along K.  Carries the reference's fp32 arithmetic (lib/layer_types.py:106-107)
  * onto tcgen05 within the 1e-3 tolerance. */
 int mpnn_split_planes(const float* src, int C, int P, void* dst, void* stream);
+
+/* three-way split: dst [3*C/8][P][8] bf16 = (hi | mid | lo), hi = bf16(x), mid = bf16(x - hi), lo = bf16(x - hi - mid):
+ * 24 significant bits.  Operand format of the "bf16x6" precision mode: a fp32 product is the six bf16 tensor-core
+ * products a_h*b_h + a_m*b_h + a_l*b_h + a_h*b_m + a_m*b_m + a_h*b_l (every term of relative size >= 2^-16; what
+ * is dropped is <= 2^-23) accumulated in fp32 -- two launches of K = 3C: A0 = dst (3C channels) against weights
+ * [hi; hi; hi], then, accumulating, A0 = dst (first 2C channels), A1 = dst (first C) against [mid; mid; lo].
+ * This is the tensor-core mode that meets the 1e-3 tolerance on gradients (lib/layer_types.py:106-107 in fp32). */
+int mpnn_split_planes3(const float* src, int C, int P, void* dst, void* stream);
 
 /* ---- training-batch augmentation (scripts/lib/data.py:24-34) -------------- */
 /* x [N][H][W][C], y [N][n_cls] fp32: the training set resident on the device.  Per output example i

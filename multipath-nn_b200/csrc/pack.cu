@@ -124,6 +124,14 @@ template <> __device__ __forceinline__ __nv_bfloat16 cvt_from_float<__nv_bfloat1
     return __float2bfloat16_rn(v);
 }
 
+// mode & 4: the residual of one bf16 rounding, w - bf16(w) (second part of a split weight);
+// mode & 8: the residual of two, w - bf16(w) - bf16(w - bf16(w)) (third part, "bf16x6" mode)
+__device__ __forceinline__ float bf16_residual(float v, int mode) {
+    if (mode & 12) v -= __bfloat162float(__float2bfloat16_rn(v));
+    if (mode & 8) v -= __bfloat162float(__float2bfloat16_rn(v));
+    return v;
+}
+
 template <typename T>
 __global__ void pack_weights_kernel(const float* __restrict__ w, int ntaps, int I, int O, int mode,
                                     int k_off, int Ktot, int n_off, int Ntot, T* __restrict__ packed) {
@@ -136,9 +144,7 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, int ntaps, int 
         if ((mode & 3) == 0) { k = k_off + i; n = n_off + o; tap = t; }
         else                 { k = k_off + o; n = n_off + i; tap = ntaps - 1 - t; }
         size_t dst = (((size_t)tap * (Ktot / 8) + (k >> 3)) * Ntot + n) * 8 + (k & 7);
-        float v = w[e];
-        if (mode & 4) v -= __bfloat162float(__float2bfloat16_rn(v));     // residual of the bf16 rounding ("lo" part)
-        packed[dst] = cvt_from_float<T>(v);
+        packed[dst] = cvt_from_float<T>(bf16_residual(w[e], mode));
     }
 }
 
@@ -162,9 +168,7 @@ __global__ void pack_weights_batched_kernel(const mpnn_pack_desc* __restrict__ d
         if ((d.mode & 3) == 0) { k = d.k_off + i; n = d.n_off + o; tap = t; }
         else                   { k = d.k_off + o; n = d.n_off + i; tap = d.ntaps - 1 - t; }
         size_t dst = (((size_t)tap * (d.Ktot / 8) + (k >> 3)) * d.Ntot + n) * 8 + (k & 7);
-        float v = __ldg(d.w + e);
-        if (d.mode & 4) v -= __bfloat162float(__float2bfloat16_rn(v));   // residual of the bf16 rounding ("lo" part)
-        packed[dst] = cvt_from_float<T>(v);
+        packed[dst] = cvt_from_float<T>(bf16_residual(__ldg(d.w + e), d.mode));
     }
 }
 
@@ -209,6 +213,35 @@ split_planes_kernel(const float* __restrict__ src, long long rows, __nv_bfloat16
         Row8<__nv_bfloat16>::store(dst + r * 8, hi);
         Row8<__nv_bfloat16>::store(dst + (rows + r) * 8, lo);
     }
+}
+
+// three-way split (hi | mid | lo), x = hi + mid + lo up to 2^-25 |x|: operand format of the "bf16x6" mode, where a
+// product is a_hi*b_hi + a_mid*b_hi + a_lo*b_hi + a_hi*b_mid + a_mid*b_mid + a_hi*b_lo (every term above 2^-24).
+__global__ void __launch_bounds__(256)
+split_planes3_kernel(const float* __restrict__ src, long long rows, __nv_bfloat16* __restrict__ dst) {
+    for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < rows; r += (long long)gridDim.x * blockDim.x) {
+        float v[8], hi[8], mid[8], lo[8];
+        Row8<float>::load(src + r * 8, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            hi[j] = __bfloat162float(__float2bfloat16_rn(v[j]));
+            const float r1 = v[j] - hi[j];
+            mid[j] = __bfloat162float(__float2bfloat16_rn(r1));
+            lo[j] = r1 - mid[j];
+        }
+        Row8<__nv_bfloat16>::store(dst + r * 8, hi);
+        Row8<__nv_bfloat16>::store(dst + (rows + r) * 8, mid);
+        Row8<__nv_bfloat16>::store(dst + (2 * rows + r) * 8, lo);
+    }
+}
+
+extern "C" int mpnn_split_planes3(const float* src, int C, int P, void* dst, void* stream) {
+    MPNN_REQUIRE(src && dst && C % 8 == 0 && C > 0 && P > 0, "split_planes3: C=%d P=%d", C, P);
+    const long long rows = (long long)(C / 8) * P;
+    long long g = (rows + 255) / 256;
+    if (g > 148 * 16) g = 148 * 16;
+    split_planes3_kernel<<<(int)g, 256, 0, (cudaStream_t)stream>>>(src, rows, (__nv_bfloat16*)dst);
+    return mpnn_check_launch("split_planes3");
 }
 
 extern "C" int mpnn_split_planes(const float* src, int C, int P, void* dst, void* stream) {

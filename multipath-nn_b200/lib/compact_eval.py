@@ -31,7 +31,7 @@ class CompactEvaluator:
         if not eng.dynamic:
             raise ValueError('compacted evaluation is for dynamically-routed nets (an SRNet has one path)')
         if eng.split:
-            raise NotImplementedError('compacted evaluation runs in fp32 or bf16 precision (not bf16x3)')
+            raise NotImplementedError('compacted evaluation runs in fp32 or bf16 precision (not the split modes bf16x3 / bf16x6)')
         if any(getattr(nd, 'maxpool', False) or getattr(nd, 'gmp', False) for nd in eng.nodes):
             raise NotImplementedError('compacted evaluation does not cover MaxPool / GlobalMaxPool blocks')
         if any(nd.loss != 'ce' for nd in eng.regs):

@@ -109,6 +109,11 @@ def _is_chain(layer, types):
 
 _PYR = [ToPyramid]
 _RCM = [MultiscaleConvMax, MultiscaleBatchNorm, MultiscaleRect]
+# split-precision modes: the launches of one source tensor as (parts of A0, parts of A1, weight pack modes along K).
+# x3 (two parts): [hi | lo | hi] x [hi; hi; lo]; x6 (three parts): [hi | mid | lo] x [hi; hi; hi], then
+# [hi | mid | hi] x [mid; mid; lo].  Pack modes: 0 = bf16(w), 4 = first residual, 8 = second residual.
+_SPLIT_PASSES = {2: [(2, 1, (0, 0, 4))], 3: [(3, 0, (0, 0, 0)), (2, 1, (4, 4, 8))]}
+
 # standalone Conv (lib/layer_types.py:55-74) as a tree node: 3x3 SAME conv + bias -> BatchNorm -> ReLU on ONE
 # tensor -- the input image, a pyramid scale picked by a leading Select, or the tensor of the node above --
 # and a classifier that flattens a tensor without a Select.  Arithmetically a one-scale MultiscaleConvMax
@@ -167,18 +172,21 @@ class Engine:
             self.dev = torch.device('cpu')
         else:
             self.dev = torch.device('cuda', torch.cuda.current_device() if device is None else device)
-        assert precision in ('fp32', 'bf16', 'bf16x3')
+        assert precision in ('fp32', 'bf16', 'bf16x3', 'bf16x6')
         # 'bf16x3': fp32 storage and elementwise arithmetic like 'fp32', but the convolutions run on the tensor
         # cores: every fp32 operand is split into two bf16 planes sets (x = hi + lo, mpnn_split_planes) and a
         # product is evaluated as a_hi*b_hi + a_lo*b_hi + a_hi*b_lo with fp32 accumulation (2^-16 relative) --
         # the reference's fp32 arithmetic (layer_types.py:106-107) on tcgen05 within the 1e-3 tolerance
-        self.split = precision == 'bf16x3'
+        # 'bf16x6': the same with three-way splits (x = hi + mid + lo, 24 significant bits, mpnn_split_planes3) and
+        # the six products of relative size >= 2^-16 -- the tensor-core mode that meets 1e-3 on gradients too.
+        # self.split = number of bf16 parts per fp32 operand (0: no splitting)
+        self.split = {'bf16x3': 2, 'bf16x6': 3}.get(precision, 0)
         self.dtype = BF16 if precision == 'bf16' else F32
         self.tdtype = torch.bfloat16 if precision == 'bf16' else torch.float32
         # stencil implementation: 0 = SIMT fp32-accumulate, 1 = tcgen05
         self.impl = (1 if (precision != 'fp32' and self.L.mpnn_has_umma()) else 0) if impl is None else impl
         if self.split and self.impl != 1:
-            raise RuntimeError('precision bf16x3 needs the tcgen05 kernels')
+            raise RuntimeError('precision %s needs the tcgen05 kernels' % precision)
         # weight gradient follows the conv implementation (per launch it drops back to the
         # SIMT kernel when the shape exceeds what the tcgen05 wgrad tiles: K0+K1 > 128)
         self.impl_w = self.impl
@@ -918,13 +926,15 @@ class _Plan:
         return self._img
 
     def _split(self, t, C, geo, lane, ops=None):
-        """bf16x3 mode: (hi | lo) bf16 copy of an fp32 planes tensor and the launch that fills it"""
+        """bf16x3 / bf16x6 modes: (hi | lo) or (hi | mid | lo) bf16 copy of an fp32 planes tensor and the launch
+        that fills it"""
         eng, L = self.eng, self.eng.L
-        dst = self.zeros((2 * C // 8, geo.P, 8), torch.bfloat16)
+        dst = self.zeros((eng.split * C // 8, geo.P, 8), torch.bfloat16)
+        fn = L.split_planes3 if eng.split == 3 else L.split_planes
 
         def sp():
-            L.split_planes(_vp(t), C, geo.P, _vp(dst), eng.stream)
-        self._tag(sp, 'split', nbytes=C * geo.P * 8)
+            fn(_vp(t), C, geo.P, _vp(dst), eng.stream)
+        self._tag(sp, 'split', nbytes=C * geo.P * (4 + 2 * eng.split))
         sp.lane = lane
         (self.fwd_ops if ops is None else ops).append(sp)
         return dst, sp
@@ -1500,13 +1510,21 @@ class _Plan:
         geo, N, K0, K1 = sc.geo, sc.N, sc.K0, sc.K1
         sc.lane = 3 + int(round(np.log2(eng.net.hypers.x0_shape[0] / geo.H)))
 
-        def pack3(w, K, Kreal):
-            W3 = self.zeros((9, 3 * K // 8, N, 8), torch.bfloat16)
-            for k_off, mode in ((0, 0), (K, 0), (2 * K, 4)):            # [hi; hi; lo] along K
-                self._pack(w, W3, Kreal, N, mode, k_off, 3 * K, 0, N)
-            return W3
-        sc.W3h = pack3(sc.wh, K0, sc.K0real)
-        sc.W3v = pack3(sc.wv, K1, K1) if sc.wv is not None else None
+        # launches of one source tensor as (parts of A0, parts of A1, weight parts along K): x3 = one launch
+        # [hi | lo | hi] x [hi; hi; lo]; x6 = two launches [hi | mid | lo] x [hi; hi; hi] and
+        # [hi | mid | hi] x [mid; mid; lo] (pack modes: 0 = hi, 4 = first residual, 8 = second residual)
+        passes = _SPLIT_PASSES[eng.split]
+
+        def packs(w, K, Kreal):
+            out = []
+            for _, _, wparts in passes:
+                W3 = self.zeros((9, 3 * K // 8, N, 8), torch.bfloat16)
+                for j, mode in enumerate(wparts):
+                    self._pack(w, W3, Kreal, N, mode, j * K, 3 * K, 0, N)
+                out.append(W3)
+            return out
+        sc.W3h = packs(sc.wh, K0, sc.K0real)
+        sc.W3v = packs(sc.wv, K1, K1) if sc.wv is not None else None
         bnp = None
         if use_stats:
             bn = sc.bn
@@ -1517,24 +1535,23 @@ class _Plan:
                                   d=float(bn.hypers.d), eps=float(bn.hypers.ε), defer=1 if eng.defer_bn else 0)
             bnp = ctypes.c_void_p(sc.bnf.ctypes.data)
         two = prev is not None
-
-        def conv_h(sc=sc):
-            L.conv_acc_bn_stats(_vp(sc.src.split), 2 * K0, _vp(sc.src.split), K0, _vp(sc.W3h), eng.tptr(sc.bk),
-                                _vp(sc.lin), N, 0, *geo.args(), None if two else bnp, BF16, F32, 1, S())
-        self._tag(conv_h, 'conv_fwd', desc='H%d K3x%d N%d' % (geo.H, K0, N), flops=3 * 2.0 * B * geo.H * geo.W * 9 * sc.K0real * N,
-                  nbytes=B * geo.H * geo.W * (3 * K0 * 2 + N * 4))
-        conv_h.lane = sc.lane
-        self._after(conv_h, sc.src.split_op)
-        self.fwd_ops.append(conv_h)
+        todo = [(sc.src.split, K0, sc.K0real, W, sc.src.split_op, 'h') for W in sc.W3h]
         if two:
-            def conv_v(sc=sc, prev=prev):
-                L.conv_acc_bn_stats(_vp(prev.pooled_split), 2 * K1, _vp(prev.pooled_split), K1, _vp(sc.W3v), None,
-                                    _vp(sc.lin), N, 1, *geo.args(), bnp, BF16, F32, 1, S())
-            self._tag(conv_v, 'conv_fwd', desc='H%d K3x%d N%d +acc' % (geo.H, K1, N), flops=3 * 2.0 * B * geo.H * geo.W * 9 * K1 * N,
-                      nbytes=B * geo.H * geo.W * (3 * K1 * 2 + 2 * N * 4))
-            conv_v.lane = sc.lane
-            self._after(conv_v, prev.post_op)
-            self.fwd_ops.append(conv_v)
+            todo += [(prev.pooled_split, K1, K1, W, prev.post_op, 'v') for W in sc.W3v]
+        for i, (src, K, Kreal, W, dep, which) in enumerate(todo):
+            na0, na1, _ = passes[i % len(passes)]
+            first, last = i == 0, i == len(todo) - 1
+
+            def conv(src=src, K=K, W=W, na0=na0, na1=na1, first=first, last=last):
+                L.conv_acc_bn_stats(_vp(src), na0 * K, _vp(src) if na1 else None, na1 * K, _vp(W),
+                                    eng.tptr(sc.bk) if first else None, _vp(sc.lin), N, 0 if first else 1, *geo.args(),
+                                    bnp if last else None, BF16, F32, 1, S())
+            self._tag(conv, 'conv_fwd', desc='H%d K3x%d N%d%s' % (geo.H, K, N, '' if first else ' +acc'),
+                      flops=3 * 2.0 * B * geo.H * geo.W * 9 * Kreal * N,
+                      nbytes=B * geo.H * geo.W * (3 * K * 2 + (1 if first else 2) * N * 4))
+            conv.lane = sc.lane
+            self._after(conv, dep)
+            self.fwd_ops.append(conv)
         if sc.live and not use_stats:
             bn = sc.bn
 
@@ -1767,17 +1784,18 @@ class _Plan:
         geo, N, K0, K1 = sc.geo, sc.N, sc.K0, sc.K1
         sc.dlin_split, sp = self._split(sc.dlin, N, geo, sc.lane, ops=self.bwd_ops)
         self._after(sp, elt)
-        lo = lambda t, C: ctypes.c_void_p(t.data_ptr() + (C // 8) * geo.P * 16)      # the lo planes of a split tensor
-        a_hi, a_lo = _vp(sc.src.split), lo(sc.src.split, K0)
-        p_hi = _vp(prev.pooled_split) if prev is not None else None
-        p_lo = lo(prev.pooled_split, K1) if prev is not None else None
-        g_hi, g_lo = _vp(sc.dlin_split), lo(sc.dlin_split, N)
+        part = lambda t, C, j: ctypes.c_void_p(t.data_ptr() + j * (C // 8) * geo.P * 16) if t is not None else None
+        psp = prev.pooled_split if prev is not None else None
         dWv = eng.gptr(sc.wv) if sc.wv is not None else None
-        for i, (a0, a1, g) in enumerate(((a_hi, p_hi, g_hi), (a_lo, p_lo, g_hi), (a_hi, p_hi, g_lo))):
+        # (activation part, gradient part) of every product kept: all pairs with i + j < number of parts
+        pairs = [(i, j) for j in range(eng.split) for i in range(eng.split - j)]
+        for n_, (i, j) in enumerate(pairs):
+            a0, a1, g = part(sc.src.split, K0, i), part(psp, K1, i), part(sc.dlin_split, N, j)
+
             def wgrad(a0=a0, a1=a1, g=g):
                 L.stencil_wgrad(a0, K0, sc.K0real, eng.gptr(sc.wh), a1, K1, K1, dWv, g, N, N, None, 9,
                                 *geo.args(), BF16, 1 if (K0 + K1 <= 128 and N <= 256) else 0, S())
-            self._tag(wgrad, 'conv_wgrad', desc='H%d K%d+%d N%d x3[%d]' % (geo.H, K0, K1, N, i),
+            self._tag(wgrad, 'conv_wgrad', desc='H%d K%d+%d N%d x%d[%d]' % (geo.H, K0, K1, N, len(pairs), n_),
                       flops=2.0 * B * geo.H * geo.W * 9 * (sc.K0real + K1) * N, nbytes=B * geo.H * geo.W * (K0 + K1 + N) * 2)
             wgrad.lane = 10 + (sc.lane - 3)
             self.bwd_ops.append(self._after(wgrad, sp))
@@ -1785,12 +1803,16 @@ class _Plan:
         N1 = K1
         if N0 + N1 == 0:
             return
-        sc.Wd3 = self.zeros((9, 3 * N // 8, N0 + N1, 8), torch.bfloat16)
-        for k_off, mode in ((0, 1), (N, 1), (2 * N, 5)):                       # [hi; hi; lo] along K (= output channels)
-            if N0:
-                self._pack(sc.wh, sc.Wd3, sc.K0real, N, mode, k_off, 3 * N, 0, N0 + N1)
-            if N1:
-                self._pack(sc.wv, sc.Wd3, K1, N, mode, k_off, 3 * N, N0, N0 + N1)
+        passes = _SPLIT_PASSES[eng.split]
+        sc.Wd3 = []
+        for _, _, wparts in passes:
+            Wd = self.zeros((9, 3 * N // 8, N0 + N1, 8), torch.bfloat16)
+            for j, mode in enumerate(wparts):                                  # parts along K (= output channels)
+                if N0:
+                    self._pack(sc.wh, Wd, sc.K0real, N, mode | 1, j * N, 3 * N, 0, N0 + N1)
+                if N1:
+                    self._pack(sc.wv, Wd, K1, N, mode | 1, j * N, 3 * N, N0, N0 + N1)
+            sc.Wd3.append(Wd)
         acc0, out0 = 0, None
         if N0:
             slot = sc.src
@@ -1801,17 +1823,18 @@ class _Plan:
             out0 = slot.dact
         if N1:
             prev.dpooled = self.planes(K1, geo)
-
-        def dgrad(out0=out0, acc0=acc0):
-            L.stencil_gemm(_vp(sc.dlin_split), 2 * N, _vp(sc.dlin_split), N, _vp(sc.Wd3), 9, None,
-                           _vp(out0), N0, acc0, _vp(prev.dpooled) if N1 else None, N1, 0,
-                           *geo.args(), None, 0, None, BF16, F32, 1, S())
-        self._tag(dgrad, 'conv_dgrad', desc='H%d K3x%d N%d+%d' % (geo.H, N, N0, N1), flops=3 * 2.0 * B * geo.H * geo.W * 9 * N * (N0 + N1),
-                  nbytes=B * geo.H * geo.W * (3 * N * 2 + (N0 + N1) * 4))
-        dgrad.lane = sc.lane
-        if N1:
-            prev.dpooled_op = dgrad
-        self.bwd_ops.append(dgrad)
+        for i, ((na0, na1, _), Wd) in enumerate(zip(passes, sc.Wd3)):
+            def dgrad(out0=out0, acc0=acc0 if i == 0 else 1, acc1=0 if i == 0 else 1, na0=na0, na1=na1, Wd=Wd):
+                L.stencil_gemm(_vp(sc.dlin_split), na0 * N, _vp(sc.dlin_split) if na1 else None, na1 * N, _vp(Wd), 9, None,
+                               _vp(out0), N0, acc0, _vp(prev.dpooled) if N1 else None, N1, acc1,
+                               *geo.args(), None, 0, None, BF16, F32, 1, S())
+            self._tag(dgrad, 'conv_dgrad', desc='H%d K3x%d N%d+%d%s' % (geo.H, N, N0, N1, ' +acc' if i else ''),
+                      flops=3 * 2.0 * B * geo.H * geo.W * 9 * N * (N0 + N1),
+                      nbytes=B * geo.H * geo.W * (3 * N * 2 + (N0 + N1) * 4 * (2 if i else 1)))
+            dgrad.lane = sc.lane
+            if N1:
+                prev.dpooled_op = dgrad
+            self.bwd_ops.append(dgrad)
 
     # -- router ------------------------------------------------------------ #
     def _build_router_fwd(self, nd, Balloc, dyn_k, emit_fc=True):

@@ -102,7 +102,7 @@ class Net:
 
     # ---- execution -------------------------------------------------------- #
     def configure(self, **opts):
-        """Engine options: precision='fp32'|'bf16', device, graphs=bool,
+        """Engine options: precision='fp32'|'bf16'|'bf16x3'|'bf16x6', device, graphs=bool,
         dist=bool.  Must be called before the first run."""
         if self._engine is not None:
             raise RuntimeError('configure() after the engine was built')

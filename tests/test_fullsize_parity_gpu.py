@@ -17,7 +17,9 @@ wherever that oracle's logit margin exceeds 0.15 (router logits deep in the net 
 storage).  bf16x3 mode (fp32 storage, every conv product as three bf16 tensor-core products, i.e. 16-bit
 mantissas) against the fp64 oracle: forward 1e-3 (measured 5e-5 .. 8e-5), whole gradient 1.5e-2 (measured
 1.6e-3 .. 9e-3: the backward pass through eight train-mode BatchNorms amplifies a forward perturbation 50-100x,
-in fp32 exactly as here), decisions exact outside a 1e-3 margin.
+in fp32 exactly as here), decisions exact outside a 1e-3 margin.  bf16x6 mode (three-way splits, the six bf16
+products of relative size >= 2^-16 per fp32 product: 24 significant bits on the tensor cores) is held to the fp32
+bounds: forward 1e-3, whole gradient 2e-3 + 1.5 x d, each tensor 1e-2, decisions exact outside a 1e-4 margin.
 """
 import os
 import sys
@@ -42,6 +44,8 @@ B = 128
 TOL = {'fp32': dict(fwd=1e-3, grad_all=2e-3, grad_each=1e-2, margin=1e-4),
        # fp32 storage, convolutions on the tensor cores as three bf16 products per fp32 product (2^-16 relative)
        'bf16x3': dict(fwd=1e-3, grad_all=1.5e-2, grad_each=6e-2, margin=1e-3),
+       # three-way splits, six bf16 products per fp32 product (24 significant bits): the fp32 bounds
+       'bf16x6': dict(fwd=1e-3, grad_all=2e-3, grad_each=1e-2, margin=1e-4),
        'bf16': dict(fwd=5e-2, grad_all=2.5e-1, grad_each=None, margin=1.5e-1)}
 
 CASES = {
@@ -77,7 +81,7 @@ def _build(name, prec):
     return net, x0, y, kc_dev, kc_ref
 
 
-@pytest.mark.parametrize('prec', ['fp32', 'bf16', 'bf16x3'])
+@pytest.mark.parametrize('prec', ['fp32', 'bf16', 'bf16x3', 'bf16x6'])
 @pytest.mark.parametrize('name', list(CASES))
 def test_full_architecture_matches_the_oracle(name, prec):
     tol = TOL[prec]

@@ -118,7 +118,8 @@ def test_no_cpu_fallback():
         net.train.run({net.x0: np.zeros((2, 16, 16, 3), np.float32), net.y: np.eye(10, dtype=np.float32)[:2]})
 
 
-@pytest.mark.parametrize('kind,prec', [('cnv', 'fp32'), ('cnv', 'bf16'), ('cnvpyr', 'bf16'), ('cnv', 'bf16x3')])
+@pytest.mark.parametrize('kind,prec', [('cnv', 'fp32'), ('cnv', 'bf16'), ('cnvpyr', 'bf16'), ('cnv', 'bf16x3'),
+                                       ('cnv', 'bf16x6')])
 def test_standalone_conv_chains_plan(kind, prec):
     """standalone Conv (layer_types.py:55-74) as tree nodes: Conv-BatchNorm-Rect on the image or on a pyramid
     scale picked by Select, classifier flattening the tensor; the plan uses the one-scale stage kernels"""
@@ -127,8 +128,9 @@ def test_standalone_conv_chains_plan(kind, prec):
     eng = Engine(net, precision=prec, impl=0 if prec == 'fp32' else 1, dry_run=True)
     plan = eng._plan(12, True, True)
     kinds = [getattr(op, 'kind', '') for op in plan.fwd_ops + plan.bwd_ops]
-    assert kinds.count('conv_fwd') == 2 and kinds.count('conv_wgrad') == (6 if prec == 'bf16x3' else 2)
-    assert kinds.count('conv_dgrad') == 1                  # none towards the input image
+    n_fwd, n_wg, n_dg = {'bf16x3': (2, 6, 1), 'bf16x6': (4, 12, 2)}.get(prec, (2, 2, 1))
+    assert kinds.count('conv_fwd') == n_fwd and kinds.count('conv_wgrad') == n_wg
+    assert kinds.count('conv_dgrad') == n_dg               # none towards the input image
     assert eng.n_theta >= _n_params(net)
     rec = serdes.encode_net(net)
     assert [c['type'] for c in rec['root']['comps']][-3:] == ['Conv', 'BatchNorm', 'Rect'] or kind == 'cnvpyr'

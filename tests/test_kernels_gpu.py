@@ -367,6 +367,57 @@ def test_bf16x3_conv_reaches_fp32_accuracy_on_the_tensor_cores(B, H, Cin, Cp, Co
     np.testing.assert_allclose(mr[1].cpu().numpy(), 1 / np.sqrt(ref.var((0, 1, 2)) + 1e-6), rtol=1e-3)
 
 
+@pytest.mark.parametrize('B,H,Cin,Cp,Cout', [(3, 8, 16, 0, 16), (4, 16, 16, 16, 32), (5, 4, 64, 32, 64), (6, 4, 128, 0, 128)])
+def test_bf16x6_conv_matches_fp32_arithmetic_on_the_tensor_cores(B, H, Cin, Cp, Cout):
+    """mpnn_split_planes3 + first / second residual weight packing: the conv of FP32 operands as the six bf16
+    products a_h*w_h + a_m*w_h + a_l*w_h + a_h*w_m + a_m*w_m + a_h*w_l (two accumulating launches of K = 3C per
+    source) against the exact conv: 1e-5, i.e. fp32-accumulation level (the three-product mode is held to 1e-4, plain bf16 to 4e-3)."""
+    rng = np.random.default_rng(12)
+    x = rng.standard_normal((B, H, H, Cin)).astype(np.float32)
+    xp = rng.standard_normal((B, H, H, Cp)).astype(np.float32) if Cp else None
+    wh = (rng.standard_normal((3, 3, Cin, Cout)) / np.sqrt(9 * Cin)).astype(np.float32)
+    wv = (rng.standard_normal((3, 3, Cp, Cout)) / np.sqrt(9 * Cp)).astype(np.float32) if Cp else None
+    bias = rng.standard_normal(Cout).astype(np.float32)
+    geo = Geo(B, H, H)
+
+    def split(a, C):
+        src = dev(to_planes(a, geo, C))
+        dst = torch.zeros((3 * C // 8, geo.P, 8), dtype=torch.bfloat16, device='cuda')
+        L().split_planes3(vp(src), C, geo.P, vp(dst), None)
+        return src, dst
+
+    def packs(w, C):
+        out = []
+        for modes in ((0, 0, 0), (4, 4, 8)):
+            W3 = torch.zeros((9, 3 * C // 8, Cout, 8), dtype=torch.bfloat16, device='cuda')
+            for j, mode in enumerate(modes):
+                pack_w(w, 3 * C, j * C, Cout, 0, W3, mode, BF16)
+            out.append(W3)
+        return out
+    xs, xsp = split(x, Cin)
+    parts = [xsp[j * Cin // 8:(j + 1) * Cin // 8].double().cpu().numpy() for j in range(3)]
+    assert rel_err(parts[0] + parts[1] + parts[2], xs.double().cpu().numpy()) < 1e-7      # x = hi + mid + lo to 2^-24
+    W = packs(wh, Cin)
+    w_parts = W[0][:, :Cin // 8].double() + W[1][:, :Cin // 8].double() + W[1][:, 2 * Cin // 8:].double()
+    ref_w = torch.zeros((9, Cin // 8, Cout, 8), device='cuda')
+    pack_w(wh, Cin, 0, Cout, 0, ref_w, 0, F32)
+    assert rel_err(w_parts.cpu().numpy(), ref_w.double().cpu().numpy()) < 1e-7
+    out = torch.zeros((Cout // 8, geo.P, 8), device='cuda')
+    todo = [(xsp, Cin, Wk) for Wk in W]
+    if Cp:
+        _, psp = split(xp, Cp)
+        todo += [(psp, Cp, Wk) for Wk in packs(wv, Cp)]
+    for i, (src, C, Wk) in enumerate(todo):
+        na0, na1 = (3, 0) if i % 2 == 0 else (2, 1)
+        L().conv_acc_bn_stats(vp(src), na0 * C, vp(src) if na1 else None, na1 * C, vp(Wk), vp(dev(bias)) if i == 0 else None,
+                              vp(out), Cout, 0 if i == 0 else 1, B, H, H, geo.G, geo.P, None, BF16, F32, 1, None)
+    torch.cuda.synchronize()
+    ref = _ref_conv(x, xp, wh, wv, bias, lambda a: a)
+    y = from_planes(out.cpu().numpy(), geo, Cout)
+    print('bf16x6 conv error', rel_err(y, ref))
+    assert rel_err(y, ref) < 1e-5, rel_err(y, ref)
+
+
 @pytest.mark.parametrize('dt,impl,shape', [
     (F32, 0, (6, 8, 3, 16, 32)), (BF16, 0, (6, 8, 3, 16, 32)), (BF16, 1, (6, 8, 3, 16, 32)),
     (BF16, 1, (3, 32, 16, 16, 16)), (BF16, 1, (50, 4, 64, 64, 64)), (BF16, 1, (33, 4, 128, 0, 128)),

@@ -180,13 +180,13 @@ def _check(eng, plan):
     return problems
 
 
-@pytest.mark.parametrize('prec,impl', [('bf16', 1), ('fp32', 0), ('bf16x3', 1)])
+@pytest.mark.parametrize('prec,impl', [('bf16', 1), ('fp32', 0), ('bf16x3', 1), ('bf16x6', 1)])
 @pytest.mark.parametrize('kind,hy', [('sr', {}), ('ac', dict(k_cpt=4e-9)), ('cr', dict(k_cpt=4e-9)),
                                      ('actree', dict(k_cpt=2e-9)), ('ac', dict(dyn_k_cpt=True)), ('cnv', {}),
                                      ('cnvmp', {}), ('cnvgmp', {}), ('cnvact', {}), ('cnvdrop', {}), ('aclln', dict(k_cpt=4e-9)), ('acsce', dict(k_cpt=4e-9)), ('srsq', {})])
 def test_every_conflicting_pair_of_launches_is_ordered(kind, hy, prec, impl):
-    if prec == 'bf16x3' and kind in ('cnvmp', 'cnvgmp', 'cnvact', 'cnvdrop'):
-        pytest.skip('MaxPool / GlobalMaxPool / ActivityError blocks are not served in bf16x3 precision')
+    if prec in ('bf16x3', 'bf16x6') and kind in ('cnvmp', 'cnvgmp', 'cnvact', 'cnvdrop'):
+        pytest.skip('MaxPool / GlobalMaxPool / ActivityError blocks are not served in the split-precision modes')
     net = tiny_net(kind, **hy)
     eng = E.Engine(net, precision=prec, impl=impl, dry_run=True)
     holder = {}
