@@ -48,7 +48,9 @@ struct GemmArgs {
     int stats_mode;    // 0 none, 1 moments of out (forward BN), 2 BN-backward sums on out0 (red)
     mpnn_bn_fuse bn;   // bn.acc != NULL: fused BN statistics (last CTA finalises)
     BwdRed red;
-    int dbg;           // tuning aid (MPNN_TUNE_DBG): 1 skip MMAs, 2 skip stores, 4 skip loads
+    int dbg;           // tuning aid (MPNN_TUNE_DBG): 1 skip MMAs, 2 skip stores, 4 skip loads; timing probes of the
+                       // MMA phase (results wrong by construction): 8 all taps read the unshifted tile, 16 the taps
+                       // alternate between the two accumulators, 32 three MMAs of 3x the width instead of nine
 };
 
 constexpr int kThreads = 192;
@@ -104,7 +106,7 @@ stencil_gemm_umma_kernel(const GemmArgs a) {
     float* sstat = reinterpret_cast<float*>(tmem_slot + 4);      // [4 warps][2][NB]
     float* sbias = sstat + 4 * 2 * NB;                           // [NB]
     float* sred = sbias + NB;                                    // [3][N0]: scale / shift / mean of the BN behind out0 (mode 2)
-    const uint32_t ncols = tmem_cols_pow2(2 * NB);
+    const uint32_t ncols = tmem_cols_pow2(((a.dbg & 32) && NBT ? 6 : 2) * NB);
     constexpr bool FAST = EPI != 0;
     const int stats_mode = EPI == 2 ? 2 : (EPI == 1 ? (a.stats_mode == 1 ? 1 : 0) : a.stats_mode);
 
@@ -200,7 +202,22 @@ stencil_gemm_umma_kernel(const GemmArgs a) {
                     mbar_wait(full0 + 8 * s, ph);
                     tc_fence_after();
                     const uint32_t a_lo = a_lo0 + (uint32_t)s * a_stage;
-                    if (!skip) {
+                    if (!skip && (a.dbg & 56)) {
+                        // timing probes (see GemmArgs::dbg)
+                        const uint32_t idesc3 = make_idesc(3 * NB, 0, 0);
+#pragma unroll
+                        for (int tap = 0; tap < 9; ++tap) {
+                            if ((a.dbg & 32) && NBT && tap % 3) continue;
+                            const uint32_t at = a_lo + ((a.dbg & 8) ? 0u : (uint32_t)((tap / 3 - 1) * Wp + (tap % 3 - 1)));
+                            const uint32_t bt = b_lo0 + (uint32_t)tap * b_tap;
+                            const uint32_t dc = (a.dbg & 32) && NBT ? tmem_base + (uint32_t)acc * 3 * NB
+                                              : ((a.dbg & 16) && (tap & 1) ? tmem_base + (uint32_t)(acc ^ 1) * NB : dcol);
+#pragma unroll
+                            for (int ks = 0; ks < (KS ? KS : 1); ++ks)
+                                if (leader) tc_mma2(dc, at + (uint32_t)ks * a_kstep, d_hi, bt + (uint32_t)ks * b_kstep, d_hi,
+                                                    (a.dbg & 32) && NBT ? idesc3 : idesc, (tap | ks) ? 1u : 0u);
+                        }
+                    } else if (!skip) {
 #pragma unroll
                         for (int tap = 0; tap < 9; ++tap) {
                             const uint32_t at = a_lo + (uint32_t)((tap / 3 - 1) * Wp + (tap % 3 - 1));

@@ -116,7 +116,7 @@ class CompactEvaluator:
             st = plan.node[0]
             H0, W0, C0 = hy.x0_shape
             for i, slot in enumerate(st.out):
-                L.pack_input(_vp(plan.x0), n, H0, W0, C0, 2 ** i, _vp(slot.t), slot.C, slot.geo.G, slot.geo.P,
+                L.pack_input(_vp(plan.x0), n, H0, W0, C0, 2 ** i, _vp(slot.t), min(slot.C, (C0 + 7) // 8 * 8), slot.geo.G, slot.geo.P,
                              eng.dtype, self._S())
             self.visits[0] += n
             for k in root.kids:

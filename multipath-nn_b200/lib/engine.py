@@ -917,7 +917,8 @@ class _Plan:
             t = self.planes(cpad, geo)
             slot = Ns(t=t, C=cpad, Creal=C0, geo=geo, dact=None, writers=0, sc=None, consumers=0, fused_red=False,
                       split=None, split_op=None)
-            pk = lambda: L.pack_input(_vp(self.x0), B, H0, W0, C0, 1, _vp(t), cpad, geo.G, geo.P, eng.dtype, eng.stream)
+            # (planes beyond the image's channels stay at their one-time zero fill: only the live ones are written)
+            pk = lambda: L.pack_input(_vp(self.x0), B, H0, W0, C0, 1, _vp(t), min(cpad, _ru(C0, 8)), geo.G, geo.P, eng.dtype, eng.stream)
             pk.lane = 3
             self.fwd_ops.append(pk)
             if eng.split:
@@ -1000,11 +1001,15 @@ class _Plan:
                             L.lln(_vp(self.x0), B, H0, W0, C0, 2 ** i, float(hy.σ), float(hy.ϵ), _vp(tmp), S())
                         lln.lane = 3 + i
                         self.fwd_ops.append(lln)
+                    # channel planes beyond the image's own (padding to the MMA's K = 16) are never written after the
+                    # arena's zero fill: pack only the live planes (half of the bytes for a 3-channel image)
+                    clive = min(cpad, _ru(C0, 8))
+                    if getattr(nd, 'lln', None) is not None:
                         pk = lambda t=t, geo=geo, tmp=tmp: L.pack_input(
-                            _vp(tmp), B, geo.H, geo.W, C0, 1, _vp(t), cpad, geo.G, geo.P, dt, S())
+                            _vp(tmp), B, geo.H, geo.W, C0, 1, _vp(t), clive, geo.G, geo.P, dt, S())
                     else:
                         pk = lambda t=t, i=i, geo=geo: L.pack_input(
-                            _vp(self.x0), B, H0, W0, C0, 2 ** i, _vp(t), cpad, geo.G, geo.P, dt, S())
+                            _vp(self.x0), B, H0, W0, C0, 2 ** i, _vp(t), clive, geo.G, geo.P, dt, S())
                     pk.lane = 3 + i
                     self.fwd_ops.append(pk)
                     if eng.split:
