@@ -511,7 +511,9 @@ def main():
                    'batch_per_gpu': B, 'global_batch': B * world, 'parallelism': 'dp%d' % world,
                    'l2': 'flushed between timed steps (256 MiB memset outside the event pairs)',
                    'cuda_graph': bool(eng.use_graphs), 'conv_impl': 'tcgen05' if eng.impl == 1 else 'simt',
-                   'wgrad_impl': 'tcgen05' if eng.impl_w == 1 else 'simt'},
+                   'wgrad_impl': 'tcgen05' if eng.impl_w == 1 else 'simt',
+                   'dp_tail': None if world == 1 else ('one kernel over NVLink peer memory (MPNN_DIST_FUSED=1)' if eng.fused_dp
+                                                       else 'ncclAllReduce in two buckets (deep stages under the backward pass) + optimiser')},
         'e2e': {'value': e2e, 'unit': 'images/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': B * 4,
                 'timing': 'wall clock around net.train.run(feed) with pinned host batches', 'loss': loss},
         'gpu_launches': int(launches), 'train_mflop_per_img': run.flop / 1e6,

@@ -422,6 +422,40 @@ int mpnn_comm_init_rank(void** comm /* host, out */, int world, int rank, const 
 int mpnn_comm_destroy(void* comm);
 int mpnn_allreduce_flat(void* comm, float* buf, long long n, void* stream);
 
+/* ---- the data-parallel step tail as ONE kernel over NVLink peer memory ----------------------------------
+ * Replaces mpnn_allreduce_flat + mpnn_talr_momentum_step (lib/net_types.py:24-37,96-97,178-181 on the batch
+ * sharded over one process per GPU of a node): gradient reduce-scatter by peer loads, TALR + momentum on the
+ * owned slice, all-gather of theta / momentum (and of the reduced gradient when write_back != 0) by peer
+ * stores, two flag exchanges -- see csrc/p2p.cu.
+ *   exchange buffer   one per rank, from mpnn_p2p_alloc (cudaMalloc, zero-filled):
+ *                     [MPNN_P2P_FLAG_BYTES of flags | grad (g0 moments + n, padded to 4) | theta | accum],
+ *                     the three vectors at 16-byte-aligned byte offsets off_*; identical layout on every rank.
+ *   mapping           every rank exports its buffer (mpnn_p2p_export -> MPNN_P2P_HANDLE_BYTES, a
+ *                     cudaIpcMemHandle_t), ships the handle to the other ranks of the node, and maps theirs with
+ *                     mpnn_p2p_import; base[r] is rank r's buffer as seen from this process (base[rank]: local).
+ *   the call          collective: every rank launches it once per step on its own stream (it may be captured
+ *                     into a CUDA graph); seg_* / hyp / talr as in mpnn_talr_momentum_step, use_stats = the net
+ *                     has per-node moments in grad[0:g0).  Waits are bounded: a peer that never arrives sets a
+ *                     status word (mpnn_p2p_status != 0) instead of hanging the device. */
+#define MPNN_P2P_MAX 16
+#define MPNN_P2P_HANDLE_BYTES 64
+#define MPNN_P2P_FLAG_BYTES 4096
+typedef struct {
+    void* base[MPNN_P2P_MAX];
+    int world, rank;
+    long long off_grad, off_theta, off_accum;
+    int g0, n;
+} mpnn_p2p_desc;
+int mpnn_p2p_alloc(void** ptr /* host, out */, long long bytes);
+int mpnn_p2p_free(void* ptr);
+int mpnn_p2p_export(void* ptr, void* handle64 /* host, out */);
+int mpnn_p2p_import(const void* handle64 /* host */, void** ptr /* host, out */);
+int mpnn_p2p_close(void* ptr);
+int mpnn_p2p_status(const void* local_base, int* status /* host, out */);
+int mpnn_allreduce_talr_p2p(const mpnn_p2p_desc* d /* host */, const int* seg_start, const int* seg_node,
+                            const float* seg_mult, const float* seg_l2, int n_seg, int use_stats, int talr,
+                            const float* hyp, int write_back, void* stream);
+
 /* ---- tcgen05 bring-up probe (tests only) -------------------------------- */
 /* D[128][N] = A[128][K] * B[N][K]^T through one CTA of tcgen05.mma; all
  * operands in the interleaved (no-swizzle) core-matrix layout. */

@@ -202,20 +202,21 @@ stencil_gemm_umma_kernel(const GemmArgs a) {
                     mbar_wait(full0 + 8 * s, ph);
                     tc_fence_after();
                     const uint32_t a_lo = a_lo0 + (uint32_t)s * a_stage;
-                    if (!skip && (a.dbg & 56)) {
-                        // timing probes (see GemmArgs::dbg)
+                    if (NBT != 0 && !skip && (a.dbg & 56)) {
+                        // timing probes (see GemmArgs::dbg); compiled into the 16- / 32-wide instantiations only -- in
+                        // the generic-width ones the second unrolled loop cost 40-80 registers and a resident CTA
                         const uint32_t idesc3 = make_idesc(3 * NB, 0, 0);
 #pragma unroll
                         for (int tap = 0; tap < 9; ++tap) {
-                            if ((a.dbg & 32) && NBT && tap % 3) continue;
+                            if ((a.dbg & 32) && tap % 3) continue;
                             const uint32_t at = a_lo + ((a.dbg & 8) ? 0u : (uint32_t)((tap / 3 - 1) * Wp + (tap % 3 - 1)));
                             const uint32_t bt = b_lo0 + (uint32_t)tap * b_tap;
-                            const uint32_t dc = (a.dbg & 32) && NBT ? tmem_base + (uint32_t)acc * 3 * NB
+                            const uint32_t dc = (a.dbg & 32) ? tmem_base + (uint32_t)acc * 3 * NB
                                               : ((a.dbg & 16) && (tap & 1) ? tmem_base + (uint32_t)(acc ^ 1) * NB : dcol);
 #pragma unroll
                             for (int ks = 0; ks < (KS ? KS : 1); ++ks)
                                 if (leader) tc_mma2(dc, at + (uint32_t)ks * a_kstep, d_hi, bt + (uint32_t)ks * b_kstep, d_hi,
-                                                    (a.dbg & 32) && NBT ? idesc3 : idesc, (tap | ks) ? 1u : 0u);
+                                                    (a.dbg & 32) ? idesc3 : idesc, (tap | ks) ? 1u : 0u);
                         }
                     } else if (!skip) {
 #pragma unroll

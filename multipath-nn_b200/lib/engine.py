@@ -45,6 +45,18 @@ _BN_FUSE = np.dtype([(k, '<u8') for k in ('acc', 'gamma', 'beta', 'm_avg', 'v_av
 _BN_BWD_FUSE = _struct(['acc', 'sums', 'dgamma', 'dbeta'], [])
 _BN_BWD_EPI = _struct(['lin', 'ss', 'mr', 'acc', 'sums', 'dgamma', 'dbeta'], [])
 assert _PACK.itemsize == 48 and _RT_FWD.itemsize == 136 and _RT_BWD.itemsize == 184
+# mpnn_p2p_desc (include/mpnn.h): the exchange buffers of all ranks as mapped into this process
+_P2P_MAX, _P2P_FLAG_BYTES, _P2P_HANDLE_BYTES = 16, 4096, 64
+_P2P = np.dtype([('base', '<u8', (_P2P_MAX,)), ('world', '<i4'), ('rank', '<i4'), ('off_grad', '<i8'),
+                 ('off_theta', '<i8'), ('off_accum', '<i8'), ('g0', '<i4'), ('n', '<i4')], align=True)
+assert _P2P.itemsize == 168
+
+
+class _DevMem:
+    """device memory that is not torch's (the cudaMalloc'ed exchange buffer of the fused data-parallel tail) as
+    a zero-copy torch tensor, through __cuda_array_interface__"""
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = dict(shape=(int(n),), typestr='<f4', data=(int(ptr), False), version=2)
 assert _BN_FUSE.itemsize == 80 and _BN_BWD_FUSE.itemsize == 32 and _BN_BWD_EPI.itemsize == 56
 
 
@@ -199,6 +211,10 @@ class Engine:
         self.comm = None
         self.graph_collective = os.environ.get('MPNN_DIST_GRAPH', '1') != '0'
         self.overlap_allreduce = os.environ.get('MPNN_DIST_OVERLAP', '1') != '0'
+        # data-parallel step tail as ONE kernel over NVLink peer memory (csrc/p2p.cu: reduce-scatter by peer loads,
+        # TALR + momentum on the owned slice, all-gather by peer stores) instead of ncclAllReduce + optimiser
+        self.fused_dp = bool(dist) and self.world > 1 and not self.dry and os.environ.get('MPNN_DIST_FUSED', '0') != '0'
+        self._p2p_desc = None
         self.lane_priority = os.environ.get('MPNN_LANE_PRIORITY', '0') != '0'
         # classifier / router-input heads rotate over this many lanes (1: all on the one heads lane, in stage order)
         self.head_lanes = max(1, int(os.environ.get('MPNN_HEAD_LANES', '4')))
@@ -209,6 +225,8 @@ class Engine:
         self._snapshot = False
         self._analyse()
         self._alloc_params()
+        if self.fused_dp:
+            self._init_p2p()
         self._plans = {}
         self._graphs = {}
         self._lanes = None
@@ -389,14 +407,28 @@ class Engine:
         seg_start.append(off_t)
         n_nodes = len(self.nodes)
         dev = self.dev
-        self.theta = torch.zeros(off_t, dtype=torch.float32, device=dev)
+        self.theta = None if self.fused_dp else torch.zeros(off_t, dtype=torch.float32, device=dev)
         # gradient buffer = [per-node p_tr moments (2 per node, padded to 16 bytes) | gradients]: the moments
         # travel with the gradients through the all-reduce (data-parallel TALR stays replica-consistent) and
         # sit in FRONT so that the two buckets of the overlapped all-reduce are contiguous: [moments | shallow
         # stages] and [deep stages] (their gradients are complete first, see _Plan._build)
         self.g0 = _ru(2 * n_nodes, 4)
-        self.grad = torch.zeros(self.g0 + off_t, dtype=torch.float32, device=dev)
-        self.accum = torch.zeros(off_t, dtype=torch.float32, device=dev)
+        if self.fused_dp:
+            # [flags | grad | theta | accum] in one cudaMalloc'ed, zero-filled buffer that the other ranks map (CUDA IPC)
+            ng, nt = _ru(self.g0 + off_t, 4), _ru(off_t, 4)
+            o_g = _P2P_FLAG_BYTES
+            o_t = _ru(o_g + 4 * ng, 256)
+            o_a = _ru(o_t + 4 * nt, 256)
+            base = ctypes.c_void_p()
+            with torch.cuda.device(dev):
+                self.L.p2p_alloc(ctypes.byref(base), _ru(o_a + 4 * nt, 256))
+                self.grad = torch.as_tensor(_DevMem(base.value + o_g, self.g0 + off_t), device=dev)
+                self.theta = torch.as_tensor(_DevMem(base.value + o_t, off_t), device=dev)
+                self.accum = torch.as_tensor(_DevMem(base.value + o_a, off_t), device=dev)
+            self._p2p_base, self._p2p_offs = base.value, (o_g, o_t, o_a)
+        else:
+            self.grad = torch.zeros(self.g0 + off_t, dtype=torch.float32, device=dev)
+            self.accum = torch.zeros(off_t, dtype=torch.float32, device=dev)
         self.state = torch.zeros(max(off_s, 1), dtype=torch.float32, device=dev)
         self.seg_start = torch.tensor(seg_start, dtype=torch.int32, device=dev)
         self.seg_node = torch.tensor(seg_node, dtype=torch.int32, device=dev)
@@ -649,13 +681,13 @@ class Engine:
                 g = self._capture(plan)
             g[0].replay()                        # pack + forward + backward (+ all-reduce + optimiser when captured)
             if g[1] is not None:
-                if self.dist:
+                if self.dist and not self.fused_dp:
                     self._allreduce(0, plan.ar_split)   # MPNN_DIST_GRAPH=0: issued eagerly between two graphs
                 g[1].replay()                    # TALR + momentum
             return
         self._compute_ops(plan)
         if update:
-            if self.dist:
+            if self.dist and not self.fused_dp:
                 self._allreduce(0, plan.ar_split)
             self._run(plan.opt_ops)
 
@@ -675,6 +707,42 @@ class Engine:
         with torch.cuda.device(self.dev):
             self.L.comm_init_rank(ctypes.byref(comm), self.world, rank, ctypes.c_void_p(uid.data_ptr()))
         self.comm = comm
+
+    def _init_p2p(self):
+        """exchange the CUDA-IPC handles of the exchange buffers over the process group and map the peers' buffers
+        (collective: every rank builds its engine at the same point); one node only"""
+        import torch.distributed as dist
+        rank, world = dist.get_rank(), self.world
+        if world > _P2P_MAX or int(os.environ.get('LOCAL_WORLD_SIZE', world)) != world:
+            raise RuntimeError('MPNN_DIST_FUSED: the fused data-parallel tail maps peer memory of ONE node, up to %d ranks'
+                               % _P2P_MAX)
+        h = torch.zeros(_P2P_HANDLE_BYTES, dtype=torch.uint8)
+        self.L.p2p_export(ctypes.c_void_p(self._p2p_base), ctypes.c_void_p(h.data_ptr()))
+        on_dev = dist.get_backend() == 'nccl'
+        mine = h.to(self.dev) if on_dev else h
+        hs = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(hs, mine)
+        rec = np.zeros(1, _P2P)
+        with torch.cuda.device(self.dev):
+            for r in range(world):
+                if r == rank:
+                    rec['base'][0, r] = self._p2p_base
+                else:
+                    hr = hs[r].cpu().contiguous()
+                    p = ctypes.c_void_p()
+                    self.L.p2p_import(ctypes.c_void_p(hr.data_ptr()), ctypes.byref(p))
+                    rec['base'][0, r] = p.value
+        rec['world'], rec['rank'] = world, rank
+        rec['off_grad'], rec['off_theta'], rec['off_accum'] = self._p2p_offs
+        rec['g0'], rec['n'] = self.g0, self.n_theta
+        self._p2p_desc = rec
+        dist.barrier()
+
+    def p2p_status(self):
+        """0, or 1 if a wait inside the fused tail timed out (a rank never arrived)"""
+        st = ctypes.c_int(0)
+        self.L.p2p_status(ctypes.c_void_p(self._p2p_base), ctypes.byref(st))
+        return st.value
 
     def _allreduce(self, lo=0, hi=None, stream=None):
         """the collective of a step: sum of [TALR moments | gradients] over the replicas, in place.  With the
@@ -720,10 +788,10 @@ class Engine:
         self.theta.copy_(keep[0]); self.accum.copy_(keep[1]); self.state.copy_(keep[2])
         g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
         before = self.L.launches
-        one_graph = (not self.dist) or self.graph_collective
-        if self.dist and self.comm is None:
+        one_graph = (not self.dist) or self.graph_collective or self.fused_dp
+        if self.dist and self.comm is None and not self.fused_dp:
             self._init_comm()
-        if self.dist:
+        if self.dist and not self.fused_dp:
             with torch.cuda.stream(s):           # the communicator's first collective (channel setup) stays out of capture
                 self._allreduce()
             torch.cuda.synchronize(self.dev)
@@ -739,7 +807,7 @@ class Engine:
                 # the whole step is ONE graph: with our own communicator the NCCL launch is captured like any kernel
                 with torch.cuda.graph(g1):
                     self._compute_ops(plan)
-                    if self.dist:
+                    if self.dist and not self.fused_dp:
                         self._allreduce(0, plan.ar_split)
                     self._run(plan.opt_ops)
                 g2 = None
@@ -1112,7 +1180,7 @@ class _Plan:
         # backward list.  Split = first parameter of the conv stage nearest to half of the parameters.
         self.ar_split = None                     # None: one all-reduce over the whole buffer
         split_node = None
-        if eng.dist and eng.overlap_allreduce:
+        if eng.dist and eng.overlap_allreduce and not eng.fused_dp:
             offs = {}
             for sidx, p in enumerate(eng.tparams):
                 offs.setdefault(eng.seg_node_list[sidx], p._bind[2])          # first parameter of each node
@@ -1165,10 +1233,18 @@ class _Plan:
         # ---------------- optimiser ---------------- #
         talr = 1 if (eng.dynamic and bool(net.hypers.talr)) else 0
         stats_ptr = (lambda: _vp(eng.grad)) if eng.dynamic else (lambda: None)
-        self.opt_ops.append(lambda: L.talr_momentum_step(
-            _vp(eng.theta), ctypes.c_void_p(eng.grad.data_ptr() + 4 * eng.g0), _vp(eng.accum), eng.n_theta,
-            _vp(eng.seg_start), _vp(eng.seg_node),
-            _vp(eng.seg_mult), _vp(eng.seg_l2), eng.n_seg, stats_ptr(), talr, _vp(eng.hyp), S()))
+        if eng.fused_dp:
+            # reduce-scatter + TALR / momentum + all-gather over peer memory in ONE launch (csrc/p2p.cu)
+            fused = lambda: L.allreduce_talr_p2p(
+                ctypes.c_void_p(eng._p2p_desc.ctypes.data), _vp(eng.seg_start), _vp(eng.seg_node), _vp(eng.seg_mult),
+                _vp(eng.seg_l2), eng.n_seg, 1 if eng.dynamic else 0, talr, _vp(eng.hyp), 1, S())
+            self._tag(fused, 'allreduce_talr_p2p')
+            self.opt_ops.append(fused)
+        else:
+            self.opt_ops.append(lambda: L.talr_momentum_step(
+                _vp(eng.theta), ctypes.c_void_p(eng.grad.data_ptr() + 4 * eng.g0), _vp(eng.accum), eng.n_theta,
+                _vp(eng.seg_start), _vp(eng.seg_node),
+                _vp(eng.seg_mult), _vp(eng.seg_l2), eng.n_seg, stats_ptr(), talr, _vp(eng.hyp), S()))
         self._finish_pack()
 
     # -- descriptor tables (device arrays of C structs, see include/mpnn.h) -- #

@@ -1,7 +1,10 @@
 """Two-rank data parallelism on real GPUs (NCCL): the product path -- `net.configure(dist=True)`,
 `lib.parallel.shard`, one all-reduce per step over [gradients | TALR moments] -- against the oracle.
 
-  * after 3 steps `theta`, the momentum accumulators and the reduced buffer are BIT-identical across ranks;
+  * after 3 steps `theta`, the momentum accumulators and the reduced buffer are BIT-identical across ranks --
+    with the NCCL all-reduce followed by the optimiser, and with the fused tail (MPNN_DIST_FUSED=1: ONE kernel that
+    reduce-scatters the gradients by peer loads, applies TALR + momentum to its slice and all-gathers the new
+    parameters by peer stores over NVLink, csrc/p2p.cu);
   * after the first step the parameters equal the oracle's data-parallel step on the two shards
     (per-replica BatchNorm, averaged gradients, TALR moments averaged over ranks; the restatement of
     csrc/optim.cu in tests/test_dist_cpu.py).
@@ -27,7 +30,8 @@ from util import batch, randomize_routers, record_of, tiny_net  # noqa: E402
 pytestmark = pytest.mark.gpu
 
 
-def _worker(rank, world, port, rec, x0, y, q, graphs):
+def _worker(rank, world, port, rec, x0, y, q, graphs, fused=False):
+    os.environ['MPNN_DIST_FUSED'] = '1' if fused else '0'
     os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR='127.0.0.1',
                       MASTER_PORT=str(port))
     for p in (ROOT, os.path.join(ROOT, 'multipath-nn_b200'), os.path.join(ROOT, 'tests')):
@@ -44,21 +48,26 @@ def _worker(rank, world, port, rec, x0, y, q, graphs):
         net.train.run({net.x0: xs, net.y: ys, net.mode: 'tr', net.τ: 0.8, net.λ_lrn: 0.1})
         torch.cuda.synchronize()
         snaps.append((eng.theta.cpu().numpy().copy(), eng.accum.cpu().numpy().copy(), eng.grad.cpu().numpy().copy()))
+    assert eng.fused_dp == bool(fused)
+    if fused:
+        assert eng.p2p_status() == 0, 'a wait inside the fused tail timed out'
+        snaps = [(th, ac, g[eng.g0:]) for th, ac, g in snaps]      # the per-node moments are reduced in the kernel, not in place
     q.put((rank, snaps, [(p._bind[2], p.value.size) for p in eng.tparams]))
     torch.distributed.barrier()
     torch.distributed.destroy_process_group()
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs two GPUs')
+@pytest.mark.parametrize('fused', [False, True])         # ncclAllReduce + optimiser | ONE kernel over NVLink peer memory (csrc/p2p.cu)
 @pytest.mark.parametrize('graphs', [False, True])        # eager launches | the whole step (all-reduce included) as one CUDA graph
-def test_two_rank_nccl_replicas_are_bit_identical_and_match_the_oracle(graphs):
+def test_two_rank_nccl_replicas_are_bit_identical_and_match_the_oracle(graphs, fused):
     net = randomize_routers(tiny_net('ac', k_cpt=4e-9))
     rec = record_of(net)
     x0, y = batch(32, seed=4)
     ctx = mp.get_context('spawn')
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, rec, x0, y, q, graphs)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, rec, x0, y, q, graphs, fused)) for r in range(2)]
     for p in procs:
         p.start()
     res = sorted([q.get(timeout=600) for _ in procs], key=lambda t: t[0])
