@@ -435,8 +435,11 @@ int mpnn_allreduce_flat(void* comm, float* buf, long long n, void* stream);
  *                     mpnn_p2p_import; base[r] is rank r's buffer as seen from this process (base[rank]: local).
  *   the call          collective: every rank launches it once per step on its own stream (it may be captured
  *                     into a CUDA graph); seg_* / hyp / talr as in mpnn_talr_momentum_step, use_stats = the net
- *                     has per-node moments in grad[0:g0).  Waits are bounded: a peer that never arrives sets a
- *                     status word (mpnn_p2p_status != 0) instead of hanging the device. */
+ *                     has per-node moments in grad[0:g0).  [lo, hi) is the range of parameters the call handles
+ *                     (multiples of 4; hi <= 0: up to the end) and `channel` (0..3) the flag set it uses: a step
+ *                     may issue the deep-stage parameters early, under the rest of the backward pass, and the
+ *                     remainder at its end, on different channels.  Waits are bounded: a peer that never arrives
+ *                     sets a status word (mpnn_p2p_status != 0) instead of hanging the device. */
 #define MPNN_P2P_MAX 16
 #define MPNN_P2P_HANDLE_BYTES 64
 #define MPNN_P2P_FLAG_BYTES 4096
@@ -454,7 +457,7 @@ int mpnn_p2p_close(void* ptr);
 int mpnn_p2p_status(const void* local_base, int* status /* host, out */);
 int mpnn_allreduce_talr_p2p(const mpnn_p2p_desc* d /* host */, const int* seg_start, const int* seg_node,
                             const float* seg_mult, const float* seg_l2, int n_seg, int use_stats, int talr,
-                            const float* hyp, int write_back, void* stream);
+                            const float* hyp, int write_back, int lo, int hi, int channel, void* stream);
 
 /* ---- tcgen05 bring-up probe (tests only) -------------------------------- */
 /* D[128][N] = A[128][K] * B[N][K]^T through one CTA of tcgen05.mma; all

@@ -1180,7 +1180,7 @@ class _Plan:
         # backward list.  Split = first parameter of the conv stage nearest to half of the parameters.
         self.ar_split = None                     # None: one all-reduce over the whole buffer
         split_node = None
-        if eng.dist and eng.overlap_allreduce and not eng.fused_dp:
+        if eng.dist and eng.overlap_allreduce:
             offs = {}
             for sidx, p in enumerate(eng.tparams):
                 offs.setdefault(eng.seg_node_list[sidx], p._bind[2])          # first parameter of each node
@@ -1224,8 +1224,16 @@ class _Plan:
             if nd.kind == 'rcm':
                 self._build_rcm_bwd(nd, Balloc)
             if split_node is not None and nd.idx == split_node.idx:
-                def ar_deep():
-                    eng._allreduce(self.ar_split, None, stream=S())
+                if eng.fused_dp:
+                    # the deep stages' slice of the fused tail (reduce + TALR / momentum + all-gather) on its own
+                    # flag channel, under the rest of the backward pass: nothing issued later in the step reads
+                    # those parameters (convs read the copies packed at the head of the step, and every launch
+                    # that reads a deep-stage parameter directly also writes one of its gradients)
+                    def ar_deep():
+                        self._p2p_tail(self.ar_split - eng.g0, 0, 1)
+                else:
+                    def ar_deep():
+                        eng._allreduce(self.ar_split, None, stream=S())
                 ar_deep.kind, ar_deep.lane, ar_deep.wait_all = 'allreduce', 20, True
                 self.bwd_ops.append(ar_deep)
         early = [op for op in self.bwd_ops if getattr(op, 'early', False)]
@@ -1234,10 +1242,16 @@ class _Plan:
         talr = 1 if (eng.dynamic and bool(net.hypers.talr)) else 0
         stats_ptr = (lambda: _vp(eng.grad)) if eng.dynamic else (lambda: None)
         if eng.fused_dp:
-            # reduce-scatter + TALR / momentum + all-gather over peer memory in ONE launch (csrc/p2p.cu)
-            fused = lambda: L.allreduce_talr_p2p(
-                ctypes.c_void_p(eng._p2p_desc.ctypes.data), _vp(eng.seg_start), _vp(eng.seg_node), _vp(eng.seg_mult),
-                _vp(eng.seg_l2), eng.n_seg, 1 if eng.dynamic else 0, talr, _vp(eng.hyp), 1, S())
+            # reduce-scatter + TALR / momentum + all-gather over peer memory in ONE launch (csrc/p2p.cu); with the
+            # overlapped schedule the deep stages went out earlier (ar_deep) and this is [moments | shallow stages]
+            talr_, dyn_ = talr, 1 if eng.dynamic else 0
+
+            def p2p_tail(lo, hi, channel):
+                L.allreduce_talr_p2p(ctypes.c_void_p(eng._p2p_desc.ctypes.data), _vp(eng.seg_start), _vp(eng.seg_node),
+                                     _vp(eng.seg_mult), _vp(eng.seg_l2), eng.n_seg, dyn_, talr_, _vp(eng.hyp), 1,
+                                     lo, hi, channel, S())
+            self._p2p_tail = p2p_tail
+            fused = lambda: p2p_tail(0, (self.ar_split - eng.g0) if self.ar_split is not None else 0, 0)
             self._tag(fused, 'allreduce_talr_p2p')
             self.opt_ops.append(fused)
         else:
