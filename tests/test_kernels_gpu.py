@@ -769,9 +769,10 @@ def test_router_tail(B, ns):
 
 
 @pytest.mark.parametrize('train', [1, 0])
-@pytest.mark.parametrize('B', [24, 1000, 2048 + 77])
+@pytest.mark.parametrize('B', [24, 128, 1000, 2048 + 77, 4096, 5000, 9000])
 def test_router_tail_fwd_batched_matches_single(B, train):
-    """cluster forward (8 CTAs per router, two-pass moments through DSMEM) against the single-CTA kernel"""
+    """cluster forward (8 CTAs per router, two-pass moments through DSMEM; rows resident in registers, 1 / 2 / 4 per
+    thread, up to B = 8192, the re-reading kernel beyond) against the single-CTA kernel"""
     from lib.engine import _RT_FWD
     rng = np.random.default_rng(13)
     C = 16
@@ -807,7 +808,7 @@ def test_router_tail_fwd_batched_matches_single(B, train):
             np.testing.assert_allclose(b.cpu().numpy(), a.cpu().numpy(), rtol=1e-5, atol=1e-6)
 
 
-@pytest.mark.parametrize('B', [24, 1000, 2048 + 77])
+@pytest.mark.parametrize('B', [24, 128, 1000, 2048 + 77, 4096, 5000])
 def test_router_tail_bwd_batched_matches_single(B):
     """The one-launch cluster kernel (8 CTAs per router, DSMEM reductions) against the
     single-CTA kernel validated above; routers of different fan-out in the same launch."""
