@@ -223,6 +223,15 @@ int mpnn_bn_relu_pool_bwd(const void* lin, const void* dAct, const void* dFeat, 
                           int C, int B, int H, int W, int G, int P,
                           void* dLin, float* dbias /* += column sums of dLin, or NULL */,
                           int dtype, void* stream);
+/* small tensors (B*H*W <= MPNN_BN_SMALL_MAX_PIXELS, no pooling branch): mpnn_bn_bwd_reduce_fused and
+ * mpnn_bn_relu_pool_bwd in ONE launch -- an 8-CTA cluster per 8-channel plane keeps its pixels in registers and
+ * exchanges the per-channel sums through distributed shared memory.  sums (optional) / dgamma / dbeta as in
+ * mpnn_bn_bwd_fuse; same results as the two-pass pair (fp64 sums across CTAs, fixed order). */
+#define MPNN_BN_SMALL_MAX_PIXELS 8192
+int mpnn_bn_bwd_small(const void* lin, const void* dAct, const void* dFeat, int Balloc,
+                      const float* ss, const float* mr, int C, int B, int H, int W, int G, int P,
+                      float* sums, float* dgamma, float* dbeta, double count,
+                      void* dLin, float* dbias, int dtype, void* stream);
 
 /* ---- heads: LinTrans / Softmax / CrossEntropyError (lib/layer_types.py:39-53,81-84,262-272) */
 /* Z[b][j] = sum_f X[f][b] W[f][j] (+ extra[b]*W[F][j]) + bias[j] */

@@ -388,6 +388,160 @@ bn_relu_pool_bwd_v2_kernel(const __nv_bfloat16* __restrict__ lin, const __nv_bfl
     }
 }
 
+// ---------------------------------------------------------------------------
+// Small tensors (B*H*W <= 8192 pixels, no pooling branch: the coarsest scale of a stage at the reference's
+// batch): reduction AND gradient in ONE launch.  The two-pass pair above is a chain -- partial sums, fp64
+// atomics, fence, ticket, last-CTA finalise, a second launch that reads lin / dAct again -- of ~13 us for
+// a tensor of <= 0.5 MB, eight times on the critical path of the backward pass.  Here one 8-CTA thread-block
+// cluster owns an 8-channel plane: every thread loads its <= 4 pixels once and keeps lin and dy' in
+// registers, the per-channel sums go warp -> CTA -> cluster (distributed shared memory, fixed rank order,
+// fp64 across CTAs) behind ONE cluster barrier, every CTA derives the constants and writes its part of dLin.
+// ---------------------------------------------------------------------------
+#include <cooperative_groups.h>
+namespace cgb = cooperative_groups;
+constexpr int kSmallCL = 8, kSmallT = 256, kSmallRPT = 4;
+
+template <typename T, int RPT>
+__global__ void __cluster_dims__(kSmallCL, 1, 1) __launch_bounds__(kSmallT)
+bn_bwd_small_kernel(const T* __restrict__ lin, const T* __restrict__ dAct, const T* __restrict__ dFeat, int Balloc,
+                    const float* __restrict__ ss, const float* __restrict__ mr, int C, Geom g,
+                    float* __restrict__ sums, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                    float inv_count, T* __restrict__ dLin, float* __restrict__ dbias) {
+    cgb::cluster_group cluster = cgb::this_cluster();
+    const int rank = (int)cluster.block_rank();
+    const int kg = blockIdx.y, KG = C / 8, tid = threadIdx.x;
+    const int total = g.B * g.H * g.W;
+    const int per = (total + kSmallCL - 1) / kSmallCL;
+    __shared__ float red[kSmallT / 32][16];
+    __shared__ float part[16];
+    __shared__ double tot[16];
+    float a[8], c[8], mu[8], rstd[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        a[j] = __ldg(ss + kg * 8 + j); c[j] = __ldg(ss + C + kg * 8 + j);
+        mu[j] = __ldg(mr + kg * 8 + j); rstd[j] = __ldg(mr + C + kg * 8 + j);
+    }
+    float lv[RPT][8], dy[RPT][8];
+    int prow[RPT];
+    float s0[8], s1[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s0[j] = 0.f; s1[j] = 0.f; }
+#pragma unroll
+    for (int u = 0; u < RPT; ++u) {
+        const int k = u * kSmallT + tid, i = rank * per + k;
+        prow[u] = -1;
+        if (k < per && i < total) {
+            const int w = i % g.W, r = i / g.W, h = r % g.H, n = r / g.H;
+            const int p = row_of(g, n, h, w);
+            prow[u] = p;
+            float d[8];
+            Row8<T>::load(plane_row(lin, kg, g.P, p), lv[u]);
+            load_dy<T>(dAct, dFeat, Balloc, KG, g, kg, n, h, w, p, d);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float v = fmaf(a[j], lv[u][j], c[j]) > 0.f ? d[j] : 0.f;
+                dy[u][j] = v;
+                s0[j] += v;
+                s1[j] = fmaf(v, lv[u][j] - mu[j], s1[j]);       // centred: no cancellation against mean * sum dy'
+            }
+        }
+    }
+    const int warp = tid >> 5, lane = tid & 31;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const float t0 = warp_sum(s0[j]), t1 = warp_sum(s1[j]);
+        if (lane == 0) { red[warp][j] = t0; red[warp][8 + j] = t1; }
+    }
+    __syncthreads();
+    if (tid < 16) {
+        float t = 0.f;
+#pragma unroll
+        for (int wv = 0; wv < kSmallT / 32; ++wv) t += red[wv][tid];
+        part[tid] = t;
+    }
+    cluster.sync();
+    if (tid < 16) {
+        double t = 0.0;
+        for (int k = 0; k < kSmallCL; ++k) t += (double)cluster.map_shared_rank(&part[0], k)[tid];
+        tot[tid] = t;
+    }
+    __syncthreads();
+    float pp[8], qq[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const double t0 = tot[j], sx = (double)rstd[j] * tot[8 + j];        // sum dy', sum dy'*xhat
+        const float m0 = (float)t0 * inv_count, m1 = (float)sx * inv_count;
+        pp[j] = -a[j] * rstd[j] * m1;
+        qq[j] = -a[j] * m0 + a[j] * rstd[j] * mu[j] * m1;
+    }
+    if (rank == 0 && tid < 8) {
+        const double t0 = tot[tid], sx = (double)__ldg(mr + C + kg * 8 + tid) * tot[8 + tid];
+        if (sums) { sums[kg * 8 + tid] = (float)t0; sums[C + kg * 8 + tid] = (float)sx; }
+        if (dgamma) dgamma[kg * 8 + tid] += (float)sx;
+        if (dbeta) dbeta[kg * 8 + tid] += (float)t0;
+    }
+    float bs[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) bs[j] = 0.f;
+#pragma unroll
+    for (int u = 0; u < RPT; ++u) {
+        if (prow[u] >= 0) {
+            float out[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                out[j] = fmaf(a[j], dy[u][j], fmaf(pp[j], lv[u][j], qq[j]));
+                bs[j] += out[j];
+            }
+            Row8<T>::store(plane_row(dLin, kg, g.P, prow[u]), out);
+        }
+    }
+    if (dbias) {
+        // conv bias gradient = column sums of dLin (layer_types.py:181-185: b_k is added before BN)
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float t = warp_sum(bs[j]);
+            if (lane == 0) red[warp][j] = t;
+        }
+        __syncthreads();
+        if (tid < 8) {
+            float t = 0.f;
+#pragma unroll
+            for (int wv = 0; wv < kSmallT / 32; ++wv) t += red[wv][tid];
+            atomicAdd(dbias + kg * 8 + tid, t);
+        }
+    }
+    cluster.sync();          // keep this CTA's shared memory alive until every peer has read it
+}
+
+static_assert(kSmallCL * kSmallT * kSmallRPT == MPNN_BN_SMALL_MAX_PIXELS, "bn_bwd_small capacity");
+
+extern "C" int mpnn_bn_bwd_small(const void* lin, const void* dAct, const void* dFeat, int Balloc,
+                                 const float* ss, const float* mr, int C, int B, int H, int W, int G, int P,
+                                 float* sums, float* dgamma, float* dbeta, double count,
+                                 void* dLin, float* dbias, int dtype, void* stream) {
+    MPNN_REQUIRE(C % 8 == 0 && lin && ss && mr && dLin && (dAct || dFeat) && count > 0, "bn_bwd_small: args");
+    const long long total = (long long)B * H * W;
+    MPNN_REQUIRE(total <= (long long)kSmallCL * kSmallT * kSmallRPT,
+                 "bn_bwd_small: %lld pixels (at most %d: use mpnn_bn_bwd_reduce_fused + mpnn_bn_relu_pool_bwd)", total,
+                 kSmallCL * kSmallT * kSmallRPT);
+    Geom g = make_geom(B, H, W, G, P);
+    const int per = ((int)total + kSmallCL - 1) / kSmallCL;
+    const int rpt = (per + kSmallT - 1) / kSmallT;
+    dim3 grid(kSmallCL, C / 8);
+    const float inv = (float)(1.0 / count);
+    cudaStream_t st = (cudaStream_t)stream;
+#define MPNN_BN_SMALL_LAUNCH(R)                                                                             \
+    MPNN_DISPATCH_DTYPE(dtype, (bn_bwd_small_kernel<T, R><<<grid, kSmallT, 0, st>>>(                        \
+        (const T*)lin, (const T*)dAct, (const T*)dFeat, Balloc, ss, mr, C, g, sums, dgamma, dbeta, inv,     \
+        (T*)dLin, dbias)))
+    if (rpt <= 1) { MPNN_BN_SMALL_LAUNCH(1); }
+    else if (rpt <= 2) { MPNN_BN_SMALL_LAUNCH(2); }
+    else { MPNN_BN_SMALL_LAUNCH(4); }
+#undef MPNN_BN_SMALL_LAUNCH
+    return mpnn_check_launch("bn_bwd_small");
+}
+
 static inline int ilog2_exact_b(int v) {
     if (v <= 0 || (v & (v - 1))) return -1;
     int l = 0;

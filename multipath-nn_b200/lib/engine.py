@@ -47,6 +47,7 @@ _BN_BWD_EPI = _struct(['lin', 'ss', 'mr', 'acc', 'sums', 'dgamma', 'dbeta'], [])
 assert _PACK.itemsize == 48 and _RT_FWD.itemsize == 136 and _RT_BWD.itemsize == 184
 # mpnn_p2p_desc (include/mpnn.h): the exchange buffers of all ranks as mapped into this process
 _P2P_MAX, _P2P_FLAG_BYTES, _P2P_HANDLE_BYTES = 16, 4096, 64
+_BN_SMALL_MAX_PIXELS = 8192            # MPNN_BN_SMALL_MAX_PIXELS (include/mpnn.h)
 _P2P = np.dtype([('base', '<u8', (_P2P_MAX,)), ('world', '<i4'), ('rank', '<i4'), ('off_grad', '<i8'),
                  ('off_theta', '<i8'), ('off_accum', '<i8'), ('g0', '<i4'), ('n', '<i4')], align=True)
 assert _P2P.itemsize == 168
@@ -222,6 +223,8 @@ class Engine:
         # train-mode BN statistics: the conv only accumulates the totals, the BN / ReLU / pool kernel behind it derives
         # the constants (MPNN_DEFER_BN=0: the conv's last CTA finalises them, as in round 1)
         self.defer_bn = os.environ.get('MPNN_DEFER_BN', '0') != '0'
+        # BatchNorm backward of small tensors without a pooling branch as one launch (MPNN_BN_SMALL=0: the two-pass pair)
+        self.bn_small = os.environ.get('MPNN_BN_SMALL', '1') != '0'
         self._snapshot = False
         self._analyse()
         self._alloc_params()
@@ -1773,7 +1776,11 @@ class _Plan:
                 self.bwd_ops.append(agrad)
             live = sc.live and (dact is not None or dfeat is not None)
             self._bn_bwd_bufs(sc)
-            if live and not st.out[k].fused_red:   # (fused: the sums arrive with the consumer's data gradient)
+            # small tensors without a pooling branch (the coarsest scale of a stage at the reference's batch): the
+            # reduction and the gradient in ONE launch (mpnn_bn_bwd_small: cluster per plane, rows in registers)
+            small = (live and not st.out[k].fused_red and dpooled is None and eng.bn_small
+                     and B * sc.geo.H * sc.geo.W <= _BN_SMALL_MAX_PIXELS)
+            if live and not st.out[k].fused_red and not small:   # (fused: the sums arrive with the consumer's data gradient)
 
                 def red(sc=sc, dact=dact, dfeat=dfeat):
                     L.bn_bwd_reduce_fused(_vp(sc.lin), _vp(dact), _vp(dfeat), Balloc, _vp(sc.ss), _vp(sc.mr), sc.N,
@@ -1786,13 +1793,21 @@ class _Plan:
             if not live and dpooled is None:
                 raise RuntimeError('engine: scale %d of %r has no gradient path' % (k, lay.name))
 
-            def elt(sc=sc, dact=dact, dfeat=dfeat, dpooled=dpooled, live=live):
-                L.bn_relu_pool_bwd(_vp(sc.lin), _vp(dact), _vp(dfeat), Balloc, _vp(dpooled),
-                                   sc.geo_p.P if dpooled is not None else 0,
-                                   _vp(sc.ss) if live else None, _vp(sc.mr), _vp(sc.sums),
-                                   float(B * sc.geo.H * sc.geo.W), sc.N, *sc.geo.args(), _vp(sc.dlin),
-                                   eng.gptr(sc.bk), dt, S())
-            self._tag(elt, 'bn_bwd', desc='H%d C%d' % (sc.geo.H, sc.N), nbytes=B * sc.geo.H * sc.geo.W * sc.N * (2 if dt == BF16 else 4) * (3 + 0.25 * (dpooled is not None)))
+            if small:
+                def elt(sc=sc, dact=dact, dfeat=dfeat):
+                    bn = sc.bn
+                    L.bn_bwd_small(_vp(sc.lin), _vp(dact), _vp(dfeat), Balloc, _vp(sc.ss), _vp(sc.mr), sc.N,
+                                   *sc.geo.args(), _vp(sc.sums), eng.gptr(bn.params.γ), eng.gptr(bn.params.β),
+                                   float(B * sc.geo.H * sc.geo.W), _vp(sc.dlin), eng.gptr(sc.bk), dt, S())
+            else:
+                def elt(sc=sc, dact=dact, dfeat=dfeat, dpooled=dpooled, live=live):
+                    L.bn_relu_pool_bwd(_vp(sc.lin), _vp(dact), _vp(dfeat), Balloc, _vp(dpooled),
+                                       sc.geo_p.P if dpooled is not None else 0,
+                                       _vp(sc.ss) if live else None, _vp(sc.mr), _vp(sc.sums),
+                                       float(B * sc.geo.H * sc.geo.W), sc.N, *sc.geo.args(), _vp(sc.dlin),
+                                       eng.gptr(sc.bk), dt, S())
+            self._tag(elt, 'bn_bwd', desc='H%d C%d%s' % (sc.geo.H, sc.N, ' 1-launch' if small else ''),
+                      nbytes=B * sc.geo.H * sc.geo.W * sc.N * (2 if dt == BF16 else 4) * (3 + 0.25 * (dpooled is not None)))
             elt.lane = sc.lane
             if dfeat is not None:
                 self._after(elt, getattr(st, 'dfeat_op', None))

@@ -529,6 +529,47 @@ def test_bn_relu_pool_fwd_bwd(dt, pool):
     assert rel_err(from_planes(dlin.float().cpu().numpy(), geo, C), xt.grad.numpy()) < (1e-4 if dt == F32 else 2e-2)
 
 
+@pytest.mark.parametrize('dt', [F32, BF16])
+@pytest.mark.parametrize('B,H,C,with_act,with_feat', [(5, 4, 16, True, True), (128, 4, 64, True, True), (200, 4, 16, False, True),
+                                                     (512, 4, 32, True, False), (31, 8, 8, True, False)])
+def test_bn_bwd_small_matches_the_two_pass_pair(dt, B, H, C, with_act, with_feat):
+    """mpnn_bn_bwd_small (one launch: 8-CTA cluster per plane, pixels in registers, sums through distributed shared
+    memory) against mpnn_bn_bwd_reduce_fused + mpnn_bn_relu_pool_bwd on the same operands: 1 / 2 / 4 pixels per
+    thread, with the head gradient on the flattened features, the data gradient, or both."""
+    from lib.engine import _BN_BWD_FUSE, _host_struct
+    rng = np.random.default_rng(31)
+    td = torch.float32 if dt == F32 else torch.bfloat16
+    geo = Geo(B, H, H)
+    Balloc = -(-B // 128) * 128
+    LIN = dev(to_planes(rng.standard_normal((B, H, H, C)).astype(np.float32) * 2 + 0.5, geo), td)
+    DY = dev(to_planes(rng.standard_normal((B, H, H, C)).astype(np.float32), geo), td) if with_act else None
+    DF = dev(rng.standard_normal((H * H * C // 8, Balloc, 8)).astype(np.float32), td) if with_feat else None
+    ss = dev(np.stack([rng.standard_normal(C), 0.3 * rng.standard_normal(C)]).astype(np.float32))
+    mr = dev(np.stack([0.5 + 0.2 * rng.standard_normal(C), 0.5 + rng.random(C)]).astype(np.float32))
+    count = float(B * H * H)
+    acc = torch.zeros(2 * C + 1, dtype=torch.float64, device='cuda')
+    sums_a = torch.zeros((2, C), device='cuda'); dg_a = torch.zeros(C, device='cuda'); db_a = torch.zeros(C, device='cuda')
+    f = _host_struct(_BN_BWD_FUSE, acc=vp(acc), sums=vp(sums_a), dgamma=vp(dg_a), dbeta=vp(db_a))
+    L().bn_bwd_reduce_fused(vp(LIN), vp(DY), vp(DF), Balloc, vp(ss), vp(mr), C, B, H, H, geo.G, geo.P,
+                            ctypes.c_void_p(f.ctypes.data), dt, None)
+    dlin_a = torch.zeros_like(LIN); dbias_a = torch.zeros(C, device='cuda')
+    L().bn_relu_pool_bwd(vp(LIN), vp(DY), vp(DF), Balloc, None, 0, vp(ss), vp(mr), vp(sums_a), count,
+                         C, B, H, H, geo.G, geo.P, vp(dlin_a), vp(dbias_a), dt, None)
+    sums_b = torch.zeros((2, C), device='cuda'); dg_b = torch.ones(C, device='cuda'); db_b = torch.ones(C, device='cuda')
+    dlin_b = torch.zeros_like(LIN); dbias_b = torch.zeros(C, device='cuda')
+    L().bn_bwd_small(vp(LIN), vp(DY), vp(DF), Balloc, vp(ss), vp(mr), C, B, H, H, geo.G, geo.P,
+                     vp(sums_b), vp(dg_b), vp(db_b), count, vp(dlin_b), vp(dbias_b), dt, None)
+    torch.cuda.synchronize()
+    scale = float(sums_a.abs().max())
+    np.testing.assert_allclose(sums_b.cpu().numpy(), sums_a.cpu().numpy(), rtol=2e-5, atol=2e-6 * scale)
+    np.testing.assert_allclose(dg_b.cpu().numpy() - 1, dg_a.cpu().numpy(), rtol=2e-5, atol=2e-5 * scale)      # accumulates
+    np.testing.assert_allclose(db_b.cpu().numpy() - 1, db_a.cpu().numpy(), rtol=2e-5, atol=2e-5 * scale)
+    a, b = from_planes(dlin_a.float().cpu().numpy(), geo, C), from_planes(dlin_b.float().cpu().numpy(), geo, C)
+    assert rel_err(b, a) < (1e-5 if dt == F32 else 4e-3), rel_err(b, a)
+    np.testing.assert_allclose(dbias_b.cpu().numpy(), dbias_a.cpu().numpy(), rtol=1e-3, atol=1e-3 * float(dbias_a.abs().max()) + 1e-4)
+    assert float(dlin_b.float().abs().sum()) > 0 and torch.equal(dlin_b[:, :geo.G], torch.zeros_like(dlin_b[:, :geo.G]))    # pads untouched
+
+
 # --------------------------------------------------------------------------- #
 # heads
 # --------------------------------------------------------------------------- #
