@@ -223,11 +223,19 @@ int mpnn_bn_relu_pool_bwd(const void* lin, const void* dAct, const void* dFeat, 
                           int C, int B, int H, int W, int G, int P,
                           void* dLin, float* dbias /* += column sums of dLin, or NULL */,
                           int dtype, void* stream);
+#define MPNN_BN_SMALL_MAX_PIXELS 8192
+/* small tensors (B*H*W <= MPNN_BN_SMALL_MAX_PIXELS, no pooled output): the train-mode statistics of `lin`
+ * (lib/layer_types.py:219-249: batch moments, running-average update, scale / shift) AND mpnn_bn_relu_pool_fwd in
+ * ONE launch -- replaces the statistics riding on the conv launch (mpnn_conv_bn_stats) for tensors whose conv would
+ * otherwise end in a chain of atomics, a ticket and a last-CTA finalisation.  Writes ss / mr like mpnn_bn_finalize. */
+int mpnn_bn_fwd_small(const void* lin, int C, int B, int H, int W, int G, int P,
+                      const float* gamma, const float* beta, float* m_avg, float* v_avg,
+                      float d, float eps, float* ss, float* mr,
+                      void* act, void* feat, int Balloc, int dtype, void* stream);
 /* small tensors (B*H*W <= MPNN_BN_SMALL_MAX_PIXELS, no pooling branch): mpnn_bn_bwd_reduce_fused and
  * mpnn_bn_relu_pool_bwd in ONE launch -- an 8-CTA cluster per 8-channel plane keeps its pixels in registers and
  * exchanges the per-channel sums through distributed shared memory.  sums (optional) / dgamma / dbeta as in
  * mpnn_bn_bwd_fuse; same results as the two-pass pair (fp64 sums across CTAs, fixed order). */
-#define MPNN_BN_SMALL_MAX_PIXELS 8192
 int mpnn_bn_bwd_small(const void* lin, const void* dAct, const void* dFeat, int Balloc,
                       const float* ss, const float* mr, int C, int B, int H, int W, int G, int P,
                       float* sums, float* dgamma, float* dbeta, double count,

@@ -188,3 +188,131 @@ extern "C" int mpnn_bn_relu_pool_fwd_acc(const void* lin, int C, int B, int H, i
     MPNN_REQUIRE(bn, "bn_relu_pool_fwd_acc: bn is NULL");
     return bn_relu_pool_fwd_impl(lin, C, B, H, W, G, P, nullptr, bn, act, pooled, Pp, feat, Balloc, dtype, stream);
 }
+
+// ---------------------------------------------------------------------------
+// Small tensors (B*H*W <= MPNN_BN_SMALL_MAX_PIXELS, no pooled output: the coarsest scale of a stage at the
+// reference's batch): train-mode statistics AND BN / ReLU (/ feature flatten) in ONE launch.  With the statistics
+// riding on the conv launch, a small conv ends in a chain of global round trips (fp64 atomics -> fence -> ticket ->
+// last CTA reads the totals back and writes the constants: 6.0 us instead of 2.6 for the same conv without them,
+// profiles/r02_mb_chain.txt).  Here the conv stores `lin` and nothing else; one 8-CTA cluster per 8-channel plane
+// loads its pixels once (<= 4 per thread, kept in registers), sums x and x^2 warp -> CTA -> cluster (distributed
+// shared memory, fixed rank order, fp64 across CTAs) behind ONE cluster barrier, and every CTA derives the
+// constants and writes its part of act / feat; rank 0 publishes ss / mr and updates the running moments
+// (lib/layer_types.py:219-249).
+// ---------------------------------------------------------------------------
+#include <cooperative_groups.h>
+namespace cgf = cooperative_groups;
+constexpr int kFwdCL = 8, kFwdT = 256;
+static_assert(kFwdCL * kFwdT * 4 == MPNN_BN_SMALL_MAX_PIXELS, "bn_fwd_small capacity");
+
+template <typename T, int RPT>
+__global__ void __cluster_dims__(kFwdCL, 1, 1) __launch_bounds__(kFwdT)
+bn_fwd_small_kernel(const T* __restrict__ lin, int C, Geom g, const float* __restrict__ gamma,
+                    const float* __restrict__ beta, float* __restrict__ m_avg, float* __restrict__ v_avg,
+                    float d, float eps, double count, float* __restrict__ ss, float* __restrict__ mr,
+                    T* __restrict__ act, T* __restrict__ feat, int Balloc) {
+    cgf::cluster_group cluster = cgf::this_cluster();
+    const int rank = (int)cluster.block_rank();
+    const int kg = blockIdx.y, KG = C / 8, tid = threadIdx.x;
+    const int total = g.B * g.H * g.W;
+    const int per = (total + kFwdCL - 1) / kFwdCL;
+    __shared__ float red[kFwdT / 32][16];
+    __shared__ float part[16];
+    __shared__ float sa[8], sc[8];
+    float lv[RPT][8];
+    int prow[RPT], pfeat[RPT], pn[RPT];
+    float s1[8], s2[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
+#pragma unroll
+    for (int u = 0; u < RPT; ++u) {
+        const int k = u * kFwdT + tid, i = rank * per + k;
+        prow[u] = -1;
+        if (k < per && i < total) {
+            const int w = i % g.W, r = i / g.W, h = r % g.H, n = r / g.H;
+            prow[u] = row_of(g, n, h, w);
+            pfeat[u] = (h * g.W + w) * KG + kg;
+            pn[u] = n;
+            Row8<T>::load(plane_row(lin, kg, g.P, prow[u]), lv[u]);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { s1[j] += lv[u][j]; s2[j] = fmaf(lv[u][j], lv[u][j], s2[j]); }
+        }
+    }
+    const int warp = tid >> 5, lane = tid & 31;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const float t1 = warp_sum(s1[j]), t2 = warp_sum(s2[j]);
+        if (lane == 0) { red[warp][j] = t1; red[warp][8 + j] = t2; }
+    }
+    __syncthreads();
+    if (tid < 16) {
+        float t = 0.f;
+#pragma unroll
+        for (int wv = 0; wv < kFwdT / 32; ++wv) t += red[wv][tid];
+        part[tid] = t;
+    }
+    cluster.sync();
+    if (tid < 8) {
+        double t1 = 0.0, t2 = 0.0;
+        for (int k = 0; k < kFwdCL; ++k) {
+            const float* pp = cluster.map_shared_rank(&part[0], k);
+            t1 += (double)pp[tid]; t2 += (double)pp[8 + tid];
+        }
+        const int ch = kg * 8 + tid;
+        const double m = t1 / count;
+        double v = t2 / count - m * m;
+        if (v < 0.0) v = 0.0;
+        const float mean = (float)m, var = (float)v;
+        const float rstd = 1.0f / sqrtf(var + eps);
+        const float a = gamma[ch] * rstd, sh = beta[ch] - mean * a;
+        sa[tid] = a; sc[tid] = sh;
+        if (rank == 0) {
+            ss[ch] = a; ss[C + ch] = sh;
+            mr[ch] = mean; mr[C + ch] = rstd;
+            if (m_avg) {
+                m_avg[ch] = d * m_avg[ch] + (1.f - d) * mean;
+                v_avg[ch] = d * v_avg[ch] + (1.f - d) * var;
+            }
+        }
+    }
+    __syncthreads();
+    float a[8], c[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { a[j] = sa[j]; c[j] = sc[j]; }
+#pragma unroll
+    for (int u = 0; u < RPT; ++u) {
+        if (prow[u] >= 0) {
+            float o[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = fmaxf(fmaf(a[j], lv[u][j], c[j]), 0.f);
+            if (act) Row8<T>::store(plane_row(act, kg, g.P, prow[u]), o);
+            if (feat) Row8<T>::store(plane_row(feat, pfeat[u], Balloc, pn[u]), o);
+        }
+    }
+    cluster.sync();          // keep this CTA's shared memory alive until every peer has read it
+}
+
+extern "C" int mpnn_bn_fwd_small(const void* lin, int C, int B, int H, int W, int G, int P,
+                                 const float* gamma, const float* beta, float* m_avg, float* v_avg,
+                                 float d, float eps, float* ss, float* mr,
+                                 void* act, void* feat, int Balloc, int dtype, void* stream) {
+    MPNN_REQUIRE(C % 8 == 0 && lin && gamma && beta && ss && mr && (act || feat), "bn_fwd_small: args");
+    MPNN_REQUIRE((m_avg == nullptr) == (v_avg == nullptr), "bn_fwd_small: m_avg / v_avg");
+    const long long total = (long long)B * H * W;
+    MPNN_REQUIRE(total <= MPNN_BN_SMALL_MAX_PIXELS,
+                 "bn_fwd_small: %lld pixels (at most %d: use mpnn_conv_bn_stats + mpnn_bn_relu_pool_fwd)", total,
+                 MPNN_BN_SMALL_MAX_PIXELS);
+    Geom g = make_geom(B, H, W, G, P);
+    const int per = ((int)total + kFwdCL - 1) / kFwdCL;
+    const int rpt = (per + kFwdT - 1) / kFwdT;
+    dim3 grid(kFwdCL, C / 8);
+    cudaStream_t st = (cudaStream_t)stream;
+#define MPNN_BN_FWD_SMALL_LAUNCH(R)                                                                        \
+    MPNN_DISPATCH_DTYPE(dtype, (bn_fwd_small_kernel<T, R><<<grid, kFwdT, 0, st>>>(                          \
+        (const T*)lin, C, g, gamma, beta, m_avg, v_avg, d, eps, (double)total, ss, mr, (T*)act, (T*)feat, Balloc)))
+    if (rpt <= 1) { MPNN_BN_FWD_SMALL_LAUNCH(1); }
+    else if (rpt <= 2) { MPNN_BN_FWD_SMALL_LAUNCH(2); }
+    else { MPNN_BN_FWD_SMALL_LAUNCH(4); }
+#undef MPNN_BN_FWD_SMALL_LAUNCH
+    return mpnn_check_launch("bn_fwd_small");
+}

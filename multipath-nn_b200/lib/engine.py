@@ -1493,7 +1493,11 @@ class _Plan:
                                  split=getattr(sc, 'act_split', None), split_op=getattr(sc, 'post_op', None)))
                 continue
 
-            if use_stats:
+            # small tensors without a pooled output (the coarsest scale of a stage at the reference's batch): the conv
+            # stores `lin` only, and ONE cluster launch takes the statistics and applies BN / ReLU (mpnn_bn_fwd_small)
+            small_f = (use_stats and not eng.defer_bn and eng.bn_small and sc.pooled is None
+                       and B * geo.H * geo.W <= _BN_SMALL_MAX_PIXELS and (sc.act is not None or sc.feat is not None))
+            if use_stats and not small_f:
                 # train-mode BN statistics ride on the conv launch (last CTA finalises): no bn_finalize
                 bn = sc.bn
                 sc.acc_f = self._acc_f(2 * N + 1) if eng.defer_bn else self.zeros(2 * N + 1, torch.float64)
@@ -1531,7 +1535,12 @@ class _Plan:
                 fin.lane = sc.lane
                 self.fwd_ops.append(fin)
             if sc.live or sc.pooled is not None:
-                if use_stats and eng.defer_bn:
+                if small_f:
+                    def post(sc=sc, bn=sc.bn):
+                        L.bn_fwd_small(_vp(sc.lin), sc.N, *sc.geo.args(), eng.tptr(bn.params.γ), eng.tptr(bn.params.β),
+                                       eng.tptr(bn.params.m_avg), eng.tptr(bn.params.v_avg), float(bn.hypers.d),
+                                       float(bn.hypers.ε), _vp(sc.ss), _vp(sc.mr), _vp(sc.act), _vp(sc.feat), Balloc, dt, S())
+                elif use_stats and eng.defer_bn:
                     def post(sc=sc):
                         L.bn_relu_pool_fwd_acc(_vp(sc.lin), sc.N, *sc.geo.args(), ctypes.c_void_p(sc.bnf.ctypes.data),
                                                _vp(sc.act), _vp(sc.pooled), sc.geo_p.P if sc.pooled is not None else 0,

@@ -532,6 +532,43 @@ def test_bn_relu_pool_fwd_bwd(dt, pool):
 @pytest.mark.parametrize('dt', [F32, BF16])
 @pytest.mark.parametrize('B,H,C,with_act,with_feat', [(5, 4, 16, True, True), (128, 4, 64, True, True), (200, 4, 16, False, True),
                                                      (512, 4, 32, True, False), (31, 8, 8, True, False)])
+def test_bn_fwd_small_matches_finalize_plus_bn_relu(dt, B, H, C, with_act, with_feat):
+    """mpnn_bn_fwd_small (train-mode statistics + BN / ReLU / flatten in one cluster launch) against exact channel
+    sums -> mpnn_bn_finalize -> mpnn_bn_relu_pool_fwd: constants, running moments, activations, features."""
+    rng = np.random.default_rng(32)
+    td = torch.float32 if dt == F32 else torch.bfloat16
+    rd = (lambda a: a) if dt == F32 else bf16_round
+    geo = Geo(B, H, H)
+    Balloc = -(-B // 128) * 128
+    lin = rd(rng.standard_normal((B, H, H, C)).astype(np.float32) * 2 + 0.5)
+    LIN = dev(to_planes(lin, geo), td)
+    gamma, beta = dev(rng.standard_normal(C).astype(np.float32)), dev(0.1 * rng.standard_normal(C).astype(np.float32))
+    part = dev(np.stack([lin.astype(np.float64).sum((0, 1, 2)), (lin.astype(np.float64) ** 2).sum((0, 1, 2))]).astype(np.float32))
+    mk = lambda: (torch.zeros((2, C), device='cuda'), torch.zeros((2, C), device='cuda'),
+                  torch.full((C,), 0.3, device='cuda'), torch.full((C,), 1.7, device='cuda'),
+                  torch.zeros_like(LIN) if with_act else None,
+                  torch.zeros((H * H * C // 8, Balloc, 8), dtype=td, device='cuda') if with_feat else None)
+    ss_a, mr_a, ma_a, va_a, act_a, feat_a = mk()
+    L().bn_finalize(vp(part), 1, C, float(B * H * H), vp(gamma), vp(beta), vp(ma_a), vp(va_a), 0.9, 1e-6, 1,
+                    vp(ss_a), vp(mr_a), None)
+    L().bn_relu_pool_fwd(vp(LIN), C, B, H, H, geo.G, geo.P, vp(ss_a), vp(act_a), None, 0, vp(feat_a), Balloc, dt, None)
+    ss_b, mr_b, ma_b, va_b, act_b, feat_b = mk()
+    L().bn_fwd_small(vp(LIN), C, B, H, H, geo.G, geo.P, vp(gamma), vp(beta), vp(ma_b), vp(va_b), 0.9, 1e-6,
+                     vp(ss_b), vp(mr_b), vp(act_b), vp(feat_b), Balloc, dt, None)
+    torch.cuda.synchronize()
+    for a, b in ((ss_a, ss_b), (mr_a, mr_b), (ma_a, ma_b), (va_a, va_b)):
+        np.testing.assert_allclose(b.cpu().numpy(), a.cpu().numpy(), rtol=3e-5, atol=3e-6)
+    tol = 1e-5 if dt == F32 else 4e-3
+    if with_act:
+        assert rel_err(from_planes(act_b.float().cpu().numpy(), geo, C), from_planes(act_a.float().cpu().numpy(), geo, C)) < tol
+    if with_feat:
+        assert rel_err(feat_b.float().cpu().numpy(), feat_a.float().cpu().numpy()) < tol
+        assert float(feat_b.float().abs().sum()) > 0
+
+
+@pytest.mark.parametrize('dt', [F32, BF16])
+@pytest.mark.parametrize('B,H,C,with_act,with_feat', [(5, 4, 16, True, True), (128, 4, 64, True, True), (200, 4, 16, False, True),
+                                                     (512, 4, 32, True, False), (31, 8, 8, True, False)])
 def test_bn_bwd_small_matches_the_two_pass_pair(dt, B, H, C, with_act, with_feat):
     """mpnn_bn_bwd_small (one launch: 8-CTA cluster per plane, pixels in registers, sums through distributed shared
     memory) against mpnn_bn_bwd_reduce_fused + mpnn_bn_relu_pool_bwd on the same operands: 1 / 2 / 4 pixels per

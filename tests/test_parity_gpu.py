@@ -73,7 +73,10 @@ CASES = [('sr', {}), ('ac', dict(k_cpt=4e-9)), ('cr', dict(k_cpt=4e-9)),
          # ('_bf16_grad': router gradients are DIFFERENCES of the children's costs; where those nearly cancel, the
          #  3e-2 bf16 error of the losses is amplified -- here to 0.25-0.31 on two routers, 0.1-0.2 upstream of them --
          #  while fp32 stays at 1e-3 and the other bf16 cases at 0.01-0.14: round-1 diagnostics)
-         ('sr', dict(x0_shape=(16, 16, 1))), ('ac', dict(k_cpt=4e-9, x0_shape=(16, 16, 1), n_cls=5, _bf16_grad=0.4)),
+         #  the 1-channel sr case sits at the bf16 noise level of its gradient either way: 0.134 with the BN statistics
+         #  taken of the fp32 accumulators inside the conv launch, 0.154 with the one-launch BN of small tensors, which
+         #  takes them of the stored bf16 tensor exactly as the oracle does; fp32 is at 1.5e-6 in both)
+         ('sr', dict(x0_shape=(16, 16, 1), _bf16_grad=0.2)), ('ac', dict(k_cpt=4e-9, x0_shape=(16, 16, 1), n_cls=5, _bf16_grad=0.4)),
          ('crtree', dict(k_cpt=2e-9, n_cls=2)), ('cr', dict(dyn_k_cpt=True, optimistic=True)),
          # standalone Conv chains: on the image, and on a pyramid scale picked by Select
          ('cnv', {}), ('cnvpyr', dict(x0_shape=(16, 16, 1))),
