@@ -622,6 +622,14 @@ int mpnn_stencil_gemm_umma(const void* A0, int K0, const void* A1, int K1, const
         }
     }
     MPNN_REQUIRE(split > 0, "stencil_gemm(tcgen05): K=%d N=%d does not fit shared memory", K0 + K1, N);
+    // fully-connected data gradients at small batches (one or two row tiles, N = 256 .. 2048 outputs): the slice
+    // width above leaves a handful of CTAs, each walking up to 16 accumulator chunks through the generic epilogue
+    // (15 us for 128 x 2048 outputs at K = 32).  While the grid is below one CTA per SM, halve the slices.
+    static const int tune_fcsplit = getenv("MPNN_TUNE_FC_SPLIT") ? atoi(getenv("MPNN_TUNE_FC_SPLIT")) : 1;
+    if (ntaps == 1 && tune_fcsplit) {
+        const int nt = ceil_div(g.rows, 128);
+        while ((long long)nt * split * 2 <= 148 && NB % 64 == 0) { split *= 2; NB /= 2; }
+    }
     size_t w = ((size_t)ntaps * KG * NB * 16 + 127) & ~(size_t)127;
     // CTAs per SM by shared memory, TMEM columns (alloc blocks when exhausted) and registers.  The kernel
     // is latency-bound per CTA, so residency beats pipeline depth: take the deepest ring that still gives

@@ -1146,7 +1146,13 @@ class _Plan:
             tails = lambda: L.router_tail_fwd_batched(
                 _vp(tab), len(self.rt_fwd), B, 16, float(bn0.hypers.d), float(bn0.hypers.ε),
                 1 if self.bn_train else 0, S())
-            self.fwd_ops.append(self._after(tails, *(self.head_ops or [self.last_head_op])))   # needs every head GEMM / loss
+            # the tails need the head GEMMs that write a router's first layer -- not the classifiers' losses, and not the
+            # head of a stage without a router (the last stage: its GEMM and loss then run beside the tails and the
+            # routing walk instead of in front of them; the backward list starts when every lane has drained)
+            feeders = [op for op in self.head_ops if getattr(op, 'feeds_router', False)]
+            if os.environ.get('MPNN_TAILS_WAIT_ALL', '0') != '0':      # A/B switch: the round-2 dependency (every head op)
+                feeders = []
+            self.fwd_ops.append(self._after(tails, *(feeders or self.head_ops or [self.last_head_op])))
         if eng.dynamic:
             self._build_routing()
 
@@ -1333,6 +1339,7 @@ class _Plan:
                            B, 0, 0, 0, Balloc, None, 0, None, BF16, 2, 1, S())
         self._tag(gemm, 'fc_fwd', desc='F%d N%d' % (Fext, hd.N), flops=2.0 * B * F * hd.N, nbytes=B * F * 2)
         gemm.lane = hd.lane
+        gemm.feeds_router = rt is not None
         self._after(gemm, getattr(st, 'feat_op', None))
         self.last_head_op = gemm
         self.head_ops.append(gemm)
