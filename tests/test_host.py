@@ -244,3 +244,43 @@ def test_every_pdl_launched_kernel_waits_for_its_predecessor():
         assert variants, kernel
         for fn in variants:
             assert any('ACQBULK' in l for l in body[fn]), '%s is launched with PDL but never waits' % fn
+
+
+def test_split_precision_passes_cover_exactly_the_products_kept():
+    """The launch lists of the split-precision modes (lib/engine.py::_SPLIT_PASSES), restated in NumPy: bf16x3 keeps
+    a_h*w_h + a_l*w_h + a_h*w_l of a two-way bf16 split (relative error ~2^-16), bf16x6 the six products of relative
+    size >= 2^-16 of a three-way split (what is dropped is <= 2^-23) -- so a K = 1152 dot product (3x3 taps, 128
+    channels) of fp32 operands comes out at fp32-accumulation accuracy in bf16x6 and at ~1e-5 in bf16x3."""
+    from lib.engine import _SPLIT_PASSES
+
+    def bf16(a):                       # round-to-nearest-even to 8 significant bits, as __float2bfloat16_rn
+        u = np.asarray(a, np.float32).view(np.uint32).astype(np.uint64)
+        u = (u + 0x7FFF + ((u >> 16) & 1)) & 0xFFFF0000
+        return u.astype(np.uint32).view(np.float32)
+
+    def parts(x, n):                   # mpnn_split_planes / mpnn_split_planes3, pack modes 0 / 4 / 8
+        out, r = [], np.asarray(x, np.float32)
+        for _ in range(n):
+            h = bf16(r)
+            out.append(h)
+            r = (r - h).astype(np.float32)
+        return out
+    rng = np.random.default_rng(5)
+    a = rng.standard_normal((64, 1152)).astype(np.float32)
+    w = (rng.standard_normal((1152, 32)) / np.sqrt(1152)).astype(np.float32)
+    exact = a.astype(np.float64) @ w.astype(np.float64)
+    mode_part = {0: 0, 4: 1, 8: 2}
+    errs = {}
+    for n, passes in _SPLIT_PASSES.items():
+        ap, wp = parts(a, n), parts(w, n)
+        assert np.abs(sum(p.astype(np.float64) for p in ap) - a).max() <= 2.0 ** (-8 * n) * np.abs(a).max()
+        acc, kept = np.zeros_like(exact), set()
+        for na0, na1, wmodes in passes:
+            a_idx = list(range(na0)) + list(range(na1))          # A0 = the first na0 parts, A1 = the first na1
+            assert len(a_idx) == len(wmodes) == 3
+            for i, m in zip(a_idx, wmodes):
+                kept.add((i, mode_part[m]))
+                acc += ap[i].astype(np.float64) @ wp[mode_part[m]].astype(np.float64)
+        assert kept == {(i, j) for i in range(n) for j in range(n) if i + j < n}      # the pairs the weight gradient uses too
+        errs[n] = float(np.linalg.norm(acc - exact) / np.linalg.norm(exact))
+    assert 1e-7 < errs[2] < 3e-5 and errs[3] < 3e-7, errs
