@@ -626,9 +626,12 @@ int mpnn_stencil_gemm_umma(const void* A0, int K0, const void* A1, int K1, const
     // width above leaves a handful of CTAs, each walking up to 16 accumulator chunks through the generic epilogue
     // (15 us for 128 x 2048 outputs at K = 32).  While the grid is below one CTA per SM, halve the slices.
     static const int tune_fcsplit = getenv("MPNN_TUNE_FC_SPLIT") ? atoi(getenv("MPNN_TUNE_FC_SPLIT")) : 1;
-    if (ntaps == 1 && tune_fcsplit) {
+    // (MPNN_TUNE_CONV_SPLIT=1: the same for the 3x3 convs -- measured with the statistics riding on the conv launch it
+    //  lost 2 %: every slice re-reads the input tile and adds a round of fp64 atomics; off by default)
+    static const int tune_convsplit = getenv("MPNN_TUNE_CONV_SPLIT") ? atoi(getenv("MPNN_TUNE_CONV_SPLIT")) : 0;
+    if ((ntaps == 1 && tune_fcsplit) || (ntaps == 9 && tune_convsplit && !bwd)) {
         const int nt = ceil_div(g.rows, 128);
-        while ((long long)nt * split * 2 <= 148 && NB % 64 == 0) { split *= 2; NB /= 2; }
+        while ((long long)nt * split * 2 <= 148 && NB % 64 == 0 && (N0 == 0 || N0 % (NB / 2) == 0)) { split *= 2; NB /= 2; }
     }
     size_t w = ((size_t)ntaps * KG * NB * 16 + 127) & ~(size_t)127;
     // CTAs per SM by shared memory, TMEM columns (alloc blocks when exhausted) and registers.  The kernel
