@@ -284,3 +284,28 @@ def test_split_precision_passes_cover_exactly_the_products_kept():
         assert kept == {(i, j) for i in range(n) for j in range(n) if i + j < n}      # the pairs the weight gradient uses too
         errs[n] = float(np.linalg.norm(acc - exact) / np.linalg.norm(exact))
     assert 1e-7 < errs[2] < 3e-5 and errs[3] < 3e-7, errs
+
+
+def test_small_batch_plan_choices():
+    """What the planner picks at the reference's batch and above it (dry run; arch_and_hypers.py:19-35):
+    the coarsest scale of every stage takes the one-launch BatchNorm kernels while its tensor has at most 8192 pixels
+    (B <= 512 at 4x4) and the two-pass pair beyond; the router tails wait for the head GEMMs that feed a router only."""
+    import arch_and_hypers as ah
+    from lib import layer_types
+    from lib.engine import Engine
+    layer_types.seed(0)
+    net = ah.ac_chain(k_cpt=4e-9)((32, 32, 3), (10,))
+    eng = Engine(net, precision='bf16', impl=1, dry_run=True)
+    for B, small in ((128, True), (512, True), (1024, False)):
+        plan = eng._plan(B, True, True)
+        ops = plan.fwd_ops + plan.bwd_ops
+        one = [op for op in ops if getattr(op, 'kind', '') == 'bn_bwd' and '1-launch' in getattr(op, 'desc', '')]
+        red_h4 = [op for op in ops if getattr(op, 'kind', '') == 'bn_bwd_reduce' and getattr(op, 'desc', '').startswith('H4 ')]
+        assert (len(one) == 8 and not red_h4) if small else (not one and red_h4), (B, len(one), len(red_h4))
+        assert all(op.desc.startswith('H4 ') for op in one)
+    plan = eng._plan(128, True, True)
+    tails = [op for op in plan.fwd_ops if getattr(op, 'deps', None) and all(getattr(d, 'kind', '') == 'fc_fwd' for d in op.deps)
+             and len(op.deps) >= 2 and getattr(op, 'lane', 0) == 0]
+    assert len(tails) == 1 and len(tails[0].deps) == 7 and all(d.feeds_router for d in tails[0].deps)     # 8 stages, 7 routers
+    heads = [op for op in plan.fwd_ops if getattr(op, 'kind', '') == 'fc_fwd']
+    assert len(heads) == 8 and sum(1 for h in heads if not h.feeds_router) == 1
