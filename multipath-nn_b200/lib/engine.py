@@ -417,7 +417,9 @@ class Engine:
         # stages] and [deep stages] (their gradients are complete first, see _Plan._build)
         self.g0 = _ru(2 * n_nodes, 4)
         if self.fused_dp:
-            # [flags | grad | theta | accum] in one cudaMalloc'ed, zero-filled buffer that the other ranks map (CUDA IPC)
+            # [flags | grad | theta | accum] in one cudaMalloc'ed, zero-filled buffer that the other ranks map (CUDA IPC).
+            # It is deliberately never freed: a peer may still hold the mapping when this engine goes away, and the
+            # flag epochs must stay monotonic for the life of the process (a few MB per engine).
             ng, nt = _ru(self.g0 + off_t, 4), _ru(off_t, 4)
             o_g = _P2P_FLAG_BYTES
             o_t = _ru(o_g + 4 * ng, 256)
